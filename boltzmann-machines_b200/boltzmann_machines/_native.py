@@ -1,0 +1,297 @@
+"""ctypes binding of ``libbm.so`` (C-ABI in ``include/bm.h``) and the engine
+objects the model classes talk to.
+
+There is deliberately no fallback here: if the shared library is missing, was
+not built for this GPU, or no GPU is visible, construction raises
+``RuntimeError`` with the library's own message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbm.so')
+
+UNIT_KINDS = {'bernoulli': 0, 'multinomial': 1, 'gaussian': 2}
+DTYPES = {'float32': 0, 'float64': 1}
+COMPUTE = {'fp32': 0, 'bf16': 1}
+METRIC_BITS = {'l2_loss': 1, 'msre': 2, 'pll': 4, 'free_energy': 8}
+METRIC_SLOTS = {'l2_loss': 0, 'msre': 1, 'pll': 2, 'free_energy': 3}
+
+# every symbol include/bm.h declares (tests check the library exports all of them)
+EXPORTS = (
+    'bm_version', 'bm_last_error', 'bm_device_count', 'bm_ctx_create', 'bm_ctx_destroy', 'bm_ctx_sync',
+    'bm_ctx_timer_start', 'bm_ctx_timer_stop', 'bm_ctx_flush_l2', 'bm_host_alloc', 'bm_host_free',
+    'bm_ctx_launch_count', 'bm_comm_unique_id', 'bm_ctx_comm_init',
+    'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
+    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_transform', 'bm_rbm_metrics',
+    'bm_rbm_get_activation',
+)
+
+
+class RbmCfg(C.Structure):
+    _fields_ = [
+        ('n_visible', C.c_int32), ('n_hidden', C.c_int32),
+        ('v_kind', C.c_int32), ('h_kind', C.c_int32),
+        ('dtype', C.c_int32), ('compute', C.c_int32),
+        ('sample_v', C.c_int32), ('sample_h', C.c_int32),
+        ('max_batch', C.c_int32), ('reserved0', C.c_int32),
+        ('l2', C.c_double), ('dropout_keep', C.c_double),
+        ('sparsity_target', C.c_double), ('sparsity_cost', C.c_double), ('sparsity_damping', C.c_double),
+        ('propup_mult', C.c_double), ('propdown_mult', C.c_double),
+        ('v_n_samples', C.c_double), ('h_n_samples', C.c_double),
+        ('sigma', C.POINTER(C.c_double)),
+    ]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libbm.so and declare the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise RuntimeError("native library not found at '{0}': build it with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)".format(p))
+    lib = C.CDLL(p)
+    vp, i32, u32, u64, i64, dbl, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_int64, C.c_double, C.c_size_t
+    lib.bm_version.restype = C.c_char_p
+    lib.bm_last_error.restype = C.c_char_p
+    protos = {
+        'bm_device_count': [C.POINTER(C.c_int)],
+        'bm_ctx_create': [C.c_int, C.POINTER(vp)],
+        'bm_ctx_sync': [vp], 'bm_ctx_timer_start': [vp], 'bm_ctx_timer_stop': [vp, C.POINTER(C.c_float)],
+        'bm_ctx_flush_l2': [vp], 'bm_host_alloc': [C.POINTER(vp), sz], 'bm_host_free': [vp],
+        'bm_ctx_launch_count': [vp, C.POINTER(u64)],
+        'bm_comm_unique_id': [vp], 'bm_ctx_comm_init': [vp, vp, C.c_int, C.c_int],
+        'bm_rbm_create': [vp, C.POINTER(RbmCfg), C.POINTER(vp)],
+        'bm_rbm_set_param': [vp, C.c_char_p, vp, sz], 'bm_rbm_get_param': [vp, C.c_char_p, vp, sz],
+        'bm_rbm_init_weights': [vp, dbl, u64],
+        'bm_rbm_train_step': [vp, vp, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
+        'bm_rbm_set_data': [vp, vp, i64],
+        'bm_rbm_train_step_at': [vp, i64, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
+        'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
+        'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
+        'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
+    }
+    for name, argtypes in protos.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.bm_ctx_destroy.argtypes = [vp]
+    lib.bm_ctx_destroy.restype = None
+    lib.bm_rbm_destroy.argtypes = [vp]
+    lib.bm_rbm_destroy.restype = None
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libbm: ' + load_library().bm_last_error().decode('utf-8', 'replace'))
+
+
+def device_count():
+    n = C.c_int(0)
+    check(load_library().bm_device_count(C.byref(n)))
+    return n.value
+
+
+class Context(object):
+    """One GPU + compute stream (+ optional NCCL communicator)."""
+    _default = {}
+
+    def __init__(self, device=None):
+        lib = load_library()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', os.environ.get('BM_DEVICE', '0')))
+        self.device = device
+        h = C.c_void_p()
+        check(lib.bm_ctx_create(device, C.byref(h)))
+        self.handle = h
+        self.rank, self.nranks = 0, 1
+
+    @classmethod
+    def default(cls, device=None):
+        key = device
+        if key not in cls._default:
+            cls._default[key] = cls(device)
+        return cls._default[key]
+
+    def sync(self):
+        check(load_library().bm_ctx_sync(self.handle))
+
+    def timer_start(self):
+        check(load_library().bm_ctx_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(load_library().bm_ctx_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(load_library().bm_ctx_flush_l2(self.handle))
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        check(load_library().bm_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    def comm_init(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(load_library().bm_ctx_comm_init(self.handle, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        check(load_library().bm_comm_unique_id(buf))
+        return buf.raw
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array over page-locked host memory (for the per-batch feed path)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(load_library().bm_host_alloc(C.byref(p), n))
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr
+
+
+def _mask(names):
+    m = 0
+    for n in names:
+        m |= METRIC_BITS[n]
+    return m
+
+
+class CudaRBM(object):
+    """Engine object for ``BaseRBM``: a ``bm_rbm`` handle."""
+
+    def __init__(self, cfg, ctx=None):
+        self._lib = load_library()
+        self.ctx = ctx or Context.default()
+        self.cfg = dict(cfg)
+        self.V, self.H = int(cfg['n_visible']), int(cfg['n_hidden'])
+        self.dt = np.dtype(cfg.get('dtype', 'float32'))
+        c = RbmCfg()
+        c.n_visible, c.n_hidden = self.V, self.H
+        c.v_kind = UNIT_KINDS[cfg.get('v_kind', 'bernoulli')]
+        c.h_kind = UNIT_KINDS[cfg.get('h_kind', 'bernoulli')]
+        c.dtype = DTYPES[self.dt.name]
+        compute = cfg.get('compute') or os.environ.get('BM_COMPUTE') or \
+            ('bf16' if self.dt == np.float32 else 'fp32')
+        self.compute = compute
+        c.compute = COMPUTE[compute]
+        c.sample_v, c.sample_h = int(cfg.get('sample_v', False)), int(cfg.get('sample_h', True))
+        c.max_batch = int(cfg.get('max_batch', 0))
+        c.l2 = float(cfg.get('l2', 0.))
+        keep = cfg.get('dropout', None)
+        c.dropout_keep = -1.0 if keep is None else float(keep)
+        c.sparsity_target = float(cfg.get('sparsity_target', 0.1))
+        c.sparsity_cost = float(cfg.get('sparsity_cost', 0.))
+        c.sparsity_damping = float(cfg.get('sparsity_damping', 0.9))
+        c.propup_mult = 2.0 if cfg.get('dbm_first', False) else 1.0
+        c.propdown_mult = 2.0 if cfg.get('dbm_last', False) else 1.0
+        c.v_n_samples = float(cfg.get('v_n_samples', 100))
+        c.h_n_samples = float(cfg.get('h_n_samples', 100))
+        self._sigma = None
+        if cfg.get('sigma', None) is not None:
+            self._sigma = np.ascontiguousarray(
+                np.broadcast_to(np.asarray(cfg['sigma'], dtype=np.float64), (self.V,)))
+            c.sigma = self._sigma.ctypes.data_as(C.POINTER(C.c_double))
+        h = C.c_void_p()
+        check(self._lib.bm_rbm_create(self.ctx.handle, C.byref(c), C.byref(h)))
+        self.handle = h
+        self._names = ['W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'] + (['sigma'] if self._sigma is not None else [])
+        self._shapes = {'W': (self.V, self.H), 'dW': (self.V, self.H), 'vb': (self.V,), 'dvb': (self.V,),
+                        'hb': (self.H,), 'dhb': (self.H,), 'q_means': (self.H,), 'sigma': (self.V,)}
+        self._metrics_buf = (C.c_double * 4)()
+
+    # ---- variables ---------------------------------------------------------------
+    def set_params(self, d):
+        for k, v in d.items():
+            if k == 'sigma':
+                continue                      # fixed at construction (rbm/rbm.py:101-107)
+            a = np.ascontiguousarray(v, dtype=self.dt).reshape(self._shapes[k])
+            check(self._lib.bm_rbm_set_param(self.handle, k.encode(), a.ctypes.data, a.nbytes))
+
+    def get_params(self, names=None):
+        out = {}
+        for k in (names or self._names):
+            a = np.empty(self._shapes[k], dtype=self.dt)
+            check(self._lib.bm_rbm_get_param(self.handle, k.encode(), a.ctypes.data, a.nbytes))
+            out[k] = a
+        return out
+
+    def init_normal_W(self, stddev, op_seed):
+        check(self._lib.bm_rbm_init_weights(self.handle, float(stddev), int(op_seed) & (2 ** 64 - 1)))
+
+    # ---- compute -------------------------------------------------------------------
+    def _batch(self, X):
+        X = np.ascontiguousarray(X, dtype=self.dt)
+        if X.ndim != 2 or X.shape[1] != self.V:
+            raise ValueError('batch has shape {0}, expected (rows, {1})'.format(X.shape, self.V))
+        return X
+
+    def _collect(self, names):
+        return {n: float(self._metrics_buf[METRIC_SLOTS[n]]) for n in names}
+
+    def train_step(self, X, lr, momentum, k, seed, tick, metrics=()):
+        X = self._batch(X)
+        check(self._lib.bm_rbm_train_step(self.handle, X.ctypes.data, X.shape[0], lr, momentum, int(k),
+                                          int(seed), int(tick), _mask(metrics), self._metrics_buf))
+        return self._collect(metrics) if metrics else None
+
+    def set_data(self, X):
+        X = self._batch(X)
+        check(self._lib.bm_rbm_set_data(self.handle, X.ctypes.data, X.shape[0]))
+
+    def train_step_at(self, first_row, rows, lr, momentum, k, seed, tick, metrics=()):
+        check(self._lib.bm_rbm_train_step_at(self.handle, int(first_row), int(rows), lr, momentum, int(k),
+                                             int(seed), int(tick), _mask(metrics), self._metrics_buf))
+        return self._collect(metrics) if metrics else None
+
+    def transform(self, X, k, seed, tick):
+        X = self._batch(X)
+        Hout = np.empty((X.shape[0], self.H), dtype=self.dt)
+        check(self._lib.bm_rbm_transform(self.handle, X.ctypes.data, X.shape[0], int(k), int(seed), int(tick),
+                                         Hout.ctypes.data))
+        return Hout
+
+    def metrics(self, X, k, seed, tick, names):
+        X = self._batch(X)
+        check(self._lib.bm_rbm_metrics(self.handle, X.ctypes.data, X.shape[0], int(k), int(seed), int(tick),
+                                       _mask(names), self._metrics_buf))
+        return self._collect(names)
+
+    def get_activation(self, name, rows):
+        n = self.V if name in ('X', 'v_means', 'v_states') else self.H
+        dt = np.float32 if self.compute == 'bf16' else self.dt
+        a = np.empty((rows, n), dtype=dt)
+        check(self._lib.bm_rbm_get_activation(self.handle, name.encode(), a.ctypes.data, a.nbytes))
+        return a
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self._lib.bm_rbm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_factory(kind):
+    load_library()
+    if kind == 'rbm':
+        return CudaRBM
+    raise RuntimeError("no native engine for '{0}'".format(kind))

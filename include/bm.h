@@ -1,0 +1,123 @@
+/* bm.h -- C-ABI of libbm.so: the B200-native RBM/DBM engine.
+ *
+ * This is the drop-in boundary.  In the reference (yell/boltzmann-machines) the
+ * operator boundary of the hot path is "a TensorFlow graph with named
+ * collections executed by Session.run(fetches, feed_dict)"; each entry point
+ * below names the reference interface it replaces (paths relative to
+ * /root/reference/boltzmann_machines/).  Plain C types only: handles, pointers to
+ * caller-owned host buffers (C-contiguous), sizes.  Every function returns
+ * BM_OK (0) or a negative BM_E* code; bm_last_error() gives the thread-local
+ * message.  Handles are not thread-safe; one context per GPU / per process rank.
+ *
+ * Random numbers: every stochastic call takes (seed, tick).  Element (row r,
+ * column c) of draw site s at Gibbs index t uses Philox-4x32-10 with
+ * key = (seed & 0xffffffff, seed >> 32) and counter = (c / 4, row0 + r,
+ * s | t << 8, tick), word lane c % 4 -- see DESIGN.md "RNG layout".  Results do
+ * not depend on tile shapes or on the number of GPUs.
+ */
+#ifndef BM_H_
+#define BM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BM_OK            0
+#define BM_EINVAL       -1   /* bad argument / shape / name                     */
+#define BM_ECUDA        -2   /* CUDA runtime or driver error                    */
+#define BM_ENOGPU       -3   /* no usable sm_100 device                         */
+#define BM_ENCCL        -4   /* NCCL missing or failed                          */
+#define BM_EUNSUPPORTED -5   /* configuration not implemented by the engine     */
+
+typedef struct bm_ctx bm_ctx;   /* device + streams (+ NCCL communicator)          */
+typedef struct bm_rbm bm_rbm;   /* one RBM: parameters, accumulators, workspaces    */
+typedef struct bm_dbm bm_dbm;   /* one DBM: layers, variational params, particles   */
+
+enum { BM_UNIT_BERNOULLI = 0, BM_UNIT_MULTINOMIAL = 1, BM_UNIT_GAUSSIAN = 2 };  /* layers.py:39-89 */
+enum { BM_DTYPE_F32 = 0, BM_DTYPE_F64 = 1 };                                     /* base/mixin.py:14-25 */
+enum { BM_COMPUTE_FP32 = 0,   /* CUDA-core FMA, storage dtype everywhere (parity anchor) */
+       BM_COMPUTE_BF16 = 1 }; /* tcgen05 bf16 operands, fp32 accumulate (F32 models only) */
+
+/* metric selection bits / slots of the double[4] result (base_rbm.py:482-517) */
+enum { BM_METRIC_L2_LOSS = 1, BM_METRIC_MSRE = 2, BM_METRIC_PLL = 4, BM_METRIC_FREE_ENERGY = 8 };
+enum { BM_SLOT_L2_LOSS = 0, BM_SLOT_MSRE = 1, BM_SLOT_PLL = 2, BM_SLOT_FREE_ENERGY = 3 };
+
+/* Static configuration of an RBM: what BaseRBM._make_constants/_make_vars bake
+ * into the graph (rbm/base_rbm.py:244-327) plus the layer classes' parameters. */
+typedef struct bm_rbm_cfg {
+    int32_t n_visible, n_hidden;
+    int32_t v_kind, h_kind;          /* BM_UNIT_*                                   */
+    int32_t dtype;                   /* BM_DTYPE_* : storage type of every variable  */
+    int32_t compute;                 /* BM_COMPUTE_*                                 */
+    int32_t sample_v, sample_h;      /* sample_v_states / sample_h_states            */
+    int32_t max_batch;               /* sizing hint (workspaces grow on demand)      */
+    int32_t reserved0;
+    double  l2;
+    double  dropout_keep;            /* < 0: no dropout; else keep probability       */
+    double  sparsity_target, sparsity_cost, sparsity_damping;
+    double  propup_mult, propdown_mult;   /* 1 or 2 (dbm_first / dbm_last)           */
+    double  v_n_samples, h_n_samples;     /* MultinomialLayer.n_samples              */
+    const double* sigma;             /* [n_visible] for a gaussian visible layer, else NULL */
+} bm_rbm_cfg;
+
+/* ---- library / context -------------------------------------------------------- */
+const char* bm_version(void);
+const char* bm_last_error(void);
+int  bm_device_count(int* n);                                   /* 0 devices is BM_OK with *n = 0 */
+int  bm_ctx_create(int device, bm_ctx** out);                   /* replaces tf.Session creation, base/tf_model.py:26,33 */
+void bm_ctx_destroy(bm_ctx* ctx);
+int  bm_ctx_sync(bm_ctx* ctx);
+/* device-side stopwatch on the context's compute stream (CUDA events) */
+int  bm_ctx_timer_start(bm_ctx* ctx);
+int  bm_ctx_timer_stop(bm_ctx* ctx, float* ms);
+int  bm_ctx_flush_l2(bm_ctx* ctx);                              /* writes a >L2-sized scratch buffer */
+int  bm_host_alloc(void** p, size_t bytes);                     /* pinned host memory for the feed path */
+int  bm_host_free(void* p);
+int  bm_ctx_launch_count(bm_ctx* ctx, uint64_t* n);             /* kernels launched by this library on ctx */
+
+/* ---- multi-GPU: one process per GPU, chains sharded by rows, sum-allreduce of the
+ *      gradient statistics (no counterpart in the reference: it is single-device) */
+int  bm_comm_unique_id(void* id128);                            /* 128-byte NCCL unique id (rank 0) */
+int  bm_ctx_comm_init(bm_ctx* ctx, const void* id128, int rank, int nranks);
+
+/* ---- RBM ----------------------------------------------------------------------- */
+int  bm_rbm_create(bm_ctx* ctx, const bm_rbm_cfg* cfg, bm_rbm** out);   /* BaseRBM._make_tf_model, base_rbm.py:527-531 */
+void bm_rbm_destroy(bm_rbm* rbm);
+/* variables by name: "W" [V,H], "vb" [V], "hb" [H], "dW", "dvb", "dhb", "q_means" [H]
+ * (get_tf_params / Saver.restore, base/tf_model.py:183-202,22-28); element type = cfg.dtype */
+int  bm_rbm_set_param(bm_rbm* rbm, const char* name, const void* host, size_t bytes);
+int  bm_rbm_get_param(bm_rbm* rbm, const char* name, void* host, size_t bytes);
+/* W <- N(0, stddev) with the stream of tf.random_normal(seed=op_seed) (base_rbm.py:277-279) */
+int  bm_rbm_init_weights(bm_rbm* rbm, double stddev, uint64_t op_seed);
+/* one mini-batch of CD-k: session.run(train_op, feed_dict) (base_rbm.py:415-479, 566).
+ * X: host [rows, n_visible] of cfg.dtype.  On a context with an initialised
+ * communicator X is this rank's shard: every rank passes the same `rows`, the
+ * global batch is rows*nranks, this shard's first global row is rank*rows, and the
+ * gradient statistics are sum-allreduced before the (identical) update on every rank.
+ * metric_mask != 0: also fill metrics_out[4] (computed with the pre-update weights). */
+int  bm_rbm_train_step(bm_rbm* rbm, const void* X, int32_t rows, double lr, double momentum,
+                       int32_t n_gibbs_steps, uint64_t seed, uint32_t tick,
+                       uint32_t metric_mask, double* metrics_out);
+/* dataset-resident variant: upload once, then step on row ranges */
+int  bm_rbm_set_data(bm_rbm* rbm, const void* X, int64_t n_rows);
+int  bm_rbm_train_step_at(bm_rbm* rbm, int64_t first_row, int32_t rows, double lr, double momentum,
+                          int32_t n_gibbs_steps, uint64_t seed, uint32_t tick,
+                          uint32_t metric_mask, double* metrics_out);
+/* transform_op: chain-end E[h | v_k] (base_rbm.py:438-440, 687-700); H_out host [rows, n_hidden] */
+int  bm_rbm_transform(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_steps,
+                      uint64_t seed, uint32_t tick, void* H_out);
+/* msre / pll / l2_loss / free_energy_op on a batch without training (base_rbm.py:573-621) */
+int  bm_rbm_metrics(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_steps,
+                    uint64_t seed, uint32_t tick, uint32_t metric_mask, double* metrics_out);
+/* debugging / parity hooks: activations of the last train_step/transform/metrics call.
+ * name in {"X","h0_means","h0_states","v_means","v_states","h_means"}; element type float32
+ * in BF16 compute mode (widened), cfg.dtype otherwise. */
+int  bm_rbm_get_activation(bm_rbm* rbm, const char* name, void* host, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BM_H_ */

@@ -30,6 +30,24 @@ def oracle_engines():
     set_engine_factory('dbm', old_d)
 
 
+@pytest.fixture(params=['oracle',
+                        pytest.param('cuda-fp32', marks=pytest.mark.gpu),
+                        pytest.param('cuda-bf16', marks=pytest.mark.gpu)])
+def engines(request, monkeypatch):
+    """The engine behind the package's models: numpy oracle (CPU) or libbm.so (GPU)."""
+    from boltzmann_machines.base import set_engine_factory
+    if request.param == 'oracle':
+        from oracle.rbm import rbm_factory
+        old = set_engine_factory('rbm', rbm_factory)
+        yield request.param
+        set_engine_factory('rbm', old)
+    else:
+        monkeypatch.setenv('BM_COMPUTE', request.param.split('-')[1])
+        old = set_engine_factory('rbm', None)
+        yield request.param
+        set_engine_factory('rbm', old)
+
+
 @pytest.fixture
 def workdir(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)

@@ -1,0 +1,168 @@
+"""Parity of the CUDA engine (through the C-ABI) against the CPU oracle on the same seeded
+inputs.  fp32/fp64 compute: element-wise to ~1e-5 (float: summation order and libm differ
+by ulps; a Bernoulli draw can only differ where |u - p| is at rounding level).  bf16 compute:
+against the oracle that rounds at the same points (operands in bf16, fp32 accumulate).
+"""
+import numpy as np
+import pytest
+
+from boltzmann_machines import _native
+from oracle.rbm import OracleRBM
+
+pytestmark = pytest.mark.gpu
+
+ACTS = ('X', 'h0_means', 'h0_states', 'v_means', 'v_states', 'h_means')
+
+
+def make_cfg(kind, V, H, B, dtype='float32', compute='fp32', **kw):
+    cfg = dict(n_visible=V, n_hidden=H, dtype=dtype, compute=compute, l2=1e-4, max_batch=B,
+               sample_v=True, sample_h=True, sparsity_cost=0.01, sparsity_target=0.2)
+    if kind == 'bernoulli':
+        cfg.update(v_kind='bernoulli', h_kind='bernoulli')
+    elif kind == 'gaussian':
+        cfg.update(v_kind='gaussian', h_kind='bernoulli',
+                   sigma=np.linspace(0.5, 1.5, V))
+    elif kind == 'multinomial':
+        cfg.update(v_kind='bernoulli', h_kind='multinomial', h_n_samples=20)
+    cfg.update(kw)
+    return cfg
+
+
+def make_pair(cfg, seed=0):
+    rng = np.random.RandomState(seed)
+    V, H = cfg['n_visible'], cfg['n_hidden']
+    dt = np.dtype(cfg['dtype'])
+    init = dict(W=(0.1 * rng.randn(V, H)).astype(dt), vb=(0.1 * rng.randn(V)).astype(dt),
+                hb=(0.1 * rng.randn(H)).astype(dt))
+    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg)
+    eng.set_params(init), ora.set_params(init)
+    return eng, ora
+
+
+def make_data(cfg, B, seed=1):
+    rng = np.random.RandomState(seed)
+    V = cfg['n_visible']
+    if cfg['v_kind'] == 'gaussian':
+        return rng.randn(B, V).astype(cfg['dtype'])
+    return (rng.rand(B, V) < 0.3).astype(cfg['dtype'])
+
+
+def oracle_acts(ora, X, k, seed, tick):
+    Xp = ora.prepare_input(X, seed, tick)
+    h0_means, v_states, v_means, _, h_means = ora.chain(Xp, k, seed, tick)
+    # recompute h0 states exactly as chain() drew them
+    from oracle import philox as P
+    if ora.cfg.get('sample_h', True):
+        h0s = ora._sample_h(ora.means_h_given_v(Xp), seed, P.SITE_H0, 0, tick, 0)
+    else:
+        h0s = h0_means
+    return dict(X=Xp, h0_means=h0_means, h0_states=h0s, v_means=v_means, v_states=v_states, h_means=h_means)
+
+
+SHAPES = [(37, 29, 19), (784, 16, 32), (130, 70, 65)]
+
+
+@pytest.mark.parametrize('kind', ['bernoulli', 'gaussian', 'multinomial'])
+@pytest.mark.parametrize('V,H,B', SHAPES)
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+def test_cd1_activations_and_update_match_oracle(kind, V, H, B, dtype):
+    """BASELINE configs[0]-style check: one CD-1 step, every intermediate and every variable."""
+    cfg = make_cfg(kind, V, H, B, dtype=dtype, dropout=0.9)
+    eng, ora = make_pair(cfg)
+    X = make_data(cfg, B)
+    seed, tick = 0x1234567, 3
+    want = oracle_acts(ora, X, 1, seed, tick)
+    eng.train_step(X, 0.05, 0.5, 1, seed, tick)
+    tol = 2e-5 if dtype == 'float32' else 1e-9
+    for name in ACTS:
+        got = eng.get_activation(name, B)
+        if name.endswith('states') and kind != 'gaussian' or (name == 'h0_states'):
+            bad = np.mean(got != want[name])
+            assert bad <= 2e-3, (name, bad)
+        else:
+            np.testing.assert_allclose(got, want[name], atol=tol * max(1.0, np.abs(want[name]).max()), err_msg=name)
+    ora.train_step(X, 0.05, 0.5, 1, seed, tick)
+    g, w = eng.get_params(), ora.get_params()
+    for k in ('W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'):
+        np.testing.assert_allclose(g[k], w[k], atol=5e-6 if dtype == 'float32' else 1e-10, err_msg=k)
+    eng.close()
+
+
+@pytest.mark.parametrize('kind', ['bernoulli', 'gaussian', 'multinomial'])
+def test_metrics_match_oracle(kind):
+    cfg = make_cfg(kind, 130, 70, 65, sample_v=False)
+    eng, ora = make_pair(cfg)
+    X = make_data(cfg, 65)
+    names = ('l2_loss', 'msre', 'pll', 'free_energy') if kind != 'gaussian' else ('l2_loss', 'msre', 'free_energy')
+    got = eng.metrics(X, 2, 77, 5, names)
+    want = ora.metrics(X, 2, 77, 5, names)
+    for n in names:
+        assert got[n] == pytest.approx(want[n], rel=2e-4, abs=2e-4), n
+    # metrics returned by a training step see the pre-update weights
+    got = eng.train_step(X, 0.05, 0.5, 2, 78, 6, metrics=names)
+    want = ora.train_step(X, 0.05, 0.5, 2, 78, 6, metrics=names)
+    for n in names:
+        assert got[n] == pytest.approx(want[n], rel=2e-4, abs=2e-4), n
+    eng.close()
+
+
+def test_cdk_trajectory_stays_with_oracle():
+    """10 CD-3 steps, probabilities for visibles (no sampling noise amplification on v)."""
+    cfg = make_cfg('bernoulli', 96, 48, 64, sample_v=False, sparsity_cost=0.0)
+    eng, ora = make_pair(cfg)
+    rng = np.random.RandomState(5)
+    for it in range(10):
+        X = (rng.rand(64, 96) < 0.25).astype(np.float32)
+        eng.train_step(X, 0.05, 0.6, 3, 4242, it)
+        ora.train_step(X, 0.05, 0.6, 3, 4242, it)
+    g, w = eng.get_params(['W', 'hb', 'vb']), ora.get_params(['W', 'hb', 'vb'])
+    for k in g:
+        np.testing.assert_allclose(g[k], w[k], atol=2e-4, err_msg=k)
+    eng.close()
+
+
+def test_transform_matches_oracle_and_ragged_batches():
+    cfg = make_cfg('bernoulli', 50, 20, 16, sample_v=False)
+    eng, ora = make_pair(cfg)
+    for rows in (1, 7, 16, 33):      # 33 > max_batch: workspaces grow on demand
+        X = make_data(cfg, rows, seed=rows)
+        np.testing.assert_allclose(eng.transform(X, 2, 9, rows), ora.transform(X, 2, 9, rows), atol=2e-5)
+    eng.close()
+
+
+def test_resident_dataset_equals_fed_batches():
+    cfg = make_cfg('bernoulli', 64, 32, 16, sample_v=False)
+    a, _ = make_pair(cfg)
+    b, _ = make_pair(cfg)
+    X = make_data(cfg, 64)
+    b.set_data(X)
+    for it in range(4):
+        a.train_step(X[it * 16:(it + 1) * 16], 0.05, 0.5, 1, 11, it)
+        b.train_step_at(it * 16, 16, 0.05, 0.5, 1, 11, it)
+    for k, v in a.get_params().items():
+        np.testing.assert_array_equal(v, b.get_params()[k])
+    a.close(), b.close()
+
+
+def test_init_weights_matches_tf_stream():
+    from oracle import philox as P
+    for dtype in ('float32', 'float64'):
+        eng = _native.CudaRBM(make_cfg('bernoulli', 12, 8, 4, dtype=dtype))
+        eng.init_normal_W(0.01, 1337)
+        W = eng.get_params(['W'])['W']
+        np.testing.assert_allclose(W, P.tf_random_normal((12, 8), 0.01, 1337, dtype), atol=1e-8)
+        np.testing.assert_almost_equal(W[0][0], -0.0094548017 if dtype == 'float32' else -0.0077341544416)
+        eng.close()
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    eng = _native.CudaRBM(make_cfg('bernoulli', 12, 8, 4))
+    with pytest.raises(ValueError):
+        eng.train_step(np.zeros((4, 11), np.float32), 0.1, 0.5, 1, 1, 0)
+    with pytest.raises(RuntimeError):
+        eng.train_step(np.zeros((4, 12), np.float32), 0.1, 0.5, 0, 1, 0)      # k = 0
+    with pytest.raises(RuntimeError):
+        eng.train_step_at(0, 4, 0.1, 0.5, 1, 1, 0)                            # no resident data
+    with pytest.raises(KeyError):
+        eng.set_params({'nope': np.zeros(3)})
+    eng.close()

@@ -1,8 +1,8 @@
 """Port of the reference's RBM tests
 (/root/reference/boltzmann_machines/rbm/tests/test_rbm.py) exercising the
 package's host logic -- schedules, save/load, resume, determinism -- with the
-numpy oracle plugged in as the engine (CPU).  tests/test_rbm_gpu.py runs the
-same scenarios against the CUDA engine."""
+numpy oracle plugged in as the engine (CPU, `-m "not gpu"`), and with the CUDA
+engine in both compute modes (`-m gpu`): the `engines` fixture is parametrised."""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose, assert_almost_equal
@@ -50,18 +50,18 @@ def test_unknown_kwarg_raises():
         BernoulliRBM(n_visible=4, n_hidden=3, no_such_parameter=1)
 
 
-def test_use_before_fit_raises(oracle_engines, workdir):
+def test_use_before_fit_raises(engines, workdir):
     with pytest.raises(RuntimeError):
         BernoulliRBM(n_visible=4, n_hidden=3, model_path='m/').transform(np.zeros((2, 4)))
 
 
-def test_set_params_rejects_unknown(oracle_engines):
+def test_set_params_rejects_unknown(engines):
     with pytest.raises(ValueError):
         BernoulliRBM(n_visible=4, n_hidden=3).set_params(bogus=1)
 
 
 @pytest.mark.parametrize('C,dtype', CASES)
-def test_initialization_kat(oracle_engines, workdir, C, dtype):
+def test_initialization_kat(engines, workdir, C, dtype):
     rbm = C(max_epoch=2, model_path='test_rbm_1/', dtype=dtype, **config())
     rbm.init()
     w00 = rbm.get_tf_params(scope='weights')['W'][0][0]
@@ -69,7 +69,7 @@ def test_initialization_kat(oracle_engines, workdir, C, dtype):
 
 
 @pytest.mark.parametrize('C,dtype', CASES)
-def test_consistency(oracle_engines, workdir, C, dtype):
+def test_consistency(engines, workdir, C, dtype):
     X, X_val = data()
     mk = lambda path: C(max_epoch=2, model_path=path, dtype=dtype, **config())
     r1, r2 = mk('test_rbm_1/'), mk('test_rbm_2/')
@@ -91,7 +91,7 @@ def test_consistency(oracle_engines, workdir, C, dtype):
     same_weights(r1, r2), same_transforms(r1, r2, X_val)
 
 
-def test_consistency_val(oracle_engines, workdir):
+def test_consistency_val(engines, workdir):
     X, X_val = data()
     mk = lambda path: BernoulliRBM(max_epoch=2, model_path=path,
                                    metrics_config=dict(msre=True, pll=True, feg=True, l2_loss=True,
@@ -102,7 +102,7 @@ def test_consistency_val(oracle_engines, workdir):
     same_weights(r1, r2), same_transforms(r1, r2, X_val)
 
 
-def test_resume_equals_reload(oracle_engines, workdir):
+def test_resume_equals_reload(engines, workdir):
     """continuing in memory == reloading from disk and continuing"""
     X, _ = data()
     a = BernoulliRBM(max_epoch=2, model_path='a/', **config()).fit(X)
@@ -113,7 +113,7 @@ def test_resume_equals_reload(oracle_engines, workdir):
     same_weights(a, b)
 
 
-def test_init_from(oracle_engines, workdir):
+def test_init_from(engines, workdir):
     X, _ = data()
     a = BernoulliRBM(max_epoch=1, model_path='a/', **config()).fit(X)
     b = BernoulliRBM(max_epoch=2, model_path='b/', **config())
@@ -125,7 +125,7 @@ def test_init_from(oracle_engines, workdir):
         GaussianRBM(n_visible=N_VISIBLE, n_hidden=N_HIDDEN).init_from(a)
 
 
-def test_get_tf_params_scopes(oracle_engines, workdir):
+def test_get_tf_params_scopes(engines, workdir):
     r = BernoulliRBM(n_visible=5, n_hidden=3, model_path='m/', random_seed=1).init()
     assert set(r.get_tf_params(scope='weights')) == {'W', 'vb', 'hb'}
     assert set(r.get_tf_params(scope='grads_accumulators')) == {'dW', 'dvb', 'dhb'}
