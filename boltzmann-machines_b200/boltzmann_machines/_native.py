@@ -26,7 +26,7 @@ EXPORTS = (
     'bm_ctx_launch_count', 'bm_comm_unique_id', 'bm_ctx_comm_init',
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
     'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_transform', 'bm_rbm_metrics',
-    'bm_rbm_get_activation',
+    'bm_rbm_get_activation', 'bm_debug_tc_gemm',
 )
 
 
@@ -77,6 +77,7 @@ def load_library(path=None):
         'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
+        'bm_debug_tc_gemm': [vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)
@@ -162,6 +163,27 @@ def pinned_empty(shape, dtype=np.float32):
     buf = (C.c_char * n).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
     return arr
+
+
+def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None):
+    """Raw tensor-core GEMM (test hook): C = A' B'^T (+/- A2' B2'^T) with the operands stored as
+    given: A is [M,K] (or [K,M] if a_t), B is [N,K] (or [K,N] if b_t)."""
+    ctx = ctx or Context.default()
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    M, K = (A.shape[1], A.shape[0]) if a_t else A.shape
+    N = B.shape[1] if b_t else B.shape[0]
+    K2 = 0
+    p2a = p2b = None
+    if A2 is not None:
+        A2 = np.ascontiguousarray(A2, dtype=np.float32)
+        B2 = np.ascontiguousarray(B2, dtype=np.float32)
+        K2 = A2.shape[0] if a_t else A2.shape[1]
+        p2a, p2b = A2.ctypes.data, B2.ctypes.data
+    Cout = np.empty((M, N), dtype=np.float32)
+    check(load_library().bm_debug_tc_gemm(ctx.handle, M, N, K, A.ctypes.data, int(a_t), B.ctypes.data, int(b_t),
+                                          K2, p2a, p2b, int(neg2), int(splits), Cout.ctypes.data))
+    return Cout
 
 
 def _mask(names):

@@ -1,7 +1,261 @@
-#include "bm_internal.h"
+// Tensor-core RBM engine (BM_COMPUTE_BF16): the product path for float32 models.
+//
+// Variables (W, biases, momentum accumulators, q_means) stay in fp32 exactly as in the
+// reference; every GEMM of the CD-k step -- h0, the 2k chain half-steps and the fused
+// positive-minus-negative dW -- runs on tcgen05 with bf16 operands and fp32 accumulation
+// (bm_tc.cu).  Activations live in HBM/L2 as bf16 only (binary samples are exact in bf16).
+// A bf16 shadow of W is refreshed by the weight-update kernel.  Metrics (free energy / PLL)
+// are evaluated in fp32 by the inherited CUDA-core kernels.
+#include "bm_rbm.h"
+
 namespace bm {
-struct RbmBase;
-RbmBase* make_rbm_tc(Ctx*, const bm_rbm_cfg&) {
-    throw Error(BM_EUNSUPPORTED, "bf16 tensor-core engine not built yet");
-}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct RbmTC : RbmSimt<float> {
+    typedef __nv_bfloat16 bf16;
+    int ldw, ldv, ldh;
+    DevBuf<bf16> Wb, Xb, h0m_b, h0s_b, vm_b, vs_b, hm_b, hs_b, data_b;
+    DevBuf<float> partials, widen;
+    int tc_cap = 0;
+    bool tc_kinds;
+    // state of the last chain
+    const bf16* X_b = nullptr; int X_ld = 0; int X_row0 = 0; int X_rows_total = 0;
+    const bf16* vstate_b = nullptr;
+    const bf16* h0state_b = nullptr;
+    bool last_was_tc = false;
+
+    RbmTC(Ctx* c, const bm_rbm_cfg& f) : RbmSimt<float>(c, f) {
+        ldw = round_up(H, 64); ldv = round_up(V, 64); ldh = round_up(H, 64);
+        Wb.ensure((size_t)V * ldw);
+        Wb.zero(ctx->stream);
+        tc_kinds = (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
+        reserve_tc(f.max_batch > 0 ? f.max_batch : 1);
+    }
+
+    void reserve_tc(int rows) {
+        if (rows <= tc_cap) return;
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_cap = rows;
+        Xb.ensure((size_t)rows * ldv); vm_b.ensure((size_t)rows * ldv); vs_b.ensure((size_t)rows * ldv);
+        h0m_b.ensure((size_t)rows * ldh); h0s_b.ensure((size_t)rows * ldh);
+        hm_b.ensure((size_t)rows * ldh); hs_b.ensure((size_t)rows * ldh);
+        widen.ensure((size_t)rows * (V > H ? V : H));
+    }
+
+    void refresh_shadow() { launch_f32_to_bf16(ctx, W.p, H, Wb.p, ldw, V, H); }
+
+    void set_param(const char* name, const void* host, size_t bytes) override {
+        RbmSimt<float>::set_param(name, host, bytes);
+        if (!strcmp(name, "W")) { refresh_shadow(); BM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    }
+    void init_weights(double stddev, uint64_t op_seed) override {
+        RbmSimt<float>::init_weights(stddev, op_seed);
+        refresh_shadow();
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void set_data(const void* X, int64_t n_rows) override {
+        RbmSimt<float>::set_data(X, n_rows);
+        data_b.ensure((size_t)n_rows * ldv);
+        launch_f32_to_bf16(ctx, data.p, V, data_b.p, ldv, (int)n_rows, V);
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    TcMat mat(const bf16* p, int rows, int cols, int ld) const { TcMat m; m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; return m; }
+
+    // one conditional on the tensor cores
+    void layer_tc(bool up, TcMat in, int in_row0, bf16* means, bf16* states, bool sample,
+                  uint32_t site, uint32_t t, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
+        TcGemm g;
+        g.M = rows; g.N = up ? H : V;
+        g.A[0] = in; g.a_row0[0] = in_row0; g.K[0] = up ? V : H;
+        g.B[0] = mat(Wb.p, V, H, ldw);
+        g.b_t[0] = up;                 // v W: W is [K=V, N=H] (N contiguous); h W^T: W is [N=V, K=H] (K contiguous)
+        const float mult = (float)(up ? cfg.propup_mult : cfg.propdown_mult);
+        g.acc_scale = mult; g.bias_scale = mult;
+        g.bias = up ? hb.p : vb.p;
+        g.rng = make_rng(seed, site, t, tick, row0);
+        g.out_mean_bf = means; g.ld_mean_bf = up ? ldh : ldv;
+        const int kind = up ? cfg.h_kind : cfg.v_kind;
+        if (kind == BM_UNIT_BERNOULLI) {
+            g.act = ACT_SIGMOID;
+            if (sample) { g.sample = SMP_BERNOULLI; g.out_state_bf = states; g.ld_state_bf = g.ld_mean_bf; }
+        } else {
+            g.act = ACT_LINEAR; g.sigma = sigma.p;
+            if (sample) { g.sample = SMP_GAUSSIAN; g.noise_sigma = sigma.p; g.out_state_bf = states; g.ld_state_bf = g.ld_mean_bf; }
+        }
+        launch_tc_gemm(ctx, g);
+    }
+
+    // input staging: fp32 prepared batch (inherited) -> bf16, or a slice of the resident bf16 dataset
+    void stage_tc(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
+        reserve_tc(rows);
+        const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
+        if (!X_host && plain) {
+            BM_REQUIRE(first_row >= 0 && first_row + rows <= data_rows, "row range outside the resident dataset");
+            reserve(rows);
+            X_b = data_b.p; X_ld = ldv; X_row0 = (int)first_row; X_rows_total = (int)data_rows;
+            Xcur = data.p + (size_t)first_row * V;
+        } else {
+            const float* X = stage_input(X_host, first_row, rows, seed, tick, row0);
+            launch_f32_to_bf16(ctx, X, V, Xb.p, ldv, rows, V);
+            X_b = Xb.p; X_ld = ldv; X_row0 = 0; X_rows_total = rows;
+            Xcur = X;
+        }
+        last_rows = rows;
+    }
+
+    void chain_tc(int rows, int k, uint64_t seed, uint32_t tick, uint32_t row0) {
+        BM_REQUIRE(k >= 1, "n_gibbs_steps must be >= 1");
+        const bool sh = cfg.sample_h != 0, sv = cfg.sample_v != 0;
+        // rows of X beyond `rows` (resident data) only produce output rows >= M, which are masked
+        layer_tc(true, mat(X_b, X_rows_total, V, X_ld), X_row0, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows, seed, tick, row0);
+        h0state_b = sh ? h0s_b.p : h0m_b.p;
+        const bf16* hstate = h0state_b;
+        for (int t = 1; t <= k; ++t) {
+            layer_tc(false, mat(hstate, rows, H, ldh), 0, vm_b.p, vs_b.p, sv, SITE_V, t, rows, seed, tick, row0);
+            vstate_b = sv ? vs_b.p : vm_b.p;
+            const bool smp = sh && t < k;
+            layer_tc(true, mat(vstate_b, rows, V, ldv), 0, hm_b.p, hs_b.p, smp, SITE_H, t, rows, seed, tick, row0);
+            hstate = smp ? hs_b.p : hm_b.p;
+        }
+        last_was_tc = true;
+    }
+
+    void train_step(const void* X_host, int64_t first_row, int rows, double lr, double mom, int k,
+                    uint64_t seed, uint32_t tick, uint32_t mask, double* out) override {
+        if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::train_step(X_host, first_row, rows, lr, mom, k, seed, tick, mask, out); refresh_shadow(); return; }
+        BM_REQUIRE(rows >= 1, "empty batch");
+        const uint32_t row0 = (uint32_t)(ctx->rank * rows);
+        stage_tc(X_host, first_row, rows, seed, tick, row0);
+        chain_tc(rows, k, seed, tick, row0);
+        if (mask) {
+            if (mask & BM_METRIC_MSRE) launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
+            run_metrics(mask, rows, seed, tick, row0, out);
+        }
+
+        float* G = stats.p;
+        float* dvb_sum = G + (size_t)V * H;
+        float* dhb_sum = dvb_sum + V;
+        float* q_sum = dhb_sum + H;
+        // dW_positive - dW_negative as ONE GEMM over the concatenated batch dimension (base_rbm.py:447-448)
+        TcGemm g;
+        g.M = V; g.N = H; g.n_pairs = 2;
+        g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_k0[0] = X_row0;
+        g.B[0] = mat(h0m_b.p, rows, H, ldh); g.b_t[0] = true; g.K[0] = rows;
+        g.A[1] = mat(vstate_b, rows, V, ldv); g.a_t[1] = true;
+        g.B[1] = mat(hm_b.p, rows, H, ldh); g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
+        const int tiles = ((V + 127) / 128) * ((H + 255) / 256);
+        const int chunks = 2 * ((rows + 63) / 64);
+        int splits = ctx->sm_count / (tiles > 0 ? tiles : 1);
+        if (splits < 1) splits = 1;
+        if (splits > chunks) splits = chunks;
+        g.splits = splits; g.split_stride = (size_t)V * H;
+        partials.ensure((size_t)splits * V * H);
+        g.out_f32 = splits > 1 ? partials.p : G; g.ld_f32 = H;
+        launch_tc_gemm(ctx, g);
+        if (splits > 1) launch_reduce_partials(ctx, partials.p, (size_t)V * H, splits, G, (size_t)V * H);
+        launch_colsum_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, rows, V, 1.f, -1.f, dvb_sum);   // :451
+        launch_colsum_bf16(ctx, h0m_b.p, ldh, hm_b.p, ldh, rows, H, 1.f, -1.f, dhb_sum);                          // :453
+        launch_colsum_bf16(ctx, hm_b.p, ldh, nullptr, 0, rows, H, 1.f, 0.f, q_sum);                               // :457
+        allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
+        const float N = (float)((double)rows * ctx->nranks);
+
+        BiasUpdate<float> u;
+        u.V = V; u.H = H; u.dvb_raw = dvb_sum; u.dhb_raw = dhb_sum; u.qsum = q_sum;
+        u.vb = vb.p; u.hb = hb.p; u.dvb = dvb.p; u.dhb = dhb.p; u.q_means = q.p; u.pen = pen.p;
+        u.n_div = N; u.lr = (float)lr; u.mom = (float)mom;
+        u.damp = (float)cfg.sparsity_damping; u.cost = (float)cfg.sparsity_cost; u.target = (float)cfg.sparsity_target;
+        launch_bias_update<float>(ctx, u);
+        launch_weight_update<float>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr, (float)mom, Wb.p, ldw);
+    }
+
+    void transform(const void* X_host, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) override {
+        if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::transform(X_host, rows, k, seed, tick, H_out); return; }
+        BM_REQUIRE(rows >= 1, "empty batch");
+        stage_tc(X_host, 0, rows, seed, tick, 0);
+        chain_tc(rows, k, seed, tick, 0);
+        launch_bf16_to_f32(ctx, hm_b.p, ldh, widen.p, H, rows, H);
+        BM_CUDA(cudaMemcpyAsync(H_out, widen.p, (size_t)rows * H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    void metrics(const void* X_host, int rows, int k, uint64_t seed, uint32_t tick, uint32_t mask, double* out) override {
+        if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::metrics(X_host, rows, k, seed, tick, mask, out); return; }
+        BM_REQUIRE(rows >= 1, "empty batch");
+        stage_tc(X_host, 0, rows, seed, tick, 0);
+        if (mask & BM_METRIC_MSRE) {
+            chain_tc(rows, k, seed, tick, 0);
+            launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
+        }
+        run_metrics(mask, rows, seed, tick, 0, out);
+    }
+
+    void get_activation(const char* name, void* host, size_t bytes) override {
+        if (!last_was_tc) { RbmSimt<float>::get_activation(name, host, bytes); return; }
+        const bf16* src = nullptr; int n = 0, ld = 0;
+        if (!strcmp(name, "X")) { src = X_b + (size_t)X_row0 * X_ld; n = V; ld = X_ld; }
+        else if (!strcmp(name, "h0_means")) { src = h0m_b.p; n = H; ld = ldh; }
+        else if (!strcmp(name, "h0_states")) { src = h0state_b; n = H; ld = ldh; }
+        else if (!strcmp(name, "v_means")) { src = vm_b.p; n = V; ld = ldv; }
+        else if (!strcmp(name, "v_states")) { src = vstate_b; n = V; ld = ldv; }
+        else if (!strcmp(name, "h_means")) { src = hm_b.p; n = H; ld = ldh; }
+        else throw Error(BM_EINVAL, std::string("unknown activation '") + name + "'");
+        BM_REQUIRE(src != nullptr && last_rows > 0, "no step has run yet");
+        BM_REQUIRE(bytes == (size_t)last_rows * n * sizeof(float), "size mismatch");
+        launch_bf16_to_f32(ctx, src, ld, widen.p, n, last_rows, n);
+        BM_CUDA(cudaMemcpyAsync(host, widen.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+};
+
+RbmBase* make_rbm_tc(Ctx* ctx, const bm_rbm_cfg& cfg) { return new RbmTC(ctx, cfg); }
+
+}  // namespace bm
+
+using namespace bm;
+
+extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t a_t,
+                                const float* B, int32_t b_t, int32_t K2, const float* A2, const float* B2,
+                                int32_t neg2, int32_t splits, float* C) {
+    BM_API_BEGIN
+    Ctx* ctx = reinterpret_cast<Ctx*>(hctx);
+    BM_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+    BM_CUDA(cudaSetDevice(ctx->device));
+    TcGemm g;
+    g.M = M; g.N = N; g.n_pairs = (K2 > 0) ? 2 : 1;
+    DevBuf<float> stage; DevBuf<__nv_bfloat16> bufs[4]; DevBuf<float> out;
+    const float* hosts[4] = {A, B, A2, B2};
+    for (int i = 0; i < 2 * g.n_pairs; ++i) {
+        const int pr = i / 2; const bool isA = (i % 2) == 0;
+        const int Kp = pr ? K2 : K;
+        const bool t = isA ? (a_t != 0) : (b_t != 0);
+        const int mn = isA ? M : N;
+        const int rows = t ? Kp : mn, cols = t ? mn : Kp;
+        const int ld = round_up(cols, 8);
+        stage.ensure((size_t)rows * cols);
+        bufs[i].ensure((size_t)rows * ld);
+        BM_CUDA(cudaMemcpyAsync(stage.p, hosts[i], (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        launch_f32_to_bf16(ctx, stage.p, cols, bufs[i].p, ld, rows, cols);
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        TcMat m; m.ptr = bufs[i].p; m.rows = rows; m.cols = cols; m.ld = ld;
+        if (isA) { g.A[pr] = m; g.a_t[pr] = t; } else { g.B[pr] = m; g.b_t[pr] = t; }
+        g.K[pr] = Kp;
+    }
+    g.neg[1] = neg2 != 0;
+    g.splits = splits > 0 ? splits : 1;
+    g.split_stride = (size_t)M * N;
+    out.ensure((size_t)g.splits * M * N);
+    g.out_f32 = out.p; g.ld_f32 = N;
+    launch_tc_gemm(ctx, g);
+    DevBuf<float> red;
+    const float* res = out.p;
+    if (g.splits > 1) {
+        red.ensure((size_t)M * N);
+        launch_reduce_partials(ctx, out.p, (size_t)M * N, g.splits, red.p, (size_t)M * N);
+        res = red.p;
+    }
+    BM_CUDA(cudaMemcpyAsync(C, res, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    BM_API_END
 }

@@ -1,3 +1,56 @@
-// Tensor-core (tcgen05) path: declarations.  See bm_tc.cu.
+// Tensor-core (tcgen05 / TMEM / TMA) path of libbm.so: host-side description of one fused
+// "layer op" and its launcher.  Kernel in bm_tc.cu.
 #pragma once
 #include "bm_internal.h"
+
+namespace bm {
+
+// A row-major bf16 matrix in HBM: `rows` x `cols`, leading dimension `ld` (elements, multiple of 8),
+// 16-byte aligned base.
+struct TcMat {
+    const __nv_bfloat16* ptr = nullptr;
+    int rows = 0, cols = 0, ld = 0;
+};
+
+// C[M,N] (fp32, TMEM) = sum over pairs of  (+/-) A_p[M,K_p] * B_p[N,K_p]^T
+//   a_t == false: A_p is stored [M, K] (K contiguous, "K-major");  true: stored [K, M] (M contiguous, "MN-major")
+//   b_t == false: B_p is stored [N, K] (K-major);                 true: stored [K, N] (MN-major)
+// then the same fused epilogue as the CUDA-core LayerOp (bias, scale, activation, Philox sampling),
+// writing bf16 (operands of the next GEMM) and/or fp32 (host-visible results, dW partials).
+struct TcGemm {
+    int M = 0, N = 0;
+    int n_pairs = 1;
+    TcMat A[2], B[2];
+    bool a_t[2] = {false, false}, b_t[2] = {false, false};
+    bool neg[2] = {false, false};     // subtract this pair (tcgen05 a_negate)
+    int K[2] = {0, 0};
+    int a_row0[2] = {0, 0};           // first row of A_p inside its buffer (resident dataset slices; !a_t only)
+    int a_k0[2] = {0, 0};             // first K row of A_p inside its buffer (a_t only)
+    // split-K: the concatenated K range is cut into `splits` parts; part s writes out_f32 + s * split_stride
+    int splits = 1;
+    size_t split_stride = 0;
+    // epilogue
+    float acc_scale = 1.f, bias_scale = 1.f;
+    const float* bias = nullptr;
+    const float* sigma = nullptr;
+    const float* noise_sigma = nullptr;
+    int act = ACT_LINEAR;
+    int sample = SMP_NONE;
+    RngKey rng{};
+    __nv_bfloat16* out_mean_bf = nullptr;  int ld_mean_bf = 0;
+    __nv_bfloat16* out_state_bf = nullptr; int ld_state_bf = 0;
+    float* out_f32 = nullptr;              int ld_f32 = 0;     // fp32 means (or raw accumulators)
+};
+
+void launch_tc_gemm(Ctx* ctx, const TcGemm& g);
+
+// helpers on bf16 activations
+void launch_f32_to_bf16(Ctx* ctx, const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols);
+void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst, int ldd, int rows, int cols);
+// out[n] = s1 * sum_r P[r,n] + s2 * sum_r Q[r,n]  (bf16 inputs, Q nullable, fp32 out)
+void launch_colsum_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq,
+                        int rows, int cols, float s1, float s2, float* out);
+// G[i] = sum_s partial[s * stride + i]
+void launch_reduce_partials(Ctx* ctx, const float* partial, size_t stride, int splits, float* G, size_t n);
+
+}  // namespace bm
