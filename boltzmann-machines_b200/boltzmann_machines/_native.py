@@ -23,7 +23,7 @@ METRIC_SLOTS = {'l2_loss': 0, 'msre': 1, 'pll': 2, 'free_energy': 3}
 EXPORTS = (
     'bm_version', 'bm_last_error', 'bm_device_count', 'bm_ctx_create', 'bm_ctx_destroy', 'bm_ctx_sync',
     'bm_ctx_timer_start', 'bm_ctx_timer_stop', 'bm_ctx_flush_l2', 'bm_host_alloc', 'bm_host_free',
-    'bm_ctx_launch_count', 'bm_comm_unique_id', 'bm_ctx_comm_init',
+    'bm_ctx_launch_count', 'bm_ctx_profile_tc', 'bm_ctx_profile_read', 'bm_comm_unique_id', 'bm_ctx_comm_init',
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
     'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_transform', 'bm_rbm_metrics',
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
@@ -67,6 +67,8 @@ def load_library(path=None):
         'bm_ctx_sync': [vp], 'bm_ctx_timer_start': [vp], 'bm_ctx_timer_stop': [vp, C.POINTER(C.c_float)],
         'bm_ctx_flush_l2': [vp], 'bm_host_alloc': [C.POINTER(vp), sz], 'bm_host_free': [vp],
         'bm_ctx_launch_count': [vp, C.POINTER(u64)],
+        'bm_ctx_profile_tc': [vp, C.c_int],
+        'bm_ctx_profile_read': [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(u64)],
         'bm_comm_unique_id': [vp], 'bm_ctx_comm_init': [vp, vp, C.c_int, C.c_int],
         'bm_rbm_create': [vp, C.POINTER(RbmCfg), C.POINTER(vp)],
         'bm_rbm_set_param': [vp, C.c_char_p, vp, sz], 'bm_rbm_get_param': [vp, C.c_char_p, vp, sz],
@@ -142,6 +144,15 @@ class Context(object):
         n = C.c_uint64(0)
         check(load_library().bm_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    def profile_tc(self, enable):
+        check(load_library().bm_ctx_profile_tc(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """(algorithmic FLOPs, device ms, launches) of the tensor-core kernel since profiling was enabled."""
+        f, ms, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        check(load_library().bm_ctx_profile_read(self.handle, C.byref(f), C.byref(ms), C.byref(n)))
+        return f.value, ms.value, n.value
 
     def comm_init(self, unique_id, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id), 128)

@@ -60,6 +60,29 @@ void allreduce_sum(Ctx* ctx, void* buf, size_t count, bool is_double) {
     count_launch(ctx);
 }
 
+cudaEvent_t profile_event(Ctx* c) {
+    if (c->prof_used == c->prof_events.size()) {
+        if (c->prof_events.size() >= 16384) profile_drain(c);
+        else {
+            cudaEvent_t e;
+            BM_CUDA(cudaEventCreate(&e));
+            c->prof_events.push_back(e);
+        }
+    }
+    return c->prof_events[c->prof_used++];
+}
+
+void profile_drain(Ctx* c) {
+    if (c->prof_used == 0) return;
+    BM_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float ms = 0.f;
+        BM_CUDA(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+        c->prof_ms += ms;
+    }
+    c->prof_used = 0;
+}
+
 }  // namespace bm
 
 using namespace bm;
@@ -114,6 +137,7 @@ void bm_ctx_destroy(bm_ctx* h) {
     if (c->nccl_comm) {
         try { NcclApi* a = nccl_api(); if (a->CommDestroy) a->CommDestroy(c->nccl_comm); } catch (...) {}
     }
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->l2_scratch) cudaFree(c->l2_scratch);
     cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); cudaEventDestroy(c->copy_done);
     cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
@@ -177,6 +201,25 @@ int bm_ctx_launch_count(bm_ctx* h, uint64_t* n) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     BM_REQUIRE(c && n, "null argument");
     *n = c->launches;
+    BM_API_END
+}
+
+int bm_ctx_profile_tc(bm_ctx* h, int enable) {
+    BM_API_BEGIN
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    BM_REQUIRE(c, "null context");
+    profile_drain(c);
+    c->profile_tc = enable != 0;
+    if (enable) { c->prof_flops = 0.0; c->prof_ms = 0.0; c->prof_launches = 0; }
+    BM_API_END
+}
+
+int bm_ctx_profile_read(bm_ctx* h, double* flops, double* ms, uint64_t* launches) {
+    BM_API_BEGIN
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    BM_REQUIRE(c && flops && ms && launches, "null argument");
+    profile_drain(c);
+    *flops = c->prof_flops; *ms = c->prof_ms; *launches = c->prof_launches;
     BM_API_END
 }
 

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <stdexcept>
+#include <vector>
 
 #include "bm_rng.cuh"
 #include "../../include/bm.h"
@@ -48,12 +49,20 @@ struct Ctx {
     uint64_t launches = 0;
     void* l2_scratch = nullptr;
     size_t l2_scratch_bytes = 0;
+    // optional per-launch timing of the tensor-core kernel (bm_ctx_profile_tc)
+    bool profile_tc = false;
+    std::vector<cudaEvent_t> prof_events;     // pairs (start, stop)
+    size_t prof_used = 0;
+    double prof_flops = 0.0, prof_ms = 0.0;
+    uint64_t prof_launches = 0;
     // NCCL (resolved at run time with dlopen; see bm_comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
 };
 
 inline void count_launch(Ctx* c) { c->launches++; }
+void profile_drain(Ctx* c);      // fold recorded event pairs into prof_ms (synchronises the stream)
+cudaEvent_t profile_event(Ctx* c);
 void allreduce_sum(Ctx* ctx, void* buf, size_t count, bool is_double);
 
 // ---- activation / sampling selectors of the fused epilogue ------------------------

@@ -459,8 +459,16 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     BM_REQUIRE(!g.out_state_bf || (g.ld_state_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    if (ctx->profile_tc) BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
     tc_layer_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     BM_CUDA(cudaGetLastError());
+    if (ctx->profile_tc) {
+        BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
+        double k_total = 0.0;
+        for (int i = 0; i < g.n_pairs; ++i) k_total += g.K[i];
+        ctx->prof_flops += 2.0 * g.M * g.N * k_total;       // algorithmic FLOPs (no padding counted)
+        ctx->prof_launches++;
+    }
     count_launch(ctx);
 }
 

@@ -77,6 +77,10 @@ int  bm_ctx_flush_l2(bm_ctx* ctx);                              /* writes a >L2-
 int  bm_host_alloc(void** p, size_t bytes);                     /* pinned host memory for the feed path */
 int  bm_host_free(void* p);
 int  bm_ctx_launch_count(bm_ctx* ctx, uint64_t* n);             /* kernels launched by this library on ctx */
+/* per-launch CUDA-event timing of the tensor-core layer kernel (the roofline's dominant kernel):
+ * enable, run, then read the accumulated algorithmic FLOPs, device milliseconds and launch count */
+int  bm_ctx_profile_tc(bm_ctx* ctx, int enable);
+int  bm_ctx_profile_read(bm_ctx* ctx, double* flops, double* ms, uint64_t* launches);
 
 /* ---- multi-GPU: one process per GPU, chains sharded by rows, sum-allreduce of the
  *      gradient statistics (no counterpart in the reference: it is single-device) */
