@@ -218,8 +218,11 @@ class CudaRBM(object):
         c.v_kind = UNIT_KINDS[cfg.get('v_kind', 'bernoulli')]
         c.h_kind = UNIT_KINDS[cfg.get('h_kind', 'bernoulli')]
         c.dtype = DTYPES[self.dt.name]
-        compute = cfg.get('compute') or os.environ.get('BM_COMPUTE') or \
-            ('bf16' if self.dt == np.float32 else 'fp32')
+        # float32 models run on the tensor cores (bf16 operands, fp32 accumulate) unless told
+        # otherwise; float64 models always use the storage-precision CUDA-core path
+        compute = 'fp32'
+        if self.dt == np.float32:
+            compute = cfg.get('compute') or os.environ.get('BM_COMPUTE') or 'bf16'
         self.compute = compute
         c.compute = COMPUTE[compute]
         c.sample_v, c.sample_h = int(cfg.get('sample_v', False)), int(cfg.get('sample_h', True))

@@ -113,10 +113,13 @@ struct RbmTC : RbmSimt<float> {
         h0state_b = sh ? h0s_b.p : h0m_b.p;
         const bf16* hstate = h0state_b;
         for (int t = 1; t <= k; ++t) {
-            layer_tc(false, mat(hstate, rows, H, ldh), 0, vm_b.p, vs_b.p, sv, SITE_V, t, rows, seed, tick, row0);
+            // outputs nobody reads are not written: sampled visibles need their means only at the
+            // last step (MSRE), sampled mid-chain hiddens never need theirs
+            const bool last = (t == k);
+            layer_tc(false, mat(hstate, rows, H, ldh), 0, (sv && !last) ? nullptr : vm_b.p, vs_b.p, sv, SITE_V, t, rows, seed, tick, row0);
             vstate_b = sv ? vs_b.p : vm_b.p;
-            const bool smp = sh && t < k;
-            layer_tc(true, mat(vstate_b, rows, V, ldv), 0, hm_b.p, hs_b.p, smp, SITE_H, t, rows, seed, tick, row0);
+            const bool smp = sh && !last;
+            layer_tc(true, mat(vstate_b, rows, V, ldv), 0, smp ? nullptr : hm_b.p, hs_b.p, smp, SITE_H, t, rows, seed, tick, row0);
             hstate = smp ? hs_b.p : hm_b.p;
         }
         last_was_tc = true;
@@ -155,9 +158,8 @@ struct RbmTC : RbmSimt<float> {
         g.out_f32 = splits > 1 ? partials.p : G; g.ld_f32 = H;
         launch_tc_gemm(ctx, g);
         if (splits > 1) launch_reduce_partials(ctx, partials.p, (size_t)V * H, splits, G, (size_t)V * H);
-        launch_colsum_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, rows, V, 1.f, -1.f, dvb_sum);   // :451
-        launch_colsum_bf16(ctx, h0m_b.p, ldh, hm_b.p, ldh, rows, H, 1.f, -1.f, dhb_sum);                          // :453
-        launch_colsum_bf16(ctx, hm_b.p, ldh, nullptr, 0, rows, H, 1.f, 0.f, q_sum);                               // :457
+        launch_cd_statistics_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, h0m_b.p, hm_b.p, ldh,
+                                  rows, V, H, dvb_sum, dhb_sum, q_sum);                                           // :451-457
         allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
         const float N = (float)((double)rows * ctx->nranks);
 

@@ -8,12 +8,13 @@
 // per training step the two dW GEMMs (base_rbm.py:447-448) as ONE GEMM over the concatenated
 // batch dimension with the negative phase subtracted by the MMA's a_negate bit.
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d, 128B-swizzled tiles, 4-stage mbarrier ring
 //   warp 1   MMA issuer:   one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16)
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
-//   warps 4-7 epilogue:    tcgen05.ld 32x32b (thread = one accumulator row), bias/activation,
-//            Philox-4x32-10 in registers, bf16/fp32 stores; overlaps the next tile's MMAs.
+//   warps 4-11 epilogue:   tcgen05.ld 32x32b.x32 (thread = one accumulator row, 32 columns), bias,
+//            sigmoid, Philox-4x32-10 in registers, bf16/fp32 stores; two warps per TMEM lane
+//            quarter alternate over the column chunks; overlaps the next tile's MMAs.
 // Operand layouts: both K-major and MN-major shared-memory descriptors are used so that a single
 // bf16 copy of W serves v->h (W as MN-major B), h->v (W as K-major B) and no activation is ever
 // transposed in memory (dW takes X and h as MN-major A and B).
@@ -34,7 +35,8 @@ constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;          // 32 KiB (BN <= 256)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
 
 struct TcParams {
     int M, N, BN;
@@ -130,10 +132,58 @@ __device__ __forceinline__ float fast_softplus(float x) { return fmaxf(x, 0.f) +
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+// Epilogue specialisations: MODE 0 reads act/sample/outputs from TcParams at run time (every
+// combination); MODE 1..4 fix them at compile time for the hot CD-k shapes so that the per-element
+// instruction count stays near the Philox + sigmoid minimum.
+enum : int {
+    MODE_GENERIC = 0,
+    MODE_SIG_BERN_MEAN_STATE = 1,    // h0: sigmoid, Bernoulli draw, bf16 means + bf16 states
+    MODE_SIG_BERN_STATE = 2,         // mid-chain hidden: states only
+    MODE_SIG_MEAN = 3,               // probabilities only (visible means, last hidden means)
+    MODE_RAW_F32 = 4                 // raw fp32 accumulators (dW partials, linear pre-activations)
+};
+
+template <int MODE> struct EpiCfg {
+    static constexpr bool fixed = MODE != MODE_GENERIC;
+    static constexpr int act = (MODE == MODE_RAW_F32) ? ACT_LINEAR : ACT_SIGMOID;
+    static constexpr int sample = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE) ? SMP_BERNOULLI : SMP_NONE;
+    static constexpr bool mean_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_MEAN);
+    static constexpr bool state_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE);
+    static constexpr bool f32 = (MODE == MODE_RAW_F32);
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)): ex2.approx + rcp.approx keep the *relative* error of small
+// probabilities at ~1e-7 (tanh.approx would not)
+__device__ __forceinline__ float sigmoid_from_neg_log2(float t) {   // t = -x * log2(e)
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h2);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const TcParams p) {
+    typedef EpiCfg<MODE> E;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -150,7 +200,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -241,9 +291,23 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ================================ epilogue ==========================================
-        const int ew = warp - 4;                         // TMEM lane quarter this warp may read
-        const int row = ew * 32 + lane;
+        // ================================ epilogue (8 warps) =================================
+        // warp w may read TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter alternate over
+        // the tile's 32-column chunks.
+        const int ew = warp - 4;
+        const int quarter = ew & 3, half = ew >> 2;
+        const int row = quarter * 32 + lane;
+        const int act = E::fixed ? E::act : p.act;
+        const int smp = E::fixed ? E::sample : p.sample;
+        __nv_bfloat16* const out_mean = (E::fixed && !E::mean_bf) ? nullptr : p.out_mean_bf;
+        __nv_bfloat16* const out_state = (E::fixed && !E::state_bf) ? nullptr : p.out_state_bf;
+        float* const out_f32_base = (E::fixed && !E::f32) ? nullptr : p.out_f32;
+        const float kNegLog2e = -1.4426950408889634f;
+        // fold the sigmoid's -log2(e) into the affine map of the accumulator
+        const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * kNegLog2e : p.acc_scale;
+        const float b_s = (act == ACT_SIGMOID) ? p.bias_scale * kNegLog2e : p.bias_scale;
+        const bool has_sigma = !E::fixed && p.sigma != nullptr;
+        const int n_chunks32 = (p.BN + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int split = unit % p.splits;
@@ -253,30 +317,54 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const bool row_ok = m < p.M;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-            float* out_f32 = p.out_f32 ? p.out_f32 + (size_t)split * p.split_stride : nullptr;
-            const int n_chunks = p.BN / 16;
-            for (int ch = 0; ch < n_chunks; ++ch) {
-                uint32_t v[16];
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            float* out_f32 = out_f32_base ? out_f32_base + (size_t)split * p.split_stride : nullptr;
+            int last_ch = -1;
+            for (int ch = half; ch < n_chunks32; ch += 2) last_ch = ch;
+            if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            for (int ch = half; ch < n_chunks32; ch += 2) {
+                uint32_t v[32];
                 __syncwarp();                            // tcgen05.ld is warp-collective (.sync.aligned)
-                tmem_ld16(t_row + (uint32_t)(ch * 16), v);
+                if (ch * 32 + 32 <= p.BN) {
+                    tmem_ld32(t_row + (uint32_t)(ch * 32), v);
+                } else {                                 // BN is a multiple of 16: a trailing half chunk
+                    uint32_t lo[16];
+                    tmem_ld16(t_row + (uint32_t)(ch * 32), lo);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { v[e] = lo[e]; v[16 + e] = 0u; }
+                }
                 tmem_ld_wait();
-                if (ch == n_chunks - 1) {
+                if (ch == last_ch) {
                     // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                const int n0 = n_blk * p.BN + ch * 16;
-                if (n0 >= p.N) continue;
-                float mean[16], state[16];
+                const int n0 = n_blk * p.BN + ch * 32;
+                if (n0 >= p.N || !row_ok) continue;
+                const int n_valid = min(32, min(p.N, n_blk * p.BN + p.BN) - n0);
+                const bool full_chunk = (n_valid == 32);
+                uint32_t mean_pk[16], state_pk[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
+                    float bq[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.bias) {
+                        if (full_chunk) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
+                            bq[0] = b4.x; bq[1] = b4.y; bq[2] = b4.z; bq[3] = b4.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) bq[j] = p.bias[n0 + q * 4 + j];
+                        }
+                    }
                     U4 w{0, 0, 0, 0};
-                    if (p.sample != SMP_NONE) w = site_block(p.rng, (uint32_t)m, (uint32_t)((n0 >> 2) + q));
+                    if (smp != SMP_NONE) w = site_block(p.rng, (uint32_t)m, (uint32_t)((n0 >> 2) + q));
                     const uint32_t words[4] = {w.x, w.y, w.z, w.w};
                     float g[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.sample == SMP_GAUSSIAN) {
+                    if (!E::fixed && smp == SMP_GAUSSIAN) {
                         const float u1a = fmaxf(u32_to_unit_float(w.x), 1.0e-7f), u1b = fmaxf(u32_to_unit_float(w.z), 1.0e-7f);
                         const float ra = sqrtf(-2.0f * __logf(u1a)), rb = sqrtf(-2.0f * __logf(u1b));
                         float sa, ca, sb, cb;
@@ -284,63 +372,56 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         __sincosf(6.2831853071795864769f * u32_to_unit_float(w.w), &sb, &cb);
                         g[0] = sa * ra; g[1] = ca * ra; g[2] = sb * rb; g[3] = cb * rb;
                     }
+                    float mu[4], st[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int e = q * 4 + j;
-                        const int n = n0 + e;
-                        const bool col_ok = n < p.N;
-                        float x = p.acc_scale * __uint_as_float(v[e]);
-                        if (p.sigma && col_ok) x *= p.sigma[n];
-                        if (p.bias && col_ok) x = fmaf(p.bias_scale, p.bias[n], x);
-                        float mu = x;
-                        if (p.act == ACT_SIGMOID) mu = fast_sigmoid(x);
-                        else if (p.act == ACT_SOFTPLUS) mu = fast_softplus(x);
-                        float st = mu;
-                        if (p.sample == SMP_BERNOULLI) st = (u32_to_unit_float(words[j]) < mu) ? 1.0f : 0.0f;
-                        else if (p.sample == SMP_GAUSSIAN) st = mu + (p.noise_sigma && col_ok ? p.noise_sigma[n] : 1.0f) * g[j];
-                        mean[e] = mu; state[e] = st;
+                        float x = a_s * __uint_as_float(v[e]);
+                        if (has_sigma && e < n_valid) x *= p.sigma[n0 + e];
+                        x = fmaf(b_s, bq[j], x);
+                        float m_ = x;
+                        if (act == ACT_SIGMOID) m_ = sigmoid_from_neg_log2(x);
+                        else if (!E::fixed && act == ACT_SOFTPLUS) m_ = fast_softplus(x);
+                        float s_ = m_;
+                        if (smp == SMP_BERNOULLI) s_ = (u32_to_unit_float(words[j]) < m_) ? 1.0f : 0.0f;
+                        else if (!E::fixed && smp == SMP_GAUSSIAN)
+                            s_ = m_ + ((p.noise_sigma && e < n_valid) ? p.noise_sigma[n0 + e] : 1.0f) * g[j];
+                        mu[j] = m_; st[j] = s_;
                     }
-                }
-                if (!row_ok) continue;
-                const bool full_chunk = (n0 + 16 <= p.N);
-                if (p.out_mean_bf) {
-                    __nv_bfloat16* dst = p.out_mean_bf + (size_t)m * p.ld_mean_bf + n0;
-                    if (full_chunk) {
-                        uint32_t pk[8];
+                    if (out_mean) { mean_pk[2 * q] = pack_bf16(mu[0], mu[1]); mean_pk[2 * q + 1] = pack_bf16(mu[2], mu[3]); }
+                    if (out_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
+                    if (out_f32) {
+                        float* dst = out_f32 + (size_t)m * p.ld_f32 + n0 + q * 4;
+                        if (full_chunk && (p.ld_f32 & 3) == 0) {
+                            *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(mean[2 * e], mean[2 * e + 1]);
-                            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                            for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) dst[j] = mu[j];
                         }
-                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    } else {
-                        for (int e = 0; e < 16 && n0 + e < p.N; ++e) dst[e] = __float2bfloat16_rn(mean[e]);
                     }
                 }
-                if (p.out_state_bf) {
-                    __nv_bfloat16* dst = p.out_state_bf + (size_t)m * p.ld_state_bf + n0;
+                if (out_mean) {
+                    __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
                     if (full_chunk) {
-                        uint32_t pk[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(state[2 * e], state[2 * e + 1]);
-                            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<uint4*>(dst)[i] = make_uint4(mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
                     } else {
-                        for (int e = 0; e < 16 && n0 + e < p.N; ++e) dst[e] = __float2bfloat16_rn(state[e]);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (e < n_valid) reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(mean_pk[e >> 1] >> ((e & 1) * 16));
                     }
                 }
-                if (out_f32) {
-                    float* dst = out_f32 + (size_t)m * p.ld_f32 + n0;
-                    if (full_chunk && (p.ld_f32 & 3) == 0) {
+                if (out_state) {
+                    __nv_bfloat16* dst = out_state + (size_t)m * p.ld_state_bf + n0;
+                    if (full_chunk) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            reinterpret_cast<float4*>(dst)[e] = make_float4(mean[4 * e], mean[4 * e + 1], mean[4 * e + 2], mean[4 * e + 3]);
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<uint4*>(dst)[i] = make_uint4(state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
                     } else {
-                        for (int e = 0; e < 16 && n0 + e < p.N; ++e) dst[e] = mean[e];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (e < n_valid) reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(state_pk[e >> 1] >> ((e & 1) * 16));
                     }
                 }
             }
@@ -353,6 +434,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+
+static TcKernelFn tc_kernel_for(int mode) {
+    switch (mode) {
+        case MODE_SIG_BERN_MEAN_STATE: return tc_layer_kernel<MODE_SIG_BERN_MEAN_STATE>;
+        case MODE_SIG_BERN_STATE: return tc_layer_kernel<MODE_SIG_BERN_STATE>;
+        case MODE_SIG_MEAN: return tc_layer_kernel<MODE_SIG_MEAN>;
+        case MODE_RAW_F32: return tc_layer_kernel<MODE_RAW_F32>;
+        default: return tc_layer_kernel<MODE_GENERIC>;
     }
 }
 
@@ -403,18 +496,20 @@ static CUtensorMap make_map(const TcMat& m, int box0, int box1) {
     return tm;
 }
 
-static int pick_bn(int N, bool need64, int m_tiles, int sms) {
-    // candidates: multiples of 16 (64 for MN-major B) up to 256; minimise waves * BN (time), then padding
+static int pick_bn(int N, bool need64, int m_units, int chunks, int sms) {
+    // Tile width: multiples of 16 (64 when B is MN-major) up to 256.  Cycle model per CTA:
+    //   waves * MMA(bn) + EPI(bn):  MMA(bn) = chunks * 4 * bn/2 (tcgen05 M=128: bn/2 cycles per K=16),
+    //   EPI(bn) ~ 15 * bn (the last tile's epilogue is not hidden by a following MMA);
+    //   narrow tiles re-read the A tile from shared memory more often per FLOP.
     const int step = need64 ? 64 : 16;
     int best = step; double best_cost = 1e30;
     for (int bn = step; bn <= 256; bn += step) {
         const int nt = (N + bn - 1) / bn;
-        const long tiles = (long)nt * m_tiles;
+        const long tiles = (long)nt * m_units;
         const long waves = (tiles + sms - 1) / sms;
-        // smaller N tiles pay relatively more for the A operand's shared-memory reads
-        const double eff = bn >= 128 ? 1.0 : (bn >= 64 ? 1.15 : 1.5);
-        const double cost = (double)waves * bn * eff + 1e-3 * nt * bn;
-        if (cost < best_cost) { best_cost = cost; best = bn; }
+        const double eff = bn >= 128 ? 1.0 : (bn >= 96 ? 1.1 : (bn >= 64 ? 1.3 : 1.8));
+        const double cost = (double)waves * 2.0 * chunks * bn * eff + 15.0 * bn;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
 }
@@ -423,7 +518,8 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     BM_REQUIRE(g.M > 0 && g.N > 0 && g.n_pairs >= 1 && g.n_pairs <= 2, "bad tensor-core GEMM shape");
     static bool attr_set = false;
     if (!attr_set) {
-        BM_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        for (int md = 0; md <= 4; ++md)
+            BM_CUDA(cudaFuncSetAttribute(tc_kernel_for(md), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     TcParams p{};
@@ -431,7 +527,10 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     p.m_tiles = (g.M + BM - 1) / BM;
     bool need64 = false;
     for (int i = 0; i < g.n_pairs; ++i) need64 = need64 || g.b_t[i];
-    p.BN = pick_bn(g.N, need64, p.m_tiles * (g.splits > 0 ? g.splits : 1), ctx->sm_count);
+    int chunks_total = 0;
+    for (int i = 0; i < g.n_pairs; ++i) chunks_total += (g.K[i] + BK - 1) / BK;
+    const int nsplit = g.splits > 0 ? g.splits : 1;
+    p.BN = pick_bn(g.N, need64, p.m_tiles * nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count);
     p.n_tiles = (g.N + p.BN - 1) / p.BN;
     p.splits = g.splits > 0 ? g.splits : 1;
     p.split_stride = g.split_stride;
@@ -460,7 +559,15 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     if (ctx->profile_tc) BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
-    tc_layer_kernel<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    int mode = MODE_GENERIC;
+    if (!g.sigma && !g.noise_sigma) {
+        const bool mb = g.out_mean_bf != nullptr, sb = g.out_state_bf != nullptr, f = g.out_f32 != nullptr;
+        if (g.act == ACT_SIGMOID && g.sample == SMP_BERNOULLI && mb && sb && !f) mode = MODE_SIG_BERN_MEAN_STATE;
+        else if (g.act == ACT_SIGMOID && g.sample == SMP_BERNOULLI && !mb && sb && !f) mode = MODE_SIG_BERN_STATE;
+        else if (g.act == ACT_SIGMOID && g.sample == SMP_NONE && mb && !sb && !f) mode = MODE_SIG_MEAN;
+        else if (g.act == ACT_LINEAR && g.sample == SMP_NONE && !mb && !sb && f) mode = MODE_RAW_F32;
+    }
+    tc_kernel_for(mode)<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     BM_CUDA(cudaGetLastError());
     if (ctx->profile_tc) {
         BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
@@ -505,33 +612,95 @@ void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst,
     count_launch(ctx);
 }
 
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ P, int ldp, const __nv_bfloat16* __restrict__ Q, int ldq,
-                                   int rows, int cols, float s1, float s2, float* __restrict__ out) {
-    // 32 columns x 32 row-lanes per block; fp32 partial sums combined in a fixed order (deterministic)
-    __shared__ float part[32][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
-    float a = 0.f;
+// ---- column statistics of bf16 activations: up to 3 jobs (dvb, dhb, q) in one pair of launches ----
+struct ColsumJobs {
+    const __nv_bfloat16* P[3]; int ldp[3];
+    const __nv_bfloat16* Q[3]; int ldq[3];
+    float s1[3], s2[3];
+    float* out[3];
+    int cols[3];
+    int rows, n;
+};
+constexpr int CS_RSPLIT = 32;
+
+__global__ void colsum_bf16_partial_kernel(ColsumJobs j, float* __restrict__ partial, int max_cols) {
+    // block: 32 x 8 threads; 64 columns (2 per thread) x one row slab; fixed combine order
+    __shared__ float2 part[8][33];
+    const int job = blockIdx.z;
+    const int cols = j.cols[job];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+    const int slab = (j.rows + CS_RSPLIT - 1) / CS_RSPLIT;
+    const int r0 = blockIdx.y * slab, r1 = min(j.rows, r0 + slab);
+    float2 a = make_float2(0.f, 0.f);
     if (c < cols) {
-        for (int r = threadIdx.y; r < rows; r += 32) {
-            float v = s1 * __bfloat162float(P[(size_t)r * ldp + c]);
-            if (Q) v = fmaf(s2, __bfloat162float(Q[(size_t)r * ldq + c]), v);
-            a += v;
+        const __nv_bfloat16* P = j.P[job]; const __nv_bfloat16* Q = j.Q[job];
+        const float s1 = j.s1[job], s2 = j.s2[job];
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(P + (size_t)r * j.ldp[job] + c));
+            a.x = fmaf(s1, p.x, a.x); a.y = fmaf(s1, p.y, a.y);
+            if (Q) {
+                const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Q + (size_t)r * j.ldq[job] + c));
+                a.x = fmaf(s2, q.x, a.x); a.y = fmaf(s2, q.y, a.y);
+            }
         }
     }
     part[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
-        float s = 0.f;
+        float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s += part[i][threadIdx.x];
-        out[c] = s;
+        for (int i = 0; i < 8; ++i) { s.x += part[i][threadIdx.x].x; s.y += part[i][threadIdx.x].y; }
+        float* dst = partial + ((size_t)job * CS_RSPLIT + blockIdx.y) * max_cols + c;
+        dst[0] = s.x;
+        if (c + 1 < cols) dst[1] = s.y;
     }
+}
+__global__ void colsum_bf16_finish_kernel(ColsumJobs j, const float* __restrict__ partial, int max_cols) {
+    const int job = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= j.cols[job]) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < CS_RSPLIT; ++i) s += partial[((size_t)job * CS_RSPLIT + i) * max_cols + c];
+    j.out[job][c] = s;
+}
+static float* colsum_scratch(Ctx* ctx, size_t floats) {
+    static float* buf[64] = {nullptr};
+    static size_t cap[64] = {0};
+    if (cap[ctx->device] < floats) {
+        if (buf[ctx->device]) { BM_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(buf[ctx->device]); }
+        BM_CUDA(cudaMalloc(&buf[ctx->device], floats * sizeof(float)));
+        cap[ctx->device] = floats;
+    }
+    return buf[ctx->device];
+}
+static void run_colsum_jobs(Ctx* ctx, const ColsumJobs& j) {
+    int max_cols = 0;
+    for (int i = 0; i < j.n; ++i) max_cols = j.cols[i] > max_cols ? j.cols[i] : max_cols;
+    if (max_cols <= 0 || j.rows <= 0) return;
+    max_cols = (max_cols + 1) & ~1;
+    float* scratch = colsum_scratch(ctx, (size_t)3 * CS_RSPLIT * max_cols);
+    colsum_bf16_partial_kernel<<<dim3((max_cols + 63) / 64, CS_RSPLIT, j.n), dim3(32, 8), 0, ctx->stream>>>(j, scratch, max_cols);
+    count_launch(ctx);
+    colsum_bf16_finish_kernel<<<dim3((max_cols + 255) / 256, j.n), 256, 0, ctx->stream>>>(j, scratch, max_cols);
+    count_launch(ctx);
 }
 void launch_colsum_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq,
                         int rows, int cols, float s1, float s2, float* out) {
-    if (cols <= 0) return;
-    colsum_bf16_kernel<<<(cols + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, s1, s2, out);
-    count_launch(ctx);
+    ColsumJobs j{};
+    j.P[0] = P; j.ldp[0] = ldp; j.Q[0] = Q; j.ldq[0] = ldq; j.s1[0] = s1; j.s2[0] = s2; j.out[0] = out; j.cols[0] = cols;
+    j.rows = rows; j.n = 1;
+    run_colsum_jobs(ctx, j);
+}
+void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* v, int ldv,
+                               const __nv_bfloat16* h0, const __nv_bfloat16* hk, int ldh, int rows, int V, int H,
+                               float* dvb_sum, float* dhb_sum, float* q_sum) {
+    ColsumJobs j{};
+    j.P[0] = X;  j.ldp[0] = ldx; j.Q[0] = v;  j.ldq[0] = ldv; j.s1[0] = 1.f; j.s2[0] = -1.f; j.out[0] = dvb_sum; j.cols[0] = V;   // base_rbm.py:451
+    j.P[1] = h0; j.ldp[1] = ldh; j.Q[1] = hk; j.ldq[1] = ldh; j.s1[1] = 1.f; j.s2[1] = -1.f; j.out[1] = dhb_sum; j.cols[1] = H;   // :453
+    j.P[2] = hk; j.ldp[2] = ldh; j.Q[2] = nullptr; j.ldq[2] = 0; j.s1[2] = 1.f; j.s2[2] = 0.f; j.out[2] = q_sum; j.cols[2] = H;   // :457
+    j.rows = rows; j.n = 3;
+    run_colsum_jobs(ctx, j);
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t stride, int splits, float* __restrict__ G, size_t n) {

@@ -50,6 +50,10 @@ void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst,
 // out[n] = s1 * sum_r P[r,n] + s2 * sum_r Q[r,n]  (bf16 inputs, Q nullable, fp32 out)
 void launch_colsum_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq,
                         int rows, int cols, float s1, float s2, float* out);
+// the three column statistics of a CD step in one pass: sum(X - v), sum(h0 - hk), sum(hk)
+void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* v, int ldv,
+                               const __nv_bfloat16* h0, const __nv_bfloat16* hk, int ldh, int rows, int V, int H,
+                               float* dvb_sum, float* dhb_sum, float* q_sum);
 // G[i] = sum_s partial[s * stride + i]
 void launch_reduce_partials(Ctx* ctx, const float* partial, size_t stride, int splits, float* G, size_t n);
 
