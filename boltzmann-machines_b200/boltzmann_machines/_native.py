@@ -79,7 +79,7 @@ def load_library(path=None):
         'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
-        'bm_debug_tc_gemm': [vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],
+        'bm_debug_tc_gemm': [vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)
@@ -176,7 +176,8 @@ def pinned_empty(shape, dtype=np.float32):
     return arr
 
 
-def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None):
+def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None,
+                  force_bn=0, force_cluster=0):
     """Raw tensor-core GEMM (test hook): C = A' B'^T (+/- A2' B2'^T) with the operands stored as
     given: A is [M,K] (or [K,M] if a_t), B is [N,K] (or [K,N] if b_t)."""
     ctx = ctx or Context.default()
@@ -193,7 +194,8 @@ def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, spli
         p2a, p2b = A2.ctypes.data, B2.ctypes.data
     Cout = np.empty((M, N), dtype=np.float32)
     check(load_library().bm_debug_tc_gemm(ctx.handle, M, N, K, A.ctypes.data, int(a_t), B.ctypes.data, int(b_t),
-                                          K2, p2a, p2b, int(neg2), int(splits), Cout.ctypes.data))
+                                          K2, p2a, p2b, int(neg2), int(splits), int(force_bn), int(force_cluster),
+                                          Cout.ctypes.data))
     return Cout
 
 

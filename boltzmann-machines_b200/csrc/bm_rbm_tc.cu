@@ -219,7 +219,7 @@ using namespace bm;
 
 extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t a_t,
                                 const float* B, int32_t b_t, int32_t K2, const float* A2, const float* B2,
-                                int32_t neg2, int32_t splits, float* C) {
+                                int32_t neg2, int32_t splits, int32_t force_bn, int32_t force_cluster, float* C) {
     BM_API_BEGIN
     Ctx* ctx = reinterpret_cast<Ctx*>(hctx);
     BM_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
@@ -246,6 +246,7 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     }
     g.neg[1] = neg2 != 0;
     g.splits = splits > 0 ? splits : 1;
+    g.force_bn = force_bn; g.force_cluster = force_cluster;
     g.split_stride = (size_t)M * N;
     out.ensure((size_t)g.splits * M * N);
     g.out_f32 = out.p; g.ld_f32 = N;

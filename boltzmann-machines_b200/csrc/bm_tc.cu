@@ -41,6 +41,8 @@ constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
 struct TcParams {
     int M, N, BN;
     int m_tiles, n_tiles, splits;
+    int cluster;                   // CTAs per cluster (1, 2 or 4): adjacent row blocks share the B tile by TMA multicast
+    int m_groups;                  // ceil(m_tiles / cluster)
     int n_pairs;
     int chunks[2];                 // K chunks (of BK) per pair
     int a_mn[2], b_mn[2], a_neg[2];
@@ -88,6 +90,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and
+// completes `bytes` on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -104,6 +120,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -199,7 +219,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (p.n_pairs > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.cluster); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -208,22 +228,28 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_chunks = p.chunks[0] + (p.n_pairs > 1 ? p.chunks[1] : 0);
-    const int units = p.m_tiles * p.n_tiles * p.splits;
+    // work units are (row-block group, column block, K split); the CTAs of a cluster walk the same
+    // sequence of units and take consecutive row blocks of the group
+    const int units = p.m_groups * p.n_tiles * p.splits;
+    const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
+    const int unit0 = (p.cluster > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int unit_step = (p.cluster > 1) ? (int)cluster_count_x() : (int)gridDim.x;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
 
     if (warp == 0) {
         // ================================ TMA producer =====================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = A_BYTES + (uint32_t)p.BN * BK * 2;
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            for (int unit = unit0; unit < units; unit += unit_step) {
                 const int split = unit % p.splits;
                 const int tile = unit / p.splits;
-                const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+                const int m_blk = (tile / p.n_tiles) * p.cluster + crank, n_blk = tile % p.n_tiles;
                 const int c_begin = (int)(((long long)total_chunks * split) / p.splits);
                 const int c_end = (int)(((long long)total_chunks * (split + 1)) / p.splits);
                 for (int c = c_begin; c < c_end; ++c) {
@@ -241,11 +267,21 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         tma_load_2d(sA, mA, &full[stage], m_blk * BM, p.a_k0[pr] + kc);
                         tma_load_2d(sA + 8192, mA, &full[stage], m_blk * BM + 64, p.a_k0[pr] + kc);
                     }
-                    if (!p.b_mn[pr]) {
-                        tma_load_2d(sB, mB, &full[stage], kc, n_blk * p.BN);
+                    if (p.cluster == 1) {
+                        if (!p.b_mn[pr]) {
+                            tma_load_2d(sB, mB, &full[stage], kc, n_blk * p.BN);
+                        } else {
+                            for (int j = 0; j < p.BN / 64; ++j)
+                                tma_load_2d(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc);
+                        }
+                    } else if (!p.b_mn[pr]) {
+                        // this CTA fetches rows [crank, crank+1) * BN/cluster of the B tile for everybody
+                        const int part = p.BN / p.cluster;
+                        tma_load_2d_mc(sB + crank * part * 128, mB, &full[stage], kc, n_blk * p.BN + crank * part, cmask);
                     } else {
-                        for (int j = 0; j < p.BN / 64; ++j)
-                            tma_load_2d(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc);
+                        const int per = (p.BN / 64) / p.cluster;
+                        for (int j = crank * per; j < (crank + 1) * per; ++j)
+                            tma_load_2d_mc(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc, cmask);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -259,7 +295,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13),
             // a_negate 13, a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            for (int unit = unit0; unit < units; unit += unit_step) {
                 const int split = unit % p.splits;
                 const int c_begin = (int)(((long long)total_chunks * split) / p.splits);
                 const int c_end = (int)(((long long)total_chunks * (split + 1)) / p.splits);
@@ -283,7 +319,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                         accumulate = 1;
                     }
-                    umma_commit(&empty[stage]);          // smem slot is free once these MMAs retire
+                    // the slot is free once these MMAs retire; with multicast every producer of the
+                    // cluster writes into this CTA's slot, so every CTA's `empty` barrier is told
+                    if (p.cluster > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
@@ -309,10 +347,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const bool has_sigma = !E::fixed && p.sigma != nullptr;
         const int n_chunks32 = (p.BN + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        for (int unit = unit0; unit < units; unit += unit_step) {
             const int split = unit % p.splits;
             const int tile = unit / p.splits;
-            const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+            const int m_blk = (tile / p.n_tiles) * p.cluster + crank, n_blk = tile % p.n_tiles;
             const int m = m_blk * BM + row;
             const bool row_ok = m < p.M;
             mbar_wait(&tfull[acc], acc_phase);
@@ -430,7 +468,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
+    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -496,20 +535,37 @@ static CUtensorMap make_map(const TcMat& m, int box0, int box1) {
     return tm;
 }
 
-static int pick_bn(int N, bool need64, int m_units, int chunks, int sms) {
-    // Tile width: multiples of 16 (64 when B is MN-major) up to 256.  Cycle model per CTA:
-    //   waves * MMA(bn) + EPI(bn):  MMA(bn) = chunks * 4 * bn/2 (tcgen05 M=128: bn/2 cycles per K=16),
-    //   EPI(bn) ~ 15 * bn (the last tile's epilogue is not hidden by a following MMA);
-    //   narrow tiles re-read the A tile from shared memory more often per FLOP.
-    const int step = need64 ? 64 : 16;
-    int best = step; double best_cost = 1e30;
-    for (int bn = step; bn <= 256; bn += step) {
-        const int nt = (N + bn - 1) / bn;
-        const long tiles = (long)nt * m_units;
-        const long waves = (tiles + sms - 1) / sms;
-        const double eff = bn >= 128 ? 1.0 : (bn >= 96 ? 1.1 : (bn >= 64 ? 1.3 : 1.8));
-        const double cost = (double)waves * 2.0 * chunks * bn * eff + 15.0 * bn;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+struct TilePick { int bn, cluster; };
+
+static TilePick pick_tile(int N, bool b_mn, int m_tiles, int splits, int chunks, int sms) {
+    // Tile width BN (multiple of 16; 64 when B is MN-major) and cluster size C (CTAs with adjacent row
+    // blocks that share one B tile through TMA multicast).  Cycle model per CTA, in SM cycles:
+    //   MMA  = waves * chunks * 4 * BN/2          tcgen05 M=128: BN/2 cycles per K=16 slice
+    //   L2   = bytes moved L2->SMEM / 5000 B/clk  (A tile per CTA + B tile per cluster, per K chunk)
+    //   EPI  = 15 * BN                             the last tile's epilogue is not hidden
+    // time = max(MMA, L2) + EPI.  Narrow tiles also re-read A from shared memory more often per FLOP.
+    TilePick best{b_mn ? 64 : 16, 1};
+    double best_cost = 1e30;
+    const int step = b_mn ? 64 : 16;
+    for (int c = 1; c <= 4; c *= 2) {
+        if (c > 1 && m_tiles < c) break;
+        const int max_clusters = (c == 4 ? 132 : sms) / c;          // cluster size 4 strands some SMs
+        for (int bn = step; bn <= 256; bn += step) {
+            if (c > 1) {
+                if (b_mn) { if ((bn / 64) % c) continue; }
+                else if ((bn / c) % 8) continue;                    // keep each part on whole 8-row swizzle atoms
+            }
+            const int nt = (N + bn - 1) / bn;
+            const int m_groups = (m_tiles + c - 1) / c;
+            const long cunits = (long)m_groups * nt * splits;
+            const long waves = (cunits + max_clusters - 1) / max_clusters;
+            const double eff = bn >= 128 ? 1.0 : (bn >= 96 ? 1.1 : (bn >= 64 ? 1.3 : 1.8));
+            const double mma = (double)waves * chunks * 2.0 * bn * eff;
+            const double bytes = (double)cunits * chunks * (c * 16384.0 + bn * 128.0);
+            const double l2 = bytes / 5000.0 / (double)(waves > 0 ? 1 : 1) / 1.0;   // whole-chip L2 cycles
+            const double cost = (mma > l2 / 1.0 ? mma : l2) + 15.0 * bn + (c > 1 ? 400.0 : 0.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best.bn = bn; best.cluster = c; }
+        }
     }
     return best;
 }
@@ -530,7 +586,10 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     int chunks_total = 0;
     for (int i = 0; i < g.n_pairs; ++i) chunks_total += (g.K[i] + BK - 1) / BK;
     const int nsplit = g.splits > 0 ? g.splits : 1;
-    p.BN = pick_bn(g.N, need64, p.m_tiles * nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count);
+    TilePick tp = pick_tile(g.N, need64, p.m_tiles, nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count);
+    if (g.force_bn > 0) { tp.bn = g.force_bn; tp.cluster = g.force_cluster > 0 ? g.force_cluster : 1; }
+    p.BN = tp.bn; p.cluster = tp.cluster;
+    p.m_groups = (p.m_tiles + p.cluster - 1) / p.cluster;
     p.n_tiles = (g.N + p.BN - 1) / p.BN;
     p.splits = g.splits > 0 ? g.splits : 1;
     p.split_stride = g.split_stride;
@@ -542,7 +601,7 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
         p.a_row0[i] = g.a_row0[j]; p.a_k0[i] = g.a_k0[j];
         // K-major: box = 64 k x (128 | BN) rows; MN-major: box = 64 mn x 64 k
         maps[2 * i] = g.a_t[j] ? make_map(g.A[j], 64, 64) : make_map(g.A[j], 64, BM);
-        maps[2 * i + 1] = g.b_t[j] ? make_map(g.B[j], 64, 64) : make_map(g.B[j], 64, p.BN);
+        maps[2 * i + 1] = g.b_t[j] ? make_map(g.B[j], 64, 64) : make_map(g.B[j], 64, p.BN / p.cluster);
         BM_REQUIRE(i >= g.n_pairs || g.K[j] > 0, "tensor-core GEMM pair with K == 0");
     }
     const int total_chunks = p.chunks[0] + (g.n_pairs > 1 ? p.chunks[1] : 0);
@@ -556,8 +615,10 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     p.out_f32 = g.out_f32; p.ld_f32 = g.ld_f32;
     BM_REQUIRE(!g.out_mean_bf || (g.ld_mean_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
     BM_REQUIRE(!g.out_state_bf || (g.ld_state_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
-    const int units = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    const int units = p.m_groups * p.n_tiles * p.splits;
+    const int max_clusters = (p.cluster == 4 ? 132 : ctx->sm_count) / p.cluster;
+    const int n_clusters = units < max_clusters ? units : max_clusters;
+    const int grid = n_clusters * p.cluster;
     if (ctx->profile_tc) BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
     int mode = MODE_GENERIC;
     if (!g.sigma && !g.noise_sigma) {
@@ -567,7 +628,13 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
         else if (g.act == ACT_SIGMOID && g.sample == SMP_NONE && mb && !sb && !f) mode = MODE_SIG_MEAN;
         else if (g.act == ACT_LINEAR && g.sample == SMP_NONE && !mb && !sb && f) mode = MODE_RAW_F32;
     }
-    tc_kernel_for(mode)<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    BM_CUDA(cudaLaunchKernelEx(&lc, tc_kernel_for(mode), maps[0], maps[1], maps[2], maps[3], p));
     BM_CUDA(cudaGetLastError());
     if (ctx->profile_tc) {
         BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));

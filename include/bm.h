@@ -124,10 +124,11 @@ int  bm_rbm_get_activation(bm_rbm* rbm, const char* name, void* host, size_t byt
 /* ---- test hook: the raw tensor-core GEMM (no counterpart in the reference) -----------------
  * C[M,N] (fp32) = A * B^T (+/- A2 * B2^T), operands given as host fp32 and rounded to bf16.
  * a_t == 0: A is [M,K] row-major, else [K,M];  b_t == 0: B is [N,K] row-major, else [K,N]
- * (the second pair uses the same orientations).  splits > 1 exercises the split-K path. */
+ * (the second pair uses the same orientations).  splits > 1 exercises the split-K path;
+ * force_bn / force_cluster > 0 override the tile-width / TMA-multicast-cluster heuristic. */
 int  bm_debug_tc_gemm(bm_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t a_t,
                       const float* B, int32_t b_t, int32_t K2, const float* A2, const float* B2,
-                      int32_t neg2, int32_t splits, float* C);
+                      int32_t neg2, int32_t splits, int32_t force_bn, int32_t force_cluster, float* C);
 
 #ifdef __cplusplus
 }
