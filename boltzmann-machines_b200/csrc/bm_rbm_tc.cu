@@ -7,6 +7,7 @@
 // A bf16 shadow of W is refreshed by the weight-update kernel.  Metrics (free energy / PLL)
 // are evaluated in fp32 by the inherited CUDA-core kernels.
 #include "bm_rbm.h"
+#include <stdlib.h>
 
 namespace bm {
 
@@ -247,9 +248,15 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     g.neg[1] = neg2 != 0;
     g.splits = splits > 0 ? splits : 1;
     g.force_bn = force_bn; g.force_cluster = force_cluster;
+    DevBuf<unsigned long long> dbg;
+    const char* tl = getenv("BM_TC_TIMELINE");
+    if (tl) { dbg.ensure(64); dbg.zero(ctx->stream); g.dbg = dbg.p; }
     g.split_stride = (size_t)M * N;
     out.ensure((size_t)g.splits * M * N);
     g.out_f32 = out.p; g.ld_f32 = N;
+    const char* reps = getenv("BM_TC_REPS");
+    for (int i = 0, n = reps ? atoi(reps) : 0; i < n; ++i) { g.dbg = nullptr; launch_tc_gemm(ctx, g); }
+    g.dbg = tl ? dbg.p : nullptr;
     launch_tc_gemm(ctx, g);
     DevBuf<float> red;
     const float* res = out.p;
@@ -260,5 +267,17 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     }
     BM_CUDA(cudaMemcpyAsync(C, res, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (tl) {
+        unsigned long long h[64];
+        BM_CUDA(cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "timeline(ns from kernel start): setup=%llu mma_done=%llu epi_start=%llu epi_done=%llu exit=%llu\n",
+                h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0]);
+        fprintf(stderr, "  sm clock: %llu cycles over %llu ns = %.0f MHz\n", h[7] - h[6], h[5] - h[0], 1e3 * (double)(h[7] - h[6]) / (double)(h[5] - h[0]));
+        fprintf(stderr, "  tma_issue:");
+        for (int i = 0; i < 24 && h[8 + i]; ++i) fprintf(stderr, " %llu", h[8 + i] - h[0]);
+        fprintf(stderr, "\n  mma_ready:");
+        for (int i = 0; i < 24 && h[32 + i]; ++i) fprintf(stderr, " %llu", h[32 + i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     BM_API_END
 }

@@ -28,20 +28,22 @@ namespace bm {
 
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int BK = 64;             // K per pipeline stage = one 128-byte swizzle atom of bf16
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;       // 4 x 48 KiB (one CTA per tile) or 6 x 32 KiB (CTA pair: each CTA holds half of B)
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;      // TMEM columns per accumulator stage
 constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;          // 32 KiB (BN <= 256)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int RING_BYTES = 4 * STAGE_BYTES;   // == 6 * (A_BYTES + B_BYTES / 2)
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
 
 struct TcParams {
     int M, N, BN;
     int m_tiles, n_tiles, splits;
-    int cluster;                   // CTAs per cluster (1, 2 or 4): adjacent row blocks share the B tile by TMA multicast
+    int cluster;                   // 1: one CTA per 128-row tile; 2: CTA pair, tcgen05 cta_group::2 (M = 256, each CTA holds half of B)
+    int stages, stage_bytes;       // shared-memory ring geometry
     int m_groups;                  // ceil(m_tiles / cluster)
     int n_pairs;
     int chunks[2];                 // K chunks (of BK) per pair
@@ -57,6 +59,7 @@ struct TcParams {
     __nv_bfloat16* out_mean_bf;  int ld_mean_bf;
     __nv_bfloat16* out_state_bf; int ld_state_bf;
     float* out_f32;              int ld_f32;
+    unsigned long long* dbg;     // optional timeline (globaltimer ns) of CTA 0: see bm_debug_tc_timeline
 };
 
 // ------------------------------------------------------------------------------------------
@@ -97,6 +100,33 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// cta_group::2 loads: data lands in the issuing CTA, the transaction bytes are counted on the
+// LEADER CTA's mbarrier (address with the peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -107,6 +137,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DBG_MARK(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[(slot)] = gtime(); } while (0)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -206,31 +238,40 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     typedef EpiCfg<MODE> E;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { DBG_MARK(0); if (p.dbg && blockIdx.x == 0) p.dbg[6] = (unsigned long long)clock64(); }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB0);
         if (p.n_pairs > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.cluster); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+        // pair: the leader's `full` collects its own expect_tx-arrive and the peer's arrive; its `tempty`
+        // collects the epilogue warps of both CTAs; `empty`/`tfull` get one multicast commit each
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], (uint32_t)p.cluster); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)(EPI_WARPS * p.cluster)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (p.cluster == 2) {        // one warp of each CTA of the pair allocates collectively
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG_MARK(1);
 
     const int total_chunks = p.chunks[0] + (p.n_pairs > 1 ? p.chunks[1] : 0);
     // work units are (row-block group, column block, K split); the CTAs of a cluster walk the same
@@ -239,13 +280,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
     const int unit0 = (p.cluster > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
     const int unit_step = (p.cluster > 1) ? (int)cluster_count_x() : (int)gridDim.x;
-    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const bool pair = (p.cluster == 2);
+    const int half_bn = p.BN >> 1;
 
     if (warp == 0) {
         // ================================ TMA producer =====================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = A_BYTES + (uint32_t)p.BN * BK * 2;
+            const uint32_t tx_bytes = pair ? 2u * (A_BYTES + (uint32_t)half_bn * BK * 2) : A_BYTES + (uint32_t)p.BN * BK * 2;
             for (int unit = unit0; unit < units; unit += unit_step) {
                 const int split = unit % p.splits;
                 const int tile = unit / p.splits;
@@ -258,8 +300,28 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     const CUtensorMap* mA = pr ? &tmA1 : &tmA0;
                     const CUtensorMap* mB = pr ? &tmB1 : &tmB0;
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * STAGE_BYTES;
+                    uint8_t* sA = smem + stage * p.stage_bytes;
                     uint8_t* sB = sA + A_BYTES;
+                    if (c - c_begin < 24) DBG_MARK(8 + (c - c_begin));
+                    if (pair) {
+                        // both CTAs load their own A rows and their half of the B tile; bytes are counted on the leader
+                        const uint32_t lbar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
+                        if (!p.a_mn[pr]) {
+                            tma_load_2d_2sm(sA, mA, lbar, kc, p.a_row0[pr] + m_blk * BM);
+                        } else {
+                            tma_load_2d_2sm(sA, mA, lbar, m_blk * BM, p.a_k0[pr] + kc);
+                            tma_load_2d_2sm(sA + 8192, mA, lbar, m_blk * BM + 64, p.a_k0[pr] + kc);
+                        }
+                        if (!p.b_mn[pr]) {
+                            tma_load_2d_2sm(sB, mB, lbar, kc, n_blk * p.BN + crank * half_bn);
+                        } else {
+                            for (int j = 0; j < half_bn / 64; ++j)
+                                tma_load_2d_2sm(sB + j * 8192, mB, lbar, n_blk * p.BN + crank * half_bn + j * 64, kc);
+                        }
+                        if (crank == 0) mbar_expect_tx(&full[stage], tx_bytes); else mbar_arrive_remote(&full[stage], 0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full[stage], tx_bytes);
                     if (!p.a_mn[pr]) {
                         tma_load_2d(sA, mA, &full[stage], kc, p.a_row0[pr] + m_blk * BM);
@@ -267,34 +329,24 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         tma_load_2d(sA, mA, &full[stage], m_blk * BM, p.a_k0[pr] + kc);
                         tma_load_2d(sA + 8192, mA, &full[stage], m_blk * BM + 64, p.a_k0[pr] + kc);
                     }
-                    if (p.cluster == 1) {
-                        if (!p.b_mn[pr]) {
-                            tma_load_2d(sB, mB, &full[stage], kc, n_blk * p.BN);
-                        } else {
-                            for (int j = 0; j < p.BN / 64; ++j)
-                                tma_load_2d(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc);
-                        }
-                    } else if (!p.b_mn[pr]) {
-                        // this CTA fetches rows [crank, crank+1) * BN/cluster of the B tile for everybody
-                        const int part = p.BN / p.cluster;
-                        tma_load_2d_mc(sB + crank * part * 128, mB, &full[stage], kc, n_blk * p.BN + crank * part, cmask);
+                    if (!p.b_mn[pr]) {
+                        tma_load_2d(sB, mB, &full[stage], kc, n_blk * p.BN);
                     } else {
-                        const int per = (p.BN / 64) / p.cluster;
-                        for (int j = crank * per; j < (crank + 1) * per; ++j)
-                            tma_load_2d_mc(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc, cmask);
+                        for (int j = 0; j < p.BN / 64; ++j)
+                            tma_load_2d(sB + j * 8192, mB, &full[stage], n_blk * p.BN + j * 64, kc);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ========================================
-        if (lane == 0) {
+        // ================================ MMA issuer (the pair's leader CTA only) ============
+        if (lane == 0 && crank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13),
             // a_negate 13, a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
             for (int unit = unit0; unit < units; unit += unit_step) {
                 const int split = unit % p.splits;
                 const int c_begin = (int)(((long long)total_chunks * split) / p.splits);
@@ -307,8 +359,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     const int pr = (c >= p.chunks[0]) ? 1 : 0;
                     const uint32_t idesc = idesc_base | ((uint32_t)p.a_neg[pr] << 13) | ((uint32_t)p.a_mn[pr] << 15) | ((uint32_t)p.b_mn[pr] << 16);
                     mbar_wait(&full[stage], phase);
+                    if (c - c_begin < 24) DBG_MARK(32 + (c - c_begin));
                     tc_fence_after();
-                    const uint32_t aaddr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t aaddr = smem_u32(smem + stage * p.stage_bytes);
                     const uint32_t baddr = aaddr + A_BYTES;
                     const uint32_t a_step = p.a_mn[pr] ? 2048u : 32u;    // bytes per K=16 slice
                     const uint32_t b_step = p.b_mn[pr] ? 2048u : 32u;
@@ -316,15 +369,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(aaddr + k * a_step, p.a_mn[pr]);
                         const uint64_t bdesc = make_smem_desc(baddr + k * b_step, p.b_mn[pr]);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                        if (pair) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, accumulate); else umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                         accumulate = 1;
                     }
                     // the slot is free once these MMAs retire; with multicast every producer of the
                     // cluster writes into this CTA's slot, so every CTA's `empty` barrier is told
-                    if (p.cluster > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (pair) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
+                if (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+                DBG_MARK(2);
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -355,13 +409,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const bool row_ok = m < p.M;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (threadIdx.x == 128) DBG_MARK(3);
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
             float* out_f32 = out_f32_base ? out_f32_base + (size_t)split * p.split_stride : nullptr;
             int last_ch = -1;
             for (int ch = half; ch < n_chunks32; ch += 2) last_ch = ch;
             if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) { if (pair && crank == 1) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]); }
             }
             for (int ch = half; ch < n_chunks32; ch += 2) {
                 uint32_t v[32];
@@ -379,7 +434,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) { if (pair && crank == 1) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]); }
                 }
                 const int n0 = n_blk * p.BN + ch * 32;
                 if (n0 >= p.N || !row_ok) continue;
@@ -463,6 +518,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     }
                 }
             }
+            if (threadIdx.x == 128) DBG_MARK(4);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -472,8 +528,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (p.cluster > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    if (threadIdx.x == 0) { DBG_MARK(5); if (p.dbg && blockIdx.x == 0) p.dbg[7] = (unsigned long long)clock64(); }
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
@@ -538,32 +596,25 @@ static CUtensorMap make_map(const TcMat& m, int box0, int box1) {
 struct TilePick { int bn, cluster; };
 
 static TilePick pick_tile(int N, bool b_mn, int m_tiles, int splits, int chunks, int sms) {
-    // Tile width BN (multiple of 16; 64 when B is MN-major) and cluster size C (CTAs with adjacent row
-    // blocks that share one B tile through TMA multicast).  Cycle model per CTA, in SM cycles:
-    //   MMA  = waves * chunks * 4 * BN/2          tcgen05 M=128: BN/2 cycles per K=16 slice
-    //   L2   = bytes moved L2->SMEM / 5000 B/clk  (A tile per CTA + B tile per cluster, per K chunk)
-    //   EPI  = 15 * BN                             the last tile's epilogue is not hidden
-    // time = max(MMA, L2) + EPI.  Narrow tiles also re-read A from shared memory more often per FLOP.
+    // Tile width BN and CTA grouping.  A single SM ingests ~55-64 B/clk from L2 (measured: the
+    // 4-stage ring of a 128x256 tile refills at 53 B/clk), while tcgen05 at M=128 consumes
+    // 8192*(1/128 + 1/BN) B/clk of operands: a lone CTA is ingest-bound (~55% MMA duty).  A CTA pair
+    // (cta_group::2, M=256) halves the B bytes each SM needs -> 64 B/clk at BN=256.
+    // Cycle model per CTA: waves * chunks * max(mma, ingest) + epilogue of the last tile.
     TilePick best{b_mn ? 64 : 16, 1};
     double best_cost = 1e30;
-    const int step = b_mn ? 64 : 16;
-    for (int c = 1; c <= 4; c *= 2) {
-        if (c > 1 && m_tiles < c) break;
-        const int max_clusters = (c == 4 ? 132 : sms) / c;          // cluster size 4 strands some SMs
+    for (int c = 1; c <= 2; ++c) {
+        if (c == 2 && m_tiles < 2) break;
+        const int step = b_mn ? 64 * c : 16 * c;          // every CTA of a pair holds BN/2 columns of B
+        const int slots = sms / c;
         for (int bn = step; bn <= 256; bn += step) {
-            if (c > 1) {
-                if (b_mn) { if ((bn / 64) % c) continue; }
-                else if ((bn / c) % 8) continue;                    // keep each part on whole 8-row swizzle atoms
-            }
             const int nt = (N + bn - 1) / bn;
             const int m_groups = (m_tiles + c - 1) / c;
-            const long cunits = (long)m_groups * nt * splits;
-            const long waves = (cunits + max_clusters - 1) / max_clusters;
-            const double eff = bn >= 128 ? 1.0 : (bn >= 96 ? 1.1 : (bn >= 64 ? 1.3 : 1.8));
-            const double mma = (double)waves * chunks * 2.0 * bn * eff;
-            const double bytes = (double)cunits * chunks * (c * 16384.0 + bn * 128.0);
-            const double l2 = bytes / 5000.0 / (double)(waves > 0 ? 1 : 1) / 1.0;   // whole-chip L2 cycles
-            const double cost = (mma > l2 / 1.0 ? mma : l2) + 15.0 * bn + (c > 1 ? 400.0 : 0.0);
+            const long units = (long)m_groups * nt * splits;
+            const long waves = (units + slots - 1) / slots;
+            const double mma = 4.0 * (bn / 2.0);                                  // cycles per K chunk (4 x K=16)
+            const double ingest = (16384.0 + (bn / c) * 128.0) / 55.0;           // bytes per chunk per SM / (B/clk)
+            const double cost = (double)waves * chunks * (mma > ingest ? mma : ingest) + 12.0 * bn;
             if (cost < best_cost - 1e-9) { best_cost = cost; best.bn = bn; best.cluster = c; }
         }
     }
@@ -588,9 +639,13 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     const int nsplit = g.splits > 0 ? g.splits : 1;
     TilePick tp = pick_tile(g.N, need64, p.m_tiles, nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count);
     if (g.force_bn > 0) { tp.bn = g.force_bn; tp.cluster = g.force_cluster > 0 ? g.force_cluster : 1; }
+    BM_REQUIRE(tp.cluster == 1 || tp.cluster == 2, "cluster must be 1 or 2");
+    BM_REQUIRE(tp.cluster == 1 || (need64 ? tp.bn % 128 == 0 : tp.bn % 32 == 0), "CTA-pair tiles need BN/2 on whole boxes / swizzle atoms");
     p.BN = tp.bn; p.cluster = tp.cluster;
     p.m_groups = (p.m_tiles + p.cluster - 1) / p.cluster;
     p.n_tiles = (g.N + p.BN - 1) / p.BN;
+    p.stages = p.cluster == 2 ? 6 : 4;
+    p.stage_bytes = p.cluster == 2 ? (A_BYTES + B_BYTES / 2) : STAGE_BYTES;
     p.splits = g.splits > 0 ? g.splits : 1;
     p.split_stride = g.split_stride;
     CUtensorMap maps[4];
@@ -613,10 +668,11 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     p.out_mean_bf = g.out_mean_bf; p.ld_mean_bf = g.ld_mean_bf;
     p.out_state_bf = g.out_state_bf; p.ld_state_bf = g.ld_state_bf;
     p.out_f32 = g.out_f32; p.ld_f32 = g.ld_f32;
+    p.dbg = g.dbg;
     BM_REQUIRE(!g.out_mean_bf || (g.ld_mean_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
     BM_REQUIRE(!g.out_state_bf || (g.ld_state_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
     const int units = p.m_groups * p.n_tiles * p.splits;
-    const int max_clusters = (p.cluster == 4 ? 132 : ctx->sm_count) / p.cluster;
+    const int max_clusters = ctx->sm_count / p.cluster;
     const int n_clusters = units < max_clusters ? units : max_clusters;
     const int grid = n_clusters * p.cluster;
     if (ctx->profile_tc) BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));

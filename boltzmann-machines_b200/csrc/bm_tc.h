@@ -26,6 +26,7 @@ struct TcGemm {
     int K[2] = {0, 0};
     int a_row0[2] = {0, 0};           // first row of A_p inside its buffer (resident dataset slices; !a_t only)
     int a_k0[2] = {0, 0};             // first K row of A_p inside its buffer (a_t only)
+    unsigned long long* dbg = nullptr;     // device buffer of 64 timestamps (debug timeline)
     int force_bn = 0, force_cluster = 0;   // tests: override the tile heuristic
     // split-K: the concatenated K range is cut into `splits` parts; part s writes out_f32 + s * split_stride
     int splits = 1;

@@ -32,18 +32,20 @@ def test_raw_gemm_all_layouts(M, N, K, a_t, b_t):
     np.testing.assert_allclose(C, want, atol=2e-3 * np.sqrt(K), rtol=1e-3)
 
 
-@pytest.mark.parametrize('cluster,bn', [(2, 128), (4, 256), (2, 64), (4, 64), (2, 208), (4, 224), (2, 16 * 2), (4, 32)])
+@pytest.mark.parametrize('cluster,bn', [(2, 128), (2, 256), (2, 64), (2, 208), (2, 32), (2, 224), (1, 112), (1, 256)])
+@pytest.mark.parametrize('a_t', [False, True])
 @pytest.mark.parametrize('b_t', [False, True])
-def test_cluster_multicast_tiles(cluster, bn, b_t):
-    """B tile fetched once per cluster by TMA multicast; ragged row-block groups (M = 5 tiles)."""
-    if b_t and (bn % 64 or (bn // 64) % cluster):
-        pytest.skip('MN-major B tiles are whole 64-column boxes per CTA')
+def test_cta_pair_tiles(cluster, bn, a_t, b_t):
+    """cta_group::2: a CTA pair computes a 256-row tile, each CTA holding half of the B tile;
+    ragged row-block pairs (M = 5 tiles -> the last pair has an empty peer), many K chunks."""
+    if b_t and bn % (64 * cluster):
+        pytest.skip('MN-major B: every CTA holds whole 64-column boxes')
     rng = np.random.RandomState(cluster * 1000 + bn)
-    M, N, K = 600, 784, 328
-    A = rng.randn(M, K)
+    M, N, K = 600, 784, 840
+    A = rng.randn(K, M) if a_t else rng.randn(M, K)
     B = rng.randn(K, N) if b_t else rng.randn(N, K)
-    C = _native.debug_tc_gemm(A, B, b_t=b_t, force_bn=bn, force_cluster=cluster)
-    np.testing.assert_allclose(C, ref_gemm(A, B, False, b_t), atol=2e-3 * np.sqrt(K), rtol=1e-3)
+    C = _native.debug_tc_gemm(A, B, a_t=a_t, b_t=b_t, force_bn=bn, force_cluster=cluster)
+    np.testing.assert_allclose(C, ref_gemm(A, B, a_t, b_t), atol=2e-3 * np.sqrt(K), rtol=1e-3)
 
 
 @pytest.mark.parametrize('splits', [1, 3, 5])
