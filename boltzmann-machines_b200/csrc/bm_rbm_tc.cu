@@ -270,9 +270,9 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     if (tl) {
         unsigned long long h[64];
         BM_CUDA(cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "timeline(ns from kernel start): setup=%llu mma_done=%llu epi_start=%llu epi_done=%llu exit=%llu\n",
+        fprintf(stderr, "timeline(SM cycles from kernel start): setup=%llu mma_done=%llu epi_start=%llu epi_done=%llu exit=%llu\n",
                 h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0]);
-        fprintf(stderr, "  sm clock: %llu cycles over %llu ns = %.0f MHz\n", h[7] - h[6], h[5] - h[0], 1e3 * (double)(h[7] - h[6]) / (double)(h[5] - h[0]));
+        fprintf(stderr, "  sm clock: %llu cycles over %llu ns = %.0f MHz\n", h[5] - h[0], h[7] - h[6], 1e3 * (double)(h[5] - h[0]) / (double)(h[7] - h[6]));
         fprintf(stderr, "  tma_issue:");
         for (int i = 0; i < 24 && h[8 + i]; ++i) fprintf(stderr, " %llu", h[8 + i] - h[0]);
         fprintf(stderr, "\n  mma_ready:");

@@ -138,7 +138,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define DBG_MARK(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[(slot)] = gtime(); } while (0)
+#define DBG_MARK(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[(slot)] = (unsigned long long)clock64(); } while (0)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h2);
 }
 
-template <int MODE>
+template <int MODE, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -245,7 +245,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { DBG_MARK(0); if (p.dbg && blockIdx.x == 0) p.dbg[6] = (unsigned long long)clock64(); }
+    if (threadIdx.x == 0) { DBG_MARK(0); if (p.dbg && blockIdx.x == 0) p.dbg[6] = gtime(); }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB0);
@@ -254,12 +254,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (warp == 1 && lane == 0) {
         // pair: the leader's `full` collects its own expect_tx-arrive and the peer's arrive; its `tempty`
         // collects the epilogue warps of both CTAs; `empty`/`tfull` get one multicast commit each
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], (uint32_t)p.cluster); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)(EPI_WARPS * p.cluster)); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], (uint32_t)CL); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)(EPI_WARPS * CL)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        if (p.cluster == 2) {        // one warp of each CTA of the pair allocates collectively
+        if constexpr (CL == 2) {     // one warp of each CTA of the pair allocates collectively
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
         } else {
@@ -268,7 +268,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
     }
     tc_fence_before();
-    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any remote arrive
+    if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) DBG_MARK(1);
@@ -277,10 +277,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // work units are (row-block group, column block, K split); the CTAs of a cluster walk the same
     // sequence of units and take consecutive row blocks of the group
     const int units = p.m_groups * p.n_tiles * p.splits;
-    const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
-    const int unit0 = (p.cluster > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int unit_step = (p.cluster > 1) ? (int)cluster_count_x() : (int)gridDim.x;
-    const bool pair = (p.cluster == 2);
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int unit0 = (CL > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int unit_step = (CL > 1) ? (int)cluster_count_x() : (int)gridDim.x;
+    constexpr bool pair = (CL == 2);
     const int half_bn = p.BN >> 1;
 
     if (warp == 0) {
@@ -291,7 +291,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (int unit = unit0; unit < units; unit += unit_step) {
                 const int split = unit % p.splits;
                 const int tile = unit / p.splits;
-                const int m_blk = (tile / p.n_tiles) * p.cluster + crank, n_blk = tile % p.n_tiles;
+                const int m_blk = (tile / p.n_tiles) * CL + crank, n_blk = tile % p.n_tiles;
                 const int c_begin = (int)(((long long)total_chunks * split) / p.splits);
                 const int c_end = (int)(((long long)total_chunks * (split + 1)) / p.splits);
                 for (int c = c_begin; c < c_end; ++c) {
@@ -303,7 +303,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     uint8_t* sA = smem + stage * p.stage_bytes;
                     uint8_t* sB = sA + A_BYTES;
                     if (c - c_begin < 24) DBG_MARK(8 + (c - c_begin));
-                    if (pair) {
+                    if constexpr (pair) {
                         // both CTAs load their own A rows and their half of the B tile; bytes are counted on the leader
                         const uint32_t lbar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
                         if (!p.a_mn[pr]) {
@@ -369,15 +369,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(aaddr + k * a_step, p.a_mn[pr]);
                         const uint64_t bdesc = make_smem_desc(baddr + k * b_step, p.b_mn[pr]);
-                        if (pair) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, accumulate); else umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                        if constexpr (pair) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, accumulate); else umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                         accumulate = 1;
                     }
                     // the slot is free once these MMAs retire; with multicast every producer of the
                     // cluster writes into this CTA's slot, so every CTA's `empty` barrier is told
-                    if (pair) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+                    if constexpr (pair) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+                if constexpr (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
                 DBG_MARK(2);
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
@@ -404,7 +404,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int unit = unit0; unit < units; unit += unit_step) {
             const int split = unit % p.splits;
             const int tile = unit / p.splits;
-            const int m_blk = (tile / p.n_tiles) * p.cluster + crank, n_blk = tile % p.n_tiles;
+            const int m_blk = (tile / p.n_tiles) * CL + crank, n_blk = tile % p.n_tiles;
             const int m = m_blk * BM + row;
             const bool row_ok = m < p.M;
             mbar_wait(&tfull[acc], acc_phase);
@@ -416,7 +416,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (int ch = half; ch < n_chunks32; ch += 2) last_ch = ch;
             if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
                 __syncwarp();
-                if (lane == 0) { if (pair && crank == 1) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]); }
+                if (lane == 0) { if (pair && crank == 1) { if constexpr (pair) mbar_arrive_remote(&tempty[acc], 0); } else mbar_arrive(&tempty[acc]); }
             }
             for (int ch = half; ch < n_chunks32; ch += 2) {
                 uint32_t v[32];
@@ -434,7 +434,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (pair && crank == 1) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]); }
+                    if (lane == 0) { if (pair && crank == 1) { if constexpr (pair) mbar_arrive_remote(&tempty[acc], 0); } else mbar_arrive(&tempty[acc]); }
                 }
                 const int n0 = n_blk * p.BN + ch * 32;
                 if (n0 >= p.N || !row_ok) continue;
@@ -525,26 +525,29 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
     tc_fence_before();
     // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
-    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
-    if (threadIdx.x == 0) { DBG_MARK(5); if (p.dbg && blockIdx.x == 0) p.dbg[7] = (unsigned long long)clock64(); }
+    if (threadIdx.x == 0) { DBG_MARK(5); if (p.dbg && blockIdx.x == 0) p.dbg[7] = gtime(); }
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
-static TcKernelFn tc_kernel_for(int mode) {
+template <int CL> static TcKernelFn tc_kernel_mode(int mode) {
     switch (mode) {
-        case MODE_SIG_BERN_MEAN_STATE: return tc_layer_kernel<MODE_SIG_BERN_MEAN_STATE>;
-        case MODE_SIG_BERN_STATE: return tc_layer_kernel<MODE_SIG_BERN_STATE>;
-        case MODE_SIG_MEAN: return tc_layer_kernel<MODE_SIG_MEAN>;
-        case MODE_RAW_F32: return tc_layer_kernel<MODE_RAW_F32>;
-        default: return tc_layer_kernel<MODE_GENERIC>;
+        case MODE_SIG_BERN_MEAN_STATE: return tc_layer_kernel<MODE_SIG_BERN_MEAN_STATE, CL>;
+        case MODE_SIG_BERN_STATE: return tc_layer_kernel<MODE_SIG_BERN_STATE, CL>;
+        case MODE_SIG_MEAN: return tc_layer_kernel<MODE_SIG_MEAN, CL>;
+        case MODE_RAW_F32: return tc_layer_kernel<MODE_RAW_F32, CL>;
+        default: return tc_layer_kernel<MODE_GENERIC, CL>;
     }
 }
+// kernels that contain cta_group::2 instructions must be launched as clusters of 2, so the
+// single-CTA and CTA-pair variants are separate instantiations
+static TcKernelFn tc_kernel_for(int mode, int cluster) { return cluster == 2 ? tc_kernel_mode<2>(mode) : tc_kernel_mode<1>(mode); }
 
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps (driver entry point resolved at run time -> no libcuda link dependency)
@@ -605,7 +608,7 @@ static TilePick pick_tile(int N, bool b_mn, int m_tiles, int splits, int chunks,
     double best_cost = 1e30;
     for (int c = 1; c <= 2; ++c) {
         if (c == 2 && m_tiles < 2) break;
-        const int step = b_mn ? 64 * c : 16 * c;          // every CTA of a pair holds BN/2 columns of B
+        const int step = b_mn ? 64 * c : 16;              // every CTA of a pair holds BN/2 columns of B (whole boxes / 8-row atoms)
         const int slots = sms / c;
         for (int bn = step; bn <= 256; bn += step) {
             const int nt = (N + bn - 1) / bn;
@@ -626,7 +629,8 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     static bool attr_set = false;
     if (!attr_set) {
         for (int md = 0; md <= 4; ++md)
-            BM_CUDA(cudaFuncSetAttribute(tc_kernel_for(md), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            for (int cl = 1; cl <= 2; ++cl)
+                BM_CUDA(cudaFuncSetAttribute(tc_kernel_for(md, cl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     TcParams p{};
@@ -640,7 +644,7 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     TilePick tp = pick_tile(g.N, need64, p.m_tiles, nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count);
     if (g.force_bn > 0) { tp.bn = g.force_bn; tp.cluster = g.force_cluster > 0 ? g.force_cluster : 1; }
     BM_REQUIRE(tp.cluster == 1 || tp.cluster == 2, "cluster must be 1 or 2");
-    BM_REQUIRE(tp.cluster == 1 || (need64 ? tp.bn % 128 == 0 : tp.bn % 32 == 0), "CTA-pair tiles need BN/2 on whole boxes / swizzle atoms");
+    BM_REQUIRE(tp.cluster == 1 || (need64 ? tp.bn % 128 == 0 : tp.bn % 16 == 0), "CTA-pair tiles need BN/2 on whole boxes / swizzle atoms");
     p.BN = tp.bn; p.cluster = tp.cluster;
     p.m_groups = (p.m_tiles + p.cluster - 1) / p.cluster;
     p.n_tiles = (g.N + p.BN - 1) / p.BN;
@@ -690,7 +694,7 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    BM_CUDA(cudaLaunchKernelEx(&lc, tc_kernel_for(mode), maps[0], maps[1], maps[2], maps[3], p));
+    BM_CUDA(cudaLaunchKernelEx(&lc, tc_kernel_for(mode, p.cluster), maps[0], maps[1], maps[2], maps[3], p));
     BM_CUDA(cudaGetLastError());
     if (ctx->profile_tc) {
         BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
