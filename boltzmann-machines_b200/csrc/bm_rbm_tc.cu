@@ -2,12 +2,15 @@
 //
 // Variables (W, biases, momentum accumulators, q_means) stay in fp32 exactly as in the
 // reference; every GEMM of the CD-k step -- h0, the 2k chain half-steps and the fused
-// positive-minus-negative dW -- runs on tcgen05 with bf16 operands and fp32 accumulation
-// (bm_tc.cu).  Activations live in HBM/L2 as bf16 only (binary samples are exact in bf16).
-// A bf16 shadow of W is refreshed by the weight-update kernel.  Metrics (free energy / PLL)
-// are evaluated in fp32 by the inherited CUDA-core kernels.
+// positive-minus-negative dW -- runs on tcgen05 with bf16 operands and fp32 accumulation, as ONE
+// persistent dataflow launch (bm_tc.cu: TcProgram).  Activations live in L2/HBM as bf16 only
+// (binary samples are exact in bf16).  A bf16 shadow of W is refreshed by the weight-update
+// kernel.  Metrics (free energy / PLL) are evaluated in fp32 by the inherited CUDA-core kernels.
 #include "bm_rbm.h"
 #include <stdlib.h>
+#include <map>
+#include <memory>
+#include <tuple>
 
 namespace bm {
 
@@ -25,6 +28,9 @@ struct RbmTC : RbmSimt<float> {
     const bf16* vstate_b = nullptr;
     const bf16* h0state_b = nullptr;
     bool last_was_tc = false;
+    // cached programs, keyed by (rows, k, with_dw, input buffer is the resident dataset)
+    std::map<std::tuple<int, int, int, int>, std::unique_ptr<TcProgram>> progs;
+    int dw_splits = 1;
 
     RbmTC(Ctx* c, const bm_rbm_cfg& f) : RbmSimt<float>(c, f) {
         ldw = round_up(H, 64); ldv = round_up(V, 64); ldh = round_up(H, 64);
@@ -42,6 +48,7 @@ struct RbmTC : RbmSimt<float> {
         h0m_b.ensure((size_t)rows * ldh); h0s_b.ensure((size_t)rows * ldh);
         hm_b.ensure((size_t)rows * ldh); hs_b.ensure((size_t)rows * ldh);
         widen.ensure((size_t)rows * (V > H ? V : H));
+        progs.clear();                         // buffers moved: cached descriptors are stale
     }
 
     void refresh_shadow() { launch_f32_to_bf16(ctx, W.p, H, Wb.p, ldw, V, H); }
@@ -60,32 +67,33 @@ struct RbmTC : RbmSimt<float> {
         data_b.ensure((size_t)n_rows * ldv);
         launch_f32_to_bf16(ctx, data.p, V, data_b.p, ldv, (int)n_rows, V);
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        progs.clear();
     }
 
     TcMat mat(const bf16* p, int rows, int cols, int ld) const { TcMat m; m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; return m; }
 
-    // one conditional on the tensor cores
-    void layer_tc(bool up, TcMat in, int in_row0, bf16* means, bf16* states, bool sample,
-                  uint32_t site, uint32_t t, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
+    // one conditional (a Gibbs half-step) as a tensor-core op
+    TcGemm layer_op(bool up, TcMat in, bool in_is_batch_cursor, bf16* means, bf16* states, bool sample,
+                    uint32_t site, uint32_t t, int rows) {
         TcGemm g;
         g.M = rows; g.N = up ? H : V;
-        g.A[0] = in; g.a_row0[0] = in_row0; g.K[0] = up ? V : H;
+        g.A[0] = in; g.a_batch[0] = in_is_batch_cursor; g.K[0] = up ? V : H;
         g.B[0] = mat(Wb.p, V, H, ldw);
         g.b_t[0] = up;                 // v W: W is [K=V, N=H] (N contiguous); h W^T: W is [N=V, K=H] (K contiguous)
-        const float mult = (float)(up ? cfg.propup_mult : cfg.propdown_mult);
+        const float mult = (float)(up ? cfg.propup_mult : cfg.propdown_mult);    // base_rbm.py:342-343,356-357
         g.acc_scale = mult; g.bias_scale = mult;
         g.bias = up ? hb.p : vb.p;
-        g.rng = make_rng(seed, site, t, tick, row0);
+        g.rng = make_rng(0, site, t, 0, 0);
         g.out_mean_bf = means; g.ld_mean_bf = up ? ldh : ldv;
         const int kind = up ? cfg.h_kind : cfg.v_kind;
         if (kind == BM_UNIT_BERNOULLI) {
             g.act = ACT_SIGMOID;
             if (sample) { g.sample = SMP_BERNOULLI; g.out_state_bf = states; g.ld_state_bf = g.ld_mean_bf; }
         } else {
-            g.act = ACT_LINEAR; g.sigma = sigma.p;
+            g.act = ACT_LINEAR; g.sigma = sigma.p;                                // layers.py:84-86
             if (sample) { g.sample = SMP_GAUSSIAN; g.noise_sigma = sigma.p; g.out_state_bf = states; g.ld_state_bf = g.ld_mean_bf; }
         }
-        launch_tc_gemm(ctx, g);
+        return g;
     }
 
     // input staging: fp32 prepared batch (inherited) -> bf16, or a slice of the resident bf16 dataset
@@ -106,23 +114,63 @@ struct RbmTC : RbmSimt<float> {
         last_rows = rows;
     }
 
-    void chain_tc(int rows, int k, uint64_t seed, uint32_t tick, uint32_t row0) {
+    // The whole chain (base_rbm.py:421-426, 367-384) -- and, for training, the fused dW
+    // (base_rbm.py:447-448) -- as ONE persistent launch.
+    void run_program(int rows, int k, bool with_dw, uint64_t seed, uint32_t tick, uint32_t row0) {
         BM_REQUIRE(k >= 1, "n_gibbs_steps must be >= 1");
+        const bool resident = (X_b == data_b.p);
+        auto key = std::make_tuple(rows, k, with_dw ? 1 : 0, resident ? 1 : 0);
+        std::unique_ptr<TcProgram>& slot = progs[key];
+        if (!slot) slot.reset(new TcProgram());
+        TcProgram& prog = *slot;
         const bool sh = cfg.sample_h != 0, sv = cfg.sample_v != 0;
-        // rows of X beyond `rows` (resident data) only produce output rows >= M, which are masked
-        layer_tc(true, mat(X_b, X_rows_total, V, X_ld), X_row0, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows, seed, tick, row0);
+        std::vector<TcGemm>& ops = prog.ops;
+        ops.clear();
+        // rows of the resident dataset beyond this batch only produce output rows >= M, which are masked
+        ops.push_back(layer_op(true, mat(X_b, X_rows_total, V, X_ld), resident, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows));
+        if (!resident) ops.back().a_row0[0] = X_row0;
         h0state_b = sh ? h0s_b.p : h0m_b.p;
         const bf16* hstate = h0state_b;
+        int prev = 0;
         for (int t = 1; t <= k; ++t) {
             // outputs nobody reads are not written: sampled visibles need their means only at the
             // last step (MSRE), sampled mid-chain hiddens never need theirs
             const bool last = (t == k);
-            layer_tc(false, mat(hstate, rows, H, ldh), 0, (sv && !last) ? nullptr : vm_b.p, vs_b.p, sv, SITE_V, t, rows, seed, tick, row0);
+            TcGemm gv = layer_op(false, mat(hstate, rows, H, ldh), false, (sv && !last) ? nullptr : vm_b.p, vs_b.p, sv, SITE_V, t, rows);
+            gv.n_deps = 1; gv.dep[0] = prev;
+            ops.push_back(gv); prev = (int)ops.size() - 1;
             vstate_b = sv ? vs_b.p : vm_b.p;
             const bool smp = sh && !last;
-            layer_tc(true, mat(vstate_b, rows, V, ldv), 0, smp ? nullptr : hm_b.p, hs_b.p, smp, SITE_H, t, rows, seed, tick, row0);
+            TcGemm gh = layer_op(true, mat(vstate_b, rows, V, ldv), false, smp ? nullptr : hm_b.p, hs_b.p, smp, SITE_H, t, rows);
+            gh.n_deps = 1; gh.dep[0] = prev;
+            ops.push_back(gh); prev = (int)ops.size() - 1;
             hstate = smp ? hs_b.p : hm_b.p;
         }
+        if (with_dw) {
+            // dW_positive - dW_negative as one GEMM over the concatenated batch dimension, K split so
+            // that every CTA pair gets a slice; needs ALL row blocks of h0, v_k and h_k
+            TcGemm g;
+            g.M = V; g.N = H; g.n_pairs = 2;
+            g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_batch[0] = resident;
+            if (!resident) g.a_k0[0] = X_row0;
+            g.B[0] = mat(h0m_b.p, rows, H, ldh); g.b_t[0] = true; g.K[0] = rows;
+            g.A[1] = mat(vstate_b, rows, V, ldv); g.a_t[1] = true;
+            g.B[1] = mat(hm_b.p, rows, H, ldh); g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
+            const int pair_tiles = ((V + 255) / 256) * ((H + 255) / 256);
+            const int chunks = 2 * ((rows + 63) / 64);
+            int splits = (ctx->sm_count / 2) / (pair_tiles > 0 ? pair_tiles : 1);
+            if (splits < 1) splits = 1;
+            if (splits > chunks) splits = chunks;
+            dw_splits = splits;
+            g.splits = splits; g.split_stride = (size_t)V * H;
+            partials.ensure((size_t)splits * V * H);
+            g.out_f32 = splits > 1 ? partials.p : stats.p; g.ld_f32 = H;
+            g.n_deps = 3;
+            g.dep[0] = 0; g.dep[1] = (int)ops.size() - 2; g.dep[2] = (int)ops.size() - 1;
+            g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
+            ops.push_back(g);
+        }
+        launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
         last_was_tc = true;
     }
 
@@ -132,7 +180,7 @@ struct RbmTC : RbmSimt<float> {
         BM_REQUIRE(rows >= 1, "empty batch");
         const uint32_t row0 = (uint32_t)(ctx->rank * rows);
         stage_tc(X_host, first_row, rows, seed, tick, row0);
-        chain_tc(rows, k, seed, tick, row0);
+        run_program(rows, k, true, seed, tick, row0);
         if (mask) {
             if (mask & BM_METRIC_MSRE) launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
             run_metrics(mask, rows, seed, tick, row0, out);
@@ -142,23 +190,7 @@ struct RbmTC : RbmSimt<float> {
         float* dvb_sum = G + (size_t)V * H;
         float* dhb_sum = dvb_sum + V;
         float* q_sum = dhb_sum + H;
-        // dW_positive - dW_negative as ONE GEMM over the concatenated batch dimension (base_rbm.py:447-448)
-        TcGemm g;
-        g.M = V; g.N = H; g.n_pairs = 2;
-        g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_k0[0] = X_row0;
-        g.B[0] = mat(h0m_b.p, rows, H, ldh); g.b_t[0] = true; g.K[0] = rows;
-        g.A[1] = mat(vstate_b, rows, V, ldv); g.a_t[1] = true;
-        g.B[1] = mat(hm_b.p, rows, H, ldh); g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
-        const int tiles = ((V + 127) / 128) * ((H + 255) / 256);
-        const int chunks = 2 * ((rows + 63) / 64);
-        int splits = ctx->sm_count / (tiles > 0 ? tiles : 1);
-        if (splits < 1) splits = 1;
-        if (splits > chunks) splits = chunks;
-        g.splits = splits; g.split_stride = (size_t)V * H;
-        partials.ensure((size_t)splits * V * H);
-        g.out_f32 = splits > 1 ? partials.p : G; g.ld_f32 = H;
-        launch_tc_gemm(ctx, g);
-        if (splits > 1) launch_reduce_partials(ctx, partials.p, (size_t)V * H, splits, G, (size_t)V * H);
+        if (dw_splits > 1) launch_reduce_partials(ctx, partials.p, (size_t)V * H, dw_splits, G, (size_t)V * H);
         launch_cd_statistics_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, h0m_b.p, hm_b.p, ldh,
                                   rows, V, H, dvb_sum, dhb_sum, q_sum);                                           // :451-457
         allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
@@ -177,7 +209,7 @@ struct RbmTC : RbmSimt<float> {
         if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::transform(X_host, rows, k, seed, tick, H_out); return; }
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
-        chain_tc(rows, k, seed, tick, 0);
+        run_program(rows, k, false, seed, tick, 0);
         launch_bf16_to_f32(ctx, hm_b.p, ldh, widen.p, H, rows, H);
         BM_CUDA(cudaMemcpyAsync(H_out, widen.p, (size_t)rows * H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -188,7 +220,7 @@ struct RbmTC : RbmSimt<float> {
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
         if (mask & BM_METRIC_MSRE) {
-            chain_tc(rows, k, seed, tick, 0);
+            run_program(rows, k, false, seed, tick, 0);
             launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
         }
         run_metrics(mask, rows, seed, tick, 0, out);
@@ -254,6 +286,17 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     g.split_stride = (size_t)M * N;
     out.ensure((size_t)g.splits * M * N);
     g.out_f32 = out.p; g.ld_f32 = N;
+    // BM_TC_EPI=1|2|3: time the hot bf16 epilogues instead of the raw fp32 one (results are not returned)
+    DevBuf<__nv_bfloat16> obf1, obf2;
+    const char* epi = getenv("BM_TC_EPI");
+    if (epi && g.splits == 1) {
+        const int md = atoi(epi);
+        const int ldo = round_up(N, 8);
+        obf1.ensure((size_t)M * ldo); obf2.ensure((size_t)M * ldo);
+        g.out_f32 = nullptr; g.act = ACT_SIGMOID;
+        if (md == 1 || md == 3) { g.out_mean_bf = obf1.p; g.ld_mean_bf = ldo; }
+        if (md == 1 || md == 2) { g.out_state_bf = obf2.p; g.ld_state_bf = ldo; g.sample = SMP_BERNOULLI; g.rng = make_rng(1, 1, 0, 0, 0); }
+    }
     const char* reps = getenv("BM_TC_REPS");
     for (int i = 0, n = reps ? atoi(reps) : 0; i < n; ++i) { g.dbg = nullptr; launch_tc_gemm(ctx, g); }
     g.dbg = tl ? dbg.p : nullptr;
@@ -265,7 +308,7 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
         launch_reduce_partials(ctx, out.p, (size_t)M * N, g.splits, red.p, (size_t)M * N);
         res = red.p;
     }
-    BM_CUDA(cudaMemcpyAsync(C, res, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g.out_f32) BM_CUDA(cudaMemcpyAsync(C, res, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     BM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (tl) {
         unsigned long long h[64];

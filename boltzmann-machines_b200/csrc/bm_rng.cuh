@@ -41,11 +41,8 @@ __host__ __device__ __forceinline__ RngKey make_rng(uint64_t seed, uint32_t site
 struct U4 { uint32_t x, y, z, w; };
 
 __host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-    lo = a * b; hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
-#endif
+    // one 32x32->64 multiply (IMAD.WIDE.U32 on the GPU) instead of separate lo / hi products
+    const uint64_t p = (uint64_t)a * (uint64_t)b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
 }
 
 __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -1,7 +1,9 @@
-// Tensor-core (tcgen05 / TMEM / TMA) path of libbm.so: host-side description of one fused
-// "layer op" and its launcher.  Kernel in bm_tc.cu.
+// Tensor-core (tcgen05 / TMEM / TMA) path of libbm.so: host-side description of fused
+// "layer ops" and of multi-phase programs (a whole Gibbs chain + dW in ONE persistent launch).
+// Kernel in bm_tc.cu.
 #pragma once
 #include "bm_internal.h"
+#include <vector>
 
 namespace bm {
 
@@ -26,6 +28,7 @@ struct TcGemm {
     int K[2] = {0, 0};
     int a_row0[2] = {0, 0};           // first row of A_p inside its buffer (resident dataset slices; !a_t only)
     int a_k0[2] = {0, 0};             // first K row of A_p inside its buffer (a_t only)
+    bool a_batch[2] = {false, false}; // add the launch's batch_row to a_row0 / a_k0 (resident dataset cursor)
     unsigned long long* dbg = nullptr;     // device buffer of 64 timestamps (debug timeline)
     int force_bn = 0, force_cluster = 0;   // tests: override the tile heuristic
     // split-K: the concatenated K range is cut into `splits` parts; part s writes out_f32 + s * split_stride
@@ -38,13 +41,34 @@ struct TcGemm {
     const float* noise_sigma = nullptr;
     int act = ACT_LINEAR;
     int sample = SMP_NONE;
-    RngKey rng{};
+    RngKey rng{};                     // single launches: full key; programs: only c2 (site | t << 8) is used
     __nv_bfloat16* out_mean_bf = nullptr;  int ld_mean_bf = 0;
     __nv_bfloat16* out_state_bf = nullptr; int ld_state_bf = 0;
     float* out_f32 = nullptr;              int ld_f32 = 0;     // fp32 means (or raw accumulators)
+    // dataflow inside a program: this op reads what ops dep[i] (indices into the program) wrote.
+    //   dep_all[i] == false: row block g of this op needs row block g of dep[i]   (A rows = batch rows)
+    //   dep_all[i] == true : every unit needs all of dep[i]                        (K runs over the batch: dW)
+    int n_deps = 0;
+    int dep[3] = {-1, -1, -1};
+    bool dep_all[3] = {false, false, false};
 };
 
 void launch_tc_gemm(Ctx* ctx, const TcGemm& g);
+
+// A program = ops executed by ONE persistent kernel: every CTA pair walks the same global list of
+// (op, row-block pair, column block) units in order; a unit starts as soon as the row blocks it reads
+// are complete (per-row-block counters in global memory), so the epilogue of one half-step overlaps
+// the MMAs of the next and no kernel boundary separates the 2k+1 GEMMs of a CD-k chain and its dW.
+struct TcProgram {
+    std::vector<TcGemm> ops;
+    // device-side cache (owned by the program): descriptors + counters
+    void* dev_phases = nullptr; size_t dev_phases_bytes = 0;
+    int* dev_counters = nullptr; size_t n_counters = 0;
+    std::vector<unsigned char> host_image;      // last uploaded descriptor image
+    ~TcProgram();
+};
+// seed/tick/row0 of `rng` are shared by all ops; batch_row shifts the ops' a_batch operands
+void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row);
 
 // helpers on bf16 activations
 void launch_f32_to_bf16(Ctx* ctx, const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols);
