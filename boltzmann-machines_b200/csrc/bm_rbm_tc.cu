@@ -284,8 +284,10 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     const char* tl = getenv("BM_TC_TIMELINE");
     if (tl) { dbg.ensure(64); dbg.zero(ctx->stream); g.dbg = dbg.p; }
     g.split_stride = (size_t)M * N;
-    out.ensure((size_t)g.splits * M * N);
-    g.out_f32 = out.p; g.ld_f32 = N;
+    const int ldc = round_up(N, 4);
+    g.split_stride = (size_t)M * ldc;
+    out.ensure((size_t)g.splits * M * ldc);
+    g.out_f32 = out.p; g.ld_f32 = ldc;
     // BM_TC_EPI=1|2|3: time the hot bf16 epilogues instead of the raw fp32 one (results are not returned)
     DevBuf<__nv_bfloat16> obf1, obf2;
     const char* epi = getenv("BM_TC_EPI");
@@ -304,11 +306,12 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     DevBuf<float> red;
     const float* res = out.p;
     if (g.splits > 1) {
-        red.ensure((size_t)M * N);
-        launch_reduce_partials(ctx, out.p, (size_t)M * N, g.splits, red.p, (size_t)M * N);
+        red.ensure((size_t)M * ldc);
+        launch_reduce_partials(ctx, out.p, (size_t)M * ldc, g.splits, red.p, (size_t)M * ldc);
         res = red.p;
     }
-    if (g.out_f32) BM_CUDA(cudaMemcpyAsync(C, res, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g.out_f32) BM_CUDA(cudaMemcpy2DAsync(C, (size_t)N * sizeof(float), res, (size_t)ldc * sizeof(float), (size_t)N * sizeof(float), M,
+                                             cudaMemcpyDeviceToHost, ctx->stream));
     BM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (tl) {
         unsigned long long h[64];

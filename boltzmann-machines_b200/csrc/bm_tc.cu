@@ -33,6 +33,7 @@
 #include <tuple>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace bm {
 
@@ -44,7 +45,7 @@ constexpr int ACC_COLS = 256;      // TMEM columns per accumulator stage
 constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;          // 32 KiB (BN <= 256)
 constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);   // == 6 * (A_BYTES + B_BYTES / 2)
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BARRIER_BYTES = 256;
 constexpr int EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
 
@@ -56,8 +57,9 @@ enum : int {
     MODE_RAW_F32 = 4                 // raw fp32 accumulators (dW partials, linear pre-activations)
 };
 
-struct alignas(64) TcPhase {
-    CUtensorMap tmA[2], tmB[2];
+// everything of an op except its tensor maps: copied to shared memory at kernel start so that no
+// role ever waits on global memory for a descriptor field
+struct TcPhaseLite {
     int M, N, BN, m_groups, n_tiles, splits, n_pairs;
     int chunks[2], a_mn[2], b_mn[2], a_neg[2], a_row0[2], a_k0[2], a_batch[2];
     int unit_begin, unit_end;        // this op's slice of the program's global unit sequence
@@ -75,6 +77,15 @@ struct alignas(64) TcPhase {
     const int* dep_ctr[3]; int dep_need[3]; int dep_groups[3];   // dep_groups == 0: same row group only
     int* done_ctr;                   // [m_groups] completion counters of this op (nullable)
 };
+struct alignas(64) TcPhase {
+    CUtensorMap tmA[2], tmB[2];      // read by the TMA unit from global / parameter memory
+    TcPhaseLite l;
+};
+constexpr int MAX_PHASES = 64;
+constexpr int SPH_BYTES = MAX_PHASES * (int)sizeof(TcPhaseLite);
+constexpr int SBIAS_BYTES = ACC_STAGES * 256 * (int)sizeof(float);
+
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + SMEM_BARRIER_BYTES + SBIAS_BYTES + SPH_BYTES;
 
 struct TcLaunch {
     TcPhase inl;                     // single-op launches carry their descriptor in the parameters
@@ -144,6 +155,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define DBG_MARK(slot) do { if (L.dbg && blockIdx.x == 0) L.dbg[(slot)] = (unsigned long long)clock64(); } while (0)
+// per-unit marks of CTA 0: slot 64 + ord * 8 + kind (ord = ordinal of the unit within this CTA, < 24)
+#define DBG_UNIT(kind, ord) do { if (L.dbg && blockIdx.x == 0 && (ord) < 24) L.dbg[64 + (ord) * 8 + (kind)] = (unsigned long long)clock64(); } while (0)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -215,8 +228,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h2);
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+// Polling uses relaxed loads: an acquire load makes ptxas emit CCTL.IVALL (a full L1 invalidation) on
+// every iteration, which evicted the epilogue warps' bias/constant lines for as long as a producer
+// warp was waiting.  One acquire fence follows the successful poll.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+    int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -231,20 +247,120 @@ template <int MODE> struct EpiCfg {
     static constexpr bool f32 = (MODE == MODE_RAW_F32);
 };
 
+// the epilogue's view of a phase, copied into registers once per unit (the descriptor itself lives in
+// global memory; reading it inside the element loops would put L2 latency on every use)
+struct EpiPhase {
+    int M, N, BN, act, sample;
+    float acc_scale, bias_scale;
+    const float* __restrict__ bias;
+    const float* __restrict__ sigma;
+    const float* __restrict__ noise_sigma;
+    __nv_bfloat16* __restrict__ out_mean_bf;  int ld_mean_bf;
+    __nv_bfloat16* __restrict__ out_state_bf; int ld_state_bf;
+    float* __restrict__ out_f32;              int ld_f32;
+    unsigned long long split_stride;
+};
 struct EpiCtx {
-    const TcPhase* ph;
+    EpiPhase p;
     RngKey rng;
     int m, n_blk, split;          // this thread's global row, the tile's column block and K split
     uint32_t t_row;               // TMEM address of this thread's lane, column 0 of the accumulator stage
     uint64_t* tempty;             // accumulator-free barrier (leader's in pair mode)
     int half, lane;
+    const float* sbias;           // shared memory: bias_scale * bias (x -log2 e for sigmoid) of the tile's columns
     bool remote_arrive;           // pair mode, peer CTA: signal the leader's barrier
 };
+
+template <int MODE, bool FULL>
+__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
+    typedef EpiCfg<MODE> E;
+    const EpiPhase& p = c.p;
+    const int act = E::fixed ? E::act : p.act;
+    const int smp = E::fixed ? E::sample : p.sample;
+    __nv_bfloat16* const out_mean = (E::fixed && !E::mean_bf) ? nullptr : p.out_mean_bf;
+    __nv_bfloat16* const out_state = (E::fixed && !E::state_bf) ? nullptr : p.out_state_bf;
+    float* const out_f32 = ((E::fixed && !E::f32) || !p.out_f32) ? nullptr : p.out_f32 + (size_t)c.split * p.split_stride;
+    const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * -1.4426950408889634f : p.acc_scale;
+    const bool has_sigma = !E::fixed && p.sigma != nullptr;
+    const int m = c.m;
+    constexpr bool full_chunk = FULL;
+    // in the fixed modes which outputs exist is known at compile time (no per-group branches)
+    const bool do_mean = E::fixed ? E::mean_bf : (out_mean != nullptr);
+    const bool do_state = E::fixed ? E::state_bf : (out_state != nullptr);
+    const bool do_f32 = E::fixed ? E::f32 : (out_f32 != nullptr);
+    uint32_t mean_pk[16], state_pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + ch * 32 + q * 4);   // broadcast LDS.128
+        const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+        U4 w{0, 0, 0, 0};
+        if (smp != SMP_NONE) w = site_block(c.rng, (uint32_t)m, (uint32_t)((n0 >> 2) + q));
+        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!E::fixed && smp == SMP_GAUSSIAN) {
+            const float u1a = fmaxf(u32_to_unit_float(w.x), 1.0e-7f), u1b = fmaxf(u32_to_unit_float(w.z), 1.0e-7f);
+            const float ra = sqrtf(-2.0f * __logf(u1a)), rb = sqrtf(-2.0f * __logf(u1b));
+            float sa, ca, sb, cb;
+            __sincosf(6.2831853071795864769f * u32_to_unit_float(w.y), &sa, &ca);
+            __sincosf(6.2831853071795864769f * u32_to_unit_float(w.w), &sb, &cb);
+            g[0] = sa * ra; g[1] = ca * ra; g[2] = sb * rb; g[3] = cb * rb;
+        }
+        float mu[4], st[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = q * 4 + j;
+            float x = a_s * __uint_as_float(v[e]);
+            if (has_sigma && e < n_valid) x *= p.sigma[n0 + e];
+            x += bq[j];
+            float m_ = x;
+            if (act == ACT_SIGMOID) m_ = sigmoid_from_neg_log2(x);
+            else if (!E::fixed && act == ACT_SOFTPLUS) m_ = fast_softplus(x);
+            float s_ = m_;
+            if (smp == SMP_BERNOULLI) s_ = (u32_to_unit_float(words[j]) < m_) ? 1.0f : 0.0f;
+            else if (!E::fixed && smp == SMP_GAUSSIAN)
+                s_ = m_ + ((p.noise_sigma && e < n_valid) ? p.noise_sigma[n0 + e] : 1.0f) * g[j];
+            mu[j] = m_; st[j] = s_;
+        }
+        if (full_chunk) {
+            if (do_mean) { mean_pk[2 * q] = pack_bf16(mu[0], mu[1]); mean_pk[2 * q + 1] = pack_bf16(mu[2], mu[3]); }
+            if (do_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
+        } else {              // ragged right edge: element-wise stores, no packed staging
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (q * 4 + j < n_valid) {
+                    if (do_mean) out_mean[(size_t)m * p.ld_mean_bf + n0 + q * 4 + j] = __float2bfloat16_rn(mu[j]);
+                    if (do_state) out_state[(size_t)m * p.ld_state_bf + n0 + q * 4 + j] = __float2bfloat16_rn(st[j]);
+                }
+            }
+        }
+        if (do_f32) {
+            float* dst = out_f32 + (size_t)m * p.ld_f32 + n0 + q * 4;
+            if (full_chunk) {                 // rows are 16-byte aligned (checked by the caller)
+                *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) dst[j] = mu[j];
+            }
+        }
+    }
+    if (do_mean && full_chunk) {
+        __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
+    }
+    if (do_state && full_chunk) {
+        __nv_bfloat16* dst = out_state + (size_t)m * p.ld_state_bf + n0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
+    }
+}
 
 template <int MODE, bool PAIR>
 __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     typedef EpiCfg<MODE> E;
-    const TcPhase& p = *c.ph;
+    const EpiPhase& p = c.p;
     const int act = E::fixed ? E::act : p.act;
     const int smp = E::fixed ? E::sample : p.sample;
     __nv_bfloat16* const out_mean = (E::fixed && !E::mean_bf) ? nullptr : p.out_mean_bf;
@@ -253,7 +369,6 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     const float kNegLog2e = -1.4426950408889634f;
     // fold the sigmoid's -log2(e) into the affine map of the accumulator
     const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * kNegLog2e : p.acc_scale;
-    const float b_s = (act == ACT_SIGMOID) ? p.bias_scale * kNegLog2e : p.bias_scale;
     const bool has_sigma = !E::fixed && p.sigma != nullptr;
     const int BN = p.BN;
     const int n_chunks32 = (BN + 31) / 32;
@@ -291,84 +406,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
         const int n0 = c.n_blk * BN + ch * 32;
         if (n0 >= p.N || !row_ok) continue;
         const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
-        const bool full_chunk = (n_valid == 32);
-        uint32_t mean_pk[16], state_pk[16];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float bq[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.bias) {
-                if (full_chunk) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
-                    bq[0] = b4.x; bq[1] = b4.y; bq[2] = b4.z; bq[3] = b4.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) bq[j] = p.bias[n0 + q * 4 + j];
-                }
-            }
-            U4 w{0, 0, 0, 0};
-            if (smp != SMP_NONE) w = site_block(c.rng, (uint32_t)m, (uint32_t)((n0 >> 2) + q));
-            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (!E::fixed && smp == SMP_GAUSSIAN) {
-                const float u1a = fmaxf(u32_to_unit_float(w.x), 1.0e-7f), u1b = fmaxf(u32_to_unit_float(w.z), 1.0e-7f);
-                const float ra = sqrtf(-2.0f * __logf(u1a)), rb = sqrtf(-2.0f * __logf(u1b));
-                float sa, ca, sb, cb;
-                __sincosf(6.2831853071795864769f * u32_to_unit_float(w.y), &sa, &ca);
-                __sincosf(6.2831853071795864769f * u32_to_unit_float(w.w), &sb, &cb);
-                g[0] = sa * ra; g[1] = ca * ra; g[2] = sb * rb; g[3] = cb * rb;
-            }
-            float mu[4], st[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = q * 4 + j;
-                float x = a_s * __uint_as_float(v[e]);
-                if (has_sigma && e < n_valid) x *= p.sigma[n0 + e];
-                x = fmaf(b_s, bq[j], x);
-                float m_ = x;
-                if (act == ACT_SIGMOID) m_ = sigmoid_from_neg_log2(x);
-                else if (!E::fixed && act == ACT_SOFTPLUS) m_ = fast_softplus(x);
-                float s_ = m_;
-                if (smp == SMP_BERNOULLI) s_ = (u32_to_unit_float(words[j]) < m_) ? 1.0f : 0.0f;
-                else if (!E::fixed && smp == SMP_GAUSSIAN)
-                    s_ = m_ + ((p.noise_sigma && e < n_valid) ? p.noise_sigma[n0 + e] : 1.0f) * g[j];
-                mu[j] = m_; st[j] = s_;
-            }
-            if (out_mean) { mean_pk[2 * q] = pack_bf16(mu[0], mu[1]); mean_pk[2 * q + 1] = pack_bf16(mu[2], mu[3]); }
-            if (out_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
-            if (out_f32) {
-                float* dst = out_f32 + (size_t)m * p.ld_f32 + n0 + q * 4;
-                if (full_chunk && (p.ld_f32 & 3) == 0) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) dst[j] = mu[j];
-                }
-            }
-        }
-        if (out_mean) {
-            __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
-            if (full_chunk) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    reinterpret_cast<uint4*>(dst)[i] = make_uint4(mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (e < n_valid) reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(mean_pk[e >> 1] >> ((e & 1) * 16));
-            }
-        }
-        if (out_state) {
-            __nv_bfloat16* dst = out_state + (size_t)m * p.ld_state_bf + n0;
-            if (full_chunk) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    reinterpret_cast<uint4*>(dst)[i] = make_uint4(state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (e < n_valid) reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(state_pk[e >> 1] >> ((e & 1) * 16));
-            }
-        }
+        // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
+        // sigmoid / Philox chains of a thread can be interleaved by the scheduler
+        // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
+        if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, v, ch, n0, 32);
+        else chunk_body<MODE, false>(c, v, ch, n0, n_valid);
     }
 }
 
@@ -377,11 +419,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
 // ------------------------------------------------------------------------------------------
 struct UnitInfo { int split, m_group, n_blk, c_begin, c_end, total_chunks; };
 
-__device__ __forceinline__ const TcPhase* phase_of(const TcPhase* ph, int unit) {
-    while (unit >= ph->unit_end) ++ph;
-    return ph;
+__device__ __forceinline__ int phase_of(const TcPhaseLite* sph, int pi, int unit) {
+    while (unit >= sph[pi].unit_end) ++pi;
+    return pi;
 }
-__device__ __forceinline__ UnitInfo decode_unit(const TcPhase* ph, int unit) {
+__device__ __forceinline__ UnitInfo decode_unit(const TcPhaseLite* ph, int unit) {
     UnitInfo u;
     const int local = unit - ph->unit_begin;
     u.split = local % ph->splits;
@@ -408,10 +450,17 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { DBG_MARK(0); if (L.dbg && blockIdx.x == 0) L.dbg[6] = gtime(); }
-    const TcPhase* const ph0 = L.n_phases ? L.phases : &L.inl;
-
+    float* const s_bias = reinterpret_cast<float*>(smem + RING_BYTES + SMEM_BARRIER_BYTES);
+    TcPhaseLite* const sph = reinterpret_cast<TcPhaseLite*>(smem + RING_BYTES + SMEM_BARRIER_BYTES + SBIAS_BYTES);
+    const TcPhase* const gph = L.n_phases ? L.phases : &L.inl;
+    {   // descriptors (minus the tensor maps) -> shared memory
+        const int nph = L.n_phases ? L.n_phases : 1;
+        constexpr int W = (int)(sizeof(TcPhaseLite) / 4);
+        for (int i = threadIdx.x; i < nph * W; i += TC_THREADS)
+            reinterpret_cast<uint32_t*>(sph)[i] = reinterpret_cast<const uint32_t*>(&gph[i / W].l)[i % W];
+    }
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&ph0->tmA[0]); tma_prefetch_desc(&ph0->tmB[0]);
+        tma_prefetch_desc(&gph->tmA[0]); tma_prefetch_desc(&gph->tmB[0]);
     }
     if (warp == 1 && lane == 0) {
         // pair: the leader's `full` collects its own expect_tx-arrive and the peer's arrive; its `tempty`
@@ -445,10 +494,15 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         // The whole warp walks the K chunks; for each chunk lane 0 arms the barrier and lanes
         // 0..n_ops-1 issue one bulk-tensor copy each in the same warp instruction.
         int stage = 0; uint32_t phase = 0;
-        const TcPhase* ph = ph0;
+        int pi = 0;
+        int ord = -1;
         for (int unit = unit0; unit < units; unit += unit_step) {
-            ph = phase_of(ph, unit);
+            ++ord;
+            pi = phase_of(sph, pi, unit);
+            const TcPhaseLite* ph = &sph[pi];
+            const TcPhase* gp = &gph[pi];
             const UnitInfo u = decode_unit(ph, unit);
+            if (lane == 0) DBG_UNIT(0, ord);
             const int BN = ph->BN;
             const int half_bn = BN >> 1;
             const uint32_t tx_bytes = pair ? 2u * (A_BYTES + (uint32_t)half_bn * BK * 2) : A_BYTES + (uint32_t)BN * BK * 2;
@@ -462,22 +516,25 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                         const int* ctr = ph->dep_ctr[d];
                         const int need = ph->dep_need[d];
                         if (ph->dep_groups[d] == 0) {
-                            while (ld_acquire(ctr + u.m_group) < need) __nanosleep(32);
+                            while (ld_relaxed(ctr + u.m_group) < need) __nanosleep(64);
                         } else {
                             for (int gq = 0; gq < ph->dep_groups[d]; ++gq)
-                                while (ld_acquire(ctr + gq) < need) __nanosleep(32);
+                                while (ld_relaxed(ctr + gq) < need) __nanosleep(64);
                         }
                     }
-                    // the producers wrote with generic-proxy stores; TMA reads through the async proxy
+                    // acquire the producers' (generic-proxy) stores, then order them before this unit's
+                    // TMA reads, which go through the async proxy
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 __syncwarp();
             }
+            if (lane == 0) DBG_UNIT(1, ord);
             for (int c = u.c_begin; c < u.c_end; ++c) {
                 const int pr = (c >= ph->chunks[0]) ? 1 : 0;
                 const int kc = (pr ? c - ph->chunks[0] : c) * BK;
-                const CUtensorMap* mA = &ph->tmA[pr];
-                const CUtensorMap* mB = &ph->tmB[pr];
+                const CUtensorMap* mA = &gp->tmA[pr];
+                const CUtensorMap* mB = &gp->tmB[pr];
                 const int shift = ph->a_batch[pr] ? L.batch_row : 0;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * L.stage_bytes;
@@ -515,9 +572,12 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         if (lane == 0 && crank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const TcPhase* ph = ph0;
+            int pi = 0;
+            int ord = -1;
             for (int unit = unit0; unit < units; unit += unit_step) {
-                ph = phase_of(ph, unit);
+                ++ord;
+                pi = phase_of(sph, pi, unit);
+                const TcPhaseLite* ph = &sph[pi];
                 const UnitInfo u = decode_unit(ph, unit);
                 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13),
                 // a_negate 13, a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
@@ -532,6 +592,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                     const int a_mn = ph->a_mn[pr], b_mn = ph->b_mn[pr];
                     const uint32_t idesc = idesc_base | ((uint32_t)ph->a_neg[pr] << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
                     mbar_wait(&full[stage], phase);
+                    if (c == u.c_begin) DBG_UNIT(2, ord);
                     if (c - u.c_begin < 24) DBG_MARK(32 + (c - u.c_begin));
                     tc_fence_after();
                     const uint32_t aaddr = smem_u32(smem + stage * L.stage_bytes);
@@ -550,7 +611,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                     if (++stage == L.stages) { stage = 0; phase ^= 1; }
                 }
                 if constexpr (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
-                DBG_MARK(2);
+                DBG_MARK(2); DBG_UNIT(3, ord);
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -564,33 +625,52 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         c.half = ew >> 2; c.lane = lane;
         c.remote_arrive = pair && crank == 1;
         int acc = 0; uint32_t acc_phase = 0;
-        const TcPhase* ph = ph0;
+        int pi = 0;
+        int ord = -1;
+        const int et = threadIdx.x - 128;          // 0..255 among the epilogue threads
         for (int unit = unit0; unit < units; unit += unit_step) {
-            ph = phase_of(ph, unit);
+            ++ord;
+            pi = phase_of(sph, pi, unit);
+            const TcPhaseLite* ph = &sph[pi];
             const UnitInfo u = decode_unit(ph, unit);
-            c.ph = ph;
+            {   // this tile's (pre-scaled) bias slice -> shared memory, while the MMAs are still running
+                const float bsc = (ph->act == ACT_SIGMOID) ? ph->bias_scale * -1.4426950408889634f : ph->bias_scale;
+                const int n = u.n_blk * ph->BN + et;
+                s_bias[acc * 256 + et] = (ph->bias && et < ph->BN && n < ph->N) ? bsc * __ldg(ph->bias + n) : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                c.sbias = s_bias + acc * 256;
+            }
+            c.p.M = ph->M; c.p.N = ph->N; c.p.BN = ph->BN; c.p.act = ph->act; c.p.sample = ph->sample;
+            c.p.acc_scale = ph->acc_scale; c.p.bias_scale = ph->bias_scale;
+            c.p.bias = ph->bias; c.p.sigma = ph->sigma; c.p.noise_sigma = ph->noise_sigma;
+            c.p.out_mean_bf = ph->out_mean_bf; c.p.ld_mean_bf = ph->ld_mean_bf;
+            c.p.out_state_bf = ph->out_state_bf; c.p.ld_state_bf = ph->ld_state_bf;
+            c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
+            const int ph_mode = ph->mode;
+            int* const ph_done = ph->done_ctr;
             c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
             c.tempty = &tempty[acc];
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            if (threadIdx.x == 128) DBG_MARK(3);
+            if (threadIdx.x == 128) { DBG_MARK(3); DBG_UNIT(4, ord); }
             c.t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-            switch (ph->mode) {
+            switch (ph_mode) {
                 case MODE_SIG_BERN_MEAN_STATE: epilogue_tile<MODE_SIG_BERN_MEAN_STATE, pair>(c); break;
                 case MODE_SIG_BERN_STATE: epilogue_tile<MODE_SIG_BERN_STATE, pair>(c); break;
                 case MODE_SIG_MEAN: epilogue_tile<MODE_SIG_MEAN, pair>(c); break;
                 case MODE_RAW_F32: epilogue_tile<MODE_RAW_F32, pair>(c); break;
                 default: epilogue_tile<MODE_GENERIC, pair>(c); break;
             }
+            if (threadIdx.x == 128) DBG_UNIT(5, ord);
             // publish: this warp's part of the unit's output is in global memory
-            if (ph->done_ctr) {
+            if (ph_done) {
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(ph->done_ctr + u.m_group, 1);
+                if (lane == 0) atomicAdd(ph_done + u.m_group, 1);
             }
-            if (threadIdx.x == 128) DBG_MARK(4);
+            if (threadIdx.x == 128) { DBG_MARK(4); DBG_UNIT(6, ord); }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -693,9 +773,10 @@ static int epilogue_mode(const TcGemm& g) {
 }
 
 // fills everything of a phase descriptor except the dataflow fields and the unit range
-static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& p) {
+static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
+    TcPhaseLite& p = ph.l;
     BM_REQUIRE(g.M > 0 && g.N > 0 && g.n_pairs >= 1 && g.n_pairs <= 2, "bad tensor-core GEMM shape");
-    memset(&p, 0, sizeof(p));
+    memset(&ph, 0, sizeof(ph));
     p.M = g.M; p.N = g.N; p.n_pairs = g.n_pairs;
     const int m_tiles = (g.M + BM - 1) / BM;
     bool need64 = false;
@@ -719,8 +800,8 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& p) {
         p.a_mn[i] = g.a_t[j]; p.b_mn[i] = g.b_t[j]; p.a_neg[i] = g.neg[j];
         p.a_row0[i] = g.a_row0[j]; p.a_k0[i] = g.a_k0[j]; p.a_batch[i] = g.a_batch[j];
         // K-major: box = 64 k x (128 | BN/cluster) rows; MN-major: box = 64 mn x 64 k
-        p.tmA[i] = g.a_t[j] ? make_map(g.A[j], 64, 64) : make_map(g.A[j], 64, BM);
-        p.tmB[i] = g.b_t[j] ? make_map(g.B[j], 64, 64) : make_map(g.B[j], 64, p.BN / cluster);
+        ph.tmA[i] = g.a_t[j] ? make_map(g.A[j], 64, 64) : make_map(g.A[j], 64, BM);
+        ph.tmB[i] = g.b_t[j] ? make_map(g.B[j], 64, 64) : make_map(g.B[j], 64, p.BN / cluster);
         BM_REQUIRE(i >= g.n_pairs || g.K[j] > 0, "tensor-core GEMM pair with K == 0");
     }
     BM_REQUIRE(p.splits <= chunks_total, "more K splits than K chunks");
@@ -783,9 +864,9 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     TcLaunch L;
     memset(&L, 0, sizeof(L));
     fill_phase(ctx, g, cluster, L.inl);
-    L.inl.unit_begin = 0;
-    L.inl.unit_end = L.inl.m_groups * L.inl.n_tiles * L.inl.splits;
-    L.total_units = L.inl.unit_end;
+    L.inl.l.unit_begin = 0;
+    L.inl.l.unit_end = L.inl.l.m_groups * L.inl.l.n_tiles * L.inl.l.splits;
+    L.total_units = L.inl.l.unit_end;
     L.k0 = g.rng.k0; L.k1 = g.rng.k1; L.tick = g.rng.tick; L.row0 = g.rng.row0;
     L.dbg = g.dbg;
     do_launch(ctx, L, cluster, gemm_flops(g));
@@ -798,7 +879,7 @@ TcProgram::~TcProgram() {
 
 void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     const int n = (int)prog.ops.size();
-    BM_REQUIRE(n >= 1, "empty program");
+    BM_REQUIRE(n >= 1 && n <= MAX_PHASES, "a program holds 1..64 ops");
     const int cluster = 2;            // programs always run on CTA pairs (all CTAs walk one unit list)
     std::vector<unsigned char> image((size_t)n * sizeof(TcPhase));
     TcPhase* ph = reinterpret_cast<TcPhase*>(image.data());
@@ -809,11 +890,11 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     double flops = 0.0;
     for (int i = 0; i < n; ++i) {
         fill_phase(ctx, prog.ops[i], cluster, ph[i]);
-        ph[i].unit_begin = unit;
-        unit += ph[i].m_groups * ph[i].n_tiles * ph[i].splits;
-        ph[i].unit_end = unit;
+        ph[i].l.unit_begin = unit;
+        unit += ph[i].l.m_groups * ph[i].l.n_tiles * ph[i].l.splits;
+        ph[i].l.unit_end = unit;
         ctr_off[i] = n_ctr;
-        n_ctr += (size_t)ph[i].m_groups;
+        n_ctr += (size_t)ph[i].l.m_groups;
         flops += gemm_flops(prog.ops[i]);
     }
     if (n_ctr > prog.n_counters) {
@@ -825,17 +906,17 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     }
     for (int i = 0; i < n; ++i) {
         const TcGemm& g = prog.ops[i];
-        ph[i].done_ctr = prog.dev_counters + ctr_off[i];
-        ph[i].n_deps = g.n_deps;
+        ph[i].l.done_ctr = prog.dev_counters + ctr_off[i];
+        ph[i].l.n_deps = g.n_deps;
         for (int d = 0; d < g.n_deps; ++d) {
             const int j = g.dep[d];
             BM_REQUIRE(j >= 0 && j < i, "a program op may only depend on earlier ops");
-            ph[i].dep_ctr[d] = prog.dev_counters + ctr_off[j];
-            ph[i].dep_need[d] = ph[j].n_tiles * ph[j].splits * cluster * EPI_WARPS;
-            if (g.dep_all[d]) ph[i].dep_groups[d] = ph[j].m_groups;
+            ph[i].l.dep_ctr[d] = prog.dev_counters + ctr_off[j];
+            ph[i].l.dep_need[d] = ph[j].l.n_tiles * ph[j].l.splits * cluster * EPI_WARPS;
+            if (g.dep_all[d]) ph[i].l.dep_groups[d] = ph[j].l.m_groups;
             else {
-                ph[i].dep_groups[d] = 0;
-                BM_REQUIRE(ph[i].m_groups <= ph[j].m_groups, "row-block dependency on an op with fewer row blocks");
+                ph[i].l.dep_groups[d] = 0;
+                BM_REQUIRE(ph[i].l.m_groups <= ph[j].l.m_groups, "row-block dependency on an op with fewer row blocks");
             }
         }
     }
@@ -859,7 +940,30 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     L.total_units = unit;
     L.k0 = rng.k0; L.k1 = rng.k1; L.tick = rng.tick; L.row0 = rng.row0;
     L.batch_row = batch_row;
+    static unsigned long long* dbg_buf = nullptr;
+    static int dbg_left = -1;
+    if (dbg_left < 0) { const char* e = getenv("BM_TC_PROGRAM_TIMELINE"); dbg_left = e ? atoi(e) : 0; }
+    const bool dbg = dbg_left > 0;
+    if (dbg) {
+        if (!dbg_buf) BM_CUDA(cudaMalloc(&dbg_buf, 512 * sizeof(unsigned long long)));
+        BM_CUDA(cudaMemsetAsync(dbg_buf, 0, 512 * sizeof(unsigned long long), ctx->stream));
+        L.dbg = dbg_buf;
+    }
     do_launch(ctx, L, cluster, flops);
+    if (dbg) {
+        --dbg_left;
+        unsigned long long h[512];
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        BM_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "program timeline (SM cycles, CTA 0): setup=%llu exit=%llu wall=%llu ns, %d units total\n",
+                h[1] - h[0], h[5] - h[0], h[7] - h[6], unit);
+        fprintf(stderr, "  ord: start dep_ok mma_first mma_done epi_start epi_done published\n");
+        for (int o = 0; o < 24 && h[64 + o * 8]; ++o) {
+            fprintf(stderr, "  %2d:", o);
+            for (int k = 0; k < 7; ++k) fprintf(stderr, " %7llu", h[64 + o * 8 + k] ? h[64 + o * 8 + k] - h[0] : 0ull);
+            fprintf(stderr, "\n");
+        }
+    }
 }
 
 }  // namespace bm
