@@ -84,6 +84,7 @@ struct RbmTC : RbmSimt<float> {
         g.acc_scale = mult; g.bias_scale = mult;
         g.bias = up ? hb.p : vb.p;
         g.rng = make_rng(0, site, t, 0, 0);
+        { const char* e = getenv(up ? "BM_TC_BN_UP" : "BM_TC_BN_DOWN"); if (e) g.force_bn = atoi(e); }
         g.out_mean_bf = means; g.ld_mean_bf = up ? ldh : ldv;
         const int kind = up ? cfg.h_kind : cfg.v_kind;
         if (kind == BM_UNIT_BERNOULLI) {

@@ -34,6 +34,8 @@
 #include <mutex>
 #include <string.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <utility>
 
 namespace bm {
 
@@ -59,6 +61,8 @@ enum : int {
 
 // everything of an op except its tensor maps: copied to shared memory at kernel start so that no
 // role ever waits on global memory for a descriptor field
+constexpr int MAX_KCHUNKS = 128;    // chunk-ordered dataflow covers K <= 8192
+
 struct TcPhaseLite {
     int M, N, BN, m_groups, n_tiles, splits, n_pairs;
     int chunks[2], a_mn[2], b_mn[2], a_neg[2], a_row0[2], a_k0[2], a_batch[2];
@@ -76,12 +80,20 @@ struct TcPhaseLite {
     int n_deps;
     const int* dep_ctr[3]; int dep_need[3]; int dep_groups[3];   // dep_groups == 0: same row group only
     int* done_ctr;                   // [m_groups] completion counters of this op (nullable)
+    // chunk-level dataflow (row-block dependencies): the producer op publishes every 32-column chunk
+    // of a row-block group as soon as it is stored; the consumer walks its K chunks in the order in
+    // which the producer's epilogues finish them, so its MMAs overlap the producer's epilogue.
+    int* chunk_ctr;                  // [m_groups * ncol32] of this op (nullable)
+    int ncol32;                      // ceil(N / 32)
+    const int* dep_chunk_ctr;        // the producer's chunk counters (nullable: unit-level waits only)
+    int dep_ncol32, dep_chunk_need;
+    unsigned char k_order[MAX_KCHUNKS];   // order in which this op consumes its K chunks
 };
 struct alignas(64) TcPhase {
     CUtensorMap tmA[2], tmB[2];      // read by the TMA unit from global / parameter memory
     TcPhaseLite l;
 };
-constexpr int MAX_PHASES = 64;
+constexpr int MAX_PHASES = 48;
 constexpr int SPH_BYTES = MAX_PHASES * (int)sizeof(TcPhaseLite);
 constexpr int SBIAS_BYTES = ACC_STAGES * 256 * (int)sizeof(float);
 
@@ -267,12 +279,25 @@ struct EpiCtx {
     uint32_t t_row;               // TMEM address of this thread's lane, column 0 of the accumulator stage
     uint64_t* tempty;             // accumulator-free barrier (leader's in pair mode)
     int half, lane;
+    int* chunk_ctr;               // this unit's row of the op's chunk counters (nullable)
     const float* sbias;           // shared memory: bias_scale * bias (x -log2 e for sigmoid) of the tile's columns
     bool remote_arrive;           // pair mode, peer CTA: signal the leader's barrier
 };
 
+// Chunk publication is software-pipelined: chunk r is published just before chunk r+1's stores are
+// issued, i.e. after a whole chunk's worth of arithmetic, when chunk r's stores have long drained and
+// the gpu-scope fence does not stall.
+__device__ __forceinline__ void publish_pending(const EpiCtx& c, int& pending) {
+    if (pending >= 0) {
+        __threadfence();
+        __syncwarp();
+        if (c.lane == 0) atomicAdd(c.chunk_ctr + pending, 1);
+        pending = -1;
+    }
+}
+
 template <int MODE, bool FULL>
-__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
+__device__ __forceinline__ void chunk_body(const EpiCtx& c, int& pending, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
     typedef EpiCfg<MODE> E;
     const EpiPhase& p = c.p;
     const int act = E::fixed ? E::act : p.act;
@@ -284,6 +309,7 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
     const bool has_sigma = !E::fixed && p.sigma != nullptr;
     const int m = c.m;
     constexpr bool full_chunk = FULL;
+    if (!full_chunk || !E::fixed || E::f32) publish_pending(c, pending);     // these paths store inside the loop below
     // in the fixed modes which outputs exist is known at compile time (no per-group branches)
     const bool do_mean = E::fixed ? E::mean_bf : (out_mean != nullptr);
     const bool do_state = E::fixed ? E::state_bf : (out_state != nullptr);
@@ -343,6 +369,7 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
             }
         }
     }
+    if (full_chunk && E::fixed && !E::f32) publish_pending(c, pending);     // arithmetic done, stores not yet issued
     if (do_mean && full_chunk) {
         __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
 #pragma unroll
@@ -376,6 +403,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     const int m = c.m;
 
     int last_ch = -1;
+    int pending = -1;
     for (int ch = c.half; ch < n_chunks32; ch += 2) last_ch = ch;
     if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
         __syncwarp();
@@ -404,14 +432,20 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
             }
         }
         const int n0 = c.n_blk * BN + ch * 32;
-        if (n0 >= p.N || !row_ok) continue;
-        const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
-        // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
-        // sigmoid / Philox chains of a thread can be interleaved by the scheduler
-        // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
-        if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, v, ch, n0, 32);
-        else chunk_body<MODE, false>(c, v, ch, n0, n_valid);
+        if (n0 >= p.N) continue;
+        if (row_ok) {
+            const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
+            // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
+            // sigmoid / Philox chains of a thread can be interleaved by the scheduler
+            // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
+            if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, pending, v, ch, n0, 32);
+            else chunk_body<MODE, false>(c, pending, v, ch, n0, n_valid);
+        } else {
+            publish_pending(c, pending);
+        }
+        if (c.chunk_ctr) pending = n0 >> 5;      // this 32-column chunk is published one chunk later
     }
+    publish_pending(c, pending);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -516,6 +550,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                         const int* ctr = ph->dep_ctr[d];
                         const int need = ph->dep_need[d];
                         if (ph->dep_groups[d] == 0) {
+                            if (ph->dep_chunk_ctr) continue;          // handled chunk by chunk below
                             while (ld_relaxed(ctr + u.m_group) < need) __nanosleep(64);
                         } else {
                             for (int gq = 0; gq < ph->dep_groups[d]; ++gq)
@@ -530,7 +565,27 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 __syncwarp();
             }
             if (lane == 0) DBG_UNIT(1, ord);
-            for (int c = u.c_begin; c < u.c_end; ++c) {
+            const int* const cdep = ph->dep_chunk_ctr ? ph->dep_chunk_ctr + (size_t)u.m_group * ph->dep_ncol32 : nullptr;
+            int fenced_upto = u.c_begin;         // K positions [c_begin, fenced_upto) are known ready and fenced
+            for (int ci = u.c_begin; ci < u.c_end; ++ci) {
+                const int c = cdep ? (int)ph->k_order[ci] : ci;
+                if (cdep && ci >= fenced_upto) {
+                    if (lane == 0) {
+                        const int need = ph->dep_chunk_need, nc = ph->dep_ncol32;
+                        int n = ci;
+                        for (;;) {       // wait for position ci, then take every following position already ready
+                            const int j = (int)ph->k_order[n];
+                            const int a = 2 * j, b = (2 * j + 1 < nc) ? 2 * j + 1 : 2 * j;
+                            if (n == ci) { while (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) __nanosleep(32); }
+                            else if (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) break;
+                            if (++n == u.c_end) break;
+                        }
+                        fenced_upto = n;
+                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    fenced_upto = __shfl_sync(0xffffffffu, fenced_upto, 0);
+                }
                 const int pr = (c >= ph->chunks[0]) ? 1 : 0;
                 const int kc = (pr ? c - ph->chunks[0] : c) * BK;
                 const CUtensorMap* mA = &gp->tmA[pr];
@@ -539,7 +594,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * L.stage_bytes;
                 uint8_t* sB = sA + A_BYTES;
-                if (lane == 0 && c - u.c_begin < 24) DBG_MARK(8 + (c - u.c_begin));
+                if (lane == 0 && ci - u.c_begin < 24) DBG_MARK(8 + (ci - u.c_begin));
                 const int nA = ph->a_mn[pr] ? 2 : 1;
                 const int nB = ph->b_mn[pr] ? b_cols / 64 : 1;
                 void* dst = nullptr; const CUtensorMap* map = nullptr; int c0 = 0, c1 = 0;
@@ -587,13 +642,14 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                 uint32_t accumulate = 0;
-                for (int c = u.c_begin; c < u.c_end; ++c) {
+                for (int ci = u.c_begin; ci < u.c_end; ++ci) {
+                    const int c = ph->dep_chunk_ctr ? (int)ph->k_order[ci] : ci;     // same order as the producer warp
                     const int pr = (c >= ph->chunks[0]) ? 1 : 0;
                     const int a_mn = ph->a_mn[pr], b_mn = ph->b_mn[pr];
                     const uint32_t idesc = idesc_base | ((uint32_t)ph->a_neg[pr] << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
                     mbar_wait(&full[stage], phase);
-                    if (c == u.c_begin) DBG_UNIT(2, ord);
-                    if (c - u.c_begin < 24) DBG_MARK(32 + (c - u.c_begin));
+                    if (ci == u.c_begin) DBG_UNIT(2, ord);
+                    if (ci - u.c_begin < 24) DBG_MARK(32 + (ci - u.c_begin));
                     tc_fence_after();
                     const uint32_t aaddr = smem_u32(smem + stage * L.stage_bytes);
                     const uint32_t baddr = aaddr + A_BYTES;
@@ -648,6 +704,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
             const int ph_mode = ph->mode;
             int* const ph_done = ph->done_ctr;
+            c.chunk_ctr = ph->chunk_ctr ? ph->chunk_ctr + (size_t)u.m_group * ph->ncol32 : nullptr;
             c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
@@ -883,9 +940,9 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     const int cluster = 2;            // programs always run on CTA pairs (all CTAs walk one unit list)
     std::vector<unsigned char> image((size_t)n * sizeof(TcPhase));
     TcPhase* ph = reinterpret_cast<TcPhase*>(image.data());
-    // counters: one int per row-block pair of every op
+    // counters: per op one int per row-block group (unit level) + one per (row-block group, 32-column chunk)
     size_t n_ctr = 0;
-    std::vector<size_t> ctr_off(n);
+    std::vector<size_t> ctr_off(n), cctr_off(n);
     int unit = 0;
     double flops = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -895,6 +952,9 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         ph[i].l.unit_end = unit;
         ctr_off[i] = n_ctr;
         n_ctr += (size_t)ph[i].l.m_groups;
+        ph[i].l.ncol32 = (ph[i].l.N + 31) / 32;
+        cctr_off[i] = n_ctr;
+        n_ctr += (size_t)ph[i].l.m_groups * ph[i].l.ncol32;
         flops += gemm_flops(prog.ops[i]);
     }
     if (n_ctr > prog.n_counters) {
@@ -917,6 +977,33 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
             else {
                 ph[i].l.dep_groups[d] = 0;
                 BM_REQUIRE(ph[i].l.m_groups <= ph[j].l.m_groups, "row-block dependency on an op with fewer row blocks");
+                // chunk-level dataflow: this op's A operand is op j's output (K = its N); only for the
+                // first such dependency, single-pair ops without split-K and BN_j on 32-column chunks
+                const TcPhaseLite& pj = ph[j].l;
+                const int kchunks = ph[i].l.chunks[0];
+                if (d == 0 && g.n_pairs == 1 && ph[i].l.splits == 1 && pj.splits == 1 && kchunks <= MAX_KCHUNKS &&
+                    pj.BN % 32 == 0 && g.K[0] == pj.N && getenv("BM_TC_CHUNK_DEPS")) {   // off by default: the per-chunk
+                    // gpu-scope fences cost the producer more than the consumer gains (measured)
+                    ph[j].l.chunk_ctr = prog.dev_counters + cctr_off[j];
+                    ph[i].l.dep_chunk_ctr = prog.dev_counters + cctr_off[j];
+                    ph[i].l.dep_ncol32 = pj.ncol32;
+                    ph[i].l.dep_chunk_need = cluster * 4;          // 4 lane-quarter warps per CTA store each chunk
+                    // consume K chunks in the order the producer's epilogues finish them: chunk c covers
+                    // 32-column chunks 2c, 2c+1, finished in round (local index within the producer tile)
+                    std::vector<std::pair<int, int>> order;
+                    for (int c = 0; c < kchunks; ++c) {
+                        int rank = 0;
+                        for (int h = 0; h < 2; ++h) {
+                            const int c32 = 2 * c + h;
+                            if (c32 >= pj.ncol32) continue;
+                            const int local = (c32 * 32 % pj.BN) / 32;
+                            rank = local > rank ? local : rank;
+                        }
+                        order.push_back(std::make_pair(rank, c));
+                    }
+                    std::stable_sort(order.begin(), order.end());
+                    for (int c = 0; c < kchunks; ++c) ph[i].l.k_order[c] = (unsigned char)order[c].second;
+                }
             }
         }
     }
