@@ -9,3 +9,5 @@ from . import layers
 from . import ebm
 from . import rbm
 from .rbm import BaseRBM, BernoulliRBM, MultinomialRBM, GaussianRBM, logit_mean
+from . import dbm
+from .dbm import DBM

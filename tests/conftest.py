@@ -38,14 +38,19 @@ def engines(request, monkeypatch):
     from boltzmann_machines.base import set_engine_factory
     if request.param == 'oracle':
         from oracle.rbm import rbm_factory
+        from oracle.dbm import dbm_factory
         old = set_engine_factory('rbm', rbm_factory)
+        old_d = set_engine_factory('dbm', dbm_factory)
         yield request.param
         set_engine_factory('rbm', old)
+        set_engine_factory('dbm', old_d)
     else:
         monkeypatch.setenv('BM_COMPUTE', request.param.split('-')[1])
         old = set_engine_factory('rbm', None)
+        old_d = set_engine_factory('dbm', None)
         yield request.param
         set_engine_factory('rbm', old)
+        set_engine_factory('dbm', old_d)
 
 
 @pytest.fixture
