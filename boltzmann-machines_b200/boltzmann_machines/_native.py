@@ -27,6 +27,9 @@ EXPORTS = (
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
     'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_transform', 'bm_rbm_metrics',
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
+    'bm_dbm_create', 'bm_dbm_destroy', 'bm_dbm_set_param', 'bm_dbm_get_param', 'bm_dbm_init_particles',
+    'bm_dbm_train_step', 'bm_dbm_val_metrics', 'bm_dbm_transform', 'bm_dbm_reconstruct', 'bm_dbm_log_proba',
+    'bm_dbm_sample_v', 'bm_dbm_ais',
 )
 
 
@@ -41,6 +44,24 @@ class RbmCfg(C.Structure):
         ('sparsity_target', C.c_double), ('sparsity_cost', C.c_double), ('sparsity_damping', C.c_double),
         ('propup_mult', C.c_double), ('propdown_mult', C.c_double),
         ('v_n_samples', C.c_double), ('h_n_samples', C.c_double),
+        ('sigma', C.POINTER(C.c_double)),
+    ]
+
+
+class DbmCfg(C.Structure):
+    _fields_ = [
+        ('n_layers', C.c_int32), ('n_visible', C.c_int32),
+        ('n_hiddens', C.POINTER(C.c_int32)),
+        ('v_kind', C.c_int32),
+        ('h_kinds', C.POINTER(C.c_int32)),
+        ('h_n_samples', C.POINTER(C.c_double)),
+        ('dtype', C.c_int32), ('compute', C.c_int32),
+        ('n_particles', C.c_int32), ('batch_size', C.c_int32), ('max_mf_updates', C.c_int32),
+        ('sample_v', C.c_int32),
+        ('sample_h', C.POINTER(C.c_int32)),
+        ('mf_tol', C.c_double), ('l2', C.c_double), ('max_norm', C.c_double), ('sparsity_damping', C.c_double),
+        ('sparsity_target', C.POINTER(C.c_double)),
+        ('sparsity_cost', C.POINTER(C.c_double)),
         ('sigma', C.POINTER(C.c_double)),
     ]
 
@@ -80,6 +101,14 @@ def load_library(path=None):
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
         'bm_debug_tc_gemm': [vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp],
+        'bm_dbm_create': [vp, C.POINTER(DbmCfg), C.POINTER(vp)],
+        'bm_dbm_set_param': [vp, C.c_char_p, vp, sz], 'bm_dbm_get_param': [vp, C.c_char_p, vp, sz],
+        'bm_dbm_init_particles': [vp, u64],
+        'bm_dbm_train_step': [vp, vp, i32, dbl, dbl, i32, u64, u32, i32, C.POINTER(dbl)],
+        'bm_dbm_val_metrics': [vp, vp, i32, i32, u64, u32, C.POINTER(dbl)],
+        'bm_dbm_transform': [vp, vp, i32, vp], 'bm_dbm_reconstruct': [vp, vp, i32, vp],
+        'bm_dbm_log_proba': [vp, vp, i32, vp], 'bm_dbm_sample_v': [vp, i32, u64, u32, vp],
+        'bm_dbm_ais': [vp, i32, i32, i32, u64, vp],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)
@@ -89,6 +118,8 @@ def load_library(path=None):
     lib.bm_ctx_destroy.restype = None
     lib.bm_rbm_destroy.argtypes = [vp]
     lib.bm_rbm_destroy.restype = None
+    lib.bm_dbm_destroy.argtypes = [vp]
+    lib.bm_dbm_destroy.restype = None
     if path is None:
         _lib = lib
     return lib
@@ -328,8 +359,136 @@ class CudaRBM(object):
             pass
 
 
+def _sfx(i):
+    return '' if i == 0 else '_{0}'.format(i)
+
+
+class CudaDBM(object):
+    """Engine object for ``DBM``: a ``bm_dbm`` handle."""
+
+    def __init__(self, cfg, ctx=None):
+        self._lib = load_library()
+        self.ctx = ctx or Context.default()
+        self.cfg = dict(cfg)
+        self.V = int(cfg['n_visible'])
+        self.Hs = [int(h) for h in cfg['n_hiddens']]
+        self.L = len(self.Hs)
+        self.M, self.B = int(cfg['n_particles']), int(cfg['batch_size'])
+        self.dt = np.dtype(cfg.get('dtype', 'float32'))
+        i32arr = lambda xs: (C.c_int32 * len(xs))(*[int(x) for x in xs])
+        dblarr = lambda xs: (C.c_double * len(xs))(*[float(x) for x in xs])
+        c = DbmCfg()
+        c.n_layers, c.n_visible = self.L, self.V
+        self._keep = [i32arr(self.Hs), i32arr([UNIT_KINDS[k] for k in cfg.get('h_kinds', ['bernoulli'] * self.L)]),
+                      dblarr(cfg.get('h_n_samples', [100.] * self.L)), i32arr(cfg.get('sample_h', [True] * self.L)),
+                      dblarr(cfg.get('sparsity_target', [0.1] * self.L)), dblarr(cfg.get('sparsity_cost', [0.] * self.L))]
+        c.n_hiddens, c.h_kinds, c.h_n_samples, c.sample_h, c.sparsity_target, c.sparsity_cost = self._keep
+        c.v_kind = UNIT_KINDS[cfg.get('v_kind', 'bernoulli')]
+        c.dtype = DTYPES[self.dt.name]
+        c.compute = COMPUTE['fp32']
+        c.n_particles, c.batch_size = self.M, self.B
+        c.max_mf_updates = int(cfg.get('max_mf_updates', 10))
+        c.sample_v = int(cfg.get('sample_v', True))
+        c.mf_tol = float(cfg.get('mf_tol', 1e-7))
+        c.l2 = float(cfg.get('l2', 0.))
+        mn = float(cfg.get('max_norm', np.inf))
+        c.max_norm = mn if np.isfinite(mn) else 1e300
+        c.sparsity_damping = float(cfg.get('sparsity_damping', 0.9))
+        self._sigma = None
+        if cfg.get('sigma', None) is not None:
+            self._sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(cfg['sigma'], dtype=np.float64), (self.V,)))
+            c.sigma = self._sigma.ctypes.data_as(C.POINTER(C.c_double))
+        h = C.c_void_p()
+        check(self._lib.bm_dbm_create(self.ctx.handle, C.byref(c), C.byref(h)))
+        self.handle = h
+        self._shapes = {'vb': (self.V,), 'dvb': (self.V,), 'v': (self.M, self.V)}
+        sizes = [self.V] + self.Hs
+        for i in range(self.L):
+            s = _sfx(i)
+            self._shapes.update({'W' + s: (sizes[i], sizes[i + 1]), 'dW' + s: (sizes[i], sizes[i + 1]),
+                                 'hb' + s: (self.Hs[i],), 'dhb' + s: (self.Hs[i],), 'mu' + s: (self.B, self.Hs[i]),
+                                 'q_means' + s: (self.Hs[i],), 'mu_means' + s: (self.Hs[i],), 'h' + s: (self.M, self.Hs[i])})
+        self._out2 = (C.c_double * 2)()
+
+    def set_params(self, d):
+        for k, v in d.items():
+            if k == 'sigma':
+                continue
+            a = np.ascontiguousarray(v, dtype=self.dt).reshape(self._shapes[k])
+            check(self._lib.bm_dbm_set_param(self.handle, k.encode(), a.ctypes.data, a.nbytes))
+
+    def get_params(self, names=None):
+        out = {}
+        for k in (names or list(self._shapes)):
+            a = np.empty(self._shapes[k], dtype=self.dt)
+            check(self._lib.bm_dbm_get_param(self.handle, k.encode(), a.ctypes.data, a.nbytes))
+            out[k] = a
+        return out
+
+    def init_particles(self, seed):
+        check(self._lib.bm_dbm_init_particles(self.handle, int(seed) & (2 ** 64 - 1)))
+
+    def _batch(self, X):
+        X = np.ascontiguousarray(X, dtype=self.dt)
+        if X.ndim != 2 or X.shape[1] != self.V:
+            raise ValueError('batch has shape {0}, expected (rows, {1})'.format(X.shape, self.V))
+        return X
+
+    def train_step(self, X, lr, momentum, k, seed, tick, metrics=()):
+        X = self._batch(X)
+        check(self._lib.bm_dbm_train_step(self.handle, X.ctypes.data, X.shape[0], lr, momentum, int(k), int(seed), int(tick),
+                                          1 if metrics else 0, self._out2))
+        return {'msre': float(self._out2[0]), 'n_mf_updates': float(self._out2[1])} if metrics else None
+
+    def val_metrics(self, X, k, seed, tick):
+        X = self._batch(X)
+        check(self._lib.bm_dbm_val_metrics(self.handle, X.ctypes.data, X.shape[0], int(k), int(seed), int(tick), self._out2))
+        return {'msre': float(self._out2[0]), 'n_mf_updates': float(self._out2[1])}
+
+    def transform(self, X):
+        X = self._batch(X)
+        out = np.empty((X.shape[0], self.Hs[-1]), dtype=self.dt)
+        check(self._lib.bm_dbm_transform(self.handle, X.ctypes.data, X.shape[0], out.ctypes.data))
+        return out
+
+    def reconstruct(self, X):
+        X = self._batch(X)
+        out = np.empty((X.shape[0], self.V), dtype=self.dt)
+        check(self._lib.bm_dbm_reconstruct(self.handle, X.ctypes.data, X.shape[0], out.ctypes.data))
+        return out
+
+    def log_proba(self, X):
+        X = self._batch(X)
+        out = np.empty(X.shape[0], dtype=np.float64)
+        check(self._lib.bm_dbm_log_proba(self.handle, X.ctypes.data, X.shape[0], out.ctypes.data))
+        return out
+
+    def sample_v(self, k, seed, tick):
+        out = np.empty((self.M, self.V), dtype=self.dt)
+        check(self._lib.bm_dbm_sample_v(self.handle, int(k), int(seed), int(tick), out.ctypes.data))
+        return out
+
+    def ais(self, n_runs, n_betas, k, seed):
+        out = np.empty(int(n_runs), dtype=np.float64)
+        check(self._lib.bm_dbm_ais(self.handle, int(n_runs), int(n_betas), int(k), int(seed), out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self._lib.bm_dbm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def default_factory(kind):
     load_library()
+    if kind == 'dbm':
+        return CudaDBM
     if kind == 'rbm':
         return CudaRBM
     raise RuntimeError("no native engine for '{0}'".format(kind))

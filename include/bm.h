@@ -121,6 +121,47 @@ int  bm_rbm_metrics(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_st
  * in BF16 compute mode (widened), cfg.dtype otherwise. */
 int  bm_rbm_get_activation(bm_rbm* rbm, const char* name, void* host, size_t bytes);
 
+/* ---- DBM -------------------------------------------------------------------------------------
+ * Static configuration: what DBM._make_constants/_make_vars bake into the graph (dbm.py:233-383).
+ * Per-layer arrays have n_layers entries (hidden layer 0 is adjacent to the visibles). */
+typedef struct bm_dbm_cfg {
+    int32_t n_layers, n_visible;
+    const int32_t* n_hiddens;
+    int32_t v_kind;                  /* BM_UNIT_*                                          */
+    const int32_t* h_kinds;
+    const double*  h_n_samples;      /* MultinomialLayer.n_samples per layer (nullable)    */
+    int32_t dtype, compute;
+    int32_t n_particles, batch_size, max_mf_updates;
+    int32_t sample_v;
+    const int32_t* sample_h;
+    double mf_tol, l2, max_norm, sparsity_damping;
+    const double* sparsity_target;
+    const double* sparsity_cost;
+    const double* sigma;             /* [n_visible] for a gaussian visible layer, else NULL */
+} bm_dbm_cfg;
+
+int  bm_dbm_create(bm_ctx* ctx, const bm_dbm_cfg* cfg, bm_dbm** out);      /* DBM._make_tf_model, dbm.py:761-769 */
+void bm_dbm_destroy(bm_dbm* dbm);
+/* variables by TF-uniquified name (dbm.py:294-383, dbm_mnist.py:367-371): "vb", "W", "W_1", "hb", "hb_1",
+ * "dvb", "dW"..., "dhb"..., "mu"... [batch_size,H_i], "q_means"..., "mu_means"..., particles "v" [n_particles,V],
+ * "h", "h_1"... [n_particles,H_i] */
+int  bm_dbm_set_param(bm_dbm* dbm, const char* name, const void* host, size_t bytes);
+int  bm_dbm_get_param(bm_dbm* dbm, const char* name, void* host, size_t bytes);
+/* persistent particles <- the layers' own random initialisers (dbm.py:362-383) */
+int  bm_dbm_init_particles(bm_dbm* dbm, uint64_t seed);
+/* session.run(train_op): mean-field E-step, PCD particle update, parameter update (dbm.py:515-622, 805).
+ * want_metrics != 0: out2 = {msre, n_mf_updates} (dbm.py:798-803) */
+int  bm_dbm_train_step(bm_dbm* dbm, const void* X, int32_t rows, double lr, double momentum, int32_t n_gibbs_steps,
+                       uint64_t seed, uint32_t tick, int32_t want_metrics, double* out2);
+/* validation msre / n_mf_updates; like the reference it also advances the persistent chains (dbm.py:523, 810-816) */
+int  bm_dbm_val_metrics(bm_dbm* dbm, const void* X, int32_t rows, int32_t n_gibbs_steps, uint64_t seed, uint32_t tick, double* out2);
+int  bm_dbm_transform(bm_dbm* dbm, const void* X, int32_t rows, void* out);       /* mu of the last layer, dbm.py:526-528,859-872 */
+int  bm_dbm_reconstruct(bm_dbm* dbm, const void* X, int32_t rows, void* out);     /* dbm.py:626-632, 874-885 */
+int  bm_dbm_log_proba(bm_dbm* dbm, const void* X, int32_t rows, double* out);     /* variational bound + log Z, dbm.py:738-759 */
+int  bm_dbm_sample_v(bm_dbm* dbm, int32_t n_gibbs_steps, uint64_t seed, uint32_t tick, void* out);  /* dbm.py:641-648 */
+/* AIS estimates of log Z, one per run (dbm.py:650-736, 899-939) */
+int  bm_dbm_ais(bm_dbm* dbm, int32_t n_runs, int32_t n_betas, int32_t n_gibbs_steps, uint64_t seed, double* logZ);
+
 /* ---- test hook: the raw tensor-core GEMM (no counterpart in the reference) -----------------
  * C[M,N] (fp32) = A * B^T (+/- A2 * B2^T), operands given as host fp32 and rounded to bf16.
  * a_t == 0: A is [M,K] row-major, else [K,M];  b_t == 0: B is [N,K] row-major, else [K,N]

@@ -1,0 +1,106 @@
+"""DBM engine (CUDA, through the C-ABI) against the numpy oracle on the same seeded inputs:
+mean-field, PCD particles, the whole training step, the read-only queries and AIS."""
+import numpy as np
+import pytest
+
+from boltzmann_machines import _native
+from oracle.dbm import OracleDBM
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cfg(V=30, Hs=(18, 11), dtype='float32', **kw):
+    cfg = dict(n_visible=V, n_hiddens=list(Hs), v_kind='bernoulli', h_kinds=['bernoulli'] * len(Hs),
+               h_n_samples=[100.] * len(Hs), dtype=dtype, n_particles=12, batch_size=10, max_mf_updates=6, mf_tol=1e-6,
+               l2=1e-4, max_norm=3.0, sample_v=True, sample_h=[True] * len(Hs),
+               sparsity_target=[0.2] * len(Hs), sparsity_cost=[0.01] * len(Hs), sparsity_damping=0.9)
+    cfg.update(kw)
+    return cfg
+
+
+def make_pair(cfg, seed=0):
+    rng = np.random.RandomState(seed)
+    eng, ora = _native.CudaDBM(cfg), OracleDBM(cfg)
+    dt = np.dtype(cfg['dtype'])
+    sizes = [cfg['n_visible']] + cfg['n_hiddens']
+    d = {'vb': (0.1 * rng.randn(sizes[0])).astype(dt)}
+    for i in range(len(cfg['n_hiddens'])):
+        s = '' if i == 0 else '_%d' % i
+        d['W' + s] = (0.3 * rng.randn(sizes[i], sizes[i + 1])).astype(dt)
+        d['hb' + s] = (0.1 * rng.randn(sizes[i + 1])).astype(dt)
+    for e in (eng, ora):
+        e.set_params(d)
+        e.init_particles(4242)
+    return eng, ora
+
+
+def batch(cfg, rows, seed=1):
+    return (np.random.RandomState(seed).rand(rows, cfg['n_visible']) < 0.3).astype(cfg['dtype'])
+
+
+def same(eng, ora, names=None, atol=2e-5):
+    g, w = eng.get_params(names), ora.get_params(names)
+    for k in w:
+        np.testing.assert_allclose(g[k], w[k], atol=atol, err_msg=k)
+
+
+@pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7)])
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+def test_particle_init_and_training_steps(Hs, dtype):
+    cfg = make_cfg(Hs=Hs, dtype=dtype)
+    eng, ora = make_pair(cfg)
+    same(eng, ora, ['v', 'h'], atol=1e-6)
+    for it in range(3):
+        X = batch(cfg, 10, seed=it)
+        got = eng.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        want = ora.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        assert got['n_mf_updates'] == want['n_mf_updates']
+        assert got['msre'] == pytest.approx(want['msre'], rel=1e-4)
+    same(eng, ora, atol=5e-5 if dtype == 'float32' else 1e-9)
+    eng.close()
+
+
+def test_queries_match_oracle():
+    cfg = make_cfg()
+    eng, ora = make_pair(cfg)
+    X = batch(cfg, 10)
+    eng.train_step(X, 0.05, 0.5, 1, 5, 0); ora.train_step(X, 0.05, 0.5, 1, 5, 0)
+    Xq = batch(cfg, 7, seed=9)
+    np.testing.assert_allclose(eng.transform(Xq), ora.transform(Xq), atol=2e-5)
+    np.testing.assert_allclose(eng.reconstruct(Xq), ora.reconstruct(Xq), atol=2e-5)
+    np.testing.assert_allclose(eng.log_proba(Xq), ora.log_proba(Xq), rtol=1e-5, atol=1e-4)
+    g, w = eng.val_metrics(Xq, 2, 7, 3), ora.val_metrics(Xq, 2, 7, 3)
+    assert g['n_mf_updates'] == w['n_mf_updates'] and g['msre'] == pytest.approx(w['msre'], rel=1e-4)
+    np.testing.assert_allclose(eng.sample_v(3, 11, 4), ora.sample_v(3, 11, 4), atol=2e-5)
+    same(eng, ora, ['v', 'h', 'h_1', 'mu', 'mu_1'])
+    eng.close()
+
+
+def test_ais_matches_oracle_and_exact_enumeration():
+    cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
+    eng, ora = make_pair(cfg)
+    a = eng.ais(32, 500, 1, 2222)
+    b = ora.ais(32, 500, 1, 2222)
+    # same Philox stream: the runs agree individually up to float accumulation
+    np.testing.assert_allclose(a, b, atol=5e-3)
+    p = ora.get_params()
+    W0, W1 = p['W'].astype(np.float64), p['W_1'].astype(np.float64)
+    terms = []
+    for s in range(2 ** 5):
+        x = np.array([(s >> i) & 1 for i in range(5)], dtype=np.float64)
+        terms.append(x @ p['hb'] + np.logaddexp(0, W0 @ x + p['vb']).sum() + np.logaddexp(0, x @ W1 + p['hb_1']).sum())
+    exact = np.logaddexp.reduce(terms)
+    est = np.logaddexp.reduce(a) - np.log(len(a))
+    assert abs(est - exact) < 0.1, (est, exact)
+    eng.close()
+
+
+def test_ais_paper_scale_is_within_one_nat_of_the_oracle():
+    """BASELINE.json: AIS log Z within +-1.0 of the reference path (here at 784-64-32, 64 runs x 200 betas)."""
+    cfg = make_cfg(V=784, Hs=(64, 32), n_particles=4, batch_size=4)
+    eng, ora = make_pair(cfg)
+    a = eng.ais(64, 200, 1, 1)
+    b = ora.ais(64, 200, 1, 1)
+    lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
+    assert abs(lm(a) - lm(b)) < 1.0
+    eng.close()
