@@ -198,7 +198,8 @@ struct Dbm : DbmBase {
     std::vector<double> h_n_samples, sp_target, sp_cost;
     int v_kind, sample_vis, max_mf;
     double mf_tol, l2, max_norm, damping;
-    DevBuf<T> vb, dvb, sigma, v, v2, Xd, xsum, vsum, recon, rowtmp;
+    DevBuf<T> vb, dvb, sigma, v, v2, v3, Xd, xsum, vsum, recon, rowtmp;
+    std::vector<DevBuf<T>> h3;
     std::vector<DevBuf<T>> W, dW, hb, dhb, qm, mm, pen, norm, G, musum, hsum;
     std::vector<DevBuf<T>> mu, mu2, h, h2, t;
     DevBuf<unsigned int> flag;
@@ -406,13 +407,20 @@ struct Dbm : DbmBase {
 
     // ---- PCD particle update (dbm.py:480-509) --------------------------------------------------------------
     void particles_update(int n_steps, bool sample, uint64_t seed, uint32_t tick, int t0, bool commit, T** v_final) {
-        std::vector<T*> cur(L), nxt(L);
-        for (int i = 0; i < L; ++i) { cur[i] = h[i].p; nxt[i] = h2[i].p; }
-        T* vc = v.p; T* vn = v2.p;
+        std::vector<T*> cur(L), nxt(L), spare(L);
+        for (int i = 0; i < L; ++i) { cur[i] = h[i].p; nxt[i] = h2[i].p; spare[i] = nullptr; }
+        T* vc = v.p; T* vn = v2.p; T* vspare = nullptr;
+        if (!commit) {      // an uncommitted run must never write the persistent particles: ping-pong on scratch
+            v3.ensure((size_t)M * V); vspare = v3.p;
+            if (h3.size() != (size_t)L) h3.resize(L);
+            for (int i = 0; i < L; ++i) { h3[i].ensure((size_t)M * Hs[i]); spare[i] = h3[i].p; }
+        }
         for (int s = 0; s < n_steps; ++s) {
             std::vector<const T*> Hin(cur.begin(), cur.end());
             gibbs_step(vc, Hin, nxt, vn, true, sample, M, seed, (uint32_t)(t0 + s + 1), tick);
-            std::swap(cur, nxt); std::swap(vc, vn);
+            if (!commit && s == 0) {                 // from now on alternate between the two scratch sets
+                cur = nxt; nxt = spare; vc = vn; vn = vspare;
+            } else { std::swap(cur, nxt); std::swap(vc, vn); }
         }
         if (commit) {
             for (int i = 0; i < L; ++i)
