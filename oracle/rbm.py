@@ -237,19 +237,30 @@ class OracleRBM(object):
         return out
 
     # -- engine interface ----------------------------------------------------
-    def train_step(self, X, lr, momentum, k, seed, tick, metrics=()):
+    def train_step(self, X, lr, momentum, k, seed, tick, metrics=(), shard=None):
         """One ``session.run(train_op)`` (base_rbm.py:415-479).  Metrics, when
-        requested, see the pre-update parameters."""
+        requested, see the pre-update parameters.
+
+        ``shard=(rank, nranks, allreduce)`` models the engine's data-parallel mode (no counterpart in
+        the single-device reference): X is this rank's slice of a global batch of ``rows * nranks``
+        rows, draws are keyed by the global row index, and the four sufficient statistics are
+        summed over ranks by ``allreduce(array) -> array`` before the (identical) update."""
         c, p, dt = self.cfg, self.p, self.dt
-        X = self.prepare_input(X, seed, tick)
-        h0_means, v_states, v_means, _, h_means = self.chain(X, k, seed, tick)
-        out = self._metrics(metrics, X, v_means, seed, tick, 0) if metrics else None
-        N = dt.type(X.shape[0])
-        dW = (X.T @ h0_means - v_states.T @ h_means) / N - dt.type(c.get('l2', 0.)) * p['W']   # :445-449
-        dvb = np.mean(X - v_states, axis=0)          # :451
-        dhb = np.mean(h0_means - h_means, axis=0)    # :453
+        rank, nranks, allreduce = shard if shard is not None else (0, 1, None)
+        row0 = rank * np.asarray(X).shape[0]
+        X = self.prepare_input(X, seed, tick, row0)
+        h0_means, v_states, v_means, _, h_means = self.chain(X, k, seed, tick, row0)
+        out = self._metrics(metrics, X, v_means, seed, tick, row0) if metrics else None
+        N = dt.type(X.shape[0] * nranks)
+        G = X.T @ h0_means - v_states.T @ h_means
+        dvb_sum, dhb_sum, q_sum = (X - v_states).sum(axis=0), (h0_means - h_means).sum(axis=0), h_means.sum(axis=0)
+        if allreduce is not None:
+            G, dvb_sum, dhb_sum, q_sum = allreduce(G), allreduce(dvb_sum), allreduce(dhb_sum), allreduce(q_sum)
+        dW = G / N - dt.type(c.get('l2', 0.)) * p['W']   # :445-449
+        dvb = dvb_sum / N                             # :451
+        dhb = dhb_sum / N                             # :453
         damp = dt.type(c.get('sparsity_damping', 0.9))
-        q = damp * p['q_means'] + (dt.type(1) - damp) * h_means.sum(axis=0)   # :457-459
+        q = damp * p['q_means'] + (dt.type(1) - damp) * q_sum   # :457-459
         pen = dt.type(c.get('sparsity_cost', 0.)) * (q - dt.type(c.get('sparsity_target', 0.1)))
         p['q_means'] = q.astype(dt)
         dhb = dhb - pen

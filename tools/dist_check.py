@@ -1,0 +1,55 @@
+"""Run under torchrun (one process per GPU): data-parallel CD-k through the engine's NCCL allreduce
+must reproduce the single-process oracle on the concatenated batch, on every rank."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'boltzmann-machines_b200'))
+
+
+def main():
+    import torch.distributed as dist
+    from boltzmann_machines import _native
+    from oracle.rbm import OracleRBM
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    dist.init_process_group('gloo')
+    ctx = _native.Context(local)
+    uid = [_native.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    rng = np.random.RandomState(0)
+    V, H, rows = 784, 256, 128
+    X = (rng.rand(rows * world, V) < 0.2).astype(np.float32)
+    init = dict(W=(0.05 * rng.randn(V, H)).astype(np.float32), vb=(0.1 * rng.randn(V)).astype(np.float32),
+                hb=np.zeros(H, np.float32))
+    ok = True
+    for compute, tol in (('fp32', 2e-5), ('bf16', 3e-3)):
+        cfg = dict(n_visible=V, n_hidden=H, sample_v=False, sample_h=True, l2=1e-4, sparsity_cost=0.01, max_batch=rows,
+                   compute=compute, dtype='float32')
+        eng = _native.CudaRBM(cfg, ctx=ctx)
+        ora = OracleRBM(cfg)
+        eng.set_params(init); ora.set_params(init)
+        for it in range(3):
+            eng.train_step(X[rank * rows:(rank + 1) * rows], 0.05, 0.5, 2, 77, it)
+            ora.train_step(X, 0.05, 0.5, 2, 77, it)          # the whole global batch in one process
+        got, want = eng.get_params(['W', 'vb', 'hb']), ora.get_params(['W', 'vb', 'hb'])
+        err = max(float(np.max(np.abs(got[k] - want[k]))) for k in got)
+        # every rank must hold bit-identical parameters (same allreduced statistics, same update)
+        mine = np.concatenate([got[k].ravel() for k in sorted(got)])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        identical = all(np.array_equal(gathered[0], g) for g in gathered)
+        print('rank {0} compute={1}: max |engine - oracle(full batch)| = {2:.3e}, ranks identical: {3}'.format(
+            rank, compute, err, identical), flush=True)
+        ok = ok and err < tol and identical
+        eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
