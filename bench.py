@@ -50,35 +50,55 @@ def model_cfg(compute='bf16'):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons, one sample every 100 ms from before the warm-up to the end
+    of the run; every sample is stamped on arrival and only those that fall inside a timed region
+    (`mark()` ... `unmark()`) are reported, i.e. the median is a median UNDER LOAD."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.samples, self.windows, self._t0 = device, None, [], [], None
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except OSError:
             self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), line))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        self._t0 = time.perf_counter()
+
+    def unmark(self):
+        self.windows.append((self._t0, time.perf_counter()))
+
+    def n_loaded(self):
+        return sum(1 for t, _ in self.samples if any(a + 0.05 <= t <= b for a, b in self.windows))
 
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
+        self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for line in out.strip().splitlines():
+        for t, line in self.samples:
+            # a sample describes the 100 ms before it: require it to lie well inside a loaded window
+            if not any(a + 0.05 <= t <= b for a, b in self.windows):
+                continue
             f = [x.strip() for x in line.split(',')]
             if len(f) < 9:
                 continue
@@ -105,7 +125,7 @@ def measured_peaks():
 
 def recorded_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, 'profiles', 'tc_layer_kernel_traffic.json')
+    p = os.path.join(ROOT, 'profiles', 'tc_program_kernel_traffic.json')
     if os.path.isfile(p):
         with open(p) as fh:
             return json.load(fh).get('dram_bytes_per_launch')
@@ -154,7 +174,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -208,51 +228,77 @@ def main():
         eng.train_step_at((i % N_BATCHES) * B, B, LR, MOMENTUM, K_GIBBS, seed, tick[0])
         tick[0] += 1
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step_resident(i)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = ctx.launch_count()
     barrier()
+    sampler.mark()
     ctx.timer_start()
     for i in range(args.steps):
         step_resident(args.warmup + i)
     ms = ctx.timer_stop()
     barrier()
+    sampler.unmark()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     value = args.steps * B * world * K_GIBBS / (ms * 1e-3)
 
     # ---- region 2: same steps with per-launch CUDA events on the tensor-core kernel -------------
     ctx.profile_tc(True)
+    sampler.mark()
     for i in range(args.steps):
         step_resident(i)
     flops, tc_ms, tc_launches = ctx.profile_read()
+    sampler.unmark()
     ctx.profile_tc(False)
     peak, peak_src = measured_peaks()
     achieved = flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     traffic = recorded_traffic()
 
-    # ---- region 3: end to end through the per-batch feed path (host buffers) ---------------------
-    Xpin = _native.pinned_empty((B * 8, V), np.float32)
-    Xpin[:] = X[:B * 8]
-    for i in range(3):
-        eng.train_step(Xpin[:B], LR, MOMENTUM, K_GIBBS, seed, tick[0], metrics=('msre',)); tick[0] += 1
+    # ---- region 3: end to end from HOST buffers through bm_rbm_train_epoch -----------------------
+    # (the call BaseRBM._train_epoch makes): every step uploads its own float32 batch from pinned
+    # host memory (double-buffered against the previous step's compute) and reads its MSRE back.
+    Xpin = _native.pinned_copy(X)
+    def epoch_chunks(n_steps, first_tick):
+        done = 0
+        while done < n_steps:
+            nb = min(N_BATCHES, n_steps - done)
+            eng.train_epoch(Xpin[:nb * B], B, LR, MOMENTUM, K_GIBBS, seed, first_tick + done,
+                            metrics=('msre',), every=1)
+            done += nb
+    epoch_chunks(max(3, min(args.warmup, N_BATCHES)), tick[0]); tick[0] += N_BATCHES
     e2e_steps = args.steps
     barrier()
+    sampler.mark()
     ctx.timer_start()
-    for i in range(e2e_steps):
-        lo = (i % 8) * B
-        eng.train_step(Xpin[lo:lo + B], LR, MOMENTUM, K_GIBBS, seed, tick[0], metrics=('msre',)); tick[0] += 1
+    epoch_chunks(e2e_steps, tick[0]); tick[0] += e2e_steps
     e2e_ms = ctx.timer_stop()
     barrier()
+    sampler.unmark()
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = e2e_steps * B * world * K_GIBBS / (e2e_ms * 1e-3)
+
+    # clock probe: when K is so small that no 100 ms sample fell inside a timed region, keep the
+    # same load running (untimed) until a few samples exist -- same work, same clocks
+    probe = 0
+    if rank == 0:
+        sampler.mark()
+        t_end = time.perf_counter() + 3.0
+        while sampler.n_loaded() < 5 and time.perf_counter() < t_end:
+            for i in range(50):
+                step_resident(i)
+            ctx.sync()
+            sampler.windows.append((sampler._t0, time.perf_counter()))
+            probe += 50
+        clocks = sampler.stop()
+        clocks['probe_steps_after_timed_regions'] = probe
+    barrier()
 
     if rank != 0:
         return
@@ -270,12 +316,12 @@ def main():
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None, 'traffic': traffic,
-                     'kernel': 'bm::tc_layer_kernel', 'launches': int(tc_launches), 'peak_source': peak_src,
+                     'kernel': 'bm::tc_program_kernel<2>', 'launches': int(tc_launches), 'peak_source': peak_src,
                      'step_tflops': FLOP_PER_STEP * args.steps / (ms * 1e-3) / 1e12 / 1.0,
                      'step_frac': FLOP_PER_STEP * args.steps / (ms * 1e-3) / 1e12 / peak},
         'e2e': {'value': e2e_value, 'unit': 'updates/s', 'h2d_bytes_per_step': B * V * 4 * world,
-                'd2h_bytes_per_step': 32 * world, 'ms_per_step': e2e_ms / e2e_steps,
-                'path': 'engine.train_step(host float32 batch, metrics=msre): the call BaseRBM._train_epoch makes'},
+                'd2h_bytes_per_step': 64 * world, 'ms_per_step': e2e_ms / e2e_steps,
+                'path': 'bm_rbm_train_epoch(pinned host float32 dataset, msre every step): what BaseRBM._train_epoch calls'},
     }
     if world == 1 and not args.no_cpu_baseline:
         cpu_steps = 8

@@ -25,7 +25,7 @@ EXPORTS = (
     'bm_ctx_timer_start', 'bm_ctx_timer_stop', 'bm_ctx_flush_l2', 'bm_host_alloc', 'bm_host_free',
     'bm_ctx_launch_count', 'bm_ctx_profile_tc', 'bm_ctx_profile_read', 'bm_comm_unique_id', 'bm_ctx_comm_init',
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
-    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_transform', 'bm_rbm_metrics',
+    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_train_epoch', 'bm_rbm_transform', 'bm_rbm_metrics',
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
     'bm_dbm_create', 'bm_dbm_destroy', 'bm_dbm_set_param', 'bm_dbm_get_param', 'bm_dbm_init_particles',
     'bm_dbm_train_step', 'bm_dbm_val_metrics', 'bm_dbm_transform', 'bm_dbm_reconstruct', 'bm_dbm_log_proba',
@@ -97,6 +97,7 @@ def load_library(path=None):
         'bm_rbm_train_step': [vp, vp, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_set_data': [vp, vp, i64],
         'bm_rbm_train_step_at': [vp, i64, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
+        'bm_rbm_train_epoch': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
         'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
@@ -205,6 +206,18 @@ def pinned_empty(shape, dtype=np.float32):
     buf = (C.c_char * n).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
     return arr
+
+
+def pinned_free(arr):
+    """Release an array made by `pinned_empty` / `pinned_copy` (the array must not be used afterwards)."""
+    check(load_library().bm_host_free(C.c_void_p(arr.ctypes.data)))
+
+
+def pinned_copy(X):
+    """Page-locked copy of a host array: lets `train_epoch` overlap the batch uploads with compute."""
+    P = pinned_empty(X.shape, X.dtype)
+    P[...] = X
+    return P
 
 
 def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None,
@@ -317,6 +330,24 @@ class CudaRBM(object):
         check(self._lib.bm_rbm_train_step(self.handle, X.ctypes.data, X.shape[0], lr, momentum, int(k),
                                           int(seed), int(tick), _mask(metrics), self._metrics_buf))
         return self._collect(metrics) if metrics else None
+
+    def train_epoch(self, X, batch, lr, momentum, k, seed, tick0, metrics=(), every=0, iter0=0):
+        """One pass over the host dataset X in mini-batches (uploads overlap compute).  Returns
+        {metric: [value of every reporting batch]}; batch i uses tick0 + i, exactly like
+        train_step(X[i*batch:(i+1)*batch], ..., tick=tick0 + i)."""
+        X = self._batch(X)
+        nb = (X.shape[0] + batch - 1) // batch
+        out = np.zeros((nb, 4), dtype=np.float64)
+        check(self._lib.bm_rbm_train_epoch(self.handle, X.ctypes.data, X.shape[0], int(batch), lr, momentum, int(k),
+                                           int(seed), int(tick0), _mask(metrics), int(every), int(iter0), out.ctypes.data))
+        rep = [i for i in range(nb) if every and (iter0 + i + 1) % every == 0]
+        return {m: [float(out[i, METRIC_SLOTS[m]]) for i in rep] for m in metrics}
+
+    def pin(self, X):
+        return pinned_copy(self._batch(X))
+
+    def unpin(self, P):
+        pinned_free(P)
 
     def set_data(self, X):
         X = self._batch(X)

@@ -215,6 +215,13 @@ class BaseRBM(EnergyBasedModel):
         every = self.metrics_config['train_metrics_every_iter']
         sums = {m: [] for m in wanted}
         bounds = batch_bounds(len(X), self.batch_size)
+        if hasattr(self._engine, 'train_epoch') and not self.verbose:
+            # the whole batch loop in one native call: same ticks, same results, uploads overlapped
+            got = self._engine.train_epoch(X, self.batch_size, tick0=self._tick, metrics=wanted,
+                                           every=every or 0, iter0=self.iter_, **self._step_args())
+            self._tick += len(bounds)
+            self.iter_ += len(bounds)
+            return {m: (float(np.mean(got[m])) if got[m] else None) for m in wanted}
         for lo, hi in _maybe_bar(bounds, self.verbose, leave=False, ncols=64, desc='epoch'):
             self.iter_ += 1
             report = wanted if (every and self.iter_ % every == 0) else ()
@@ -254,27 +261,34 @@ class BaseRBM(EnergyBasedModel):
         if X_val is not None:
             X_val = np.ascontiguousarray(X_val, dtype=self._np_dtype)
         mc = self.metrics_config
-        for self.epoch_ in epoch_iter(start_epoch=self.epoch_, max_epoch=self.max_epoch,
-                                      verbose=self.verbose):
-            train_results = self._train_epoch(X)
-            val_results, feg = {}, None
-            if X_val is not None and self.epoch_ % mc['val_metrics_every_epoch'] == 0:
-                val_results = self._run_val_metrics(X_val)
-            if X_val is not None and mc['feg'] and self.epoch_ % mc['feg_every_epoch'] == 0:
-                feg = self._run_feg(X, X_val)
+        pinned = self._engine.pin(X) if hasattr(self._engine, 'pin') else None   # page-locked copy: async uploads
+        if pinned is not None:
+            X = pinned
+        try:
+            for self.epoch_ in epoch_iter(start_epoch=self.epoch_, max_epoch=self.max_epoch,
+                                          verbose=self.verbose):
+                train_results = self._train_epoch(X)
+                val_results, feg = {}, None
+                if X_val is not None and self.epoch_ % mc['val_metrics_every_epoch'] == 0:
+                    val_results = self._run_val_metrics(X_val)
+                if X_val is not None and mc['feg'] and self.epoch_ % mc['feg_every_epoch'] == 0:
+                    feg = self._run_feg(X, X_val)
 
-            if self.verbose:
-                line = 'epoch: {0:{1}}/{2}'.format(self.epoch_, len(str(self.max_epoch)), self.max_epoch)
-                for prefix, res in (('', train_results), ('val.', val_results)):
-                    for m in sorted(res):
-                        if res[m] is not None:
-                            line += '; {0}{1}: {2:{3}}'.format(prefix, m, res[m], mc[m + '_fmt'])
-                if feg is not None:
-                    line += ' ; feg: {0:{1}}'.format(feg, mc['feg_fmt'])
-                write_during_training(line)
+                if self.verbose:
+                    line = 'epoch: {0:{1}}/{2}'.format(self.epoch_, len(str(self.max_epoch)), self.max_epoch)
+                    for prefix, res in (('', train_results), ('val.', val_results)):
+                        for m in sorted(res):
+                            if res[m] is not None:
+                                line += '; {0}{1}: {2:{3}}'.format(prefix, m, res[m], mc[m + '_fmt'])
+                    if feg is not None:
+                        line += ' ; feg: {0:{1}}'.format(feg, mc['feg_fmt'])
+                    write_during_training(line)
 
-            if self.save_after_each_epoch:
-                self._save_model(global_step=self.epoch_)
+                if self.save_after_each_epoch:
+                    self._save_model(global_step=self.epoch_)
+        finally:
+            if pinned is not None:
+                self._engine.unpin(pinned)
 
     def init_from(self, rbm):
         """Start from another RBM's weights, momentum accumulators and

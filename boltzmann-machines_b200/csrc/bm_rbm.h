@@ -3,6 +3,7 @@
 #include "bm_internal.h"
 #include "bm_tc.h"
 #include <vector>
+#include <algorithm>
 #include <string.h>
 #include <math.h>
 
@@ -33,6 +34,8 @@ struct RbmBase {
     virtual void set_data(const void* X, int64_t n_rows) = 0;
     virtual void train_step(const void* X_host, int64_t first_row, int rows, double lr, double mom, int k,
                             uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
+    virtual void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
+                             uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out) = 0;
     virtual void transform(const void* X, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) = 0;
     virtual void metrics(const void* X, int rows, int k, uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
     virtual void get_activation(const char* name, void* host, size_t bytes) = 0;
@@ -154,7 +157,9 @@ struct RbmSimt : RbmBase {
     const T* stage_input(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve(rows);
         const T* src;
-        if (X_host) {
+        if (staged_dev) {
+            src = staged_dev;                       // already copied by train_epoch's copy stream
+        } else if (X_host) {
             BM_CUDA(cudaMemcpyAsync(Xin.p, X_host, (size_t)rows * V * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
             src = Xin.p;
         } else {
@@ -221,8 +226,15 @@ struct RbmSimt : RbmBase {
         }
         if (mask & BM_METRIC_FREE_ENERGY) free_energy(Xcur, rows, 3, seed, tick, 2);
         double h[8];
+        if (defer_dst) {                            // train_epoch: read back without stalling the stream
+            BM_CUDA(cudaMemcpyAsync(defer_dst, scal.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            return;
+        }
         BM_CUDA(cudaMemcpyAsync(h, scal.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        finish_metrics(h, mask, out);
+    }
+    void finish_metrics(const double* h, uint32_t mask, double* out) const {
         double fe_const = 0.0;
         if (cfg.h_kind == BM_UNIT_MULTINOMIAL) {
             const double M = cfg.h_n_samples, K = (double)H;
@@ -270,6 +282,75 @@ struct RbmSimt : RbmBase {
         u.damp = (T)cfg.sparsity_damping; u.cost = (T)cfg.sparsity_cost; u.target = (T)cfg.sparsity_target;
         launch_bias_update<T>(ctx, u);
         launch_weight_update<T>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (T)cfg.l2, (T)lr, (T)mom, nullptr, 0);
+    }
+
+    // ---- one epoch over a host dataset (base_rbm.py:549-571) -----------------------------------
+    // Batch i+1 is copied host->device on a second stream while batch i computes (two staging
+    // buffers); requested metrics are read back asynchronously into pinned memory, so the compute
+    // stream never waits for the host inside the epoch.
+    ~RbmSimt() override {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int b = 0; b < 2; ++b) { if (ev_copied[b]) cudaEventDestroy(ev_copied[b]); if (ev_consumed[b]) cudaEventDestroy(ev_consumed[b]); }
+        if (epoch_host) cudaFreeHost(epoch_host);
+    }
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    DevBuf<T> epoch_stage[2];
+    const T* staged_dev = nullptr;
+    double* defer_dst = nullptr;
+    double* epoch_host = nullptr;
+    size_t epoch_host_cap = 0;
+
+    void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
+                     uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out) override {
+        BM_REQUIRE(X_host != nullptr && n_rows >= 1 && batch >= 1, "empty dataset or batch");
+        BM_REQUIRE(!mask || out != nullptr, "metrics requested without an output buffer");
+        const int64_t nb = (n_rows + batch - 1) / batch;
+        if (!copy_stream) {
+            BM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                BM_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+                BM_CUDA(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
+            }
+        }
+        for (int b = 0; b < 2; ++b) epoch_stage[b].ensure((size_t)batch * V);
+        if ((size_t)nb * 8 > epoch_host_cap) {
+            if (epoch_host) cudaFreeHost(epoch_host);
+            epoch_host = nullptr; epoch_host_cap = 0;
+            BM_CUDA(cudaMallocHost((void**)&epoch_host, (size_t)nb * 8 * sizeof(double)));
+            epoch_host_cap = (size_t)nb * 8;
+        }
+        // the staging buffers may still be read by work already queued on the compute stream
+        for (int b = 0; b < 2; ++b) BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
+        const T* Xh = (const T*)X_host;
+        double unused[4];
+        try {
+            for (int64_t i = 0; i < nb; ++i) {
+                const int b = (int)(i & 1);
+                const int rows = (int)std::min<int64_t>(batch, n_rows - i * batch);
+                BM_CUDA(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
+                BM_CUDA(cudaMemcpyAsync(epoch_stage[b].p, Xh + (size_t)i * batch * V, (size_t)rows * V * sizeof(T),
+                                        cudaMemcpyHostToDevice, copy_stream));
+                BM_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
+                BM_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
+                staged_dev = epoch_stage[b].p;
+                const bool report = mask && every > 0 && ((iter0 + i + 1) % every == 0);
+                defer_dst = epoch_host + 8 * i;
+                train_step(nullptr, 0, rows, lr, mom, k, seed, tick0 + (uint32_t)i, report ? mask : 0u, unused);
+                BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
+            }
+        } catch (...) {
+            staged_dev = nullptr; defer_dst = nullptr;
+            cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(ctx->stream);
+            throw;
+        }
+        staged_dev = nullptr; defer_dst = nullptr;
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < nb && mask; ++i) {
+            const bool report = every > 0 && ((iter0 + i + 1) % every == 0);
+            if (report) finish_metrics(epoch_host + 8 * i, mask, out + 4 * i);
+            else for (int j = 0; j < 4; ++j) out[4 * i + j] = 0.0;
+        }
     }
 
     void transform(const void* X_host, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) override {

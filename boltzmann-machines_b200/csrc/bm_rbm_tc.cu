@@ -101,7 +101,7 @@ struct RbmTC : RbmSimt<float> {
     void stage_tc(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve_tc(rows);
         const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
-        if (!X_host && plain) {
+        if (!X_host && !staged_dev && plain) {
             BM_REQUIRE(first_row >= 0 && first_row + rows <= data_rows, "row range outside the resident dataset");
             reserve(rows);
             X_b = data_b.p; X_ld = ldv; X_row0 = (int)first_row; X_rows_total = (int)data_rows;

@@ -111,6 +111,15 @@ int  bm_rbm_train_step_at(bm_rbm* rbm, int64_t first_row, int32_t rows, double l
                           int32_t n_gibbs_steps, uint64_t seed, uint32_t tick,
                           uint32_t metric_mask, double* metrics_out);
 /* transform_op: chain-end E[h | v_k] (base_rbm.py:438-440, 687-700); H_out host [rows, n_hidden] */
+/* BaseRBM._train_epoch (rbm/base_rbm.py:549-571): the whole mini-batch loop of one epoch over a HOST dataset
+ * X[n_rows, n_visible].  Batch i = rows [i*batch, min(n_rows, (i+1)*batch)) runs exactly bm_rbm_train_step(..., tick0 + i);
+ * its host->device copy is double-buffered on a copy stream and overlaps batch i-1's compute (full overlap needs X in
+ * pinned memory, bm_host_alloc; pageable memory works but serialises).  Metrics selected by `mask` are computed for
+ * the batches with (iter0 + i + 1) % metrics_every == 0 (train_metrics_every_iter, base_rbm.py:560-567; 0 = never),
+ * read back asynchronously and returned in out[4*i .. 4*i+3] (other rows are zeroed); out may be NULL if mask is 0. */
+int  bm_rbm_train_epoch(bm_rbm* rbm, const void* X, int64_t n_rows, int32_t batch, double lr, double momentum,
+                        int32_t n_gibbs_steps, uint64_t seed, uint32_t tick0, uint32_t metric_mask,
+                        int32_t metrics_every, int64_t iter0, double* out);
 int  bm_rbm_transform(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_steps,
                       uint64_t seed, uint32_t tick, void* H_out);
 /* msre / pll / l2_loss / free_energy_op on a batch without training (base_rbm.py:573-621) */

@@ -145,6 +145,32 @@ def test_resident_dataset_equals_fed_batches():
     a.close(), b.close()
 
 
+@pytest.mark.parametrize('compute', ['fp32', 'bf16'])
+@pytest.mark.parametrize('pinned', [False, True])
+def test_train_epoch_equals_the_per_batch_loop(compute, pinned):
+    """bm_rbm_train_epoch (double-buffered uploads, deferred metric read-back) is the same
+    computation as calling bm_rbm_train_step per batch, ragged last batch included."""
+    cfg = make_cfg('bernoulli', 96, 48, 16, compute=compute, sample_v=False, dropout=0.8)
+    a, _ = make_pair(cfg)
+    b, _ = make_pair(cfg)
+    X = make_data(cfg, 16 * 5 + 7)
+    Xh = _native.pinned_copy(X) if pinned else X
+    want = []
+    for i, lo in enumerate(range(0, len(X), 16)):
+        m = a.train_step(X[lo:lo + 16], 0.05, 0.5, 2, 11, 3 + i, metrics=('msre', 'pll') if (4 + i + 1) % 2 == 0 else ())
+        if m:
+            want.append(m)
+    got = b.train_epoch(Xh, 16, 0.05, 0.5, 2, 11, 3, metrics=('msre', 'pll'), every=2, iter0=4)
+    assert len(got['msre']) == len(want) == 3
+    np.testing.assert_allclose(got['msre'], [m['msre'] for m in want], rtol=1e-12)
+    np.testing.assert_allclose(got['pll'], [m['pll'] for m in want], rtol=1e-12)
+    for k, v in a.get_params().items():
+        np.testing.assert_array_equal(v, b.get_params()[k])
+    if pinned:
+        _native.pinned_free(Xh)
+    a.close(), b.close()
+
+
 def test_init_weights_matches_tf_stream():
     from oracle import philox as P
     for dtype in ('float32', 'float64'):
