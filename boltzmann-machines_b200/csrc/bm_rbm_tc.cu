@@ -322,6 +322,7 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
         fprintf(stderr, "  sm clock: %llu cycles over %llu ns = %.0f MHz\n", h[5] - h[0], h[7] - h[6], 1e3 * (double)(h[5] - h[0]) / (double)(h[7] - h[6]));
         fprintf(stderr, "  tma_issue:");
         for (int i = 0; i < 24 && h[8 + i]; ++i) fprintf(stderr, " %llu", h[8 + i] - h[0]);
+        fprintf(stderr, "\n  mma iteration 12: wait_full=%llu mma_x4=%llu commit=%llu", h[57] - h[56], h[58] - h[57], h[59] - h[58]);
         fprintf(stderr, "\n  mma_ready:");
         for (int i = 0; i < 24 && h[32 + i]; ++i) fprintf(stderr, " %llu", h[32 + i] - h[0]);
         fprintf(stderr, "\n");

@@ -41,13 +41,14 @@ namespace bm {
 
 constexpr int BM = 128;            // rows per CTA tile = TMEM lanes
 constexpr int BK = 64;             // K per pipeline stage = one 128-byte swizzle atom of bf16
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 10;
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;      // TMEM columns per accumulator stage
 constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;          // 32 KiB (BN <= 256)
 constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);   // == 6 * (A_BYTES + B_BYTES / 2)
-constexpr int SMEM_BARRIER_BYTES = 256;
+constexpr int SMEM_BARRIER_BYTES = 320;   // full/empty ring, tfull/tempty, TMEM slot, unit/granule barriers
+constexpr int MAX_GRAN = 4;               // 64-column granules per tile (BN <= 256)
 constexpr int EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
 
@@ -61,7 +62,7 @@ enum : int {
 
 // everything of an op except its tensor maps: copied to shared memory at kernel start so that no
 // role ever waits on global memory for a descriptor field
-constexpr int MAX_KCHUNKS = 128;    // chunk-ordered dataflow covers K <= 8192
+constexpr int MAX_KCHUNKS = 32;     // granule-ordered dataflow covers K <= 2048
 
 struct TcPhaseLite {
     int M, N, BN, m_groups, n_tiles, splits, n_pairs;
@@ -80,24 +81,31 @@ struct TcPhaseLite {
     int n_deps;
     const int* dep_ctr[3]; int dep_need[3]; int dep_groups[3];   // dep_groups == 0: same row group only
     int* done_ctr;                   // [m_groups] completion counters of this op (nullable)
-    // chunk-level dataflow (row-block dependencies): the producer op publishes every 32-column chunk
-    // of a row-block group as soon as it is stored; the consumer walks its K chunks in the order in
-    // which the producer's epilogues finish them, so its MMAs overlap the producer's epilogue.
-    int* chunk_ctr;                  // [m_groups * ncol32] of this op (nullable)
-    int ncol32;                      // ceil(N / 32)
-    const int* dep_chunk_ctr;        // the producer's chunk counters (nullable: unit-level waits only)
-    int dep_ncol32, dep_chunk_need;
+    // granule-level dataflow (row-block dependencies): the producer op publishes every 64-column
+    // granule of a tile (two 32-column epilogue chunks) as soon as it is stored; the consumer walks its
+    // K chunks in the order in which the producer's epilogues finish them, so its MMAs overlap the
+    // producer's epilogue instead of waiting for the whole row block.
+    int* chunk_ctr;                  // [m_groups * n_tiles * gran_per_tile] of this op (nullable)
+    int gran_per_tile;               // ceil(BN / 64)
+    const int* dep_chunk_ctr;        // the producer's granule counters (nullable: unit-level waits only)
+    int dep_gran_row, dep_chunk_need;     // counters per producer row group; arrivals per granule
     unsigned char k_order[MAX_KCHUNKS];   // order in which this op consumes its K chunks
+    unsigned char k_dep_a[MAX_KCHUNKS], k_dep_b[MAX_KCHUNKS];   // producer granules K chunk c overlaps
 };
 struct alignas(64) TcPhase {
     CUtensorMap tmA[2], tmB[2];      // read by the TMA unit from global / parameter memory
     TcPhaseLite l;
 };
-constexpr int MAX_PHASES = 48;
-constexpr int SPH_BYTES = MAX_PHASES * (int)sizeof(TcPhaseLite);
+constexpr int MAX_PHASES = 96;
 constexpr int SBIAS_BYTES = ACC_STAGES * 256 * (int)sizeof(float);
 
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + SMEM_BARRIER_BYTES + SBIAS_BYTES + SPH_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + SMEM_BARRIER_BYTES + SBIAS_BYTES;
+
+// The ops of the running launch.  Constant memory on purpose: indexed by warp-uniform values it is read
+// through the uniform datapath, so the TMA / MMA issue loops keep their descriptors, coordinates and
+// trip counts in uniform registers -- with per-thread registers every UTMALDG / UTCHMMA is wrapped in
+// an ELECT + R2UR "waterfall" loop of ~100 cycles, which made the issue loops the bottleneck.
+__constant__ TcPhaseLite c_ph[MAX_PHASES];
 
 struct TcLaunch {
     TcPhase inl;                     // single-op launches carry their descriptor in the parameters
@@ -135,17 +143,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 // cta_group::2 loads: data lands in the issuing CTA, the transaction bytes are counted on the
 // LEADER CTA's mbarrier (address with the peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, uint64_t map, uint32_t leader_bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     asm volatile(
@@ -165,6 +173,19 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas knows that exactly one thread
+// executes the guarded code and moves its operands to uniform registers without an ELECT/R2UR loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define DBG_MARK(slot) do { if (L.dbg && blockIdx.x == 0) L.dbg[(slot)] = (unsigned long long)clock64(); } while (0)
 // per-unit marks of CTA 0: slot 64 + ord * 8 + kind (ord = ordinal of the unit within this CTA, < 24)
@@ -172,21 +193,30 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// descriptors are passed as (lo, hi) halves: only `lo` (the start address) changes between MMAs
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -279,25 +309,13 @@ struct EpiCtx {
     uint32_t t_row;               // TMEM address of this thread's lane, column 0 of the accumulator stage
     uint64_t* tempty;             // accumulator-free barrier (leader's in pair mode)
     int half, lane;
-    int* chunk_ctr;               // this unit's row of the op's chunk counters (nullable)
+    uint64_t* gran_bar;           // shared-memory barriers of this accumulator stage's granules (nullable)
     const float* sbias;           // shared memory: bias_scale * bias (x -log2 e for sigmoid) of the tile's columns
     bool remote_arrive;           // pair mode, peer CTA: signal the leader's barrier
 };
 
-// Chunk publication is software-pipelined: chunk r is published just before chunk r+1's stores are
-// issued, i.e. after a whole chunk's worth of arithmetic, when chunk r's stores have long drained and
-// the gpu-scope fence does not stall.
-__device__ __forceinline__ void publish_pending(const EpiCtx& c, int& pending) {
-    if (pending >= 0) {
-        __threadfence();
-        __syncwarp();
-        if (c.lane == 0) atomicAdd(c.chunk_ctr + pending, 1);
-        pending = -1;
-    }
-}
-
 template <int MODE, bool FULL>
-__device__ __forceinline__ void chunk_body(const EpiCtx& c, int& pending, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
+__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
     typedef EpiCfg<MODE> E;
     const EpiPhase& p = c.p;
     const int act = E::fixed ? E::act : p.act;
@@ -309,7 +327,6 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, int& pending, const 
     const bool has_sigma = !E::fixed && p.sigma != nullptr;
     const int m = c.m;
     constexpr bool full_chunk = FULL;
-    if (!full_chunk || !E::fixed || E::f32) publish_pending(c, pending);     // these paths store inside the loop below
     // in the fixed modes which outputs exist is known at compile time (no per-group branches)
     const bool do_mean = E::fixed ? E::mean_bf : (out_mean != nullptr);
     const bool do_state = E::fixed ? E::state_bf : (out_state != nullptr);
@@ -369,7 +386,6 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, int& pending, const 
             }
         }
     }
-    if (full_chunk && E::fixed && !E::f32) publish_pending(c, pending);     // arithmetic done, stores not yet issued
     if (do_mean && full_chunk) {
         __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
 #pragma unroll
@@ -403,7 +419,6 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     const int m = c.m;
 
     int last_ch = -1;
-    int pending = -1;
     for (int ch = c.half; ch < n_chunks32; ch += 2) last_ch = ch;
     if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
         __syncwarp();
@@ -411,41 +426,46 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
             if (PAIR && c.remote_arrive) { if constexpr (PAIR) mbar_arrive_remote(c.tempty, 0); } else mbar_arrive(c.tempty);
         }
     }
-    for (int ch = c.half; ch < n_chunks32; ch += 2) {
-        uint32_t v[32];
-        __syncwarp();                            // tcgen05.ld is warp-collective (.sync.aligned)
-        if (ch * 32 + 32 <= BN) {
-            tmem_ld32(c.t_row + (uint32_t)(ch * 32), v);
-        } else {                                 // BN is a multiple of 16: a trailing half chunk
-            uint32_t lo[16];
-            tmem_ld16(c.t_row + (uint32_t)(ch * 32), lo);
+    // granule g = 32-column chunks 2g (warps 0-3) and 2g+1 (warps 4-7); every warp arrives on the
+    // granule's barrier once its chunk is stored (or at once if it has none): 8 arrivals per granule
+    const int n_gran = (BN + 63) / 64;
+    for (int g = 0; g < n_gran; ++g) {
+        const int ch = 2 * g + c.half;
+        if (ch < n_chunks32) {
+            uint32_t v[32];
+            __syncwarp();                            // tcgen05.ld is warp-collective (.sync.aligned)
+            if (ch * 32 + 32 <= BN) {
+                tmem_ld32(c.t_row + (uint32_t)(ch * 32), v);
+            } else {                                 // BN is a multiple of 16: a trailing half chunk
+                uint32_t lo[16];
+                tmem_ld16(c.t_row + (uint32_t)(ch * 32), lo);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { v[e] = lo[e]; v[16 + e] = 0u; }
-        }
-        tmem_ld_wait();
-        if (ch == last_ch) {
-            // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (c.lane == 0) {
-                if (PAIR && c.remote_arrive) { if constexpr (PAIR) mbar_arrive_remote(c.tempty, 0); } else mbar_arrive(c.tempty);
+                for (int e = 0; e < 16; ++e) { v[e] = lo[e]; v[16 + e] = 0u; }
+            }
+            tmem_ld_wait();
+            if (ch == last_ch) {
+                // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (c.lane == 0) {
+                    if (PAIR && c.remote_arrive) { if constexpr (PAIR) mbar_arrive_remote(c.tempty, 0); } else mbar_arrive(c.tempty);
+                }
+            }
+            const int n0 = c.n_blk * BN + ch * 32;
+            if (n0 < p.N && row_ok) {
+                const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
+                // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
+                // sigmoid / Philox chains of a thread can be interleaved by the scheduler
+                // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
+                if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, v, ch, n0, 32);
+                else chunk_body<MODE, false>(c, v, ch, n0, n_valid);
             }
         }
-        const int n0 = c.n_blk * BN + ch * 32;
-        if (n0 >= p.N) continue;
-        if (row_ok) {
-            const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
-            // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
-            // sigmoid / Philox chains of a thread can be interleaved by the scheduler
-            // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
-            if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, pending, v, ch, n0, 32);
-            else chunk_body<MODE, false>(c, pending, v, ch, n0, n_valid);
-        } else {
-            publish_pending(c, pending);
+        if (c.gran_bar) {
+            __syncwarp();                            // the warp's stores of this granule precede the arrival
+            if (c.lane == 0) mbar_arrive(c.gran_bar + g);
         }
-        if (c.chunk_ctr) pending = n0 >> 5;      // this 32-column chunk is published one chunk later
     }
-    publish_pending(c, pending);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -453,8 +473,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
 // ------------------------------------------------------------------------------------------
 struct UnitInfo { int split, m_group, n_blk, c_begin, c_end, total_chunks; };
 
-__device__ __forceinline__ int phase_of(const TcPhaseLite* sph, int pi, int unit) {
-    while (unit >= sph[pi].unit_end) ++pi;
+__device__ __forceinline__ int phase_of(int pi, int unit) {
+    while (unit >= c_ph[pi].unit_end) ++pi;
     return pi;
 }
 __device__ __forceinline__ UnitInfo decode_unit(const TcPhaseLite* ph, int unit) {
@@ -481,18 +501,13 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+    uint64_t* unit_bar = tempty + ACC_STAGES + 1;                 // [ACC_STAGES] all epilogue warps stored the unit
+    uint64_t* gran_bar = unit_bar + ACC_STAGES;                   // [ACC_STAGES][MAX_GRAN] ... a 64-column granule
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { DBG_MARK(0); if (L.dbg && blockIdx.x == 0) L.dbg[6] = gtime(); }
     float* const s_bias = reinterpret_cast<float*>(smem + RING_BYTES + SMEM_BARRIER_BYTES);
-    TcPhaseLite* const sph = reinterpret_cast<TcPhaseLite*>(smem + RING_BYTES + SMEM_BARRIER_BYTES + SBIAS_BYTES);
-    const TcPhase* const gph = L.n_phases ? L.phases : &L.inl;
-    {   // descriptors (minus the tensor maps) -> shared memory
-        const int nph = L.n_phases ? L.n_phases : 1;
-        constexpr int W = (int)(sizeof(TcPhaseLite) / 4);
-        for (int i = threadIdx.x; i < nph * W; i += TC_THREADS)
-            reinterpret_cast<uint32_t*>(sph)[i] = reinterpret_cast<const uint32_t*>(&gph[i / W].l)[i % W];
-    }
+    const TcPhase* const gph = L.n_phases ? L.phases : &L.inl;      // tensor maps (global / parameter memory)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&gph->tmA[0]); tma_prefetch_desc(&gph->tmB[0]);
     }
@@ -500,7 +515,12 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         // pair: the leader's `full` collects its own expect_tx-arrive and the peer's arrive; its `tempty`
         // collects the epilogue warps of both CTAs; `empty`/`tfull` get one multicast commit each
         for (int s = 0; s < L.stages; ++s) { mbar_init(&full[s], (uint32_t)CL); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)(EPI_WARPS * CL)); }
+        // tempty: the epilogue warps and the publisher warp of both CTAs
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)((EPI_WARPS + 1) * CL)); }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(&unit_bar[a], EPI_WARPS);
+            for (int g = 0; g < MAX_GRAN; ++g) mbar_init(&gran_bar[a * MAX_GRAN + g], EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -519,9 +539,11 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
     if (threadIdx.x == 0) DBG_MARK(1);
 
     const int units = L.total_units;
-    const int crank = pair ? (int)cluster_ctarank() : 0;
-    const int unit0 = pair ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int unit_step = pair ? (int)cluster_count_x() : (int)gridDim.x;
+    // clusters are (2,1,1): rank = blockIdx.x & 1, cluster id = blockIdx.x >> 1 (kept as expressions of
+    // blockIdx / gridDim so that the compiler knows they are warp-uniform)
+    const int crank = pair ? (int)(blockIdx.x & 1u) : 0;
+    const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0) {
         // ================================ TMA producer =====================================
@@ -532,8 +554,8 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         int ord = -1;
         for (int unit = unit0; unit < units; unit += unit_step) {
             ++ord;
-            pi = phase_of(sph, pi, unit);
-            const TcPhaseLite* ph = &sph[pi];
+            pi = phase_of(pi, unit);
+            const TcPhaseLite* ph = &c_ph[pi];
             const TcPhase* gp = &gph[pi];
             const UnitInfo u = decode_unit(ph, unit);
             if (lane == 0) DBG_UNIT(0, ord);
@@ -565,109 +587,189 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 __syncwarp();
             }
             if (lane == 0) DBG_UNIT(1, ord);
-            const int* const cdep = ph->dep_chunk_ctr ? ph->dep_chunk_ctr + (size_t)u.m_group * ph->dep_ncol32 : nullptr;
+            const int* const cdep = ph->dep_chunk_ctr ? ph->dep_chunk_ctr + (size_t)u.m_group * ph->dep_gran_row : nullptr;
+            // ---- per-unit setup (warp-uniform: uniform registers): operand-pair configuration -------
+            const int chunks0 = ph->chunks[0];
+            uint64_t mapA[2], mapB[2];
+            int a_c0[2], a_c1[2], b_c0[2], b_c1[2], a_mn[2], b_mn[2];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                const int shift = ph->a_batch[pr] ? L.batch_row : 0;
+                a_mn[pr] = ph->a_mn[pr]; b_mn[pr] = ph->b_mn[pr];
+                mapA[pr] = (uint64_t)&gp->tmA[pr]; mapB[pr] = (uint64_t)&gp->tmB[pr];
+                // box coordinates at K offset 0: K-major {k, row}; MN-major {mn, k}
+                a_c0[pr] = a_mn[pr] ? m_blk * BM : 0;
+                a_c1[pr] = a_mn[pr] ? ph->a_k0[pr] + shift : ph->a_row0[pr] + shift + m_blk * BM;
+                b_c0[pr] = b_mn[pr] ? n_col0 : 0;
+                b_c1[pr] = b_mn[pr] ? 0 : n_col0;
+            }
+            const int nB_mn = b_cols >> 6;            // 64-column boxes of an MN-major B tile
+            const uint32_t smem_base = smem_u32(smem);
+            const bool ordered = cdep != nullptr;
             int fenced_upto = u.c_begin;         // K positions [c_begin, fenced_upto) are known ready and fenced
             for (int ci = u.c_begin; ci < u.c_end; ++ci) {
-                const int c = cdep ? (int)ph->k_order[ci] : ci;
-                if (cdep && ci >= fenced_upto) {
-                    if (lane == 0) {
-                        const int need = ph->dep_chunk_need, nc = ph->dep_ncol32;
-                        int n = ci;
-                        for (;;) {       // wait for position ci, then take every following position already ready
-                            const int j = (int)ph->k_order[n];
-                            const int a = 2 * j, b = (2 * j + 1 < nc) ? 2 * j + 1 : 2 * j;
-                            if (n == ci) { while (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) __nanosleep(32); }
-                            else if (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) break;
-                            if (++n == u.c_end) break;
+                int c = ci;
+                if (ordered) {
+                    c = (int)ph->k_order[ci];
+                    if (ci >= fenced_upto) {
+                        if (lane == 0) {
+                            const int need = ph->dep_chunk_need;
+                            int n = ci;
+                            for (;;) {       // wait for position ci, then take every following position already ready
+                                const int j = (int)ph->k_order[n];
+                                const int a = (int)ph->k_dep_a[j], b = (int)ph->k_dep_b[j];
+                                if (n == ci) { while (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) __nanosleep(32); }
+                                else if (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) break;
+                                if (++n == u.c_end) break;
+                            }
+                            fenced_upto = n;
+                            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                            asm volatile("fence.proxy.async;" ::: "memory");
                         }
-                        fenced_upto = n;
-                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        fenced_upto = __shfl_sync(0xffffffffu, fenced_upto, 0);
                     }
-                    fenced_upto = __shfl_sync(0xffffffffu, fenced_upto, 0);
                 }
-                const int pr = (c >= ph->chunks[0]) ? 1 : 0;
-                const int kc = (pr ? c - ph->chunks[0] : c) * BK;
-                const CUtensorMap* mA = &gp->tmA[pr];
-                const CUtensorMap* mB = &gp->tmB[pr];
-                const int shift = ph->a_batch[pr] ? L.batch_row : 0;
+                const int pr = (c >= chunks0) ? 1 : 0;
+                const int kc = (c - (pr ? chunks0 : 0)) * BK;
+                const uint32_t sA = smem_base + (uint32_t)stage * (uint32_t)L.stage_bytes;
+                const uint32_t sB = sA + (uint32_t)A_BYTES;
+                const uint64_t mA = pr ? mapA[1] : mapA[0], mB = pr ? mapB[1] : mapB[0];
+                const int amn = pr ? a_mn[1] : a_mn[0], bmn = pr ? b_mn[1] : b_mn[0];
+                const int ac0 = pr ? a_c0[1] : a_c0[0], ac1 = pr ? a_c1[1] : a_c1[0];
+                const int bc0 = pr ? b_c0[1] : b_c0[0], bc1 = pr ? b_c1[1] : b_c1[0];
                 mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* sA = smem + stage * L.stage_bytes;
-                uint8_t* sB = sA + A_BYTES;
-                if (lane == 0 && ci - u.c_begin < 24) DBG_MARK(8 + (ci - u.c_begin));
-                const int nA = ph->a_mn[pr] ? 2 : 1;
-                const int nB = ph->b_mn[pr] ? b_cols / 64 : 1;
-                void* dst = nullptr; const CUtensorMap* map = nullptr; int c0 = 0, c1 = 0;
-                if (lane < nA) {
-                    map = mA; dst = sA + lane * 8192;
-                    if (!ph->a_mn[pr]) { c0 = kc; c1 = ph->a_row0[pr] + shift + m_blk * BM; }
-                    else { c0 = m_blk * BM + lane * 64; c1 = ph->a_k0[pr] + shift + kc; }
-                } else if (lane < nA + nB) {
-                    const int j = lane - nA;
-                    map = mB; dst = sB + j * 8192;
-                    if (!ph->b_mn[pr]) { c0 = kc; c1 = n_col0; }
-                    else { c0 = n_col0 + j * 64; c1 = kc; }
+                if (elect_one()) {               // one thread issues; every operand above is warp-uniform
+                    if (ci - u.c_begin < 24) DBG_MARK(8 + (ci - u.c_begin));
+                    const uint32_t fbar = smem_u32(&full[stage]);
+                    if constexpr (pair) {
+                        // both CTAs load their own A rows and their half of the B tile; bytes are counted on the leader
+                        const uint32_t lbar = fbar & 0xFEFFFFFFu;
+                        if (crank == 0) mbar_expect_tx(&full[stage], tx_bytes); else mbar_arrive_remote(&full[stage], 0);
+                        if (!amn) tma_load_2d_2sm(sA, mA, lbar, kc, ac1);
+                        else { tma_load_2d_2sm(sA, mA, lbar, ac0, ac1 + kc); tma_load_2d_2sm(sA + 8192u, mA, lbar, ac0 + 64, ac1 + kc); }
+                        if (!bmn) tma_load_2d_2sm(sB, mB, lbar, kc, bc1);
+                        else for (int j = 0; j < nB_mn; ++j) tma_load_2d_2sm(sB + (uint32_t)j * 8192u, mB, lbar, bc0 + j * 64, kc);
+                    } else {
+                        mbar_expect_tx(&full[stage], tx_bytes);
+                        if (!amn) tma_load_2d(sA, mA, fbar, kc, ac1);
+                        else { tma_load_2d(sA, mA, fbar, ac0, ac1 + kc); tma_load_2d(sA + 8192u, mA, fbar, ac0 + 64, ac1 + kc); }
+                        if (!bmn) tma_load_2d(sB, mB, fbar, kc, bc1);
+                        else for (int j = 0; j < nB_mn; ++j) tma_load_2d(sB + (uint32_t)j * 8192u, mB, fbar, bc0 + j * 64, kc);
+                    }
                 }
-                if constexpr (pair) {
-                    // both CTAs load their own A rows and their half of the B tile; bytes are counted on the leader
-                    const uint32_t lbar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
-                    if (map) tma_load_2d_2sm(dst, map, lbar, c0, c1);
-                    if (lane == 0) { if (crank == 0) mbar_expect_tx(&full[stage], tx_bytes); else mbar_arrive_remote(&full[stage], 0); }
-                } else {
-                    if (lane == 0) mbar_expect_tx(&full[stage], tx_bytes);
-                    __syncwarp();
-                    if (map) tma_load_2d(dst, map, &full[stage], c0, c1);
-                }
-                __syncwarp();
                 if (++stage == L.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (the pair's leader CTA only) ============
-        if (lane == 0 && crank == 0) {
+        // The whole warp runs the loop converged (all values warp-uniform -> uniform registers);
+        // lane 0 issues the tcgen05 instructions.
+        if (crank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int pi = 0;
             int ord = -1;
+            const uint32_t smem_base = smem_u32(smem);
             for (int unit = unit0; unit < units; unit += unit_step) {
                 ++ord;
-                pi = phase_of(sph, pi, unit);
-                const TcPhaseLite* ph = &sph[pi];
+                pi = phase_of(pi, unit);
+                const TcPhaseLite* ph = &c_ph[pi];
                 const UnitInfo u = decode_unit(ph, unit);
                 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13),
                 // a_negate 13, a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
                 const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ph->BN >> 3) << 17) |
                                             ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
+                // per operand pair: instruction descriptor, K=16 slice strides and the constant upper
+                // halves of the shared-memory descriptors -- the chunk loop only adds addresses
+                uint32_t idesc_p[2], a_step_p[2], b_step_p[2], a_hi_p[2], b_hi_p[2], a_lo_p[2], b_lo_p[2];
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int a_mn = ph->a_mn[pr], b_mn = ph->b_mn[pr];
+                    idesc_p[pr] = idesc_base | ((uint32_t)ph->a_neg[pr] << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+                    a_step_p[pr] = a_mn ? (2048u >> 4) : (32u >> 4);    // descriptor units (16 B) per K=16 slice
+                    b_step_p[pr] = b_mn ? (2048u >> 4) : (32u >> 4);
+                    const uint64_t da = make_smem_desc(0, a_mn), db = make_smem_desc(0, b_mn);
+                    a_hi_p[pr] = (uint32_t)(da >> 32); a_lo_p[pr] = (uint32_t)da;
+                    b_hi_p[pr] = (uint32_t)(db >> 32); b_lo_p[pr] = (uint32_t)db;
+                }
+                const int chunks0 = ph->chunks[0];
+                const bool ordered = ph->dep_chunk_ctr != nullptr;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                 uint32_t accumulate = 0;
                 for (int ci = u.c_begin; ci < u.c_end; ++ci) {
-                    const int c = ph->dep_chunk_ctr ? (int)ph->k_order[ci] : ci;     // same order as the producer warp
-                    const int pr = (c >= ph->chunks[0]) ? 1 : 0;
-                    const int a_mn = ph->a_mn[pr], b_mn = ph->b_mn[pr];
-                    const uint32_t idesc = idesc_base | ((uint32_t)ph->a_neg[pr] << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+                    const int c = ordered ? (int)ph->k_order[ci] : ci;     // same order as the producer warp
+                    const int pr = (c >= chunks0) ? 1 : 0;
+                    const uint32_t idesc = pr ? idesc_p[1] : idesc_p[0];
+                    const uint32_t a_step = pr ? a_step_p[1] : a_step_p[0], b_step = pr ? b_step_p[1] : b_step_p[0];
+                    const uint32_t a_hi = pr ? a_hi_p[1] : a_hi_p[0], b_hi = pr ? b_hi_p[1] : b_hi_p[0];
+                    const uint32_t aaddr = smem_base + (uint32_t)stage * (uint32_t)L.stage_bytes;
+                    // operand addresses are < 256 KiB: the 14-bit start-address field (16-byte units) never carries
+                    const uint32_t a_lo = (pr ? a_lo_p[1] : a_lo_p[0]) | ((aaddr & 0x3FFFFu) >> 4);
+                    const uint32_t b_lo = (pr ? b_lo_p[1] : b_lo_p[0]) | (((aaddr + A_BYTES) & 0x3FFFFu) >> 4);
                     mbar_wait(&full[stage], phase);
-                    if (ci == u.c_begin) DBG_UNIT(2, ord);
-                    if (ci - u.c_begin < 24) DBG_MARK(32 + (ci - u.c_begin));
                     tc_fence_after();
-                    const uint32_t aaddr = smem_u32(smem + stage * L.stage_bytes);
-                    const uint32_t baddr = aaddr + A_BYTES;
-                    const uint32_t a_step = a_mn ? 2048u : 32u;    // bytes per K=16 slice
-                    const uint32_t b_step = b_mn ? 2048u : 32u;
+                    if (elect_one()) {
+                        if (ci == u.c_begin) DBG_UNIT(2, ord);
+                        if (ci - u.c_begin < 24) DBG_MARK(32 + (ci - u.c_begin));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adesc = make_smem_desc(aaddr + k * a_step, a_mn);
-                        const uint64_t bdesc = make_smem_desc(baddr + k * b_step, b_mn);
-                        if constexpr (pair) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, accumulate); else umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-                        accumulate = 1;
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if constexpr (pair) umma_bf16_2sm(d_tmem, a_lo + k * a_step, a_hi, b_lo + k * b_step, b_hi, idesc, accumulate);
+                            else umma_bf16(d_tmem, a_lo + k * a_step, a_hi, b_lo + k * b_step, b_hi, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        // the smem slot is free once these MMAs retire (both CTAs' producers are told)
+                        if constexpr (pair) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
                     }
-                    // the smem slot is free once these MMAs retire (both CTAs' producers are told)
-                    if constexpr (pair) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+                    accumulate = 1;
                     if (++stage == L.stages) { stage = 0; phase ^= 1; }
                 }
-                if constexpr (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
-                DBG_MARK(2); DBG_UNIT(3, ord);
+                if (elect_one()) {
+                    if constexpr (pair) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+                    DBG_MARK(2); DBG_UNIT(3, ord);
+                }
+                __syncwarp();
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ publisher =========================================
+        // Makes finished output visible to the other SMs WITHOUT stalling the epilogue warps: they
+        // arrive on a shared-memory barrier (release.cta) when a granule / the unit is stored; this
+        // thread acquires it, issues the gpu-scope fence and bumps the global dataflow counter.
+        if (lane == 0) {
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t gran_parity = 0;
+            int pi = 0;
+            int ord = -1;
+            for (int unit = unit0; unit < units; unit += unit_step) {
+                ++ord;
+                pi = phase_of(pi, unit);
+                const TcPhaseLite* ph = &c_ph[pi];
+                const UnitInfo u = decode_unit(ph, unit);
+                if (ph->chunk_ctr) {
+                    const int gpt = ph->gran_per_tile;
+                    int* const ctr = ph->chunk_ctr + ((size_t)u.m_group * ph->n_tiles + u.n_blk) * gpt;
+                    for (int g = 0; g < gpt; ++g) {
+                        // (granule barriers only advance on units of ops that publish granules: own parity bits)
+                        const int gb = acc * MAX_GRAN + g;
+                        mbar_wait(&gran_bar[gb], (gran_parity >> gb) & 1u);
+                        gran_parity ^= 1u << gb;
+                        if (u.n_blk * ph->BN + g * 64 < ph->N) {
+                            __threadfence();
+                            atomicAdd(ctr + g, 1);
+                        }
+                    }
+                }
+                mbar_wait(&unit_bar[acc], acc_phase);
+                if (ph->done_ctr) {
+                    __threadfence();
+                    atomicAdd(ph->done_ctr + u.m_group, 1);
+                }
+                DBG_UNIT(6, ord);
+                // the barriers of this accumulator stage may be reused: part of the stage's release
+                if (pair && crank == 1) { if constexpr (pair) mbar_arrive_remote(&tempty[acc], 0); } else mbar_arrive(&tempty[acc]);
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -686,8 +788,8 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         const int et = threadIdx.x - 128;          // 0..255 among the epilogue threads
         for (int unit = unit0; unit < units; unit += unit_step) {
             ++ord;
-            pi = phase_of(sph, pi, unit);
-            const TcPhaseLite* ph = &sph[pi];
+            pi = phase_of(pi, unit);
+            const TcPhaseLite* ph = &c_ph[pi];
             const UnitInfo u = decode_unit(ph, unit);
             {   // this tile's (pre-scaled) bias slice -> shared memory, while the MMAs are still running
                 const float bsc = (ph->act == ACT_SIGMOID) ? ph->bias_scale * -1.4426950408889634f : ph->bias_scale;
@@ -703,8 +805,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.p.out_state_bf = ph->out_state_bf; c.p.ld_state_bf = ph->ld_state_bf;
             c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
             const int ph_mode = ph->mode;
-            int* const ph_done = ph->done_ctr;
-            c.chunk_ctr = ph->chunk_ctr ? ph->chunk_ctr + (size_t)u.m_group * ph->ncol32 : nullptr;
+            c.gran_bar = ph->chunk_ctr ? gran_bar + acc * MAX_GRAN : nullptr;
             c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
@@ -721,13 +822,10 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 default: epilogue_tile<MODE_GENERIC, pair>(c); break;
             }
             if (threadIdx.x == 128) DBG_UNIT(5, ord);
-            // publish: this warp's part of the unit's output is in global memory
-            if (ph_done) {
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(ph_done + u.m_group, 1);
-            }
-            if (threadIdx.x == 128) { DBG_MARK(4); DBG_UNIT(6, ord); }
+            // this warp's part of the unit is stored: the publisher warp makes it visible to other SMs
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&unit_bar[acc]);
+            if (threadIdx.x == 128) DBG_MARK(4);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -874,15 +972,33 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
     BM_REQUIRE(!g.out_state_bf || (g.ld_state_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
 }
 
-static void do_launch(Ctx* ctx, TcLaunch& L, int cluster, double flops) {
+// The ops' descriptors (minus tensor maps) go to constant memory, stream-ordered before the launch;
+// skipped when the bank already holds exactly this image (the common case: the same program every step).
+static void upload_ops(Ctx* ctx, const TcPhase* ph, int n) {
+    static std::vector<unsigned char> current;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    std::vector<unsigned char> img((size_t)n * sizeof(TcPhaseLite));
+    for (int i = 0; i < n; ++i) memcpy(img.data() + (size_t)i * sizeof(TcPhaseLite), &ph[i].l, sizeof(TcPhaseLite));
+    if (img.size() <= current.size() && memcmp(img.data(), current.data(), img.size()) == 0) return;
+    BM_CUDA(cudaMemcpyToSymbolAsync(c_ph, img.data(), img.size(), 0, cudaMemcpyHostToDevice, ctx->stream));
+    if (current.size() < img.size()) current.resize(img.size());
+    memcpy(current.data(), img.data(), img.size());
+}
+
+static void do_launch(Ctx* ctx, TcLaunch& L, int cluster, double flops, int max_bn) {
     static bool attr_set = false;
     if (!attr_set) {
         BM_CUDA(cudaFuncSetAttribute(tc_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         BM_CUDA(cudaFuncSetAttribute(tc_program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    L.stages = cluster == 2 ? 6 : 4;
-    L.stage_bytes = cluster == 2 ? (A_BYTES + B_BYTES / 2) : (A_BYTES + B_BYTES);
+    // ring stages sized for the widest tile of the launch: narrower tiles buy a deeper pipeline
+    L.stage_bytes = A_BYTES + (max_bn / cluster) * BK * 2;
+    L.stage_bytes = (L.stage_bytes + 1023) & ~1023;           // 128B-swizzle atoms are 1024-byte aligned
+    L.stages = RING_BYTES / L.stage_bytes;
+    if (L.stages > MAX_STAGES) L.stages = MAX_STAGES;
+    { const char* e = getenv("BM_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= L.stages) L.stages = atoi(e); }
     const int max_clusters = ctx->sm_count / cluster;
     const int n_clusters = L.total_units < max_clusters ? L.total_units : max_clusters;
     cudaLaunchConfig_t lc{};
@@ -926,7 +1042,8 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     L.total_units = L.inl.l.unit_end;
     L.k0 = g.rng.k0; L.k1 = g.rng.k1; L.tick = g.rng.tick; L.row0 = g.rng.row0;
     L.dbg = g.dbg;
-    do_launch(ctx, L, cluster, gemm_flops(g));
+    upload_ops(ctx, &L.inl, 1);
+    do_launch(ctx, L, cluster, gemm_flops(g), L.inl.l.BN);
 }
 
 TcProgram::~TcProgram() {
@@ -936,11 +1053,11 @@ TcProgram::~TcProgram() {
 
 void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     const int n = (int)prog.ops.size();
-    BM_REQUIRE(n >= 1 && n <= MAX_PHASES, "a program holds 1..64 ops");
+    BM_REQUIRE(n >= 1 && n <= MAX_PHASES, "a program holds 1..96 ops");
     const int cluster = 2;            // programs always run on CTA pairs (all CTAs walk one unit list)
     std::vector<unsigned char> image((size_t)n * sizeof(TcPhase));
     TcPhase* ph = reinterpret_cast<TcPhase*>(image.data());
-    // counters: per op one int per row-block group (unit level) + one per (row-block group, 32-column chunk)
+    // counters: per op one int per row-block group (unit level) + one per (row-block group, tile, 64-column granule)
     size_t n_ctr = 0;
     std::vector<size_t> ctr_off(n), cctr_off(n);
     int unit = 0;
@@ -952,9 +1069,9 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         ph[i].l.unit_end = unit;
         ctr_off[i] = n_ctr;
         n_ctr += (size_t)ph[i].l.m_groups;
-        ph[i].l.ncol32 = (ph[i].l.N + 31) / 32;
+        ph[i].l.gran_per_tile = (ph[i].l.BN + 63) / 64;
         cctr_off[i] = n_ctr;
-        n_ctr += (size_t)ph[i].l.m_groups * ph[i].l.ncol32;
+        n_ctr += (size_t)ph[i].l.m_groups * ph[i].l.n_tiles * ph[i].l.gran_per_tile;
         flops += gemm_flops(prog.ops[i]);
     }
     if (n_ctr > prog.n_counters) {
@@ -964,6 +1081,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         prog.n_counters = n_ctr;
         prog.host_image.clear();
     }
+    static int chunk_deps = -1;
+    if (chunk_deps < 0) { const char* e = getenv("BM_TC_CHUNK_DEPS"); chunk_deps = e ? atoi(e) : 1; }
     for (int i = 0; i < n; ++i) {
         const TcGemm& g = prog.ops[i];
         ph[i].l.done_ctr = prog.dev_counters + ctr_off[i];
@@ -972,34 +1091,31 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
             const int j = g.dep[d];
             BM_REQUIRE(j >= 0 && j < i, "a program op may only depend on earlier ops");
             ph[i].l.dep_ctr[d] = prog.dev_counters + ctr_off[j];
-            ph[i].l.dep_need[d] = ph[j].l.n_tiles * ph[j].l.splits * cluster * EPI_WARPS;
+            ph[i].l.dep_need[d] = ph[j].l.n_tiles * ph[j].l.splits * cluster;      // one publication per CTA and unit
             if (g.dep_all[d]) ph[i].l.dep_groups[d] = ph[j].l.m_groups;
             else {
                 ph[i].l.dep_groups[d] = 0;
                 BM_REQUIRE(ph[i].l.m_groups <= ph[j].l.m_groups, "row-block dependency on an op with fewer row blocks");
-                // chunk-level dataflow: this op's A operand is op j's output (K = its N); only for the
-                // first such dependency, single-pair ops without split-K and BN_j on 32-column chunks
+                // granule-level dataflow: this op's (K-major) A operand is op j's output (K = its N); only
+                // for the first such dependency, single-pair ops without split-K
                 const TcPhaseLite& pj = ph[j].l;
                 const int kchunks = ph[i].l.chunks[0];
-                if (d == 0 && g.n_pairs == 1 && ph[i].l.splits == 1 && pj.splits == 1 && kchunks <= MAX_KCHUNKS &&
-                    pj.BN % 32 == 0 && g.K[0] == pj.N && getenv("BM_TC_CHUNK_DEPS")) {   // off by default: the per-chunk
-                    // gpu-scope fences cost the producer more than the consumer gains (measured)
+                if (chunk_deps && d == 0 && g.n_pairs == 1 && !g.a_t[0] && ph[i].l.splits == 1 && pj.splits == 1 &&
+                    kchunks <= MAX_KCHUNKS && g.K[0] == pj.N && pj.n_tiles * pj.gran_per_tile <= 255) {
                     ph[j].l.chunk_ctr = prog.dev_counters + cctr_off[j];
                     ph[i].l.dep_chunk_ctr = prog.dev_counters + cctr_off[j];
-                    ph[i].l.dep_ncol32 = pj.ncol32;
-                    ph[i].l.dep_chunk_need = cluster * 4;          // 4 lane-quarter warps per CTA store each chunk
-                    // consume K chunks in the order the producer's epilogues finish them: chunk c covers
-                    // 32-column chunks 2c, 2c+1, finished in round (local index within the producer tile)
+                    ph[i].l.dep_gran_row = pj.n_tiles * pj.gran_per_tile;
+                    ph[i].l.dep_chunk_need = cluster;              // the publisher of each CTA of the producing pair
+                    // K chunk c = columns [64c, 64c+64) of the producer's output: the granule(s) holding its
+                    // first and last column; consumed in the order the producer's epilogues finish them
                     std::vector<std::pair<int, int>> order;
                     for (int c = 0; c < kchunks; ++c) {
-                        int rank = 0;
-                        for (int h = 0; h < 2; ++h) {
-                            const int c32 = 2 * c + h;
-                            if (c32 >= pj.ncol32) continue;
-                            const int local = (c32 * 32 % pj.BN) / 32;
-                            rank = local > rank ? local : rank;
-                        }
-                        order.push_back(std::make_pair(rank, c));
+                        const int col_a = 64 * c, col_b = std::min(64 * c + 63, pj.N - 1);
+                        const int ta = col_a / pj.BN, tb = col_b / pj.BN;
+                        const int ga = (col_a - ta * pj.BN) / 64, gb = (col_b - tb * pj.BN) / 64;
+                        ph[i].l.k_dep_a[c] = (unsigned char)(ta * pj.gran_per_tile + ga);
+                        ph[i].l.k_dep_b[c] = (unsigned char)(tb * pj.gran_per_tile + gb);
+                        order.push_back(std::make_pair(std::max(ga, gb), c));
                     }
                     std::stable_sort(order.begin(), order.end());
                     for (int c = 0; c < kchunks; ++c) ph[i].l.k_order[c] = (unsigned char)order[c].second;
@@ -1036,7 +1152,10 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         BM_CUDA(cudaMemsetAsync(dbg_buf, 0, 512 * sizeof(unsigned long long), ctx->stream));
         L.dbg = dbg_buf;
     }
-    do_launch(ctx, L, cluster, flops);
+    upload_ops(ctx, ph, n);
+    int max_bn = 16;
+    for (int i = 0; i < n; ++i) max_bn = std::max(max_bn, ph[i].l.BN);
+    do_launch(ctx, L, cluster, flops, max_bn);
     if (dbg) {
         --dbg_left;
         unsigned long long h[512];
