@@ -191,7 +191,10 @@ struct RbmTC : RbmSimt<float> {
         float* dvb_sum = G + (size_t)V * H;
         float* dhb_sum = dvb_sum + V;
         float* q_sum = dhb_sum + H;
-        if (dw_splits > 1) launch_reduce_partials(ctx, partials.p, (size_t)V * H, dw_splits, G, (size_t)V * H);
+        // one GPU: the split-K reduction is fused into the weight update; with peers the reduced gradient is
+        // needed in memory for the all-reduce
+        const bool fuse_reduce = ctx->nranks == 1 && dw_splits > 1 && H % 4 == 0 && ldw % 4 == 0;
+        if (dw_splits > 1 && !fuse_reduce) launch_reduce_partials(ctx, partials.p, (size_t)V * H, dw_splits, G, (size_t)V * H);
         launch_cd_statistics_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, h0m_b.p, hm_b.p, ldh,
                                   rows, V, H, dvb_sum, dhb_sum, q_sum);                                           // :451-457
         allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
@@ -203,7 +206,11 @@ struct RbmTC : RbmSimt<float> {
         u.n_div = N; u.lr = (float)lr; u.mom = (float)mom;
         u.damp = (float)cfg.sparsity_damping; u.cost = (float)cfg.sparsity_cost; u.target = (float)cfg.sparsity_target;
         launch_bias_update<float>(ctx, u);
-        launch_weight_update<float>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr, (float)mom, Wb.p, ldw);
+        if (fuse_reduce)
+            launch_weight_update_splitk(ctx, partials.p, (size_t)V * H, dw_splits, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr,
+                                        (float)mom, Wb.p, ldw);
+        else
+            launch_weight_update<float>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr, (float)mom, Wb.p, ldw);
     }
 
     void transform(const void* X_host, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) override {

@@ -46,11 +46,20 @@ constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;      // TMEM columns per accumulator stage
 constexpr int A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;          // 32 KiB (BN <= 256)
-constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);   // == 6 * (A_BYTES + B_BYTES / 2)
+constexpr int RING_BYTES = 160 * 1024;                // 5 x 32 KiB pair stages / 3 x 48 KiB single-CTA stages
+constexpr int N_OUT_BUF = 4;                          // bf16 output staging FIFO: 64-column x 128-row granules
+constexpr int OUT_BUF_BYTES = BM * 64 * 2;            // 16 KiB each, 128B-swizzled like the operand tiles
+constexpr int OUT_BYTES = N_OUT_BUF * OUT_BUF_BYTES;
 constexpr int SMEM_BARRIER_BYTES = 320;   // full/empty ring, tfull/tempty, TMEM slot, unit/granule barriers
-constexpr int MAX_GRAN = 4;               // 64-column granules per tile (BN <= 256)
-constexpr int EPI_WARPS = 8;
+constexpr int GRAN_COLS = 64;             // bf16 outputs leave the SM (and are published) in 64-column granules
+constexpr int EPI_WARPS = 16;        // 4 per TMEM lane quarter: the epilogue is latency-bound, it needs warps
+constexpr int EPI_SUBS = EPI_WARPS / 4;
+constexpr int CW = 16;               // accumulator columns per epilogue chunk (one tcgen05.ld.x16)
 constexpr int TC_THREADS = 32 * (4 + EPI_WARPS);
+// Warp roles.  The SM's issue arbiter prefers the highest warp id: the single-thread roles whose latency
+// is on the critical path (TMA producer, MMA issuer, publishers) get the highest ids so that sixteen busy
+// (or spinning) epilogue warps cannot starve them.
+constexpr int W_PUB0 = EPI_WARPS, W_PUB1 = EPI_WARPS + 1, W_MMA = EPI_WARPS + 2, W_TMA = EPI_WARPS + 3;
 
 enum : int {
     MODE_GENERIC = 0,                // every combination, flags read at run time
@@ -94,12 +103,13 @@ struct TcPhaseLite {
 };
 struct alignas(64) TcPhase {
     CUtensorMap tmA[2], tmB[2];      // read by the TMA unit from global / parameter memory
+    CUtensorMap tmOut[2];            // bf16 outputs (0: means, 1: states): TMA stores of 64-column granules
     TcPhaseLite l;
 };
 constexpr int MAX_PHASES = 96;
 constexpr int SBIAS_BYTES = ACC_STAGES * 256 * (int)sizeof(float);
 
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + SMEM_BARRIER_BYTES + SBIAS_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + OUT_BYTES + SMEM_BARRIER_BYTES + SBIAS_BYTES;     // 231,744 of 232,448
 
 // The ops of the running launch.  Constant memory on purpose: indexed by warp-uniform values it is read
 // through the uniform datapath, so the TMA / MMA issue loops keep their descriptors, coordinates and
@@ -115,6 +125,7 @@ struct TcLaunch {
     int batch_row;
     int stages, stage_bytes;
     unsigned long long* dbg;
+    int flags;                       // bit 0: granule polls use acquire loads (no gpu-scope fence afterwards)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -143,6 +154,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
+// for waits that are expected to be long (epilogue warps waiting for an accumulator or a staging
+// buffer): sleep between attempts instead of spinning in the issue slots of the busy roles
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -154,6 +181,21 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, uint64_t map, uint
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(uint64_t map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// release: everything this thread has observed (completed bulk stores, barrier-acquired stores of the
+// epilogue warps) is visible to whoever acquires the counter
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     asm volatile(
@@ -273,6 +315,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Polling uses relaxed loads: an acquire load makes ptxas emit CCTL.IVALL (a full L1 invalidation) on
 // every iteration, which evicted the epilogue warps' bias/constant lines for as long as a producer
 // warp was waiting.  One acquire fence follows the successful poll.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
 __device__ __forceinline__ int ld_relaxed(const int* p) {
     int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
@@ -308,33 +353,42 @@ struct EpiCtx {
     int m, n_blk, split;          // this thread's global row, the tile's column block and K split
     uint32_t t_row;               // TMEM address of this thread's lane, column 0 of the accumulator stage
     uint64_t* tempty;             // accumulator-free barrier (leader's in pair mode)
-    int half, lane;
-    uint64_t* gran_bar;           // shared-memory barriers of this accumulator stage's granules (nullable)
+    int sub, lane;                // sub: which chunks (mod EPI_SUBS) this warp takes
     const float* sbias;           // shared memory: bias_scale * bias (x -log2 e for sigmoid) of the tile's columns
     bool remote_arrive;           // pair mode, peer CTA: signal the leader's barrier
+    // bf16 outputs are staged in shared memory and leave the SM as TMA stores (publisher warp)
+    uint32_t out_base;            // shared address of the staging FIFO
+    uint32_t row_off;             // this thread's row inside a staging buffer: (row % 128) * 128 bytes
+    uint32_t row_swz;             // row & 7: XOR pattern of the 128-byte swizzle
+    uint64_t* out_full;           // [N_OUT_BUF] a staged granule is complete (16 warp arrivals)
+    uint64_t* out_free;           // [N_OUT_BUF] its TMA store has read the buffer (publisher)
+    uint32_t* seq;                // FIFO position (same sequence in every warp and in the publisher)
 };
 
-template <int MODE, bool FULL>
-__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[32], int ch, int n0, int n_valid) {
+// One CW-column chunk of one accumulator row: activation, sampling, then
+//   bf16 means / states -> this thread's row of the staging buffers (two 16-byte units each),
+//   fp32 -> global memory directly (dW partials and raw pre-activations only).
+template <int MODE>
+__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[CW], int ch, int n0, int n_valid,
+                                           uint32_t smem_mean, uint32_t smem_state, bool store_ok) {
     typedef EpiCfg<MODE> E;
     const EpiPhase& p = c.p;
     const int act = E::fixed ? E::act : p.act;
     const int smp = E::fixed ? E::sample : p.sample;
-    __nv_bfloat16* const out_mean = (E::fixed && !E::mean_bf) ? nullptr : p.out_mean_bf;
-    __nv_bfloat16* const out_state = (E::fixed && !E::state_bf) ? nullptr : p.out_state_bf;
     float* const out_f32 = ((E::fixed && !E::f32) || !p.out_f32) ? nullptr : p.out_f32 + (size_t)c.split * p.split_stride;
+    // fold the sigmoid's -log2(e) into the affine map of the accumulator
     const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * -1.4426950408889634f : p.acc_scale;
     const bool has_sigma = !E::fixed && p.sigma != nullptr;
     const int m = c.m;
-    constexpr bool full_chunk = FULL;
     // in the fixed modes which outputs exist is known at compile time (no per-group branches)
-    const bool do_mean = E::fixed ? E::mean_bf : (out_mean != nullptr);
-    const bool do_state = E::fixed ? E::state_bf : (out_state != nullptr);
+    const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
+    const bool do_state = E::fixed ? E::state_bf : (p.out_state_bf != nullptr);
     const bool do_f32 = E::fixed ? E::f32 : (out_f32 != nullptr);
-    uint32_t mean_pk[16], state_pk[16];
+    const bool f32_vec = n_valid == CW && (p.ld_f32 & 3) == 0;       // rows 16-byte aligned, whole chunk
+    uint32_t mean_pk[CW / 2], state_pk[CW / 2];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + ch * 32 + q * 4);   // broadcast LDS.128
+    for (int q = 0; q < CW / 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + ch * CW + q * 4);   // broadcast LDS.128
         const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
         U4 w{0, 0, 0, 0};
         if (smp != SMP_NONE) w = site_block(c.rng, (uint32_t)m, (uint32_t)((n0 >> 2) + q));
@@ -364,84 +418,69 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
                 s_ = m_ + ((p.noise_sigma && e < n_valid) ? p.noise_sigma[n0 + e] : 1.0f) * g[j];
             mu[j] = m_; st[j] = s_;
         }
-        if (full_chunk) {
-            if (do_mean) { mean_pk[2 * q] = pack_bf16(mu[0], mu[1]); mean_pk[2 * q + 1] = pack_bf16(mu[2], mu[3]); }
-            if (do_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
-        } else {              // ragged right edge: element-wise stores, no packed staging
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (q * 4 + j < n_valid) {
-                    if (do_mean) out_mean[(size_t)m * p.ld_mean_bf + n0 + q * 4 + j] = __float2bfloat16_rn(mu[j]);
-                    if (do_state) out_state[(size_t)m * p.ld_state_bf + n0 + q * 4 + j] = __float2bfloat16_rn(st[j]);
-                }
-            }
-        }
-        if (do_f32) {
+        if (do_mean) { mean_pk[2 * q] = pack_bf16(mu[0], mu[1]); mean_pk[2 * q + 1] = pack_bf16(mu[2], mu[3]); }
+        if (do_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
+        if (do_f32 && store_ok) {
             float* dst = out_f32 + (size_t)m * p.ld_f32 + n0 + q * 4;
-            if (full_chunk) {                 // rows are 16-byte aligned (checked by the caller)
-                *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
-            } else {
+            if (f32_vec) *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+            else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) dst[j] = mu[j];
             }
         }
     }
-    if (do_mean && full_chunk) {
-        __nv_bfloat16* dst = out_mean + (size_t)m * p.ld_mean_bf + n0;
+    // columns past N and rows past M are written to the staging buffer too: the TMA store clips them
+    const uint32_t u0 = (uint32_t)((ch * CW) & 63) >> 3;           // first 16-byte unit of this chunk in the 128-byte row
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(dst)[i] = make_uint4(mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
-    }
-    if (do_state && full_chunk) {
-        __nv_bfloat16* dst = out_state + (size_t)m * p.ld_state_bf + n0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(dst)[i] = make_uint4(state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
+    for (int i = 0; i < CW / 8; ++i) {
+        const uint32_t off = c.row_off + (((u0 + (uint32_t)i) ^ c.row_swz) << 4);
+        if (do_mean) sts128(smem_mean + off, mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
+        if (do_state) sts128(smem_state + off, state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
     }
 }
 
+// One warp's share of a tile: TMEM lane quarter (warp % 4) x the CW-column chunks ch = sub (mod EPI_SUBS).
+// All warps sweep the tile left to right together, granule (64 columns) by granule: each granule of each
+// bf16 output takes the next buffer of the staging FIFO, is written by the 16 warps and announced on the
+// buffer's `full` barrier; the publisher warp stores it with TMA and publishes it to the other SMs.
 template <int MODE, bool PAIR>
 __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     typedef EpiCfg<MODE> E;
     const EpiPhase& p = c.p;
-    const int act = E::fixed ? E::act : p.act;
-    const int smp = E::fixed ? E::sample : p.sample;
-    __nv_bfloat16* const out_mean = (E::fixed && !E::mean_bf) ? nullptr : p.out_mean_bf;
-    __nv_bfloat16* const out_state = (E::fixed && !E::state_bf) ? nullptr : p.out_state_bf;
-    float* const out_f32 = ((E::fixed && !E::f32) || !p.out_f32) ? nullptr : p.out_f32 + (size_t)c.split * p.split_stride;
-    const float kNegLog2e = -1.4426950408889634f;
-    // fold the sigmoid's -log2(e) into the affine map of the accumulator
-    const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * kNegLog2e : p.acc_scale;
-    const bool has_sigma = !E::fixed && p.sigma != nullptr;
     const int BN = p.BN;
-    const int n_chunks32 = (BN + 31) / 32;
+    const int n_chunks = BN / CW;                  // BN is a multiple of 16
     const bool row_ok = c.m < p.M;
-    const int m = c.m;
-
+    const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
+    const bool do_state = E::fixed ? E::state_bf : (p.out_state_bf != nullptr);
     int last_ch = -1;
-    for (int ch = c.half; ch < n_chunks32; ch += 2) last_ch = ch;
+    for (int ch = c.sub; ch < n_chunks; ch += EPI_SUBS) last_ch = ch;
     if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
         __syncwarp();
         if (c.lane == 0) {
             if (PAIR && c.remote_arrive) { if constexpr (PAIR) mbar_arrive_remote(c.tempty, 0); } else mbar_arrive(c.tempty);
         }
     }
-    // granule g = 32-column chunks 2g (warps 0-3) and 2g+1 (warps 4-7); every warp arrives on the
-    // granule's barrier once its chunk is stored (or at once if it has none): 8 arrivals per granule
-    const int n_gran = (BN + 63) / 64;
+    constexpr int gc = GRAN_COLS / CW;             // chunks per granule
+    const int n_gran = (n_chunks + gc - 1) / gc;
+    uint32_t seq = *c.seq;
     for (int g = 0; g < n_gran; ++g) {
-        const int ch = 2 * g + c.half;
-        if (ch < n_chunks32) {
-            uint32_t v[32];
+        uint32_t smem_mean = 0, smem_state = 0;
+        int b_mean = 0, b_state = 0;
+        if (do_mean) {
+            b_mean = (int)(seq % N_OUT_BUF);
+            mbar_wait_relaxed(&c.out_free[b_mean], ((seq / N_OUT_BUF) & 1u) ^ 1u);      // first use of a buffer passes at once
+            smem_mean = c.out_base + (uint32_t)b_mean * OUT_BUF_BYTES; ++seq;
+        }
+        if (do_state) {
+            b_state = (int)(seq % N_OUT_BUF);
+            mbar_wait_relaxed(&c.out_free[b_state], ((seq / N_OUT_BUF) & 1u) ^ 1u);
+            smem_state = c.out_base + (uint32_t)b_state * OUT_BUF_BYTES; ++seq;
+        }
+        const int ch_end = min(n_chunks, (g + 1) * gc);
+        for (int ch = g * gc + c.sub; ch < ch_end; ch += EPI_SUBS) {
+            uint32_t v[CW];
             __syncwarp();                            // tcgen05.ld is warp-collective (.sync.aligned)
-            if (ch * 32 + 32 <= BN) {
-                tmem_ld32(c.t_row + (uint32_t)(ch * 32), v);
-            } else {                                 // BN is a multiple of 16: a trailing half chunk
-                uint32_t lo[16];
-                tmem_ld16(c.t_row + (uint32_t)(ch * 32), lo);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { v[e] = lo[e]; v[16 + e] = 0u; }
-            }
+            tmem_ld16(c.t_row + (uint32_t)(ch * CW), v);
             tmem_ld_wait();
             if (ch == last_ch) {
                 // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
@@ -451,21 +490,19 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
                     if (PAIR && c.remote_arrive) { if constexpr (PAIR) mbar_arrive_remote(c.tempty, 0); } else mbar_arrive(c.tempty);
                 }
             }
-            const int n0 = c.n_blk * BN + ch * 32;
-            if (n0 < p.N && row_ok) {
-                const int n_valid = min(32, min(p.N, c.n_blk * BN + BN) - n0);
-                // the interior (whole 32-column chunks) runs a branch-free body so that the 32 independent
-                // sigmoid / Philox chains of a thread can be interleaved by the scheduler
-                // (an fp32 output whose rows are not 16-byte aligned takes the element-wise path)
-                if (n_valid == 32 && (!p.out_f32 || (p.ld_f32 & 3) == 0)) chunk_body<MODE, true>(c, v, ch, n0, 32);
-                else chunk_body<MODE, false>(c, v, ch, n0, n_valid);
+            const int n0 = c.n_blk * BN + ch * CW;
+            if (n0 < p.N) chunk_body<MODE>(c, v, ch, n0, min(CW, p.N - n0), smem_mean, smem_state, row_ok);
+        }
+        if (do_mean || do_state) {
+            fence_proxy_async_smem();                // this thread's staging writes -> visible to the TMA unit
+            __syncwarp();
+            if (c.lane == 0) {
+                if (do_mean) mbar_arrive(&c.out_full[b_mean]);
+                if (do_state) mbar_arrive(&c.out_full[b_state]);
             }
         }
-        if (c.gran_bar) {
-            __syncwarp();                            // the warp's stores of this granule precede the arrival
-            if (c.lane == 0) mbar_arrive(c.gran_bar + g);
-        }
     }
+    *c.seq = seq;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -494,36 +531,37 @@ template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_program_kernel(const __grid_constant__ TcLaunch L) {
     constexpr bool pair = (CL == 2);
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;                      // [operand ring | output staging FIFO | barriers | bias]
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need 1024-byte alignment
+    uint8_t* const out_stage = smem + RING_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES + OUT_BYTES);
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
     uint64_t* unit_bar = tempty + ACC_STAGES + 1;                 // [ACC_STAGES] all epilogue warps stored the unit
-    uint64_t* gran_bar = unit_bar + ACC_STAGES;                   // [ACC_STAGES][MAX_GRAN] ... a 64-column granule
+    uint64_t* out_full = unit_bar + ACC_STAGES;                   // [N_OUT_BUF] staged granule written by all epilogue warps
+    uint64_t* out_free = out_full + N_OUT_BUF;                    // [N_OUT_BUF] staged granule read by its TMA store
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { DBG_MARK(0); if (L.dbg && blockIdx.x == 0) L.dbg[6] = gtime(); }
-    float* const s_bias = reinterpret_cast<float*>(smem + RING_BYTES + SMEM_BARRIER_BYTES);
+    float* const s_bias = reinterpret_cast<float*>(smem + RING_BYTES + OUT_BYTES + SMEM_BARRIER_BYTES);
     const TcPhase* const gph = L.n_phases ? L.phases : &L.inl;      // tensor maps (global / parameter memory)
-    if (warp == 0 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         tma_prefetch_desc(&gph->tmA[0]); tma_prefetch_desc(&gph->tmB[0]);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         // pair: the leader's `full` collects its own expect_tx-arrive and the peer's arrive; its `tempty`
         // collects the epilogue warps of both CTAs; `empty`/`tfull` get one multicast commit each
         for (int s = 0; s < L.stages; ++s) { mbar_init(&full[s], (uint32_t)CL); mbar_init(&empty[s], 1); }
-        // tempty: the epilogue warps and the publisher warp of both CTAs
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)((EPI_WARPS + 1) * CL)); }
-        for (int a = 0; a < ACC_STAGES; ++a) {
-            mbar_init(&unit_bar[a], EPI_WARPS);
-            for (int g = 0; g < MAX_GRAN; ++g) mbar_init(&gran_bar[a * MAX_GRAN + g], EPI_WARPS);
-        }
+        // tempty: the epilogue warps and the two publisher warps of both CTAs
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (uint32_t)((EPI_WARPS + 2) * CL)); }
+        for (int a = 0; a < ACC_STAGES; ++a) mbar_init(&unit_bar[a], EPI_WARPS);
+        for (int b = 0; b < N_OUT_BUF; ++b) { mbar_init(&out_full[b], EPI_WARPS); mbar_init(&out_free[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == W_PUB0) {
         if constexpr (pair) {        // one warp of each CTA of the pair allocates collectively
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
@@ -545,7 +583,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
     const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int unit_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ================================ TMA producer =====================================
         // The whole warp walks the K chunks; for each chunk lane 0 arms the barrier and lanes
         // 0..n_ops-1 issue one bulk-tensor copy each in the same warp instruction.
@@ -612,21 +650,28 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 if (ordered) {
                     c = (int)ph->k_order[ci];
                     if (ci >= fenced_upto) {
-                        if (lane == 0) {
-                            const int need = ph->dep_chunk_need;
-                            int n = ci;
-                            for (;;) {       // wait for position ci, then take every following position already ready
-                                const int j = (int)ph->k_order[n];
-                                const int a = (int)ph->k_dep_a[j], b = (int)ph->k_dep_b[j];
-                                if (n == ci) { while (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) __nanosleep(32); }
-                                else if (ld_relaxed(cdep + a) < need || ld_relaxed(cdep + b) < need) break;
-                                if (++n == u.c_end) break;
-                            }
-                            fenced_upto = n;
-                            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                            asm volatile("fence.proxy.async;" ::: "memory");
+                        // every lane polls one K position (ci + lane): one L2 round trip tells how long the
+                        // prefix of ready positions is (a serial scan costs a round trip per position)
+                        const int need = ph->dep_chunk_need;
+                        const int n = ci + lane;
+                        int ga = 0, gb = 0;
+                        if (n < u.c_end) { const int j = (int)ph->k_order[n]; ga = (int)ph->k_dep_a[j]; gb = (int)ph->k_dep_b[j]; }
+                        int ready_prefix = 0;
+                        for (;;) {
+                            bool ok;
+                            if (L.flags & 1) ok = n < u.c_end && ld_acquire(cdep + ga) >= need && (gb == ga || ld_acquire(cdep + gb) >= need);
+                            else ok = n < u.c_end && ld_relaxed(cdep + ga) >= need && (gb == ga || ld_relaxed(cdep + gb) >= need);
+                            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                            ready_prefix = __ffs(~m) - 1;              // ~m != 0: lanes past c_end are never ready... (32 positions max)
+                            if (m == 0xffffffffu) ready_prefix = 32;
+                            if (ready_prefix > 0) break;
+                            __nanosleep(64);
                         }
-                        fenced_upto = __shfl_sync(0xffffffffu, fenced_upto, 0);
+                        fenced_upto = ci + ready_prefix;
+                        if (L.dbg && blockIdx.x == 0 && ord == 1 && lane == 0 && ci - u.c_begin < 20) { L.dbg[456 + ci - u.c_begin] = (unsigned long long)clock64(); L.dbg[480 + ci - u.c_begin] = (unsigned long long)fenced_upto; }
+                        // acquire the producers' stores, then order them before this unit's TMA reads (async proxy)
+                        if (!(L.flags & 1)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                        asm volatile("fence.proxy.async;" ::: "memory");
                     }
                 }
                 const int pr = (c >= chunks0) ? 1 : 0;
@@ -639,7 +684,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 const int bc0 = pr ? b_c0[1] : b_c0[0], bc1 = pr ? b_c1[1] : b_c1[0];
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (elect_one()) {               // one thread issues; every operand above is warp-uniform
-                    if (ci - u.c_begin < 24) DBG_MARK(8 + (ci - u.c_begin));
+                    if (ci - u.c_begin < 24 && (L.n_phases == 0 || ord == 1)) DBG_MARK(8 + (ci - u.c_begin));
                     const uint32_t fbar = smem_u32(&full[stage]);
                     if constexpr (pair) {
                         // both CTAs load their own A rows and their half of the B tile; bytes are counted on the leader
@@ -660,7 +705,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 if (++stage == L.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ================================ MMA issuer (the pair's leader CTA only) ============
         // The whole warp runs the loop converged (all values warp-uniform -> uniform registers);
         // lane 0 issues the tcgen05 instructions.
@@ -712,7 +757,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                     tc_fence_after();
                     if (elect_one()) {
                         if (ci == u.c_begin) DBG_UNIT(2, ord);
-                        if (ci - u.c_begin < 24) DBG_MARK(32 + (ci - u.c_begin));
+                        if (ci - u.c_begin < 24 && (L.n_phases == 0 || ord == 1)) DBG_MARK(32 + (ci - u.c_begin));
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             if constexpr (pair) umma_bf16_2sm(d_tmem, a_lo + k * a_step, a_hi, b_lo + k * b_step, b_hi, idesc, accumulate);
@@ -733,59 +778,81 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp == 3) {
-        // ================================ publisher =========================================
-        // Makes finished output visible to the other SMs WITHOUT stalling the epilogue warps: they
-        // arrive on a shared-memory barrier (release.cta) when a granule / the unit is stored; this
-        // thread acquires it, issues the gpu-scope fence and bumps the global dataflow counter.
+    } else if (warp == W_PUB0 || warp == W_PUB1) {
+        // ================================ publishers ========================================
+        // Send every staged 64-column granule of the bf16 outputs to global memory with a TMA store
+        // and, once that store has completed (bulk async-group wait: no MEMBAR over the SM's whole store
+        // stream -- a gpu-scope fence issued while epilogue warps stream stores only returns when they
+        // pause), bump the granule's dataflow counter with a release: consumers start on a row block's
+        // first columns while its last ones are still in the epilogue.  Two publisher threads take the
+        // even / odd granules so that one store's completion latency hides behind the other's.
+        // fp32 outputs (dW partials) are stored by the epilogue warps directly and published per unit.
         if (lane == 0) {
+            const int pub = warp - W_PUB0;
             int acc = 0; uint32_t acc_phase = 0;
-            uint32_t gran_parity = 0;
+            uint32_t seq = 0;                               // FIFO position of the unit's first granule
             int pi = 0;
             int ord = -1;
+            const uint32_t out_base = smem_u32(out_stage);
             for (int unit = unit0; unit < units; unit += unit_step) {
                 ++ord;
                 pi = phase_of(pi, unit);
                 const TcPhaseLite* ph = &c_ph[pi];
+                const TcPhase* gp = &gph[pi];
                 const UnitInfo u = decode_unit(ph, unit);
-                if (ph->chunk_ctr) {
-                    const int gpt = ph->gran_per_tile;
-                    int* const ctr = ph->chunk_ctr + ((size_t)u.m_group * ph->n_tiles + u.n_blk) * gpt;
-                    for (int g = 0; g < gpt; ++g) {
-                        // (granule barriers only advance on units of ops that publish granules: own parity bits)
-                        const int gb = acc * MAX_GRAN + g;
-                        mbar_wait(&gran_bar[gb], (gran_parity >> gb) & 1u);
-                        gran_parity ^= 1u << gb;
-                        if (u.n_blk * ph->BN + g * 64 < ph->N) {
-                            __threadfence();
-                            atomicAdd(ctr + g, 1);
-                        }
+                const bool has_mean = ph->out_mean_bf != nullptr, has_state = ph->out_state_bf != nullptr;
+                const int n_arr = (has_mean ? 1 : 0) + (has_state ? 1 : 0);
+                const int gpt = n_arr ? ph->gran_per_tile : 0;
+                const int row0 = (u.m_group * CL + crank) * BM;
+                int* const ctr = ph->chunk_ctr ? ph->chunk_ctr + ((size_t)u.m_group * ph->n_tiles + u.n_blk) * gpt : nullptr;
+                for (int g = pub; g < gpt; g += 2) {
+                    const int col0 = u.n_blk * ph->BN + g * GRAN_COLS;
+                    uint32_t sq = seq + (uint32_t)(g * n_arr);
+                    int bufs[2] = {-1, -1};
+                    for (int a = 0; a < 2; ++a) {
+                        if (!(a == 0 ? has_mean : has_state)) continue;
+                        const int b = (int)(sq % N_OUT_BUF);
+                        mbar_wait(&out_full[b], (sq / N_OUT_BUF) & 1u);
+                        if (col0 < ph->N) tma_store_2d((uint64_t)&gp->tmOut[a], out_base + (uint32_t)b * OUT_BUF_BYTES, col0, row0);
+                        bufs[a] = b; ++sq;
+                    }
+                    bulk_commit();
+                    if (L.dbg && blockIdx.x == 0 && ord < 24 && g < 4) L.dbg[256 + ord * 8 + 4 + g] = (unsigned long long)clock64();
+                    bulk_wait<0>();                          // stores complete: data is in global memory
+                    for (int a = 0; a < 2; ++a) if (bufs[a] >= 0) mbar_arrive(&out_free[bufs[a]]);
+                    if (ctr && col0 < ph->N) {
+                        red_release_add(ctr + g, 1);
+                        if (L.dbg && L.n_phases && ord == 0 && g == 0) L.dbg[512 + blockIdx.x] = gtime();
+                        if (L.dbg && L.n_phases && ord == 0 && g == 3) L.dbg[704 + blockIdx.x] = gtime();
+                        if (L.dbg && blockIdx.x == 0 && ord < 24 && g < 4) L.dbg[256 + ord * 8 + g] = (unsigned long long)clock64();
                     }
                 }
-                mbar_wait(&unit_bar[acc], acc_phase);
-                if (ph->done_ctr) {
-                    __threadfence();
-                    atomicAdd(ph->done_ctr + u.m_group, 1);
-                }
-                DBG_UNIT(6, ord);
+                seq += (uint32_t)(gpt * n_arr);
+                mbar_wait(&unit_bar[acc], acc_phase);      // every epilogue warp has finished the unit (direct fp32 stores included)
+                if (ph->done_ctr) red_release_add(ph->done_ctr + u.m_group, 1);
+                if (pub == 1) DBG_UNIT(6, ord);
                 // the barriers of this accumulator stage may be reused: part of the stage's release
                 if (pair && crank == 1) { if constexpr (pair) mbar_arrive_remote(&tempty[acc], 0); } else mbar_arrive(&tempty[acc]);
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
-        // ================================ epilogue (8 warps) =================================
-        // warp w may read TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter alternate over
-        // the tile's 32-column chunks.
-        const int ew = warp - 4;
+    } else {
+        // ================================ epilogue (16 warps) ================================
+        // warp w may read TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter interleave over
+        // the tile's 16-column chunks.
+        const int ew = warp;
         const int quarter = ew & 3;
         EpiCtx c;
-        c.half = ew >> 2; c.lane = lane;
+        c.sub = ew >> 2; c.lane = lane;
         c.remote_arrive = pair && crank == 1;
+        uint32_t out_seq = 0;
+        c.seq = &out_seq;
+        c.out_base = smem_u32(out_stage); c.out_full = out_full; c.out_free = out_free;
+        c.row_off = (uint32_t)(quarter * 32 + lane) * 128u; c.row_swz = (uint32_t)(lane & 7);
         int acc = 0; uint32_t acc_phase = 0;
         int pi = 0;
         int ord = -1;
-        const int et = threadIdx.x - 128;          // 0..255 among the epilogue threads
+        const int et = threadIdx.x;                // 0..511: the epilogue threads
         for (int unit = unit0; unit < units; unit += unit_step) {
             ++ord;
             pi = phase_of(pi, unit);
@@ -794,8 +861,8 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             {   // this tile's (pre-scaled) bias slice -> shared memory, while the MMAs are still running
                 const float bsc = (ph->act == ACT_SIGMOID) ? ph->bias_scale * -1.4426950408889634f : ph->bias_scale;
                 const int n = u.n_blk * ph->BN + et;
-                s_bias[acc * 256 + et] = (ph->bias && et < ph->BN && n < ph->N) ? bsc * __ldg(ph->bias + n) : 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < 256) s_bias[acc * 256 + et] = (ph->bias && et < ph->BN && n < ph->N) ? bsc * __ldg(ph->bias + n) : 0.f;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
                 c.sbias = s_bias + acc * 256;
             }
             c.p.M = ph->M; c.p.N = ph->N; c.p.BN = ph->BN; c.p.act = ph->act; c.p.sample = ph->sample;
@@ -805,14 +872,13 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.p.out_state_bf = ph->out_state_bf; c.p.ld_state_bf = ph->ld_state_bf;
             c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
             const int ph_mode = ph->mode;
-            c.gran_bar = ph->chunk_ctr ? gran_bar + acc * MAX_GRAN : nullptr;
             c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
             c.tempty = &tempty[acc];
-            mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait_relaxed(&tfull[acc], acc_phase);
             tc_fence_after();
-            if (threadIdx.x == 128) { DBG_MARK(3); DBG_UNIT(4, ord); }
+            if (threadIdx.x == 0) { DBG_MARK(3); DBG_UNIT(4, ord); }
             c.t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
             switch (ph_mode) {
                 case MODE_SIG_BERN_MEAN_STATE: epilogue_tile<MODE_SIG_BERN_MEAN_STATE, pair>(c); break;
@@ -821,11 +887,11 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 case MODE_RAW_F32: epilogue_tile<MODE_RAW_F32, pair>(c); break;
                 default: epilogue_tile<MODE_GENERIC, pair>(c); break;
             }
-            if (threadIdx.x == 128) DBG_UNIT(5, ord);
+            if (threadIdx.x == 0) DBG_UNIT(5, ord);
             // this warp's part of the unit is stored: the publisher warp makes it visible to other SMs
             __syncwarp();
             if (lane == 0) mbar_arrive(&unit_bar[acc]);
-            if (threadIdx.x == 128) DBG_MARK(4);
+            if (threadIdx.x == 0) DBG_MARK(4);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -833,7 +899,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
     tc_fence_before();
     // no CTA may exit while its peer can still signal its barriers or read its shared memory
     if constexpr (pair) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) {
+    if (warp == W_PUB0) {
         tc_fence_after();
         if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -890,7 +956,7 @@ static CUtensorMap make_map(const TcMat& m, int box0, int box1) {
 
 struct TilePick { int bn, cluster; };
 
-static TilePick pick_tile(int N, bool b_mn, int m_tiles, int splits, int chunks, int sms, int force_cluster) {
+static TilePick pick_tile(int N, bool b_mn, bool staged_out, int m_tiles, int splits, int chunks, int sms, int force_cluster) {
     // Tile width BN and CTA grouping.  A single SM ingests ~50 B/clk from L2 (measured: the ring of a
     // 128x256 tile refills at 52 B/clk with one CTA alone on the chip), while tcgen05 at M=128
     // consumes 8192*(1/128 + 1/BN) B/clk of operands: a lone CTA is ingest-bound.  A CTA pair
@@ -901,7 +967,9 @@ static TilePick pick_tile(int N, bool b_mn, int m_tiles, int splits, int chunks,
     for (int c = 1; c <= 2; ++c) {
         if (force_cluster && c != force_cluster) continue;
         if (!force_cluster && c == 2 && m_tiles < 2) break;
-        const int step = b_mn ? 64 * c : 16;              // every CTA of a pair holds BN/2 columns of B (whole boxes / 8-row atoms)
+        // every CTA of a pair holds BN/2 columns of B (whole boxes / 8-row atoms); bf16 outputs leave in
+        // 64-column TMA-store granules, so their tiles are whole granules wide (the tensor edge clips)
+        const int step = b_mn ? 64 * c : (staged_out ? 64 : 16);
         const int slots = sms / c;
         for (int bn = step; bn <= 256; bn += step) {
             const int nt = (N + bn - 1) / bn;
@@ -939,12 +1007,15 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
     int chunks_total = 0;
     for (int i = 0; i < g.n_pairs; ++i) chunks_total += (g.K[i] + BK - 1) / BK;
     const int nsplit = g.splits > 0 ? g.splits : 1;
-    TilePick tp = pick_tile(g.N, need64, m_tiles, nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count, cluster);
+    const bool staged_out = g.out_mean_bf != nullptr || g.out_state_bf != nullptr;
+    TilePick tp = pick_tile(g.N, need64, staged_out, m_tiles, nsplit, (chunks_total + nsplit - 1) / nsplit, ctx->sm_count, cluster);
     if (g.force_bn > 0) tp.bn = g.force_bn;
     BM_REQUIRE(tp.cluster == cluster, "tile picker returned another cluster size");
     BM_REQUIRE(cluster == 1 || (need64 ? tp.bn % 128 == 0 : tp.bn % 16 == 0), "CTA-pair tiles need BN/2 on whole boxes / swizzle atoms");
     BM_REQUIRE(tp.bn % 16 == 0 && tp.bn <= 256 && (!need64 || tp.bn % 64 == 0), "bad tile width");
+    BM_REQUIRE(!staged_out || tp.bn % 64 == 0, "ops with bf16 outputs need tiles of whole 64-column granules");
     p.BN = tp.bn;
+    p.gran_per_tile = (p.BN + GRAN_COLS - 1) / GRAN_COLS;
     p.m_groups = (m_tiles + cluster - 1) / cluster;
     p.n_tiles = (g.N + p.BN - 1) / p.BN;
     p.splits = nsplit;
@@ -968,6 +1039,9 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
     p.out_mean_bf = g.out_mean_bf; p.ld_mean_bf = g.ld_mean_bf;
     p.out_state_bf = g.out_state_bf; p.ld_state_bf = g.ld_state_bf;
     p.out_f32 = g.out_f32; p.ld_f32 = g.ld_f32;
+    // bf16 outputs leave the SM as TMA stores of (64 columns x 128 rows) granules, clipped to [M, N]
+    if (g.out_mean_bf) { TcMat o; o.ptr = g.out_mean_bf; o.rows = g.M; o.cols = g.N; o.ld = g.ld_mean_bf; ph.tmOut[0] = make_map(o, GRAN_COLS, BM); }
+    if (g.out_state_bf) { TcMat o; o.ptr = g.out_state_bf; o.rows = g.M; o.cols = g.N; o.ld = g.ld_state_bf; ph.tmOut[1] = make_map(o, GRAN_COLS, BM); }
     BM_REQUIRE(!g.out_mean_bf || (g.ld_mean_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
     BM_REQUIRE(!g.out_state_bf || (g.ld_state_bf % 8 == 0), "bf16 output leading dimension must be a multiple of 8");
 }
@@ -1057,7 +1131,7 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     const int cluster = 2;            // programs always run on CTA pairs (all CTAs walk one unit list)
     std::vector<unsigned char> image((size_t)n * sizeof(TcPhase));
     TcPhase* ph = reinterpret_cast<TcPhase*>(image.data());
-    // counters: per op one int per row-block group (unit level) + one per (row-block group, tile, 64-column granule)
+    // counters: per op one int per row-block group (unit level) + one per (row-block group, tile, granule)
     size_t n_ctr = 0;
     std::vector<size_t> ctr_off(n), cctr_off(n);
     int unit = 0;
@@ -1069,7 +1143,6 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         ph[i].l.unit_end = unit;
         ctr_off[i] = n_ctr;
         n_ctr += (size_t)ph[i].l.m_groups;
-        ph[i].l.gran_per_tile = (ph[i].l.BN + 63) / 64;
         cctr_off[i] = n_ctr;
         n_ctr += (size_t)ph[i].l.m_groups * ph[i].l.n_tiles * ph[i].l.gran_per_tile;
         flops += gemm_flops(prog.ops[i]);
@@ -1091,7 +1164,7 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
             const int j = g.dep[d];
             BM_REQUIRE(j >= 0 && j < i, "a program op may only depend on earlier ops");
             ph[i].l.dep_ctr[d] = prog.dev_counters + ctr_off[j];
-            ph[i].l.dep_need[d] = ph[j].l.n_tiles * ph[j].l.splits * cluster;      // one publication per CTA and unit
+            ph[i].l.dep_need[d] = ph[j].l.n_tiles * ph[j].l.splits * cluster * 2;  // both publishers of every CTA, per unit
             if (g.dep_all[d]) ph[i].l.dep_groups[d] = ph[j].l.m_groups;
             else {
                 ph[i].l.dep_groups[d] = 0;
@@ -1112,7 +1185,7 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
                     for (int c = 0; c < kchunks; ++c) {
                         const int col_a = 64 * c, col_b = std::min(64 * c + 63, pj.N - 1);
                         const int ta = col_a / pj.BN, tb = col_b / pj.BN;
-                        const int ga = (col_a - ta * pj.BN) / 64, gb = (col_b - tb * pj.BN) / 64;
+                        const int ga = (col_a - ta * pj.BN) / GRAN_COLS, gb = (col_b - tb * pj.BN) / GRAN_COLS;
                         ph[i].l.k_dep_a[c] = (unsigned char)(ta * pj.gran_per_tile + ga);
                         ph[i].l.k_dep_b[c] = (unsigned char)(tb * pj.gran_per_tile + gb);
                         order.push_back(std::make_pair(std::max(ga, gb), c));
@@ -1143,13 +1216,14 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     L.total_units = unit;
     L.k0 = rng.k0; L.k1 = rng.k1; L.tick = rng.tick; L.row0 = rng.row0;
     L.batch_row = batch_row;
+    { static int fl = -1; if (fl < 0) { const char* e = getenv("BM_TC_FLAGS"); fl = e ? atoi(e) : 1; } L.flags = fl; }
     static unsigned long long* dbg_buf = nullptr;
     static int dbg_left = -1;
     if (dbg_left < 0) { const char* e = getenv("BM_TC_PROGRAM_TIMELINE"); dbg_left = e ? atoi(e) : 0; }
     const bool dbg = dbg_left > 0;
     if (dbg) {
-        if (!dbg_buf) BM_CUDA(cudaMalloc(&dbg_buf, 512 * sizeof(unsigned long long)));
-        BM_CUDA(cudaMemsetAsync(dbg_buf, 0, 512 * sizeof(unsigned long long), ctx->stream));
+        if (!dbg_buf) BM_CUDA(cudaMalloc(&dbg_buf, 1024 * sizeof(unsigned long long)));
+        BM_CUDA(cudaMemsetAsync(dbg_buf, 0, 1024 * sizeof(unsigned long long), ctx->stream));
         L.dbg = dbg_buf;
     }
     upload_ops(ctx, ph, n);
@@ -1158,15 +1232,27 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     do_launch(ctx, L, cluster, flops, max_bn);
     if (dbg) {
         --dbg_left;
-        unsigned long long h[512];
+        unsigned long long h[1024];
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         BM_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "program timeline (SM cycles, CTA 0): setup=%llu exit=%llu wall=%llu ns, %d units total\n",
                 h[1] - h[0], h[5] - h[0], h[7] - h[6], unit);
-        fprintf(stderr, "  ord: start dep_ok mma_first mma_done epi_start epi_done published\n");
+        fprintf(stderr, "  unit 1 tma_issue:");
+        for (int i = 0; i < 24 && h[8 + i]; ++i) fprintf(stderr, " %llu", h[8 + i] - h[0]);
+        fprintf(stderr, "\n  first-unit granule 0 / granule 3 publish time per CTA (ns after CTA 0 start):");
+        for (int i = 0; i < 148; ++i) if (h[512 + i]) fprintf(stderr, " %d:%lld/%lld", i, (long long)(h[512 + i] - h[6]), (long long)(h[704 + i] - h[6]));
+        fprintf(stderr, "\n  unit 1 poll ok (time:upto):");
+        for (int i = 0; i < 20; ++i) if (h[456 + i]) fprintf(stderr, " [%d] %llu:%llu", i, h[456 + i] - h[0], h[480 + i]);
+        fprintf(stderr, "\n  unit 1 mma_ready:");
+        for (int i = 0; i < 24 && h[32 + i]; ++i) fprintf(stderr, " %llu", h[32 + i] - h[0]);
+        fprintf(stderr, "\n  ord: start dep_ok mma_first mma_done epi_start epi_done published\n");
         for (int o = 0; o < 24 && h[64 + o * 8]; ++o) {
             fprintf(stderr, "  %2d:", o);
             for (int k = 0; k < 7; ++k) fprintf(stderr, " %7llu", h[64 + o * 8 + k] ? h[64 + o * 8 + k] - h[0] : 0ull);
+            fprintf(stderr, "   | granule staged:");
+            for (int k = 4; k < 8; ++k) fprintf(stderr, " %7llu", h[256 + o * 8 + k] ? h[256 + o * 8 + k] - h[0] : 0ull);
+            fprintf(stderr, " published:");
+            for (int k = 0; k < 4; ++k) fprintf(stderr, " %7llu", h[256 + o * 8 + k] ? h[256 + o * 8 + k] - h[0] : 0ull);
             fprintf(stderr, "\n");
         }
     }

@@ -83,4 +83,8 @@ void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const 
 // G[i] = sum_s partial[s * stride + i]
 void launch_reduce_partials(Ctx* ctx, const float* partial, size_t stride, int splits, float* G, size_t n);
 
+// W += momentum step of (sum_s partial[s]) / g_div, plus the bf16 shadow, in one pass (n_hidden % 4 == 0)
+void launch_weight_update_splitk(Ctx* ctx, const float* partial, size_t stride, int splits, float g_div, float* W, float* dW,
+                                 int V, int H, const float* pen, float l2, float lr, float mom, __nv_bfloat16* Wb, int ldwb);
+
 }  // namespace bm

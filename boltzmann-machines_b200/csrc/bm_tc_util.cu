@@ -47,38 +47,52 @@ struct ColsumJobs {
     int cols[3];
     int rows, n;
 };
-constexpr int CS_RSPLIT = 32;
+constexpr int CS_RSPLIT = 64;
 
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4& p, float s) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); a[2 * i] = fmaf(s, f.x, a[2 * i]); a[2 * i + 1] = fmaf(s, f.y, a[2 * i + 1]); }
+}
 __global__ void colsum_bf16_partial_kernel(ColsumJobs j, float* __restrict__ partial, int max_cols) {
-    // block: 32 x 8 threads; 64 columns (2 per thread) x one row slab; fixed combine order
-    __shared__ float2 part[8][33];
+    // block: 32 x 8 threads; 256 columns (8 per thread, one 16-byte load per row) x one row slab;
+    // fixed combine order (deterministic)
+    __shared__ float part[8][32][9];
     const int job = blockIdx.z;
     const int cols = j.cols[job];
-    const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int slab = (j.rows + CS_RSPLIT - 1) / CS_RSPLIT;
     const int r0 = blockIdx.y * slab, r1 = min(j.rows, r0 + slab);
-    float2 a = make_float2(0.f, 0.f);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c < cols) {
         const __nv_bfloat16* P = j.P[job]; const __nv_bfloat16* Q = j.Q[job];
         const float s1 = j.s1[job], s2 = j.s2[job];
-        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
-            const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(P + (size_t)r * j.ldp[job] + c));
-            a.x = fmaf(s1, p.x, a.x); a.y = fmaf(s1, p.y, a.y);
-            if (Q) {
-                const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Q + (size_t)r * j.ldq[job] + c));
-                a.x = fmaf(s2, q.x, a.x); a.y = fmaf(s2, q.y, a.y);
+        if (c + 8 <= cols) {                       // leading dimensions are multiples of 8: 16-byte aligned
+            for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+                const uint4 p = *reinterpret_cast<const uint4*>(P + (size_t)r * j.ldp[job] + c);
+                acc8(a, p, s1);
+                if (Q) { const uint4 q = *reinterpret_cast<const uint4*>(Q + (size_t)r * j.ldq[job] + c); acc8(a, q, s2); }
             }
+        } else {
+            for (int r = r0 + threadIdx.y; r < r1; r += 8)
+                for (int e = 0; e < cols - c; ++e) {
+                    a[e] = fmaf(s1, __bfloat162float(P[(size_t)r * j.ldp[job] + c + e]), a[e]);
+                    if (Q) a[e] = fmaf(s2, __bfloat162float(Q[(size_t)r * j.ldq[job] + c + e]), a[e]);
+                }
         }
     }
-    part[threadIdx.y][threadIdx.x] = a;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[threadIdx.y][threadIdx.x][e] = a[e];
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
-        float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s.x += part[i][threadIdx.x].x; s.y += part[i][threadIdx.x].y; }
         float* dst = partial + ((size_t)job * CS_RSPLIT + blockIdx.y) * max_cols + c;
-        dst[0] = s.x;
-        if (c + 1 < cols) dst[1] = s.y;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x][e];
+            if (c + e < cols) dst[e] = s;
+        }
     }
 }
 __global__ void colsum_bf16_finish_kernel(ColsumJobs j, const float* __restrict__ partial, int max_cols) {
@@ -104,9 +118,9 @@ static void run_colsum_jobs(Ctx* ctx, const ColsumJobs& j) {
     int max_cols = 0;
     for (int i = 0; i < j.n; ++i) max_cols = j.cols[i] > max_cols ? j.cols[i] : max_cols;
     if (max_cols <= 0 || j.rows <= 0) return;
-    max_cols = (max_cols + 1) & ~1;
+    max_cols = (max_cols + 7) & ~7;
     float* scratch = colsum_scratch(ctx, (size_t)3 * CS_RSPLIT * max_cols);
-    colsum_bf16_partial_kernel<<<dim3((max_cols + 63) / 64, CS_RSPLIT, j.n), dim3(32, 8), 0, ctx->stream>>>(j, scratch, max_cols);
+    colsum_bf16_partial_kernel<<<dim3((max_cols + 255) / 256, CS_RSPLIT, j.n), dim3(32, 8), 0, ctx->stream>>>(j, scratch, max_cols);
     count_launch(ctx);
     colsum_bf16_finish_kernel<<<dim3((max_cols + 255) / 256, j.n), 256, 0, ctx->stream>>>(j, scratch, max_cols);
     count_launch(ctx);
@@ -150,6 +164,46 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t
 void launch_reduce_partials(Ctx* ctx, const float* partial, size_t stride, int splits, float* G, size_t n) {
     const size_t threads = (n + 3) / 4;
     reduce_partials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(partial, stride, splits, G, n);
+    count_launch(ctx);
+}
+
+// Momentum update of W fused with the split-K reduction of the dW partials (single-GPU path: no
+// all-reduce needs the reduced gradient in memory) and with the refresh of the bf16 shadow the
+// tensor-core GEMMs read.  base_rbm.py:447-449, 462, 467-468.  V*H must be a multiple of 4 (checked).
+__global__ void weight_update_splitk_kernel(const float* __restrict__ partial, size_t stride, int splits, float g_div,
+                                            float* __restrict__ W, float* __restrict__ dW, int H, size_t n,
+                                            const float* __restrict__ pen, float l2, float lr, float mom,
+                                            __nv_bfloat16* __restrict__ Wb, int ldwb) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 g = *reinterpret_cast<const float4*>(partial + i);
+    for (int s = 1; s < splits; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(partial + s * stride + i);
+        g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
+    }
+    const int h = (int)(i % (size_t)H);          // H % 4 == 0: the four elements share a row
+    const size_t v = i / (size_t)H;
+    const float4 w = *reinterpret_cast<const float4*>(W + i);
+    const float4 d0 = *reinterpret_cast<const float4*>(dW + i);
+    const float4 p = *reinterpret_cast<const float4*>(pen + h);
+    float4 d, wn;
+    d.x = lr * (mom * d0.x + (g.x / g_div - l2 * w.x - p.x)); wn.x = w.x + d.x;
+    d.y = lr * (mom * d0.y + (g.y / g_div - l2 * w.y - p.y)); wn.y = w.y + d.y;
+    d.z = lr * (mom * d0.z + (g.z / g_div - l2 * w.z - p.z)); wn.z = w.z + d.z;
+    d.w = lr * (mom * d0.w + (g.w / g_div - l2 * w.w - p.w)); wn.w = w.w + d.w;
+    *reinterpret_cast<float4*>(dW + i) = d;
+    *reinterpret_cast<float4*>(W + i) = wn;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(wn.x, wn.y), hi = __floats2bfloat162_rn(wn.z, wn.w);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(Wb + v * (size_t)ldwb + h) = pk;
+}
+void launch_weight_update_splitk(Ctx* ctx, const float* partial, size_t stride, int splits, float g_div, float* W, float* dW,
+                                 int V, int H, const float* pen, float l2, float lr, float mom, __nv_bfloat16* Wb, int ldwb) {
+    BM_REQUIRE(H % 4 == 0 && ldwb % 4 == 0, "fused weight update needs n_hidden % 4 == 0");
+    const size_t n = (size_t)V * H;
+    const size_t threads = n / 4;
+    weight_update_splitk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(partial, stride, splits, g_div, W, dW, H, n,
+                                                                                           pen, l2, lr, mom, Wb, ldwb);
     count_launch(ctx);
 }
 
