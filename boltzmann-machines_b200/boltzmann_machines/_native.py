@@ -25,7 +25,7 @@ EXPORTS = (
     'bm_ctx_timer_start', 'bm_ctx_timer_stop', 'bm_ctx_flush_l2', 'bm_host_alloc', 'bm_host_free',
     'bm_ctx_launch_count', 'bm_ctx_profile_tc', 'bm_ctx_profile_read', 'bm_comm_unique_id', 'bm_ctx_comm_init',
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
-    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_train_epoch', 'bm_rbm_transform', 'bm_rbm_metrics',
+    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_train_epoch', 'bm_rbm_train_epoch_u8', 'bm_rbm_transform', 'bm_rbm_metrics',
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
     'bm_dbm_create', 'bm_dbm_destroy', 'bm_dbm_set_param', 'bm_dbm_get_param', 'bm_dbm_init_particles',
     'bm_dbm_train_step', 'bm_dbm_val_metrics', 'bm_dbm_transform', 'bm_dbm_reconstruct', 'bm_dbm_log_proba',
@@ -98,6 +98,7 @@ def load_library(path=None):
         'bm_rbm_set_data': [vp, vp, i64],
         'bm_rbm_train_step_at': [vp, i64, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_train_epoch': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
+        'bm_rbm_train_epoch_u8': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
         'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
@@ -220,6 +221,17 @@ def pinned_copy(X):
     return P
 
 
+def as_bytes(X):
+    """X as uint8 if that is lossless (all values integers in 0..255), else None."""
+    if X.size == 0:
+        return None
+    lo, hi = float(X.min()), float(X.max())
+    if not (lo >= 0.0 and hi <= 255.0):          # also false for NaN
+        return None
+    Xb = X.astype(np.uint8)
+    return Xb if np.array_equal(Xb, X) else None
+
+
 def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None,
                   force_bn=0, force_cluster=0):
     """Raw tensor-core GEMM (test hook): C = A' B'^T (+/- A2' B2'^T) with the operands stored as
@@ -335,16 +347,28 @@ class CudaRBM(object):
         """One pass over the host dataset X in mini-batches (uploads overlap compute).  Returns
         {metric: [value of every reporting batch]}; batch i uses tick0 + i, exactly like
         train_step(X[i*batch:(i+1)*batch], ..., tick=tick0 + i)."""
-        X = self._batch(X)
+        byte_valued = getattr(X, 'dtype', None) == np.uint8     # see as_bytes(): exact, 4x less host->device traffic
+        if byte_valued:
+            X = np.ascontiguousarray(X)
+            if X.ndim != 2 or X.shape[1] != self.V:
+                raise ValueError('batch has shape {0}, expected (rows, {1})'.format(X.shape, self.V))
+        else:
+            X = self._batch(X)
         nb = (X.shape[0] + batch - 1) // batch
         out = np.zeros((nb, 4), dtype=np.float64)
-        check(self._lib.bm_rbm_train_epoch(self.handle, X.ctypes.data, X.shape[0], int(batch), lr, momentum, int(k),
-                                           int(seed), int(tick0), _mask(metrics), int(every), int(iter0), out.ctypes.data))
+        fn = self._lib.bm_rbm_train_epoch_u8 if byte_valued else self._lib.bm_rbm_train_epoch
+        check(fn(self.handle, X.ctypes.data, X.shape[0], int(batch), lr, momentum, int(k),
+                 int(seed), int(tick0), _mask(metrics), int(every), int(iter0), out.ctypes.data))
         rep = [i for i in range(nb) if every and (iter0 + i + 1) % every == 0]
         return {m: [float(out[i, METRIC_SLOTS[m]]) for i in rep] for m in metrics}
 
     def pin(self, X):
-        return pinned_copy(self._batch(X))
+        """Page-locked copy of the training set for `train_epoch`.  Data whose every value is an integer in
+        0..255 (binarised MNIST: {0, 1}) is kept as one byte per unit: the engine widens it exactly on the
+        device, so results do not change and each epoch moves a quarter of the bytes over PCIe."""
+        X = self._batch(X)
+        Xb = as_bytes(X)
+        return pinned_copy(Xb if Xb is not None else X)
 
     def unpin(self, P):
         pinned_free(P)

@@ -34,8 +34,9 @@ struct RbmBase {
     virtual void set_data(const void* X, int64_t n_rows) = 0;
     virtual void train_step(const void* X_host, int64_t first_row, int rows, double lr, double mom, int k,
                             uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
+    // src_u8: X_host holds one unsigned byte per visible unit (binary / byte-valued data) instead of cfg.dtype
     virtual void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
-                             uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out) = 0;
+                             uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, bool src_u8) = 0;
     virtual void transform(const void* X, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) = 0;
     virtual void metrics(const void* X, int rows, int k, uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
     virtual void get_activation(const char* name, void* host, size_t bytes) = 0;
@@ -157,7 +158,10 @@ struct RbmSimt : RbmBase {
     const T* stage_input(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve(rows);
         const T* src;
-        if (staged_dev) {
+        if (staged_u8) {
+            launch_u8_to_real<T>(ctx, staged_u8, Xin.p, (size_t)rows * V);     // byte-valued epoch data, exact
+            src = Xin.p;
+        } else if (staged_dev) {
             src = staged_dev;                       // already copied by train_epoch's copy stream
         } else if (X_host) {
             BM_CUDA(cudaMemcpyAsync(Xin.p, X_host, (size_t)rows * V * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
@@ -213,11 +217,14 @@ struct RbmSimt : RbmBase {
         launch_mean_combine<T>(ctx, rowB.p, rowA.p, -1.0, rows, scal.p + slot);
     }
 
+    // engines that keep the chain's activations in another format compute the MSRE from them directly
+    virtual bool msre_from_activations(int /*rows*/, double* /*dst*/) { return false; }
+
     void run_metrics(uint32_t mask, int rows, uint64_t seed, uint32_t tick, uint32_t row0, double* out) {
         if (!mask) return;
         BM_REQUIRE(out != nullptr, "metrics requested without an output buffer");
         if (mask & BM_METRIC_L2_LOSS) launch_sumsq<T>(ctx, W.p, (size_t)V * H, scal.p + 0);
-        if (mask & BM_METRIC_MSRE)
+        if ((mask & BM_METRIC_MSRE) && !msre_from_activations(rows, scal.p + 1))
             launch_sqdiff_mean<T>(ctx, Xcur, V, vm.p, V, rows, V, (double)rows * V, scal.p + 1);
         if (mask & BM_METRIC_PLL) {
             launch_pll_corrupt<T>(ctx, Xcur, V, Xc.p, V, rows, V, make_rng(seed, SITE_PLL, 0, tick, row0));
@@ -296,13 +303,15 @@ struct RbmSimt : RbmBase {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf<T> epoch_stage[2];
+    DevBuf<uint8_t> epoch_stage_u8[2];
     const T* staged_dev = nullptr;
+    const uint8_t* staged_u8 = nullptr;
     double* defer_dst = nullptr;
     double* epoch_host = nullptr;
     size_t epoch_host_cap = 0;
 
     void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
-                     uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out) override {
+                     uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, bool src_u8) override {
         BM_REQUIRE(X_host != nullptr && n_rows >= 1 && batch >= 1, "empty dataset or batch");
         BM_REQUIRE(!mask || out != nullptr, "metrics requested without an output buffer");
         const int64_t nb = (n_rows + batch - 1) / batch;
@@ -313,7 +322,7 @@ struct RbmSimt : RbmBase {
                 BM_CUDA(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
             }
         }
-        for (int b = 0; b < 2; ++b) epoch_stage[b].ensure((size_t)batch * V);
+        for (int b = 0; b < 2; ++b) { if (src_u8) epoch_stage_u8[b].ensure((size_t)batch * V); else epoch_stage[b].ensure((size_t)batch * V); }
         if ((size_t)nb * 8 > epoch_host_cap) {
             if (epoch_host) cudaFreeHost(epoch_host);
             epoch_host = nullptr; epoch_host_cap = 0;
@@ -323,28 +332,33 @@ struct RbmSimt : RbmBase {
         // the staging buffers may still be read by work already queued on the compute stream
         for (int b = 0; b < 2; ++b) BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
         const T* Xh = (const T*)X_host;
+        const uint8_t* Xh8 = (const uint8_t*)X_host;
         double unused[4];
         try {
             for (int64_t i = 0; i < nb; ++i) {
                 const int b = (int)(i & 1);
                 const int rows = (int)std::min<int64_t>(batch, n_rows - i * batch);
                 BM_CUDA(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
-                BM_CUDA(cudaMemcpyAsync(epoch_stage[b].p, Xh + (size_t)i * batch * V, (size_t)rows * V * sizeof(T),
-                                        cudaMemcpyHostToDevice, copy_stream));
+                if (src_u8)
+                    BM_CUDA(cudaMemcpyAsync(epoch_stage_u8[b].p, Xh8 + (size_t)i * batch * V, (size_t)rows * V,
+                                            cudaMemcpyHostToDevice, copy_stream));
+                else
+                    BM_CUDA(cudaMemcpyAsync(epoch_stage[b].p, Xh + (size_t)i * batch * V, (size_t)rows * V * sizeof(T),
+                                            cudaMemcpyHostToDevice, copy_stream));
                 BM_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
                 BM_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
-                staged_dev = epoch_stage[b].p;
+                if (src_u8) staged_u8 = epoch_stage_u8[b].p; else staged_dev = epoch_stage[b].p;
                 const bool report = mask && every > 0 && ((iter0 + i + 1) % every == 0);
                 defer_dst = epoch_host + 8 * i;
                 train_step(nullptr, 0, rows, lr, mom, k, seed, tick0 + (uint32_t)i, report ? mask : 0u, unused);
                 BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
             }
         } catch (...) {
-            staged_dev = nullptr; defer_dst = nullptr;
+            staged_dev = nullptr; staged_u8 = nullptr; defer_dst = nullptr;
             cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(ctx->stream);
             throw;
         }
-        staged_dev = nullptr; defer_dst = nullptr;
+        staged_dev = nullptr; staged_u8 = nullptr; defer_dst = nullptr;
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int64_t i = 0; i < nb && mask; ++i) {
             const bool report = every > 0 && ((iter0 + i + 1) % every == 0);

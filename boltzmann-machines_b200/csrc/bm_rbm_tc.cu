@@ -101,7 +101,14 @@ struct RbmTC : RbmSimt<float> {
     void stage_tc(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve_tc(rows);
         const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
-        if (!X_host && !staged_dev && plain) {
+        if (staged_u8 && plain) {
+            // byte-valued epoch data goes straight to the bf16 operand buffer; the fp32 copy the CUDA-core
+            // metric kernels read is made only when such a metric is requested (ensure_fp32_input)
+            reserve(rows);
+            launch_u8_to_bf16(ctx, staged_u8, V, Xb.p, ldv, rows, V);
+            X_b = Xb.p; X_ld = ldv; X_row0 = 0; X_rows_total = rows;
+            Xcur = nullptr;
+        } else if (!X_host && !staged_dev && !staged_u8 && plain) {
             BM_REQUIRE(first_row >= 0 && first_row + rows <= data_rows, "row range outside the resident dataset");
             reserve(rows);
             X_b = data_b.p; X_ld = ldv; X_row0 = (int)first_row; X_rows_total = (int)data_rows;
@@ -113,6 +120,20 @@ struct RbmTC : RbmSimt<float> {
             Xcur = X;
         }
         last_rows = rows;
+    }
+
+    // fp32 view of the current batch for the free-energy / PLL kernels (exact: bf16 holds 0..255 and the
+    // resident/converted inputs were rounded to bf16 once already)
+    void ensure_fp32_input(int rows) {
+        if (Xcur) return;
+        launch_bf16_to_f32(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, Xin.p, V, rows, V);
+        Xcur = Xin.p;
+    }
+    // MSRE straight from the bf16 activations of the last chain (no widened copies)
+    bool msre_from_activations(int rows, double* dst) override {
+        if (!last_was_tc) return false;
+        launch_sqdiff_mean_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vm_b.p, ldv, rows, V, (double)rows * V, dst);
+        return true;
     }
 
     // The whole chain (base_rbm.py:421-426, 367-384) -- and, for training, the fused dW
@@ -183,7 +204,7 @@ struct RbmTC : RbmSimt<float> {
         stage_tc(X_host, first_row, rows, seed, tick, row0);
         run_program(rows, k, true, seed, tick, row0);
         if (mask) {
-            if (mask & BM_METRIC_MSRE) launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
+            if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
             run_metrics(mask, rows, seed, tick, row0, out);
         }
 
@@ -227,10 +248,8 @@ struct RbmTC : RbmSimt<float> {
         if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::metrics(X_host, rows, k, seed, tick, mask, out); return; }
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
-        if (mask & BM_METRIC_MSRE) {
-            run_program(rows, k, false, seed, tick, 0);
-            launch_bf16_to_f32(ctx, vm_b.p, ldv, vm.p, V, rows, V);
-        }
+        if (mask & BM_METRIC_MSRE) run_program(rows, k, false, seed, tick, 0);
+        if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
         run_metrics(mask, rows, seed, tick, 0, out);
     }
 

@@ -126,6 +126,9 @@ struct TcLaunch {
     int stages, stage_bytes;
     unsigned long long* dbg;
     int flags;                       // bit 0: granule polls use acquire loads (no gpu-scope fence afterwards)
+    // 0x007FFFFF / 0x3F800000 as RUN-TIME values: (word & mant) | one is then ONE LOP3 (register + constant-bank
+    // operand); as literals ptxas emits two LOP3 with immediates -- 16 extra instructions per 16-column chunk
+    uint32_t mant_mask, one_bits;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -308,6 +311,17 @@ __device__ __forceinline__ float sigmoid_from_neg_log2(float t) {   // t = -x * 
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
 }
+// asfloat((word & 0x7fffff) | 0x3f800000) in [1, 2): TF's Uint32ToFloat before its "- 1.0f"
+__device__ __forceinline__ float u32_to_one_two(uint32_t w, uint32_t mant_mask, uint32_t one_bits) {
+    uint32_t bits;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bits) : "r"(w), "r"(mant_mask), "r"(one_bits));
+    return __uint_as_float(bits);
+}
+// 256-bit store (sm_100+): a thread's 8 consecutive fp32 go out as one full 32-byte sector
+__device__ __forceinline__ void stg256(float* dst, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h2);
@@ -363,6 +377,7 @@ struct EpiCtx {
     uint64_t* out_full;           // [N_OUT_BUF] a staged granule is complete (16 warp arrivals)
     uint64_t* out_free;           // [N_OUT_BUF] its TMA store has read the buffer (publisher)
     uint32_t* seq;                // FIFO position (same sequence in every warp and in the publisher)
+    uint32_t mant_mask, one_bits; // TcLaunch::mant_mask / one_bits
 };
 
 // One CW-column chunk of one accumulator row: activation, sampling, then
@@ -385,6 +400,10 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
     const bool do_state = E::fixed ? E::state_bf : (p.out_state_bf != nullptr);
     const bool do_f32 = E::fixed ? E::f32 : (out_f32 != nullptr);
     const bool f32_vec = n_valid == CW && (p.ld_f32 & 3) == 0;       // rows 16-byte aligned, whole chunk
+    // rows 32-byte aligned (row pitch, split stride and base): one full sector per store instruction and thread
+    const bool f32_wide = f32_vec && (p.ld_f32 & 7) == 0 && (p.split_stride & 7) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.out_f32) & 31) == 0;
+    float f32_prev[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t mean_pk[CW / 2], state_pk[CW / 2];
 #pragma unroll
     for (int q = 0; q < CW / 4; ++q) {
@@ -410,10 +429,22 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
             if (has_sigma && e < n_valid) x *= p.sigma[n0 + e];
             x += bq[j];
             float m_ = x;
+            float s_;
+            if (MODE == MODE_SIG_BERN_STATE) {
+                // only the draw is needed: u < 1/(1+e)  <=>  u*(1+e) < 1, with u = u12 - 1 folded into one FMA
+                // (no reciprocal, no "- 1.0f"); e = inf (p = 0) gives NaN -> 0, e = 0 (p = 1) gives u < 1 -> 1
+                float e_;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_) : "f"(x));
+                const float d_ = 1.0f + e_;
+                const float u12 = u32_to_one_two(words[j], c.mant_mask, c.one_bits);
+                s_ = (fmaf(u12, d_, -d_) < 1.0f) ? 1.0f : 0.0f;
+                mu[j] = 0.f; st[j] = s_;
+                continue;
+            }
             if (act == ACT_SIGMOID) m_ = sigmoid_from_neg_log2(x);
             else if (!E::fixed && act == ACT_SOFTPLUS) m_ = fast_softplus(x);
-            float s_ = m_;
-            if (smp == SMP_BERNOULLI) s_ = (u32_to_unit_float(words[j]) < m_) ? 1.0f : 0.0f;
+            s_ = m_;
+            if (smp == SMP_BERNOULLI) s_ = ((u32_to_one_two(words[j], c.mant_mask, c.one_bits) - 1.0f) < m_) ? 1.0f : 0.0f;
             else if (!E::fixed && smp == SMP_GAUSSIAN)
                 s_ = m_ + ((p.noise_sigma && e < n_valid) ? p.noise_sigma[n0 + e] : 1.0f) * g[j];
             mu[j] = m_; st[j] = s_;
@@ -422,7 +453,10 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
         if (do_state) { state_pk[2 * q] = pack_bf16(st[0], st[1]); state_pk[2 * q + 1] = pack_bf16(st[2], st[3]); }
         if (do_f32 && store_ok) {
             float* dst = out_f32 + (size_t)m * p.ld_f32 + n0 + q * 4;
-            if (f32_vec) *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+            if (f32_wide) {                       // 32-byte stores: every other group carries the previous one with it
+                if (q & 1) { const float v8[8] = {f32_prev[0], f32_prev[1], f32_prev[2], f32_prev[3], mu[0], mu[1], mu[2], mu[3]}; stg256(dst - 4, v8); }
+                else { f32_prev[0] = mu[0]; f32_prev[1] = mu[1]; f32_prev[2] = mu[2]; f32_prev[3] = mu[3]; }
+            } else if (f32_vec) *reinterpret_cast<float4*>(dst) = make_float4(mu[0], mu[1], mu[2], mu[3]);
             else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (q * 4 + j < n_valid) dst[j] = mu[j];
@@ -671,7 +705,15 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                         if (L.dbg && blockIdx.x == 0 && ord == 1 && lane == 0 && ci - u.c_begin < 20) { L.dbg[456 + ci - u.c_begin] = (unsigned long long)clock64(); L.dbg[480 + ci - u.c_begin] = (unsigned long long)fenced_upto; }
                         // acquire the producers' stores, then order them before this unit's TMA reads (async proxy)
                         if (!(L.flags & 1)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        // The producers' data was written by TMA stores and is read here by TMA loads (the same
+                        // proxy); only the counter travels through the generic proxy.  flags bit 1 narrows the
+                        // cross-proxy fence to the global state space, bit 2 drops it (the TMA issue below is
+                        // control-dependent on the acquired counter value) -- a full fence.proxy.async also waits
+                        // for this thread's own in-flight bulk copies (~1.2 k cycles per poll, measured).
+                        if (L.flags & 4) {}
+                        else if (L.flags & 2) asm volatile("fence.proxy.async.global;" ::: "memory");
+                        else asm volatile("fence.proxy.async;" ::: "memory");
+                        if (L.dbg && blockIdx.x == 0 && ord == 1 && lane == 0 && ci - u.c_begin < 20) L.dbg[432 + ci - u.c_begin] = (unsigned long long)clock64();
                     }
                 }
                 const int pr = (c >= chunks0) ? 1 : 0;
@@ -848,6 +890,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         uint32_t out_seq = 0;
         c.seq = &out_seq;
         c.out_base = smem_u32(out_stage); c.out_full = out_full; c.out_free = out_free;
+        c.mant_mask = L.mant_mask; c.one_bits = L.one_bits;
         c.row_off = (uint32_t)(quarter * 32 + lane) * 128u; c.row_swz = (uint32_t)(lane & 7);
         int acc = 0; uint32_t acc_phase = 0;
         int pi = 0;
@@ -1116,6 +1159,7 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     L.total_units = L.inl.l.unit_end;
     L.k0 = g.rng.k0; L.k1 = g.rng.k1; L.tick = g.rng.tick; L.row0 = g.rng.row0;
     L.dbg = g.dbg;
+    L.mant_mask = 0x007FFFFFu; L.one_bits = 0x3F800000u;
     upload_ops(ctx, &L.inl, 1);
     do_launch(ctx, L, cluster, gemm_flops(g), L.inl.l.BN);
 }
@@ -1216,7 +1260,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     L.total_units = unit;
     L.k0 = rng.k0; L.k1 = rng.k1; L.tick = rng.tick; L.row0 = rng.row0;
     L.batch_row = batch_row;
-    { static int fl = -1; if (fl < 0) { const char* e = getenv("BM_TC_FLAGS"); fl = e ? atoi(e) : 1; } L.flags = fl; }
+    { static int fl = -1; if (fl < 0) { const char* e = getenv("BM_TC_FLAGS"); fl = e ? atoi(e) : 3; } L.flags = fl; }
+    L.mant_mask = 0x007FFFFFu; L.one_bits = 0x3F800000u;
     static unsigned long long* dbg_buf = nullptr;
     static int dbg_left = -1;
     if (dbg_left < 0) { const char* e = getenv("BM_TC_PROGRAM_TIMELINE"); dbg_left = e ? atoi(e) : 0; }
@@ -1243,6 +1288,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         for (int i = 0; i < 148; ++i) if (h[512 + i]) fprintf(stderr, " %d:%lld/%lld", i, (long long)(h[512 + i] - h[6]), (long long)(h[704 + i] - h[6]));
         fprintf(stderr, "\n  unit 1 poll ok (time:upto):");
         for (int i = 0; i < 20; ++i) if (h[456 + i]) fprintf(stderr, " [%d] %llu:%llu", i, h[456 + i] - h[0], h[480 + i]);
+        fprintf(stderr, "\n  unit 1 fenced:");
+        for (int i = 0; i < 20; ++i) if (h[432 + i]) fprintf(stderr, " [%d] %llu", i, h[432 + i] - h[0]);
         fprintf(stderr, "\n  unit 1 mma_ready:");
         for (int i = 0; i < 24 && h[32 + i]; ++i) fprintf(stderr, " %llu", h[32 + i] - h[0]);
         fprintf(stderr, "\n  ord: start dep_ok mma_first mma_done epi_start epi_done published\n");

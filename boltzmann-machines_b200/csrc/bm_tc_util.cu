@@ -38,6 +38,107 @@ void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst,
     count_launch(ctx);
 }
 
+// ---- byte-valued host datasets (bm_rbm_train_epoch_u8): u8 -> bf16 / fp32 / fp64, exact for 0..255 ----
+__global__ void u8_to_bf16_kernel(const uint8_t* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd, int rows, int cols) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;            // group of 8 columns
+    const int r = blockIdx.y;
+    const int c = g * 8;
+    if (c >= cols) return;
+    const uint8_t* s = src + (size_t)r * lds + c;
+    __nv_bfloat16* d = dst + (size_t)r * ldd + c;
+    if (c + 8 <= cols && ((lds & 7) == 0)) {                          // 8-byte aligned source group, 16-byte aligned destination
+        const uint2 b = *reinterpret_cast<const uint2*>(s);
+        const uint32_t w[2] = {b.x, b.y};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t word = w[i >> 1] >> ((i & 1) * 16);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)(word & 0xFFu), (float)((word >> 8) & 0xFFu));
+            o[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int e = 0; e < 8 && c + e < cols; ++e) d[e] = __float2bfloat16_rn((float)s[e]);
+    }
+}
+void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols) {
+    if (rows <= 0) return;
+    dim3 grid(((cols + 7) / 8 + 127) / 128, rows);
+    u8_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
+    count_launch(ctx);
+}
+template <typename T>
+__global__ void u8_to_real_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (T)src[i];
+}
+template <typename T>
+void launch_u8_to_real(Ctx* ctx, const uint8_t* src, T* dst, size_t n) {
+    if (!n) return;
+    const size_t blocks = (n + 255) / 256;
+    u8_to_real_kernel<T><<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, ctx->stream>>>(src, dst, n);
+    count_launch(ctx);
+}
+template void launch_u8_to_real<float>(Ctx*, const uint8_t*, float*, size_t);
+template void launch_u8_to_real<double>(Ctx*, const uint8_t*, double*, size_t);
+
+// ---- MSRE on the bf16 activations (base_rbm.py:486-488): mean((X - v_means)^2), accumulated in fp64 ----
+constexpr int SQ_BLOCKS = 592;
+__global__ void sqdiff_bf16_partial_kernel(const __nv_bfloat16* __restrict__ P, int ldp, const __nv_bfloat16* __restrict__ Q, int ldq,
+                                           int rows, int cols, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    const int gpr = (cols + 7) / 8;                                   // 8-column groups per row
+    const size_t total = (size_t)rows * gpr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / gpr), c = (int)(i % gpr) * 8;
+        const __nv_bfloat16* p = P + (size_t)r * ldp + c;
+        const __nv_bfloat16* q = Q + (size_t)r * ldq + c;
+        float acc = 0.f;
+        if (c + 8 <= cols) {                                          // leading dimensions are multiples of 8
+            const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(q);
+            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 fa = __bfloat1622float2(ha[k]), fb = __bfloat1622float2(hb[k]);
+                const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+                acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc);
+            }
+        } else {
+            for (int e = 0; c + e < cols; ++e) { const float d = __bfloat162float(p[e]) - __bfloat162float(q[e]); acc = fmaf(d, d, acc); }
+        }
+        s += (double)acc;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void sqdiff_bf16_finish_kernel(const double* __restrict__ partial, int n, double denom, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0] / denom;
+}
+void launch_sqdiff_mean_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq, int rows, int cols,
+                             double denom, double* out) {
+    static double* buf[64] = {nullptr};
+    if (!buf[ctx->device]) BM_CUDA(cudaMalloc(&buf[ctx->device], SQ_BLOCKS * sizeof(double)));
+    sqdiff_bf16_partial_kernel<<<SQ_BLOCKS, 256, 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, buf[ctx->device]);
+    count_launch(ctx);
+    sqdiff_bf16_finish_kernel<<<1, 256, 0, ctx->stream>>>(buf[ctx->device], SQ_BLOCKS, denom, out);
+    count_launch(ctx);
+}
+
 // ---- column statistics of bf16 activations: up to 3 jobs (dvb, dhb, q) in one pair of launches ----
 struct ColsumJobs {
     const __nv_bfloat16* P[3]; int ldp[3];

@@ -120,6 +120,14 @@ int  bm_rbm_train_step_at(bm_rbm* rbm, int64_t first_row, int32_t rows, double l
 int  bm_rbm_train_epoch(bm_rbm* rbm, const void* X, int64_t n_rows, int32_t batch, double lr, double momentum,
                         int32_t n_gibbs_steps, uint64_t seed, uint32_t tick0, uint32_t metric_mask,
                         int32_t metrics_every, int64_t iter0, double* out);
+/* Same epoch for BYTE-VALUED data (README.md:462 "optimize input pipeline"): X[n_rows, n_visible] holds
+ * one unsigned byte per visible unit -- {0,1} for binarised MNIST -- and is widened exactly on the device, so every
+ * result is bit-identical to bm_rbm_train_epoch on float(X) while the host->device copy is 4x (float32) / 8x (float64)
+ * smaller.  BaseRBM.fit() takes this path when the training set is exactly representable (rbm/base_rbm.py:549-571
+ * feeds the same values as float32 through feed_dict). */
+int  bm_rbm_train_epoch_u8(bm_rbm* rbm, const uint8_t* X, int64_t n_rows, int32_t batch, double lr, double momentum,
+                           int32_t n_gibbs_steps, uint64_t seed, uint32_t tick0, uint32_t metric_mask,
+                           int32_t metrics_every, int64_t iter0, double* out);
 int  bm_rbm_transform(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_steps,
                       uint64_t seed, uint32_t tick, void* H_out);
 /* msre / pll / l2_loss / free_energy_op on a batch without training (base_rbm.py:573-621) */

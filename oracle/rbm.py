@@ -251,6 +251,14 @@ class OracleRBM(object):
         X = self.prepare_input(X, seed, tick, row0)
         h0_means, v_states, v_means, _, h_means = self.chain(X, k, seed, tick, row0)
         out = self._metrics(metrics, X, v_means, seed, tick, row0) if metrics else None
+        self.apply_update(X, h0_means, v_states, h_means, lr, momentum, nranks, allreduce)
+        return out
+
+    def apply_update(self, X, h0_means, v_states, h_means, lr, momentum, nranks=1, allreduce=None):
+        """Gradients, sparsity and momentum updates of one step from the chain's activations
+        (base_rbm.py:443-474).  Separate from ``train_step`` so that full-size tests can apply it to the
+        CUDA engine's own activations (a size-independent check of the statistics + update kernels)."""
+        c, p, dt = self.cfg, self.p, self.dt
         N = dt.type(X.shape[0] * nranks)
         G = X.T @ h0_means - v_states.T @ h_means
         dvb_sum, dhb_sum, q_sum = (X - v_states).sum(axis=0), (h0_means - h_means).sum(axis=0), h_means.sum(axis=0)
@@ -272,7 +280,6 @@ class OracleRBM(object):
         p['vb'] = (p['vb'] + p['dvb']).astype(dt)
         p['dhb'] = (lr * (mom * p['dhb'] + dhb)).astype(dt)
         p['hb'] = (p['hb'] + p['dhb']).astype(dt)
-        return out
 
     def transform(self, X, k, seed, tick):
         """base_rbm.py:438-440,687-700: chain-end h_means (E[h|v_k])."""

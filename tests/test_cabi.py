@@ -44,3 +44,18 @@ def test_product_package_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(d, f)
+
+
+def test_as_bytes_is_lossless_or_declines():
+    """engine.pin keeps a training set as bytes only when that is exact (bm_rbm_train_epoch_u8)."""
+    import numpy as np
+    from boltzmann_machines import _native
+    X = (np.random.RandomState(0).rand(7, 5) < 0.3).astype(np.float32)
+    Xb = _native.as_bytes(X)
+    assert Xb.dtype == np.uint8 and np.array_equal(Xb.astype(np.float32), X)
+    assert _native.as_bytes(np.arange(256, dtype=np.float64).reshape(16, 16)).dtype == np.uint8
+    assert _native.as_bytes(X * 0.5) is None                      # grey levels
+    assert _native.as_bytes(X - 1.0) is None                      # negative
+    assert _native.as_bytes(X + 255.0) is None                    # out of range
+    assert _native.as_bytes(np.array([[np.nan, 1.0]], dtype=np.float32)) is None
+    assert _native.as_bytes(np.zeros((0, 5), dtype=np.float32)) is None

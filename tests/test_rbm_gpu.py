@@ -171,6 +171,62 @@ def test_train_epoch_equals_the_per_batch_loop(compute, pinned):
     a.close(), b.close()
 
 
+@pytest.mark.parametrize('compute,dtype', [('fp32', 'float32'), ('bf16', 'float32'), ('fp32', 'float64')])
+@pytest.mark.parametrize('dropout', [None, 0.8])
+def test_byte_valued_epoch_is_bit_identical_to_the_float_epoch(compute, dtype, dropout):
+    """bm_rbm_train_epoch_u8 (one byte per visible unit, widened on the device) = bm_rbm_train_epoch on
+    float(X): same parameters bit for bit, same metrics; V and the last batch deliberately ragged."""
+    kw = dict(compute=compute, dtype=dtype, sample_v=False)
+    if dropout:
+        kw['dropout'] = dropout
+    cfg = make_cfg('bernoulli', 100, 48, 16, **kw)
+    a, _ = make_pair(cfg)
+    b, _ = make_pair(cfg)
+    X = make_data(cfg, 16 * 4 + 5)
+    Xb = _native.as_bytes(X)
+    assert Xb is not None and Xb.dtype == np.uint8
+    P = _native.pinned_copy(Xb)
+    want = a.train_epoch(X, 16, 0.05, 0.5, 2, 11, 3, metrics=('msre', 'pll', 'free_energy'), every=2, iter0=0)
+    got = b.train_epoch(P, 16, 0.05, 0.5, 2, 11, 3, metrics=('msre', 'pll', 'free_energy'), every=2, iter0=0)
+    for m in want:
+        assert len(got[m]) == len(want[m]) == 2
+        np.testing.assert_allclose(got[m], want[m], rtol=1e-12, err_msg=m)
+    for k, v in a.get_params().items():
+        np.testing.assert_array_equal(v, b.get_params()[k], err_msg=k)
+    _native.pinned_free(P)
+    a.close(), b.close()
+
+
+def test_fit_takes_the_byte_path_for_binary_data_and_matches_float_feeding(workdir, monkeypatch):
+    """BaseRBM.fit pins binary data as bytes (engine.pin -> as_bytes); the trained weights equal those of a fit
+    whose data went through the float32 path (the reference's feed_dict values, base_rbm.py:549-571)."""
+    from boltzmann_machines.base import set_engine_factory
+    from boltzmann_machines.rbm import BernoulliRBM
+    old = set_engine_factory('rbm', None)
+    try:
+        rng = np.random.RandomState(5)
+        X = (rng.rand(200, 64) < 0.3).astype(np.float32)
+        seen = []
+        real_copy = _native.pinned_copy
+        monkeypatch.setattr(_native, 'pinned_copy', lambda Z: seen.append(Z.dtype) or real_copy(Z))
+
+        def fit(path):
+            m = BernoulliRBM(n_visible=64, n_hidden=32, batch_size=32, max_epoch=2, random_seed=7, verbose=False,
+                             sample_v_states=False, model_path=path,
+                             metrics_config=dict(msre=True, train_metrics_every_iter=2))
+            m.fit(X)
+            return m.get_tf_params('weights')['W']
+        W1 = fit('a/')
+        assert seen and seen[-1] == np.uint8
+        monkeypatch.setattr(_native, 'as_bytes', lambda Z: None)          # force the float path
+        W2 = fit('b/')
+        assert seen[-1] == np.float32
+        np.testing.assert_array_equal(W1, W2)
+        assert np.abs(W1).max() > 0
+    finally:
+        set_engine_factory('rbm', old)
+
+
 def test_init_weights_matches_tf_stream():
     from oracle import philox as P
     for dtype in ('float32', 'float64'):
