@@ -169,28 +169,79 @@ struct RbmTC : RbmSimt<float> {
             hstate = smp ? hs_b.p : hm_b.p;
         }
         if (with_dw) {
-            // dW_positive - dW_negative as one GEMM over the concatenated batch dimension, K split so
-            // that every CTA pair gets a slice; needs ALL row blocks of h0, v_k and h_k
-            TcGemm g;
-            g.M = V; g.N = H; g.n_pairs = 2;
-            g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_batch[0] = resident;
-            if (!resident) g.a_k0[0] = X_row0;
-            g.B[0] = mat(h0m_b.p, rows, H, ldh); g.b_t[0] = true; g.K[0] = rows;
-            g.A[1] = mat(vstate_b, rows, V, ldv); g.a_t[1] = true;
-            g.B[1] = mat(hm_b.p, rows, H, ldh); g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
+            // dW_positive - dW_negative (base_rbm.py:447-448): G = X^T h0_means - v_k^T h_k_means, K = the batch rows,
+            // split over K so that every CTA pair gets a slice; the slices are summed by the weight update.
+            const int total_pairs = ctx->sm_count / 2;
             const int pair_tiles = ((V + 255) / 256) * ((H + 255) / 256);
-            const int chunks = 2 * ((rows + 63) / 64);
-            int splits = (ctx->sm_count / 2) / (pair_tiles > 0 ? pair_tiles : 1);
-            if (splits < 1) splits = 1;
-            if (splits > chunks) splits = chunks;
-            dw_splits = splits;
-            g.splits = splits; g.split_stride = (size_t)V * H;
-            partials.ensure((size_t)splits * V * H);
-            g.out_f32 = splits > 1 ? partials.p : stats.p; g.ld_f32 = H;
-            g.n_deps = 3;
-            g.dep[0] = 0; g.dep[1] = (int)ops.size() - 2; g.dep[2] = (int)ops.size() - 1;
-            g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
-            ops.push_back(g);
+            const int row_chunks = (rows + 63) / 64;
+            auto half = [&](bool negative) {
+                TcGemm g;
+                g.M = V; g.N = H; g.n_pairs = 1;
+                if (!negative) {
+                    g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_batch[0] = resident;
+                    if (!resident) g.a_k0[0] = X_row0;
+                    g.B[0] = mat(h0m_b.p, rows, H, ldh);
+                } else {
+                    g.A[0] = mat(vstate_b, rows, V, ldv); g.a_t[0] = true;
+                    g.B[0] = mat(hm_b.p, rows, H, ldh); g.neg[0] = true;
+                }
+                g.b_t[0] = true; g.K[0] = rows;
+                g.split_stride = (size_t)V * H; g.ld_f32 = H;
+                return g;
+            };
+            // The positive half depends on h0 only.  When the chain leaves CTA pairs idle (cfg2: 64 units per
+            // half-step on 74 pairs) and is long enough to hide it, the positive half runs on those pairs BESIDE the
+            // chain and only the negative half is left for the end of the step.
+            if (prog.chain_units < 0)            // shapes are fixed per cached program: plan once
+                for (const TcGemm& o : ops) prog.chain_units = std::max(prog.chain_units, tc_plan_units(ctx, o));
+            const int chain_units = prog.chain_units;
+            const int spare = total_pairs - chain_units;
+            int pos_splits = 0;
+            if (spare >= 2 && pair_tiles > 0) {
+                pos_splits = std::max(1, std::min(spare / pair_tiles, row_chunks));
+                const int rounds = (pair_tiles * pos_splits + spare - 1) / spare;
+                const double pos_cycles = (double)rounds * ((double)(row_chunks / pos_splits + 1) * 600.0 + 10000.0);
+                const double chain_cycles = (double)(2 * k) * 20000.0;
+                if (pos_cycles > 0.8 * chain_cycles) pos_splits = 0;
+            }
+            { const char* e = getenv("BM_TC_DW_OVERLAP"); if (e && !atoi(e)) pos_splits = 0; }
+            const int last_v = (int)ops.size() - 2, last_h = (int)ops.size() - 1;
+            if (pos_splits > 0) {
+                int neg_splits = std::max(1, std::min(total_pairs / pair_tiles, row_chunks));
+                dw_splits = pos_splits + neg_splits;
+                partials.ensure((size_t)dw_splits * V * H);
+                TcGemm gp = half(false);
+                gp.splits = pos_splits; gp.out_f32 = partials.p;
+                gp.n_deps = 1; gp.dep[0] = 0; gp.dep_all[0] = true;
+                gp.lane = LANE_SPARE;
+                TcGemm gn = half(true);
+                gn.splits = neg_splits; gn.out_f32 = partials.p + (size_t)pos_splits * V * H;
+                gn.n_deps = 2; gn.dep[0] = last_v; gn.dep[1] = last_h; gn.dep_all[0] = gn.dep_all[1] = true;
+                gn.lane = LANE_ALL;
+                // program order: the positive half right after h0, so that the spare pairs meet it first
+                ops.insert(ops.begin() + 1, gp);
+                for (size_t i = 2; i < ops.size(); ++i)
+                    for (int d = 0; d < ops[i].n_deps; ++d) if (ops[i].dep[d] >= 1) ops[i].dep[d] += 1;
+                gn.dep[0] += 1; gn.dep[1] += 1;
+                ops.push_back(gn);
+            } else {
+                TcGemm g = half(false);
+                const TcGemm gneg = half(true);
+                g.n_pairs = 2;
+                g.A[1] = gneg.A[0]; g.a_t[1] = true; g.B[1] = gneg.B[0]; g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
+                int splits = total_pairs / (pair_tiles > 0 ? pair_tiles : 1);
+                if (splits < 1) splits = 1;
+                if (splits > 2 * row_chunks) splits = 2 * row_chunks;
+                dw_splits = splits;
+                g.splits = splits;
+                partials.ensure((size_t)splits * V * H);
+                g.out_f32 = splits > 1 ? partials.p : stats.p;
+                g.n_deps = 3;
+                g.dep[0] = 0; g.dep[1] = last_v; g.dep[2] = last_h;
+                g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
+                g.lane = LANE_ALL;
+                ops.push_back(g);
+            }
         }
         launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
         last_was_tc = true;

@@ -76,7 +76,10 @@ constexpr int MAX_KCHUNKS = 32;     // granule-ordered dataflow covers K <= 2048
 struct TcPhaseLite {
     int M, N, BN, m_groups, n_tiles, splits, n_pairs;
     int chunks[2], a_mn[2], b_mn[2], a_neg[2], a_row0[2], a_k0[2], a_batch[2];
-    int unit_begin, unit_end;        // this op's slice of the program's global unit sequence
+    // which CTA pairs execute this op: pair c takes the op's units c - pair_begin, + pair_count, + 2 pair_count ...
+    // (chain ops keep a fixed (row block, column block) -> pair map; ops that only feed the end of the step --
+    // the positive half of dW -- get the pairs the chain never uses and run beside it)
+    int pair_begin, pair_count, n_units;
     unsigned long long split_stride;
     float acc_scale, bias_scale;
     const float* bias;
@@ -129,6 +132,10 @@ struct TcLaunch {
     // 0x007FFFFF / 0x3F800000 as RUN-TIME values: (word & mant) | one is then ONE LOP3 (register + constant-bank
     // operand); as literals ptxas emits two LOP3 with immediates -- 16 extra instructions per 16-column chunk
     uint32_t mant_mask, one_bits;
+    // dataflow counters are never reset between launches of a program: launch number `epoch` (1, 2, ...) waits for
+    // epoch x the per-launch arrival counts (saves a memset per step; the host resets them every 2^20 launches)
+    int epoch;
+    int poll_ns, epi_ns;             // back-off of the granule polls / of the epilogue's wait for an accumulator
 };
 
 // ------------------------------------------------------------------------------------------
@@ -159,7 +166,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // for waits that are expected to be long (epilogue warps waiting for an accumulator or a staging
 // buffer): sleep between attempts instead of spinning in the issue slots of the busy roles
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
     for (;;) {
@@ -170,7 +177,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(128);
+        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
@@ -544,13 +551,22 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
 // ------------------------------------------------------------------------------------------
 struct UnitInfo { int split, m_group, n_blk, c_begin, c_end, total_chunks; };
 
-__device__ __forceinline__ int phase_of(int pi, int unit) {
-    while (unit >= c_ph[pi].unit_end) ++pi;
-    return pi;
+// Next unit of CTA pair `cid`: ops in program order, inside an op the units cid - pair_begin (mod pair_count).
+// (pi, l) = current op and local unit; l < 0: before the first unit of op pi.  All values are warp-uniform.
+__device__ __forceinline__ bool walk_next(int& pi, int& l, int cid, int n_ops) {
+    while (pi < n_ops) {
+        const TcPhaseLite* p = &c_ph[pi];
+        const int rel = cid - p->pair_begin;
+        if (rel >= 0 && rel < p->pair_count) {
+            l = (l < 0) ? rel : l + p->pair_count;
+            if (l < p->n_units) return true;
+        }
+        ++pi; l = -1;
+    }
+    return false;
 }
-__device__ __forceinline__ UnitInfo decode_unit(const TcPhaseLite* ph, int unit) {
+__device__ __forceinline__ UnitInfo decode_unit(const TcPhaseLite* ph, int local) {
     UnitInfo u;
-    const int local = unit - ph->unit_begin;
     u.split = local % ph->splits;
     const int tile = local / ph->splits;
     u.m_group = tile / ph->n_tiles;
@@ -610,27 +626,27 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) DBG_MARK(1);
 
-    const int units = L.total_units;
+    const int n_ops = L.n_phases ? L.n_phases : 1;
     // clusters are (2,1,1): rank = blockIdx.x & 1, cluster id = blockIdx.x >> 1 (kept as expressions of
     // blockIdx / gridDim so that the compiler knows they are warp-uniform)
     const int crank = pair ? (int)(blockIdx.x & 1u) : 0;
-    const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int unit_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int cid = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
     if (warp == W_TMA) {
         // ================================ TMA producer =====================================
         // The whole warp walks the K chunks; for each chunk lane 0 arms the barrier and lanes
         // 0..n_ops-1 issue one bulk-tensor copy each in the same warp instruction.
         int stage = 0; uint32_t phase = 0;
-        int pi = 0;
+        int pi = 0, ul = -1;
         int ord = -1;
-        for (int unit = unit0; unit < units; unit += unit_step) {
+        while (walk_next(pi, ul, cid, n_ops)) {
             ++ord;
-            pi = phase_of(pi, unit);
             const TcPhaseLite* ph = &c_ph[pi];
             const TcPhase* gp = &gph[pi];
-            const UnitInfo u = decode_unit(ph, unit);
+            const UnitInfo u = decode_unit(ph, ul);
             if (lane == 0) DBG_UNIT(0, ord);
+            // this op's tensor maps -> descriptor cache while the unit still waits for its inputs
+            if ((L.flags & 8) && lane < 2 * ph->n_pairs) tma_prefetch_desc(lane & 1 ? &gp->tmB[lane >> 1] : &gp->tmA[lane >> 1]);
             const int BN = ph->BN;
             const int half_bn = BN >> 1;
             const uint32_t tx_bytes = pair ? 2u * (A_BYTES + (uint32_t)half_bn * BK * 2) : A_BYTES + (uint32_t)BN * BK * 2;
@@ -642,7 +658,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 if (lane == 0) {
                     for (int d = 0; d < ph->n_deps; ++d) {
                         const int* ctr = ph->dep_ctr[d];
-                        const int need = ph->dep_need[d];
+                        const int need = ph->dep_need[d] * L.epoch;
                         if (ph->dep_groups[d] == 0) {
                             if (ph->dep_chunk_ctr) continue;          // handled chunk by chunk below
                             while (ld_relaxed(ctr + u.m_group) < need) __nanosleep(64);
@@ -686,7 +702,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                     if (ci >= fenced_upto) {
                         // every lane polls one K position (ci + lane): one L2 round trip tells how long the
                         // prefix of ready positions is (a serial scan costs a round trip per position)
-                        const int need = ph->dep_chunk_need;
+                        const int need = ph->dep_chunk_need * L.epoch;
                         const int n = ci + lane;
                         int ga = 0, gb = 0;
                         if (n < u.c_end) { const int j = (int)ph->k_order[n]; ga = (int)ph->k_dep_a[j]; gb = (int)ph->k_dep_b[j]; }
@@ -699,7 +715,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                             ready_prefix = __ffs(~m) - 1;              // ~m != 0: lanes past c_end are never ready... (32 positions max)
                             if (m == 0xffffffffu) ready_prefix = 32;
                             if (ready_prefix > 0) break;
-                            __nanosleep(64);
+                            __nanosleep((uint32_t)L.poll_ns);
                         }
                         fenced_upto = ci + ready_prefix;
                         if (L.dbg && blockIdx.x == 0 && ord == 1 && lane == 0 && ci - u.c_begin < 20) { L.dbg[456 + ci - u.c_begin] = (unsigned long long)clock64(); L.dbg[480 + ci - u.c_begin] = (unsigned long long)fenced_upto; }
@@ -754,14 +770,13 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         if (crank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            int pi = 0;
+            int pi = 0, ul = -1;
             int ord = -1;
             const uint32_t smem_base = smem_u32(smem);
-            for (int unit = unit0; unit < units; unit += unit_step) {
+            while (walk_next(pi, ul, cid, n_ops)) {
                 ++ord;
-                pi = phase_of(pi, unit);
                 const TcPhaseLite* ph = &c_ph[pi];
-                const UnitInfo u = decode_unit(ph, unit);
+                const UnitInfo u = decode_unit(ph, ul);
                 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13),
                 // a_negate 13, a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
                 const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ph->BN >> 3) << 17) |
@@ -833,15 +848,14 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             const int pub = warp - W_PUB0;
             int acc = 0; uint32_t acc_phase = 0;
             uint32_t seq = 0;                               // FIFO position of the unit's first granule
-            int pi = 0;
+            int pi = 0, ul = -1;
             int ord = -1;
             const uint32_t out_base = smem_u32(out_stage);
-            for (int unit = unit0; unit < units; unit += unit_step) {
+            while (walk_next(pi, ul, cid, n_ops)) {
                 ++ord;
-                pi = phase_of(pi, unit);
                 const TcPhaseLite* ph = &c_ph[pi];
                 const TcPhase* gp = &gph[pi];
-                const UnitInfo u = decode_unit(ph, unit);
+                const UnitInfo u = decode_unit(ph, ul);
                 const bool has_mean = ph->out_mean_bf != nullptr, has_state = ph->out_state_bf != nullptr;
                 const int n_arr = (has_mean ? 1 : 0) + (has_state ? 1 : 0);
                 const int gpt = n_arr ? ph->gran_per_tile : 0;
@@ -893,14 +907,13 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
         c.mant_mask = L.mant_mask; c.one_bits = L.one_bits;
         c.row_off = (uint32_t)(quarter * 32 + lane) * 128u; c.row_swz = (uint32_t)(lane & 7);
         int acc = 0; uint32_t acc_phase = 0;
-        int pi = 0;
+        int pi = 0, ul = -1;
         int ord = -1;
         const int et = threadIdx.x;                // 0..511: the epilogue threads
-        for (int unit = unit0; unit < units; unit += unit_step) {
+        while (walk_next(pi, ul, cid, n_ops)) {
             ++ord;
-            pi = phase_of(pi, unit);
             const TcPhaseLite* ph = &c_ph[pi];
-            const UnitInfo u = decode_unit(ph, unit);
+            const UnitInfo u = decode_unit(ph, ul);
             {   // this tile's (pre-scaled) bias slice -> shared memory, while the MMAs are still running
                 const float bsc = (ph->act == ACT_SIGMOID) ? ph->bias_scale * -1.4426950408889634f : ph->bias_scale;
                 const int n = u.n_blk * ph->BN + et;
@@ -919,7 +932,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
             c.tempty = &tempty[acc];
-            mbar_wait_relaxed(&tfull[acc], acc_phase);
+            mbar_wait_relaxed(&tfull[acc], acc_phase, (uint32_t)L.epi_ns);
             tc_fence_after();
             if (threadIdx.x == 0) { DBG_MARK(3); DBG_UNIT(4, ord); }
             c.t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
@@ -1117,7 +1130,8 @@ static void do_launch(Ctx* ctx, TcLaunch& L, int cluster, double flops, int max_
     if (L.stages > MAX_STAGES) L.stages = MAX_STAGES;
     { const char* e = getenv("BM_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= L.stages) L.stages = atoi(e); }
     const int max_clusters = ctx->sm_count / cluster;
-    const int n_clusters = L.total_units < max_clusters ? L.total_units : max_clusters;
+    // programs address pairs by number (TcPhaseLite::pair_begin/pair_count): launch all of them
+    const int n_clusters = L.n_phases ? max_clusters : (L.total_units < max_clusters ? L.total_units : max_clusters);
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(n_clusters * cluster); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = ctx->stream;
     cudaLaunchAttribute at[1];
@@ -1154,14 +1168,25 @@ void launch_tc_gemm(Ctx* ctx, const TcGemm& g) {
     TcLaunch L;
     memset(&L, 0, sizeof(L));
     fill_phase(ctx, g, cluster, L.inl);
-    L.inl.l.unit_begin = 0;
-    L.inl.l.unit_end = L.inl.l.m_groups * L.inl.l.n_tiles * L.inl.l.splits;
-    L.total_units = L.inl.l.unit_end;
+    L.inl.l.n_units = L.inl.l.m_groups * L.inl.l.n_tiles * L.inl.l.splits;
+    L.total_units = L.inl.l.n_units;
+    {   // every CTA pair (or CTA) of the grid takes part
+        const int max_clusters = ctx->sm_count / cluster;
+        L.inl.l.pair_begin = 0;
+        L.inl.l.pair_count = L.total_units < max_clusters ? L.total_units : max_clusters;
+    }
     L.k0 = g.rng.k0; L.k1 = g.rng.k1; L.tick = g.rng.tick; L.row0 = g.rng.row0;
     L.dbg = g.dbg;
     L.mant_mask = 0x007FFFFFu; L.one_bits = 0x3F800000u;
+    L.epoch = 1; L.poll_ns = 64; L.epi_ns = 128;
     upload_ops(ctx, &L.inl, 1);
     do_launch(ctx, L, cluster, gemm_flops(g), L.inl.l.BN);
+}
+
+int tc_plan_units(Ctx* ctx, const TcGemm& g) {
+    TcPhase ph;
+    fill_phase(ctx, g, 2, ph);
+    return ph.l.m_groups * ph.l.n_tiles * ph.l.splits;
 }
 
 TcProgram::~TcProgram() {
@@ -1182,9 +1207,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     double flops = 0.0;
     for (int i = 0; i < n; ++i) {
         fill_phase(ctx, prog.ops[i], cluster, ph[i]);
-        ph[i].l.unit_begin = unit;
-        unit += ph[i].l.m_groups * ph[i].l.n_tiles * ph[i].l.splits;
-        ph[i].l.unit_end = unit;
+        ph[i].l.n_units = ph[i].l.m_groups * ph[i].l.n_tiles * ph[i].l.splits;
+        unit += ph[i].l.n_units;
         ctr_off[i] = n_ctr;
         n_ctr += (size_t)ph[i].l.m_groups;
         cctr_off[i] = n_ctr;
@@ -1197,6 +1221,20 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         BM_CUDA(cudaMalloc(&prog.dev_counters, n_ctr * sizeof(int)));
         prog.n_counters = n_ctr;
         prog.host_image.clear();
+        prog.epoch = 0;
+    }
+    // pair assignment: chain ops on pairs [0, P), spare-lane ops on [P, total), the rest on all pairs
+    {
+        const int total = ctx->sm_count / cluster;
+        int P = 0;
+        for (int i = 0; i < n; ++i) if (prog.ops[i].lane == LANE_CHAIN) P = std::max(P, ph[i].l.n_units);
+        if (P > total || P == 0) P = total;
+        for (int i = 0; i < n; ++i) {
+            int lane = prog.ops[i].lane;
+            if (lane == LANE_SPARE && total - P < 1) lane = LANE_ALL;
+            ph[i].l.pair_begin = lane == LANE_SPARE ? P : 0;
+            ph[i].l.pair_count = lane == LANE_CHAIN ? P : (lane == LANE_SPARE ? total - P : total);
+        }
     }
     static int chunk_deps = -1;
     if (chunk_deps < 0) { const char* e = getenv("BM_TC_CHUNK_DEPS"); chunk_deps = e ? atoi(e) : 1; }
@@ -1251,8 +1289,13 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         }
         BM_CUDA(cudaMemcpy(prog.dev_phases, image.data(), image.size(), cudaMemcpyHostToDevice));
         prog.host_image = image;
+        prog.epoch = 0;                                   // another op list: other arrival counts per launch
     }
-    BM_CUDA(cudaMemsetAsync(prog.dev_counters, 0, n_ctr * sizeof(int), ctx->stream));
+    if (prog.epoch == 0 || prog.epoch >= (1 << 20)) {
+        BM_CUDA(cudaMemsetAsync(prog.dev_counters, 0, prog.n_counters * sizeof(int), ctx->stream));
+        prog.epoch = 0;
+    }
+    ++prog.epoch;
     TcLaunch L;
     memset(&L, 0, sizeof(L));
     L.phases = reinterpret_cast<const TcPhase*>(prog.dev_phases);
@@ -1260,6 +1303,11 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     L.total_units = unit;
     L.k0 = rng.k0; L.k1 = rng.k1; L.tick = rng.tick; L.row0 = rng.row0;
     L.batch_row = batch_row;
+    L.epoch = prog.epoch;
+    { static int pn = -1, en = -1;
+      if (pn < 0) { const char* e = getenv("BM_TC_POLL_NS"); pn = e ? atoi(e) : 64; }
+      if (en < 0) { const char* e = getenv("BM_TC_EPI_NS"); en = e ? atoi(e) : 128; }
+      L.poll_ns = pn; L.epi_ns = en; }
     { static int fl = -1; if (fl < 0) { const char* e = getenv("BM_TC_FLAGS"); fl = e ? atoi(e) : 3; } L.flags = fl; }
     L.mant_mask = 0x007FFFFFu; L.one_bits = 0x3F800000u;
     static unsigned long long* dbg_buf = nullptr;

@@ -51,9 +51,17 @@ struct TcGemm {
     int n_deps = 0;
     int dep[3] = {-1, -1, -1};
     bool dep_all[3] = {false, false, false};
+    // which CTA pairs of a program run this op (see launch_tc_program):
+    //   LANE_CHAIN: the first P pairs, P = the largest unit count of any chain op (fixed unit -> pair map)
+    //   LANE_SPARE: the pairs the chain ops never use (falls back to LANE_ALL when there are none)
+    //   LANE_ALL  : every pair
+    int lane = 0;
 };
+enum : int { LANE_CHAIN = 0, LANE_SPARE = 1, LANE_ALL = 2 };
 
 void launch_tc_gemm(Ctx* ctx, const TcGemm& g);
+// number of (row-block pair, column block, split) units the tile heuristic cuts `g` into inside a program
+int tc_plan_units(Ctx* ctx, const TcGemm& g);
 
 // A program = ops executed by ONE persistent kernel: every CTA pair walks the same global list of
 // (op, row-block pair, column block) units in order; a unit starts as soon as the row blocks it reads
@@ -65,6 +73,8 @@ struct TcProgram {
     void* dev_phases = nullptr; size_t dev_phases_bytes = 0;
     int* dev_counters = nullptr; size_t n_counters = 0;
     std::vector<unsigned char> host_image;      // last uploaded descriptor image
+    int epoch = 0;                              // launches since the dataflow counters were last zeroed
+    int chain_units = -1;                       // largest unit count of the chain ops (planned once by the owner)
     ~TcProgram();
 };
 // seed/tick/row0 of `rng` are shared by all ops; batch_row shifts the ops' a_batch operands
