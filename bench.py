@@ -297,24 +297,28 @@ def main():
                 eng.train_epoch(Xhost[:nb * B], B, LR, MOMENTUM, K_GIBBS, seed, t0 + done,
                                 metrics=('msre',), every=1)
                 done += nb
-        epoch_chunks(max(3, min(args.warmup, N_BATCHES)), first_tick)
-        barrier()
-        sampler.mark()
-        ctx.timer_start()
-        epoch_chunks(args.steps, first_tick + N_BATCHES)
-        t = ctx.timer_stop()
-        barrier()
-        sampler.unmark()
-        return max_over_ranks(t)
+        # warm-up: one full-size epoch call, so that every staging buffer exists before the timed passes
+        epoch_chunks(max(N_BATCHES, args.warmup), first_tick)
+        passes = []
+        for rep in range(2):                        # two timed passes of exactly K steps; both are reported
+            barrier()
+            sampler.mark()
+            ctx.timer_start()
+            epoch_chunks(args.steps, first_tick + N_BATCHES + rep * args.steps)
+            t = ctx.timer_stop()
+            barrier()
+            sampler.unmark()
+            passes.append(max_over_ranks(t))
+        return min(passes), passes
 
     Xpin = eng.pin(X)                               # uint8 for this dataset (asserted below)
     assert Xpin.dtype == np.uint8, 'engine.pin did not take the byte path for binary data'
     e2e_steps = args.steps
-    e2e_ms = e2e_region(Xpin, tick[0]); tick[0] += N_BATCHES + e2e_steps
+    e2e_ms, e2e_passes = e2e_region(Xpin, tick[0]); tick[0] += N_BATCHES + args.warmup + 2 * e2e_steps
     e2e_value = e2e_steps * B * world * K_GIBBS / (e2e_ms * 1e-3)
     _native.pinned_free(Xpin)
     Xpin32 = _native.pinned_copy(X)
-    e2e32_ms = e2e_region(Xpin32, tick[0]); tick[0] += N_BATCHES + e2e_steps
+    e2e32_ms, e2e32_passes = e2e_region(Xpin32, tick[0]); tick[0] += N_BATCHES + args.warmup + 2 * e2e_steps
     e2e32_value = e2e_steps * B * world * K_GIBBS / (e2e32_ms * 1e-3)
     _native.pinned_free(Xpin32)
 
@@ -355,10 +359,12 @@ def main():
                      'step_frac': FLOP_PER_STEP * args.steps / (ms * 1e-3) / 1e12 / peak},
         'e2e': {'value': e2e_value, 'unit': 'updates/s', 'h2d_bytes_per_step': B * V * 1 * world,
                 'd2h_bytes_per_step': 64 * world, 'ms_per_step': e2e_ms / e2e_steps,
+                'timed_passes_ms_per_step': [t / e2e_steps for t in e2e_passes], 'reported': 'faster of two passes of K steps',
                 'path': 'bm_rbm_train_epoch_u8(pinned host dataset as BaseRBM.fit/engine.pin stores binary data: 1 byte per '
                         'unit, widened exactly on the device; msre read back every step): what BaseRBM._train_epoch calls'},
         'e2e_float32': {'value': e2e32_value, 'unit': 'updates/s', 'h2d_bytes_per_step': B * V * 4 * world,
                         'd2h_bytes_per_step': 64 * world, 'ms_per_step': e2e32_ms / e2e_steps,
+                        'timed_passes_ms_per_step': [t / e2e_steps for t in e2e32_passes],
                         'path': 'bm_rbm_train_epoch(pinned host float32 dataset, msre every step): PCIe-bound'},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -1105,9 +1105,10 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
 // The ops' descriptors (minus tensor maps) go to constant memory, stream-ordered before the launch;
 // skipped when the bank already holds exactly this image (the common case: the same program every step).
 static void upload_ops(Ctx* ctx, const TcPhase* ph, int n) {
-    static std::vector<unsigned char> current;
+    static std::map<int, std::vector<unsigned char>> images;     // constant memory is per device
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
+    std::vector<unsigned char>& current = images[ctx->device];
     std::vector<unsigned char> img((size_t)n * sizeof(TcPhaseLite));
     for (int i = 0; i < n; ++i) memcpy(img.data() + (size_t)i * sizeof(TcPhaseLite), &ph[i].l, sizeof(TcPhaseLite));
     if (img.size() <= current.size() && memcmp(img.data(), current.data(), img.size()) == 0) return;
@@ -1117,11 +1118,11 @@ static void upload_ops(Ctx* ctx, const TcPhase* ph, int n) {
 }
 
 static void do_launch(Ctx* ctx, TcLaunch& L, int cluster, double flops, int max_bn) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};                         // function attributes are per device
+    if (!attr_set[ctx->device & 63]) {
         BM_CUDA(cudaFuncSetAttribute(tc_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         BM_CUDA(cudaFuncSetAttribute(tc_program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     // ring stages sized for the widest tile of the launch: narrower tiles buy a deeper pipeline
     L.stage_bytes = A_BYTES + (max_bn / cluster) * BK * 2;
