@@ -4,13 +4,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module; the product package
 (``boltzmann-machines_b200/``) never does.
 
-PARITY STATUS: the RNG primitive is pinned by the reference's own KAT
-(oracle/philox.py).  Every *trained* quantity below (Gibbs stream, dW, PLL,
-MSRE, free energy) is **parity unpinned**: the reference's tests hold no golden
-value for them and the reference (Python 2 + TensorFlow 1.3)
-cannot be executed in this image.  The formulas follow the reference line by
-line; each method cites the lines it restates (paths relative to
-/root/reference/boltzmann_machines/).
+PARITY STATUS: pinned against the reference's OWN SOURCE for the RBM path.  tests/golden/reference_rbm_cases.json holds
+results of yell/boltzmann-machines' unmodified `BernoulliRBM / GaussianRBM / MultinomialRBM` classes (`fit` with
+schedules, dropout, fixed and variable-length chains, validation metrics, free-energy gap; `transform`; `init`;
+`get_tf_params`) executed with `oracle/tf1shim.py` in place of TensorFlow 1.3 (which cannot be installed here) and with
+the random ops answered from the Philox layout of oracle/philox.py; tests/test_z_reference_golden.py replays the same
+scenarios through the host mirror on this oracle (and, on the GPU, on the CUDA engine) and matches weights, momentum
+accumulators, MSRE / PLL / L2 / free-energy-gap logs and transforms to float rounding.  The RNG primitive and TF's
+weight-initialiser stream are pinned by the reference's own KAT (oracle/philox.py; reproduced through the reference's
+`init()` in the `init_from_seed` golden case).  NOT pinned: TensorFlow's own draw order for the Gibbs stream (it depends
+on graph construction order, SURVEY.md §8c -- the engine defines its own counter layout) and TensorFlow's kernels.
+Each method cites the lines it restates (paths relative to /root/reference/boltzmann_machines/).
 
 TF-1.3 op semantics relied on: ``tf.nn.dropout(x, keep)`` = x/keep*floor(keep+u);
 ``tf.nn.l2_loss(w)`` = sum(w**2)/2; ``tf.log_sigmoid(x)`` = -softplus(-x);
