@@ -231,8 +231,14 @@ class NativeModel(BaseModel, DtypeMixin):
                 continue
             for n in names:
                 if n in state:
-                    out[n if scope else '{0}/{1}'.format(sc, n)] = state[n]
+                    shown = self._tf_name(sc, n)
+                    out[shown if scope else '{0}/{1}'.format(sc, shown)] = state[n]
         return out
+
+    def _tf_name(self, scope, name):
+        """Key under which the reference's ``get_tf_params`` reports engine variable ``name`` (TF variable name
+        minus the scope prefix); identical to the engine's name unless a subclass says otherwise."""
+        return name
 
     def _scopes(self):
         return self._SCOPES

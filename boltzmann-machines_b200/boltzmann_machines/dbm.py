@@ -165,6 +165,14 @@ class DBM(EnergyBasedModel):
             'negative_particles': ('v',) + per('h'),
         }
 
+    def _tf_name(self, scope, name):
+        # the hidden particles are created inside `tf.name_scope('h_particle')` (dbm.py:371-383): TF names them
+        # negative_particles/h_particle/h, negative_particles/h_particle_1/h, ...
+        if scope == 'negative_particles' and name.startswith('h'):
+            i = name[2:]
+            return 'h_particle{0}/h'.format('_' + i if i else '')
+        return name
+
     def _engine_cfg(self):
         if self.layers_ is None:
             raise RuntimeError('the DBM has no layer description: call `load_rbms` (or load a saved model)')

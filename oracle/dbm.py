@@ -14,13 +14,19 @@ particles) and performs what the reference runs inside ``session.run``:
   * AIS                                        dbm.py:650-736
   * variational lower bound                    dbm.py:738-759
 
-PARITY STATUS: **parity unpinned** -- the reference has no DBM tests at all
- and cannot be executed here; formulas follow the reference line
-by line, including: the first mean-field sweep reads the *previous batch's* mu
-(dbm.py:459-467), the sparsity update indexes element i of the per-unit sum
-vector (dbm.py:581-586), X W_0 is doubled in the approximate-inference pass even
-for a single layer (dbm.py:438).  Random draws use the engine's Philox layout
-(oracle/philox.py); AIS importance weights are accumulated in float64.
+PARITY STATUS: pinned against the reference's OWN SOURCE.  tests/golden/reference_dbm_case.json holds the results of
+yell/boltzmann-machines' unmodified `DBM` class -- greedy pre-training of two RBMs, `fit` (mean-field E-step with its
+stale-mu start, PCD particles with a variable number of Gibbs steps, the sparsity update, max-norm, momentum),
+`transform`, `reconstruct`, `sample_v`, `log_proba` and `log_Z` (AIS) -- executed with oracle/tf1shim.py in place of
+TensorFlow 1.3 and the random ops answered from the Philox layout of oracle/philox.py;
+tests/test_z_reference_golden.py replays the scenario through the host mirror on this oracle (and, on the GPU, on the CUDA
+engine): every variable of every scope after `fit`, the MSRE / n_mf_updates logs, the query results and the AIS
+log-weights (to 5e-6) agree.  The quirks the restatement carries over are therefore confirmed by the reference's code:
+the first mean-field sweep reads the *previous batch's* mu (dbm.py:459-467), the sparsity update indexes element i of
+the per-unit sum vector (dbm.py:581-586), X W_0 is doubled in the approximate-inference pass even for a single layer
+(dbm.py:438), validation metrics advance the persistent chains (dbm.py:523).  NOT pinned: TensorFlow's own draw order
+(the engine defines its own counter layout) and TensorFlow's kernels.  AIS importance weights are accumulated in
+float64 here (float32 in the reference's graph).
 """
 import numpy as np
 

@@ -1,12 +1,13 @@
-"""A small lazy-graph stand-in for the TensorFlow-1.3 API surface that yell/boltzmann-machines' RBM classes use
+"""A small lazy-graph stand-in for the TensorFlow-1.3 API surface that yell/boltzmann-machines' RBM and DBM classes use
 -- TEST INFRASTRUCTURE ONLY (never imported by the product package, never shipped to users).
 
 Why it exists: the reference's arithmetic lives in `tensorflow-gpu~=1.3.0` (requirements.txt:11), which cannot be
 installed in this image (Python 3.12, no network), so the reference cannot run as it is.  Its *model code*, however
 -- boltzmann_machines/rbm/base_rbm.py (graph construction, gradients, sparsity, momentum, metrics, the fit loop),
-rbm/rbm.py (free energies), layers.py (unit types), base/tf_model.py (sessions, persistence) -- is plain Python that
+rbm/rbm.py (free energies), dbm.py (mean-field, PCD, AIS), layers.py (unit types), base/tf_model.py (sessions,
+persistence) -- is plain Python that
 only CALLS TensorFlow.  `install()` registers this module as `tensorflow` (plus empty stand-ins for nose / matplotlib /
-seaborn / keras, which the reference imports but the path does not use); tests/golden/make_reference_rbm_golden.py then
+seaborn / keras, which the reference imports but the path does not use); tests/golden/make_reference_golden.py then
 imports the reference UNMODIFIED from /root/reference and runs its own `fit()` / `transform()` / `get_tf_params()`.
 What is executed is therefore the reference's formulas, in the reference's order; what is restated here is the
 semantics of ~60 TensorFlow ops on numpy arrays (matmul, sigmoid, reduce_mean, assign, ...), each a few lines.
@@ -84,6 +85,7 @@ class Graph(object):
         self.used_names = {}
         self.seed = None
         self.random_provider = default_random_provider
+        self.control_stack = []                    # tf.control_dependencies contexts being built
 
     @contextlib.contextmanager
     def as_default(self):
@@ -152,8 +154,9 @@ class RunContext(object):
         self.session, self.feed, self.run_index = session, feed, run_index
         self.memo = {}
         self.snapshot = dict(session.values)       # variable values before this run
-        self.loop_iter = None
-        self.bound = {}                            # loop variables of the while_loop being executed
+        self.loop_iter = None                      # iteration of the innermost while_loop being executed
+        self.loop_stack = ()                       # ... of every enclosing while_loop, outermost first
+        self.bound = {}                            # loop variables of the while_loops being executed
 
 
 class Tensor(object):
@@ -168,6 +171,9 @@ class Tensor(object):
         full = g.unique(g.used_names, full)
         self.name = full + ':0'
         g.by_name[self.name] = self
+        # ops created under tf.control_dependencies(ops) run after `ops`; TF-1 reference variables are read when
+        # the consuming op executes, so such an op sees the values those assigns left behind
+        self.control_inputs = [c for frame in g.control_stack for c in frame]
 
     # -- evaluation -------------------------------------------------------------------
     def _value(self, ctx):
@@ -176,6 +182,10 @@ class Tensor(object):
             return ctx.memo[key]
         if self in ctx.feed:
             v = ctx.feed[self]
+        elif self.control_inputs:
+            for c in self.control_inputs:
+                _val(ctx, c)
+            v = self.fn(ctx, *[_val_late(ctx, i) for i in self.inputs])
         else:
             v = self.fn(ctx, *[_val(ctx, i) for i in self.inputs])
         ctx.memo[key] = v
@@ -185,7 +195,7 @@ class Tensor(object):
         return (session or _default_session).run(self, feed_dict=feed_dict)
 
     def get_shape(self):
-        return self.attrs.get('static_shape')
+        return TensorShape(self.attrs.get('static_shape'))
 
     def __hash__(self):
         return id(self)
@@ -222,6 +232,30 @@ def _val(ctx, x):
     if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in x):
         return np.stack([np.asarray(_val(ctx, e)) for e in x])
     return x
+
+
+def _val_late(ctx, x):
+    """Like _val, but a Variable (also inside a list) is read NOW from the session, not from the pre-run snapshot."""
+    if isinstance(x, Variable):
+        if x in ctx.feed:
+            return ctx.feed[x]
+        return ctx.session.values[x]
+    if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in x):
+        return np.stack([np.asarray(_val_late(ctx, e)) for e in x])
+    return _val(ctx, x)
+
+
+@contextlib.contextmanager
+def control_dependencies(ops):
+    g = _default_graph
+    flat = []
+    for o in (ops or []):
+        flat.extend(o if isinstance(o, (list, tuple)) else [o])
+    g.control_stack.append([o for o in flat if isinstance(o, Tensor)])
+    try:
+        yield
+    finally:
+        g.control_stack.pop()
 
 
 def _dtype_of(x):
@@ -364,9 +398,44 @@ def multiply(a, b, name=None):
 def divide(a, b, name=None): return _binary('Div', np.true_divide, a, b)
 def square(x, name=None): return _unary('Square', np.square, x)
 def exp(x, name=None): return _unary('Exp', np.exp, x)
-def log(x, name=None): return _unary('Log', np.log, x)
+def log(x, name=None): return _unary('Log', np.log, convert_to_tensor(x))
 def sqrt(x, name=None): return _unary('Sqrt', np.sqrt, x)
 def negative(x, name=None): return _unary('Neg', np.negative, x)
+
+
+def assign(ref, value, validate_shape=None, use_locking=None, name=None):
+    return ref.assign(value)
+
+
+def minimum(a, b, name=None): return _binary('Minimum', np.minimum, a, b)
+def maximum(a, b, name=None): return _binary('Maximum', np.maximum, a, b)
+def logical_and(a, b, name=None): return _binary('LogicalAnd', np.logical_and, a, b, out_dtype=bool)
+
+
+def clip_by_value(x, lo, hi, name=None):
+    d = _dtype_of(x)
+    return Tensor('ClipByValue', [x], lambda ctx, v: np.clip(v, np.asarray(lo, dtype=d or None), np.asarray(hi, dtype=d or None)),
+                  dtype=x.dtype)
+
+
+def norm(x, ord='euclidean', axis=None, keep_dims=False, name=None):        # noqa: A002
+    def fn(ctx, v):
+        v = np.asarray(v)
+        if ord in (np.inf, 'inf'):
+            r = np.max(np.abs(v), axis=axis, keepdims=keep_dims)
+        elif ord in ('euclidean', 2, 'fro'):
+            r = np.sqrt(np.sum(np.square(v), axis=axis, keepdims=keep_dims))
+        elif ord == 1:
+            r = np.sum(np.abs(v), axis=axis, keepdims=keep_dims)
+        else:
+            raise NotImplementedError(ord)
+        return np.asarray(r, dtype=v.dtype)
+    return Tensor('Norm', [x], fn, dtype=x.dtype)
+
+
+class TensorShape(object):
+    def __init__(self, dims=None):
+        self.dims = dims
 
 
 def _lgamma(x):
@@ -520,11 +589,13 @@ def _random(kind, inputs, shape_of, dtype, op_seed=None, name=None, post=None, *
         if prov is None:
             raise RuntimeError('no random provider installed on the graph (tf1shim)')
         req = RandomRequest(kind=kind, scope=t.scope, name=t.name, shape=tuple(shape_of(*vals)),
-                            dtype=as_np_dtype(dtype), graph_seed=t.graph.seed, op_seed=op_seed,
-                            run_index=ctx.run_index, loop_iter=ctx.loop_iter, args=vals, **extra)
+                            dtype=as_np_dtype(dtype), graph_seed=t.graph.seed, op_seed=op_seed, graph=t.graph,
+                            run_index=ctx.run_index, loop_iter=ctx.loop_iter, loop_stack=ctx.loop_stack,
+                            args=vals, **extra)
         out = prov(req)
         return post(out, *vals) if post else out
     t = Tensor(kind, inputs, fn, name=name or kind, dtype=dtype)
+    t.op_seed, t.random_kind = op_seed, kind
     t_holder.append(t)
     return t
 
@@ -587,7 +658,7 @@ class _Distribution(object):
 
 class Bernoulli(_Distribution):
     def __init__(self, logits=None, probs=None, dtype=int32, name='Bernoulli'):
-        self.probs = probs
+        self.probs = probs if probs is not None else nn.sigmoid(logits)
 
     def sample(self, sample_shape=(), seed=None, name='sample'):
         return _random('bernoulli', [self.probs], lambda p: np.shape(p), int32, seed, 'Bernoulli/sample')
@@ -615,40 +686,69 @@ class Multinomial(_Distribution):
 # ------------------------------------------------------------------------------------------
 # control flow
 # ------------------------------------------------------------------------------------------
-def while_loop(cond, body, loop_vars, back_prop=True, parallel_iterations=10, name=None, **kwargs):
-    """Builds cond/body once on symbolic loop variables; every output tensor re-runs the loop when evaluated in a run
-    (memoised per run, so the six outputs of the Gibbs chain share one execution)."""
+def _flatten(struct):
+    if isinstance(struct, (list, tuple)):
+        out = []
+        for e in struct:
+            out.extend(_flatten(e))
+        return out
+    return [struct]
+
+
+def _unflatten(struct, flat):
+    """Rebuild `struct`'s nesting (lists of lists) from the iterator `flat`."""
+    if isinstance(struct, (list, tuple)):
+        return [_unflatten(e, flat) for e in struct]
+    return next(flat)
+
+
+def while_loop(cond, body, loop_vars, shape_invariants=None, back_prop=True, parallel_iterations=10, name=None, **kwargs):
+    """Builds cond/body once on symbolic loop variables (nested lists allowed); every output tensor re-runs the loop
+    when evaluated in a run (memoised per run, so the outputs of one loop share one execution).  A loop built under
+    tf.control_dependencies runs after those ops and reads Variable loop inputs as they are then."""
+    g = _default_graph
+    control = [c for frame in g.control_stack for c in frame]
     with name_scope(name or 'while'):
-        init = [convert_to_tensor(v) for v in loop_vars]
+        init = [v if isinstance(v, Tensor) else convert_to_tensor(v) for v in _flatten(loop_vars)]
         syms = []
         for i, v in enumerate(init):
             s = Tensor('loop_var', [], None, name='loop_var_%d' % i, dtype=v.dtype)
             s.fn = (lambda ss: (lambda ctx: ctx.bound[ss]))(s)
+            s.control_inputs = []
             syms.append(s)
-        cond_t = convert_to_tensor(cond(*syms))
-        outs = [convert_to_tensor(o) for o in body(*syms)]
+        sym_struct = _unflatten(loop_vars, iter(syms))
+        cond_t = convert_to_tensor(cond(*sym_struct))
+        outs = [o if isinstance(o, Tensor) else convert_to_tensor(o) for o in _flatten(list(body(*_unflatten(loop_vars, iter(syms)))))]
+        assert len(outs) == len(init), 'while_loop body returned another structure'
     state = {}
 
     def run_loop(ctx):
         key = ('while', id(state))
         if key in ctx.memo:
             return ctx.memo[key]
-        vals = [_val(ctx, v) for v in init]
-        outer_memo, outer_bound, outer_iter = ctx.memo, ctx.bound, ctx.loop_iter
+        for c in control:
+            _val(ctx, c)
+        vals = [(_val_late if control else _val)(ctx, v) for v in init]
+        outer_memo, outer_bound, outer_iter, outer_stack = ctx.memo, ctx.bound, ctx.loop_iter, ctx.loop_stack
         it = 0
         while True:
-            ctx.memo = dict((k, v) for k, v in outer_memo.items())      # nodes of the enclosing run stay evaluated once
-            ctx.bound = dict(zip(syms, vals))
-            ctx.loop_iter = it
+            ctx.memo = dict(outer_memo)             # nodes of the enclosing run / iteration stay evaluated once
+            ctx.bound = dict(outer_bound)
+            ctx.bound.update(zip(syms, vals))
+            ctx.loop_iter, ctx.loop_stack = it, outer_stack + (it,)
             if not np.asarray(_val(ctx, cond_t)).item():
                 break
             vals = [_val(ctx, o) for o in outs]
             it += 1
-        ctx.memo, ctx.bound, ctx.loop_iter = outer_memo, outer_bound, outer_iter
+        ctx.memo, ctx.bound, ctx.loop_iter, ctx.loop_stack = outer_memo, outer_bound, outer_iter, outer_stack
         ctx.memo[key] = vals
         return vals
-    return [Tensor('while_out', [], (lambda i: (lambda ctx: run_loop(ctx)[i]))(i), name='Exit', dtype=init[i].dtype)
-            for i in builtins_range(len(init))]
+    results = []
+    for i in builtins_range(len(init)):
+        t = Tensor('while_out', [], (lambda k: (lambda ctx: run_loop(ctx)[k]))(i), name='Exit', dtype=init[i].dtype)
+        t.control_inputs = []                       # handled inside run_loop
+        results.append(t)
+    return _unflatten(loop_vars, iter(results))
 
 
 import builtins as _builtins      # noqa: E402

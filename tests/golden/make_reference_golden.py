@@ -1,8 +1,9 @@
-"""Golden vectors from the REFERENCE'S OWN RBM CODE: tests/golden/reference_rbm_cases.json.
+"""Golden vectors from the REFERENCE'S OWN RBM AND DBM CODE: tests/golden/reference_rbm_cases.json,
+tests/golden/reference_dbm_case.json.
 
 Run in the build container only (reads /root/reference):
 
-    python tests/golden/make_reference_rbm_golden.py
+    python tests/golden/make_reference_golden.py
 
 yell/boltzmann-machines is imported unmodified from /root/reference with `oracle/tf1shim.py` registered as
 `tensorflow` (TensorFlow 1.3 itself cannot be installed here).  For every case below the reference's own
@@ -47,10 +48,53 @@ def gibbs_index(req):
     return False, 0
 
 
+AIS = {'seed': None, 'k': 1}     # set around DBM.log_Z: the mirror draws a dedicated AIS seed per call (dbm.py:701)
+
+
+def dbm_provider(req, seed, tick, shape):
+    """Random ops of the reference's DBM graph (dbm.py:362-383 particle initialisers, :385-427 Gibbs step,
+    :641-648 sample_v, :660-736 AIS) -> the draw sites of oracle/dbm.py."""
+    parts = req.scope.split('/')
+    if parts[0] == 'negative_particles':            # layer.init(batch_size=n_particles); *_new buffers are never read
+        leaf = req.name.split('/')[-1].split(':')[0]
+        if leaf.endswith('_1'):
+            return np.zeros(shape, dtype=req.dtype)
+        idx = 0
+        if len(parts) > 1:
+            idx = 1 + (0 if parts[1] == 'h_particle' else int(parts[1].split('_')[-1]))
+        ais_ops = [t for t in req.graph.by_name.values()
+                   if getattr(t, 'random_kind', None) == 'bernoulli' and getattr(t, 'op_seed', None) is not None]
+        assert len(ais_ops) == 1                     # Bernoulli(logits).sample(seed=self.make_random_seed()), dbm.py:701
+        return P.uniform_at(shape[0], shape[1], int(ais_ops[0].op_seed), P.SITE_PARTICLE_INIT, idx, 0).astype(req.dtype)
+    if 'annealed_importance_sampling' in parts:
+        assert req.kind == 'bernoulli'
+        p = np.asarray(req.args[0])
+        if req.op_seed is not None:                  # x_0 ~ Ber(0.5)
+            u = P.uniform_at(shape[0], shape[1], AIS['seed'], P.SITE_AIS_INIT, 0, 0)
+            return (u < np.float32(0.5)).astype(np.int32)
+        stack = req.loop_stack
+        it, s = (0, stack[0]) if len(stack) == 1 else (stack[0] + 1, stack[1])
+        leaf = req.name.split('/')[-1].split(':')[0]          # sample, sample_1, sample_2: v, h2, x_hat (creation order)
+        site = {'sample': P.SITE_AIS_V, 'sample_1': P.SITE_AIS_H2, 'sample_2': P.SITE_AIS_H1}[leaf]
+        u = P.uniform_at(shape[0], shape[1], AIS['seed'], site, 0, it * AIS['k'] + s)
+        return (u.astype(p.dtype) < p).astype(np.int32)
+    assert 'gibbs_chain' in parts and req.kind == 'bernoulli', (req.scope, req.kind)
+    leaf = [q for q in parts if q.startswith('sample_')][-1]
+    site = P.SITE_DBM_V if leaf.startswith('sample_v_hat') else P.SITE_DBM_H + int(leaf[len('sample_h'):].split('_')[0])
+    p = np.asarray(req.args[0])
+    u = P.uniform_at(shape[0], shape[1], seed, site, req.loop_iter + 1, tick)
+    return (u.astype(p.dtype) < p).astype(np.int32)
+
+
 def provider(req):
     seed = req.graph_seed if req.graph_seed is not None else FALLBACK_SEED
     tick = req.run_index
     shape = tuple(int(s) for s in req.shape)
+    top = req.scope.split('/')[0]
+    if top in ('negative_particles', 'annealed_importance_sampling') or \
+            (req.kind == 'bernoulli' and ('gibbs_chain/while' in req.scope) and 'sample_h_given_v' not in req.scope
+             and 'sample_v_given_h' not in req.scope):
+        return dbm_provider(req, seed, tick, shape)
     if req.kind == 'normal':                        # W initialiser: tf.random_normal(..., seed=random_seed)
         assert req.scope.startswith('weights') and req.op_seed is not None, req.scope
         return P.tf_random_normal(shape, req.stddev, int(req.op_seed), np.dtype(req.dtype).name)
@@ -132,6 +176,62 @@ def cases():
     return out
 
 
+def run_dbm_case(ref, workdir):
+    """Greedy pre-training of two RBMs, then DBM.fit / transform / reconstruct / sample_v / log_proba / log_Z --
+    dbm_mnist.py's sequence in miniature -- all through the reference's public API."""
+    from oracle.rbm import sigmoid as _s      # noqa: F401
+    rng = np.random.RandomState(21)
+    V, H1, H2 = 16, 10, 6
+    X = (rng.rand(24, V) < 0.3).astype(np.float32)
+    X_val = (rng.rand(16, V) < 0.3).astype(np.float32)
+    rbm_kw = [dict(n_visible=V, n_hidden=H1, W_init=(0.1 * rng.randn(V, H1)).astype(np.float32), n_gibbs_steps=1,
+                   learning_rate=0.05, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3, dbm_first=True, random_seed=101,
+                   verbose=False, save_after_each_epoch=False),
+              dict(n_visible=H1, n_hidden=H2, W_init=(0.1 * rng.randn(H1, H2)).astype(np.float32), n_gibbs_steps=2,
+                   learning_rate=0.05, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3, dbm_last=True, random_seed=202,
+                   verbose=False, save_after_each_epoch=False)]
+    dbm_kw = dict(n_particles=8, n_gibbs_steps=[1, 2], max_mf_updates=5, mf_tol=1e-5, learning_rate=[0.02, 0.01],
+                  momentum=[0.5, 0.9], max_epoch=3, batch_size=8, l2=1e-4, max_norm=0.6, sample_v_states=True,
+                  sample_h_states=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[1e-2, 5e-3],
+                  sparsity_damping=0.8, train_metrics_every_iter=2, val_metrics_every_epoch=1, verbose=False,
+                  save_after_each_epoch=True, random_seed=303)
+    rbm1 = ref.rbm.BernoulliRBM(model_path=os.path.join(workdir, 'rbm1') + '/', **rbm_kw[0])
+    rbm1.fit(X)
+    Q = rbm1.transform(X)
+    rbm2 = ref.rbm.BernoulliRBM(model_path=os.path.join(workdir, 'rbm2') + '/', **rbm_kw[1])
+    rbm2.fit(Q)
+    dbm = ref.DBM(rbms=[rbm1, rbm2], model_path=os.path.join(workdir, 'dbm') + '/', **dbm_kw)
+    log = {'train': [], 'val': []}
+    for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
+        orig = getattr(dbm, meth)
+
+        def wrapped(*a, _orig=orig, _key=key, **k):
+            r = _orig(*a, **k)
+            log[_key].append([None if v is None else float(v) for v in r])
+            return r
+        setattr(dbm, meth, wrapped)
+    dbm.fit(X, X_val)
+    rec = {'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
+           'dbm_kw': dbm_kw, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
+           'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_)}
+    scopes = ('weights', 'grads_accumulators', 'variational_params', 'hidden_means_accumulators', 'negative_particles')
+    rec['after_fit'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()} for sc in scopes}
+    rec['transform'] = tolist(dbm.transform(X[:16]))
+    rec['reconstruct'] = tolist(dbm.reconstruct(X[:8]))
+    rec['sample_v'] = tolist(dbm.sample_v(n_gibbs_steps=2))
+    rec['log_proba'] = tolist(dbm.log_proba(X_val, log_Z=0.0))
+    # the mirror's log_Z draws the call seed and then a dedicated AIS seed from the model's RNG
+    peek = type(dbm._rng)(seed=None).set_state(json.loads(json.dumps(dbm._rng.get_state())))
+    peek.randint(2 ** 31 - 1)
+    AIS['seed'], AIS['k'] = int(peek.randint(2 ** 31 - 1)), 2
+    log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=20, n_runs=6, n_gibbs_steps=2)
+    rec['log_Z'] = {'n_betas': 20, 'n_runs': 6, 'n_gibbs_steps': 2, 'log_mean': float(log_mean), 'log_low': float(log_low),
+                    'log_high': float(log_high), 'values': tolist(values)}
+    rec['after_queries'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()}
+                            for sc in ('weights', 'negative_particles')}
+    return rec
+
+
 def tolist(a):
     return None if a is None else np.asarray(a).tolist()
 
@@ -168,6 +268,24 @@ def main():
     tf1shim.default_random_provider = provider
     tf1shim.install()
     sys.path[:0] = ['/root/reference', '/root/reference/boltzmann_machines']
+    # rbm/rbm.py imports `layers` as a top-level module (rbm/env.py puts the package directory on sys.path) while dbm.py
+    # imports `.layers`: two module objects, and DBM.log_Z / log_proba assert isinstance(layer, BernoulliLayer) across
+    # them (dbm.py:927,948).  Serve the one module under both names -- an import alias, no source change.
+    import importlib.abc
+    import importlib.util
+
+    class _LayersAlias(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def find_spec(self, name, path=None, target=None):
+            if name == 'layers' and 'boltzmann_machines.layers' in sys.modules:
+                return importlib.util.spec_from_loader(name, self)
+            return None
+
+        def create_module(self, spec):
+            return sys.modules['boltzmann_machines.layers']
+
+        def exec_module(self, module):
+            pass
+    sys.meta_path.insert(0, _LayersAlias())
     import boltzmann_machines as ref                     # the reference package, unmodified
     assert ref.__file__.startswith('/root/reference/'), ref.__file__
     work = tempfile.mkdtemp(prefix='bm_golden_')
@@ -175,16 +293,22 @@ def main():
     try:
         os.chdir(work)
         recs = [run_case(ref.rbm, c, work) for c in cases()]
+        dbm_rec = run_dbm_case(ref, work)
     finally:
         os.chdir(cwd)
         shutil.rmtree(work, ignore_errors=True)
     out = {'source': 'yell/boltzmann-machines (boltzmann_machines/rbm, layers.py, base/tf_model.py) executed unmodified on '
-                     'oracle/tf1shim.py; random draws from the shared Philox layout (tests/golden/make_reference_rbm_golden.py)',
+                     'oracle/tf1shim.py; random draws from the shared Philox layout (tests/golden/make_reference_golden.py)',
            'cases': recs}
     path = os.path.join(HERE, 'reference_rbm_cases.json')
     with open(path, 'w') as fh:
         json.dump(out, fh)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(recs), 'cases')
+    dpath = os.path.join(HERE, 'reference_dbm_case.json')
+    with open(dpath, 'w') as fh:
+        json.dump({'source': out['source'].replace('boltzmann_machines/rbm, layers.py', 'boltzmann_machines/dbm.py, rbm, layers.py'),
+                   'case': dbm_rec}, fh)
+    print('wrote', dpath, os.path.getsize(dpath), 'bytes; dbm log', dbm_rec['log'], 'log_Z', dbm_rec['log_Z']['log_mean'])
     for r in recs:
         print(' ', r['name'], 'iter_', r['iter_'], 'train log', r['log']['train'][-1:] , 'feg', r['log']['feg'])
 

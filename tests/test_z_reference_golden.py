@@ -1,5 +1,5 @@
 """The host mirror + oracle (CPU) and the host mirror + CUDA engine (GPU, fp32 compute) against golden vectors
-produced by the REFERENCE'S OWN RBM code (tests/golden/make_reference_rbm_golden.py: yell/boltzmann-machines imported
+produced by the REFERENCE'S OWN RBM code (tests/golden/make_reference_golden.py: yell/boltzmann-machines imported
 unmodified, TensorFlow replaced by oracle/tf1shim.py, random ops answered from the shared Philox layout).
 
 Each case replays a whole public-API scenario -- fit() with schedules / validation metrics / free-energy gap,
@@ -92,3 +92,83 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
             close(got.get(m), v, mtol[m], 'val ' + m)
     # a free energy is a sum over ~V+H terms of magnitude ~10: float32 rounding of the batch means dominates
     close(log['feg'], case['log']['feg'], 5e-4 if dt == 'float32' else 1e-8, 'feg')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DBM: greedy pre-training, DBM.fit, transform, reconstruct, sample_v, log_proba, log_Z -- the reference's dbm.py
+# (mean-field with its stale-mu start, PCD particles, sparsity quirk, max-norm, AIS) executed on the shim
+# ---------------------------------------------------------------------------------------------------------
+DBM_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_case.json')))['case']
+
+
+@pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
+def both_engines(request, monkeypatch):
+    from boltzmann_machines.base import set_engine_factory
+    if request.param == 'oracle':
+        from oracle.rbm import rbm_factory
+        from oracle.dbm import dbm_factory
+        old = set_engine_factory('rbm', rbm_factory), set_engine_factory('dbm', dbm_factory)
+    else:
+        monkeypatch.setenv('BM_COMPUTE', 'fp32')
+        old = set_engine_factory('rbm', None), set_engine_factory('dbm', None)
+    yield request.param
+    set_engine_factory('rbm', old[0])
+    set_engine_factory('dbm', old[1])
+
+
+def test_dbm_scenario_matches_the_reference(both_engines, workdir):
+    from boltzmann_machines import DBM
+    from boltzmann_machines.rbm import BernoulliRBM
+    g = DBM_GOLD
+    tol = 2e-5 if both_engines == 'oracle' else 2e-4
+    X, X_val = np.asarray(g['X'], dtype=np.float32), np.asarray(g['X_val'], dtype=np.float32)
+    rbms = []
+    inp = X
+    for i, kw in enumerate(g['rbm_kw']):
+        kw = dict(kw)
+        kw['W_init'] = np.asarray(kw['W_init'], dtype=np.float32)
+        r = BernoulliRBM(model_path=os.path.join(str(workdir), 'rbm%d' % i) + '/', **kw)
+        r.fit(inp)
+        if i == 0:
+            inp = r.transform(X)
+            close(inp, g['Q'], tol * 5, 'rbm1.transform')
+        rbms.append(r)
+    dbm = DBM(rbms=rbms, model_path=os.path.join(str(workdir), 'dbm') + '/', **g['dbm_kw'])
+    log = {'train': [], 'val': []}
+    for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
+        orig = getattr(dbm, meth)
+
+        def wrapped(*a, _orig=orig, _key=key, **k):
+            r = _orig(*a, **k)
+            log[_key].append(list(r))
+            return r
+        setattr(dbm, meth, wrapped)
+    dbm.fit(X, X_val)
+    assert (int(dbm.epoch_), int(dbm.iter_)) == (g['epoch_'], g['iter_'])
+    for key in ('train', 'val'):
+        assert len(log[key]) == len(g['log'][key])
+        for got, want in zip(log[key], g['log'][key]):
+            close(got[0], want[0], 10 * tol, key + ' msre')
+            assert got[1] == want[1], key + ' n_mf_updates'
+    for scope, want in g['after_fit'].items():
+        got = dbm.get_tf_params(scope=scope)
+        for k, v in want.items():
+            if k.endswith('_new') or k.startswith('mu_new'):
+                continue                      # scratch buffers of the TF graph (ping-pong halves): no counterpart
+            close(got[k], v, tol, 'after fit: {0}/{1}'.format(scope, k))
+    close(dbm.transform(X[:16]), g['transform'], 5 * tol, 'transform')
+    close(dbm.reconstruct(X[:8]), g['reconstruct'], 5 * tol, 'reconstruct')
+    close(dbm.sample_v(n_gibbs_steps=2), g['sample_v'], 5 * tol, 'sample_v')
+    close(dbm.log_proba(X_val, log_Z=0.0), g['log_proba'], 2e-4, 'log_proba')
+    z = g['log_Z']
+    log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=z['n_betas'], n_runs=z['n_runs'], n_gibbs_steps=z['n_gibbs_steps'])
+    # the reference accumulates the importance weights in float32, the engines in float64
+    np.testing.assert_allclose(values, z['values'], rtol=0, atol=2e-4 if both_engines == 'oracle' else 2e-3, err_msg='AIS log-weights')
+    np.testing.assert_allclose([log_mean, log_low, log_high], [z['log_mean'], z['log_low'], z['log_high']], rtol=0, atol=1e-3 if both_engines == 'oracle' else 5e-3,
+                               err_msg='log_Z summary')
+    for scope, want in g['after_queries'].items():
+        got = dbm.get_tf_params(scope=scope)
+        for k, v in want.items():
+            if k.endswith('_new'):
+                continue
+            close(got[k], v, tol, 'after queries: {0}/{1}'.format(scope, k))
