@@ -163,6 +163,22 @@ class NativeModel(BaseModel, DtypeMixin):
         with np.load(path) as z:
             self._engine.set_params({k: z[k] for k in z.files})
 
+    # ---- scalar summaries (tf_model.py:110-115: tf.summary.FileWriter on logs/train, logs/val) ----------
+    def _log_scalars(self, kind, step, values):
+        """Append ``{"step": step, tag: value, ...}`` to ``<model>/logs/<kind>/scalars.jsonl`` -- the
+        scalar summaries the reference hands to its TensorBoard writers, as one JSON object per line
+        (``kind`` in {'train', 'val'}; tags are the reference's summary tags)."""
+        values = {k: float(v) for k, v in values.items() if v is not None}
+        if not values:
+            return
+        d = self._train_summary_dirpath if kind == 'train' else self._val_summary_dirpath
+        if not os.path.isdir(d):
+            os.makedirs(d)
+        rec = {'step': int(step)}
+        rec.update(values)
+        with open(os.path.join(d, 'scalars.jsonl'), 'a') as fh:
+            fh.write(json.dumps(rec, sort_keys=True) + '\n')
+
     def _save_model(self, global_step=None):
         for d in (self._train_summary_dirpath, self._val_summary_dirpath):
             if not os.path.exists(d):

@@ -244,6 +244,8 @@ class DBM(EnergyBasedModel):
             got = self._engine.train_step(X[lo:hi], tick=self._next_tick(), metrics=report, **self._step_args())
             if report:
                 msres.append(got['msre']); n_mfs.append(got['n_mf_updates'])
+                self._log_scalars('train', self.iter_, {'mean_squared_recon_error': got['msre'],        # dbm.py:636-639
+                                                        'n_mf_updates': got['n_mf_updates']})
         return (float(np.mean(msres)) if msres else None, float(np.mean(n_mfs)) if n_mfs else None)
 
     def _run_val_metrics(self, X_val):
@@ -252,6 +254,8 @@ class DBM(EnergyBasedModel):
         for lo, hi in batch_bounds(len(X_val), self.batch_size):
             got = self._engine.val_metrics(X_val[lo:hi], k=a['k'], seed=a['seed'], tick=self._next_tick())
             msres.append(got['msre']); n_mfs.append(got['n_mf_updates'])
+        self._log_scalars('val', self.iter_, {'mean_squared_recon_error': np.mean(msres),              # dbm.py:818-823
+                                              'n_mf_updates': np.mean(n_mfs)})
         return float(np.mean(msres)), float(np.mean(n_mfs))
 
     def _fit(self, X, X_val=None, *args, **kwargs):

@@ -58,6 +58,9 @@ class BaseRBM(EnergyBasedModel):
         'grads_accumulators': ('dW', 'dvb', 'dhb'),
         'hidden_activations_means': ('q_means',),
     }
+    # summary tags of the reference (base_rbm.py:179-184)
+    _METRIC_TAGS = {'feg': 'free_energy_gap', 'l2_loss': 'l2_loss', 'msre': 'mean_squared_reconstruction_error',
+                    'pll': 'pseudo_loglikelihood'}
     _TRAIN_METRICS = ('l2_loss', 'msre', 'pll')
     _VAL_METRICS = ('msre', 'pll')
 
@@ -220,6 +223,10 @@ class BaseRBM(EnergyBasedModel):
             got = self._engine.train_epoch(X, self.batch_size, tick0=self._tick, metrics=wanted,
                                            every=every or 0, iter0=self.iter_, **self._step_args())
             self._tick += len(bounds)
+            if every:
+                steps = [self.iter_ + i + 1 for i in range(len(bounds)) if (self.iter_ + i + 1) % every == 0]
+                for j, step in enumerate(steps):
+                    self._log_scalars('train', step, {self._METRIC_TAGS[m]: got[m][j] for m in wanted})
             self.iter_ += len(bounds)
             return {m: (float(np.mean(got[m])) if got[m] else None) for m in wanted}
         for lo, hi in _maybe_bar(bounds, self.verbose, leave=False, ncols=64, desc='epoch'):
@@ -229,6 +236,8 @@ class BaseRBM(EnergyBasedModel):
                                           metrics=report, **self._step_args())
             for m in report:
                 sums[m].append(got[m])
+            if report:
+                self._log_scalars('train', self.iter_, {self._METRIC_TAGS[m]: got[m] for m in report})
         return {m: (float(np.mean(v)) if v else None) for m, v in sums.items()}
 
     def _run_val_metrics(self, X_val):
@@ -241,7 +250,9 @@ class BaseRBM(EnergyBasedModel):
                                            tick=self._next_tick(), names=wanted)
                 for m in wanted:
                     acc[m].append(got[m])
-        return {m: (float(np.mean(v)) if v else None) for m, v in acc.items()}
+        res = {m: (float(np.mean(v)) if v else None) for m, v in acc.items()}
+        self._log_scalars('val', self.iter_, {self._METRIC_TAGS[m]: v for m, v in res.items()})   # base_rbm.py:584-589
+        return res
 
     def _mean_free_energy(self, X):
         a = self._step_args()
@@ -254,7 +265,9 @@ class BaseRBM(EnergyBasedModel):
     def _run_feg(self, X, X_val):
         """Free-energy gap (validation minus training): ~0 when not overfitting."""
         train_fe = self._mean_free_energy(X)
-        return self._mean_free_energy(X_val) - train_fe
+        feg = self._mean_free_energy(X_val) - train_fe
+        self._log_scalars('val', self.iter_, {self._METRIC_TAGS['feg']: feg})                      # base_rbm.py:617-621
+        return feg
 
     def _fit(self, X, X_val=None, *args, **kwargs):
         X = np.ascontiguousarray(X, dtype=self._np_dtype)

@@ -211,7 +211,8 @@ def run_dbm_case(ref, workdir):
             return r
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
-    rec = {'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
+    dbm_summaries = summaries_of(dbm)
+    rec = {'summaries': dbm_summaries, 'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
            'dbm_kw': dbm_kw, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
            'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_)}
     scopes = ('weights', 'grads_accumulators', 'variational_params', 'hidden_means_accumulators', 'negative_particles')
@@ -230,6 +231,15 @@ def run_dbm_case(ref, workdir):
     rec['after_queries'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()}
                             for sc in ('weights', 'negative_particles')}
     return rec
+
+
+def summaries_of(model):
+    """What the reference handed to its TensorBoard writers during the last public call: the steps of the merged
+    train summaries and the (step, {tag: value}) records of the validation writer (tf_model.py:110-115)."""
+    val = []
+    for step, proto in model._tf_val_writer.events:
+        val.append([int(step), {v.tag: float(v.simple_value) for v in proto.value}])
+    return {'train_steps': [int(step) for step, _ in model._tf_train_writer.events], 'val': val}
 
 
 def tolist(a):
@@ -256,6 +266,7 @@ def run_case(ref_rbm, case, workdir):
         model.init()
     else:
         model.fit(case['X'], case['X_val'])
+        rec['summaries'] = summaries_of(model)
         rec['transform'] = tolist(model.transform(case['X'][:case['transform_rows']]))
     rec['weights'] = {k: tolist(v) for k, v in model.get_tf_params(scope='weights').items()}
     rec['grads_accumulators'] = {k: tolist(v) for k, v in model.get_tf_params(scope='grads_accumulators').items()}

@@ -50,6 +50,21 @@ def build(case, workdir):
     return model, log, dt
 
 
+def check_summaries(model, want, tol):
+    """logs/{train,val}/scalars.jsonl against what the reference gave its TensorBoard writers."""
+    def read(d):
+        p = os.path.join(d, 'scalars.jsonl')
+        return [json.loads(l) for l in open(p)] if os.path.isfile(p) else []
+    train, val = read(model._train_summary_dirpath), read(model._val_summary_dirpath)
+    assert [r['step'] for r in train] == want['train_steps']
+    assert [r['step'] for r in val] == [s for s, _ in want['val']]
+    for rec, (_, tags) in zip(val, want['val']):
+        assert sorted(k for k in rec if k != 'step') == sorted(tags)
+        for k, v in tags.items():
+            np.testing.assert_allclose(rec[k], v, rtol=0, atol=max(tol, 2e-3) if 'loglik' in k or 'free_energy' in k else 10 * tol,
+                                       err_msg='summary ' + k)
+
+
 def close(got, want, tol, what):
     if want is None:
         assert got is None, what
@@ -70,6 +85,7 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
         X = np.asarray(case['X'], dtype=dt)
         X_val = None if case['X_val'] is None else np.asarray(case['X_val'], dtype=dt)
         model.fit(X, X_val)
+        check_summaries(model, case['summaries'], tol)
         H = model.transform(X[:case['transform_rows']])
         close(H, case['transform'], tol * 5, 'transform')
     assert (int(model.epoch_), int(model.iter_)) == (case['epoch_'], case['iter_'])
@@ -144,6 +160,7 @@ def test_dbm_scenario_matches_the_reference(both_engines, workdir):
             return r
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
+    check_summaries(dbm, g['summaries'], tol)
     assert (int(dbm.epoch_), int(dbm.iter_)) == (g['epoch_'], g['iter_'])
     for key in ('train', 'val'):
         assert len(log[key]) == len(g['log'][key])
