@@ -171,6 +171,11 @@ def cases():
                     kw=dict(n_visible=20, n_hidden=6, n_samples=10, W_init=(0.1 * rng.randn(20, 6)).astype(np.float32),
                             n_gibbs_steps=1, learning_rate=0.01, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3,
                             random_seed=9, metrics_config=dict(mc), verbose=False, save_after_each_epoch=False)))
+    out.append(dict(name='bernoulli_resume_after_load_model', cls='BernoulliRBM', X=Xb, X_val=Xb_val, transform_rows=5,
+                    resume_max_epoch=4,
+                    kw=dict(n_visible=20, n_hidden=12, W_init=W20, n_gibbs_steps=[1, 1, 2], learning_rate=[0.05, 0.04, 0.03, 0.02],
+                            momentum=[0.5, 0.6, 0.7], max_epoch=2, batch_size=10, l2=1e-3, sparsity_cost=0.02, random_seed=77,
+                            metrics_config=dict(mc), verbose=False, save_after_each_epoch=True)))
     out.append(dict(name='init_from_seed', cls='BernoulliRBM', X=None, X_val=None, transform_rows=0,
                     kw=dict(n_visible=20, n_hidden=12, W_init=0.01, vb_init=0.25, random_seed=1337, verbose=False)))
     return out
@@ -261,12 +266,27 @@ def run_case(ref_rbm, case, workdir):
             return r
         setattr(model, meth, wrapped)
     rec = {'name': case['name'], 'cls': case['cls'], 'kw': {k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in case['kw'].items()},
-           'X': tolist(case['X']), 'X_val': tolist(case['X_val']), 'transform_rows': case['transform_rows']}
+           'X': tolist(case['X']), 'X_val': tolist(case['X_val']), 'transform_rows': case['transform_rows'],
+           'resume_max_epoch': case.get('resume_max_epoch')}
     if case['X'] is None:
         model.init()
     else:
         model.fit(case['X'], case['X_val'])
         rec['summaries'] = summaries_of(model)
+        if case.get('resume_max_epoch'):
+            # a new process would do exactly this: load_model (params.json, random_state.json), more epochs
+            model = cls.load_model(kw['model_path'])
+            model.set_params(max_epoch=case['resume_max_epoch'])
+            for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val'), ('_run_feg', 'feg')):
+                orig = getattr(model, meth)
+
+                def wrapped2(*a, _orig=orig, _key=key, **k):
+                    r = _orig(*a, **k)
+                    log[_key].append(r if not isinstance(r, dict) else {m: (None if v is None else float(v)) for m, v in r.items()})
+                    return r
+                setattr(model, meth, wrapped2)
+            model.fit(case['X'], case['X_val'])
+            rec['summaries_resumed'] = summaries_of(model)
         rec['transform'] = tolist(model.transform(case['X'][:case['transform_rows']]))
     rec['weights'] = {k: tolist(v) for k, v in model.get_tf_params(scope='weights').items()}
     rec['grads_accumulators'] = {k: tolist(v) for k, v in model.get_tf_params(scope='grads_accumulators').items()}

@@ -86,6 +86,26 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
         X_val = None if case['X_val'] is None else np.asarray(case['X_val'], dtype=dt)
         model.fit(X, X_val)
         check_summaries(model, case['summaries'], tol)
+        if case.get('resume_max_epoch'):
+            from boltzmann_machines import rbm as R
+            path = model._model_dirpath
+            for d in (model._train_summary_dirpath, model._val_summary_dirpath):      # a fresh log for the second run
+                p = os.path.join(d, 'scalars.jsonl')
+                if os.path.isfile(p):
+                    os.remove(p)
+            model.close()
+            model = getattr(R, case['cls']).load_model(path)
+            model.set_params(max_epoch=case['resume_max_epoch'])
+            for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val'), ('_run_feg', 'feg')):
+                orig = getattr(model, meth)
+
+                def wrapped2(*a, _orig=orig, _key=key, **k):
+                    r = _orig(*a, **k)
+                    log[_key].append(r)
+                    return r
+                setattr(model, meth, wrapped2)
+            model.fit(X, X_val)
+            check_summaries(model, case['summaries_resumed'], tol)
         H = model.transform(X[:case['transform_rows']])
         close(H, case['transform'], tol * 5, 'transform')
     assert (int(model.epoch_), int(model.iter_)) == (case['epoch_'], case['iter_'])
