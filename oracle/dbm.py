@@ -14,7 +14,7 @@ particles) and performs what the reference runs inside ``session.run``:
   * AIS                                        dbm.py:650-736
   * variational lower bound                    dbm.py:738-759
 
-PARITY STATUS: pinned against the reference's OWN SOURCE.  tests/golden/reference_dbm_case.json holds the results of
+PARITY STATUS: pinned against the reference's OWN SOURCE.  tests/golden/reference_dbm_cases.json holds the results of
 yell/boltzmann-machines' unmodified `DBM` class -- greedy pre-training of two RBMs, `fit` (mean-field E-step with its
 stale-mu start, PCD particles with a variable number of Gibbs steps, the sparsity update, max-norm, momentum),
 `transform`, `reconstruct`, `sample_v`, `log_proba` and `log_Z` (AIS) -- executed with oracle/tf1shim.py in place of

@@ -1,5 +1,5 @@
 """Golden vectors from the REFERENCE'S OWN RBM AND DBM CODE: tests/golden/reference_rbm_cases.json,
-tests/golden/reference_dbm_case.json.
+tests/golden/reference_dbm_cases.json.
 
 Run in the build container only (reads /root/reference):
 
@@ -65,7 +65,8 @@ def dbm_provider(req, seed, tick, shape):
         ais_ops = [t for t in req.graph.by_name.values()
                    if getattr(t, 'random_kind', None) == 'bernoulli' and getattr(t, 'op_seed', None) is not None]
         assert len(ais_ops) == 1                     # Bernoulli(logits).sample(seed=self.make_random_seed()), dbm.py:701
-        return P.uniform_at(shape[0], shape[1], int(ais_ops[0].op_seed), P.SITE_PARTICLE_INIT, idx, 0).astype(req.dtype)
+        draw = P.normal_at if req.kind == 'normal' else P.uniform_at       # GaussianLayer.init multiplies by sigma itself
+        return draw(shape[0], shape[1], int(ais_ops[0].op_seed), P.SITE_PARTICLE_INIT, idx, 0).astype(req.dtype)
     if 'annealed_importance_sampling' in parts:
         assert req.kind == 'bernoulli'
         p = np.asarray(req.args[0])
@@ -78,10 +79,14 @@ def dbm_provider(req, seed, tick, shape):
         site = {'sample': P.SITE_AIS_V, 'sample_1': P.SITE_AIS_H2, 'sample_2': P.SITE_AIS_H1}[leaf]
         u = P.uniform_at(shape[0], shape[1], AIS['seed'], site, 0, it * AIS['k'] + s)
         return (u.astype(p.dtype) < p).astype(np.int32)
-    assert 'gibbs_chain' in parts and req.kind == 'bernoulli', (req.scope, req.kind)
+    assert 'gibbs_chain' in parts, (req.scope, req.kind)
     leaf = [q for q in parts if q.startswith('sample_')][-1]
     site = P.SITE_DBM_V if leaf.startswith('sample_v_hat') else P.SITE_DBM_H + int(leaf[len('sample_h'):].split('_')[0])
     p = np.asarray(req.args[0])
+    if req.kind == 'normal_loc_scale':
+        scale = np.asarray(req.args[1])
+        return (p + scale * P.normal_at(shape[0], shape[1], seed, site, req.loop_iter + 1, tick).astype(p.dtype)).astype(p.dtype)
+    assert req.kind == 'bernoulli', req.kind
     u = P.uniform_at(shape[0], shape[1], seed, site, req.loop_iter + 1, tick)
     return (u.astype(p.dtype) < p).astype(np.int32)
 
@@ -92,8 +97,7 @@ def provider(req):
     shape = tuple(int(s) for s in req.shape)
     top = req.scope.split('/')[0]
     if top in ('negative_particles', 'annealed_importance_sampling') or \
-            (req.kind == 'bernoulli' and ('gibbs_chain/while' in req.scope) and 'sample_h_given_v' not in req.scope
-             and 'sample_v_given_h' not in req.scope):
+            (('gibbs_chain/while' in req.scope) and 'sample_h_given_v' not in req.scope and 'sample_v_given_h' not in req.scope):
         return dbm_provider(req, seed, tick, shape)
     if req.kind == 'normal':                        # W initialiser: tf.random_normal(..., seed=random_seed)
         assert req.scope.startswith('weights') and req.op_seed is not None, req.scope
@@ -181,31 +185,48 @@ def cases():
     return out
 
 
-def run_dbm_case(ref, workdir):
-    """Greedy pre-training of two RBMs, then DBM.fit / transform / reconstruct / sample_v / log_proba / log_Z --
-    dbm_mnist.py's sequence in miniature -- all through the reference's public API."""
-    from oracle.rbm import sigmoid as _s      # noqa: F401
-    rng = np.random.RandomState(21)
-    V, H1, H2 = 16, 10, 6
-    X = (rng.rand(24, V) < 0.3).astype(np.float32)
-    X_val = (rng.rand(16, V) < 0.3).astype(np.float32)
-    rbm_kw = [dict(n_visible=V, n_hidden=H1, W_init=(0.1 * rng.randn(V, H1)).astype(np.float32), n_gibbs_steps=1,
-                   learning_rate=0.05, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3, dbm_first=True, random_seed=101,
-                   verbose=False, save_after_each_epoch=False),
-              dict(n_visible=H1, n_hidden=H2, W_init=(0.1 * rng.randn(H1, H2)).astype(np.float32), n_gibbs_steps=2,
-                   learning_rate=0.05, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3, dbm_last=True, random_seed=202,
-                   verbose=False, save_after_each_epoch=False)]
+def run_dbm_case(ref, workdir, variant):
+    """Greedy pre-training of the RBM stack, then DBM.fit / transform / reconstruct / sample_v (/ log_proba / log_Z for
+    the 2-layer binary model, the only one the reference implements them for) -- dbm_mnist.py's sequence in miniature --
+    all through the reference's public API.  Variants: 2 binary layers; Gaussian visibles (dbm_cifar*.py); 3 layers."""
+    rng = np.random.RandomState({'bernoulli_2layer': 21, 'gaussian_visible_2layer': 22, 'bernoulli_3layer': 23}[variant])
+    V = 16
+    sizes = [V, 10, 6] if variant != 'bernoulli_3layer' else [V, 10, 8, 5]
+    L = len(sizes) - 1
+    if variant == 'gaussian_visible_2layer':
+        X = rng.randn(24, V).astype(np.float32)
+        X_val = rng.randn(16, V).astype(np.float32)
+    else:
+        X = (rng.rand(24, V) < 0.3).astype(np.float32)
+        X_val = (rng.rand(16, V) < 0.3).astype(np.float32)
+    rbm_cls, rbm_kw = [], []
+    for i in range(L):
+        kw = dict(n_visible=sizes[i], n_hidden=sizes[i + 1], W_init=(0.1 * rng.randn(sizes[i], sizes[i + 1])).astype(np.float32),
+                  n_gibbs_steps=1 + (i % 2), learning_rate=0.05, momentum=0.5, max_epoch=2, batch_size=8, l2=1e-3,
+                  dbm_first=(i == 0), dbm_last=(i == L - 1), random_seed=101 * (i + 1), verbose=False, save_after_each_epoch=False)
+        cls = 'BernoulliRBM'
+        if i == 0 and variant == 'gaussian_visible_2layer':
+            cls = 'GaussianRBM'
+            kw.update(sigma=np.linspace(0.7, 1.3, V).tolist(), learning_rate=5e-3, sample_v_states=True)
+        rbm_cls.append(cls)
+        rbm_kw.append(kw)
     dbm_kw = dict(n_particles=8, n_gibbs_steps=[1, 2], max_mf_updates=5, mf_tol=1e-5, learning_rate=[0.02, 0.01],
                   momentum=[0.5, 0.9], max_epoch=3, batch_size=8, l2=1e-4, max_norm=0.6, sample_v_states=True,
-                  sample_h_states=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[1e-2, 5e-3],
+                  sample_h_states=[True] * L, sparsity_target=[0.2, 0.1, 0.15][:L], sparsity_cost=[1e-2, 5e-3, 2e-3][:L],
                   sparsity_damping=0.8, train_metrics_every_iter=2, val_metrics_every_epoch=1, verbose=False,
                   save_after_each_epoch=True, random_seed=303)
-    rbm1 = ref.rbm.BernoulliRBM(model_path=os.path.join(workdir, 'rbm1') + '/', **rbm_kw[0])
-    rbm1.fit(X)
-    Q = rbm1.transform(X)
-    rbm2 = ref.rbm.BernoulliRBM(model_path=os.path.join(workdir, 'rbm2') + '/', **rbm_kw[1])
-    rbm2.fit(Q)
-    dbm = ref.DBM(rbms=[rbm1, rbm2], model_path=os.path.join(workdir, 'dbm') + '/', **dbm_kw)
+    if variant == 'gaussian_visible_2layer':
+        dbm_kw.update(learning_rate=[2e-3, 1e-3], max_norm=1.5)
+    rbms, inp, Q = [], X, None
+    for i in range(L):
+        r = getattr(ref.rbm, rbm_cls[i])(model_path=os.path.join(workdir, variant, 'rbm%d' % i) + '/', **rbm_kw[i])
+        r.fit(inp)
+        if i < L - 1:
+            inp = r.transform(inp)
+            if i == 0:
+                Q = inp
+        rbms.append(r)
+    dbm = ref.DBM(rbms=rbms, model_path=os.path.join(workdir, variant, 'dbm') + '/', **dbm_kw)
     log = {'train': [], 'val': []}
     for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
         orig = getattr(dbm, meth)
@@ -217,7 +238,8 @@ def run_dbm_case(ref, workdir):
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
     dbm_summaries = summaries_of(dbm)
-    rec = {'summaries': dbm_summaries, 'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
+    rec = {'summaries': dbm_summaries, 'variant': variant, 'rbm_cls': rbm_cls,
+           'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
            'dbm_kw': dbm_kw, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
            'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_)}
     scopes = ('weights', 'grads_accumulators', 'variational_params', 'hidden_means_accumulators', 'negative_particles')
@@ -225,14 +247,15 @@ def run_dbm_case(ref, workdir):
     rec['transform'] = tolist(dbm.transform(X[:16]))
     rec['reconstruct'] = tolist(dbm.reconstruct(X[:8]))
     rec['sample_v'] = tolist(dbm.sample_v(n_gibbs_steps=2))
-    rec['log_proba'] = tolist(dbm.log_proba(X_val, log_Z=0.0))
-    # the mirror's log_Z draws the call seed and then a dedicated AIS seed from the model's RNG
-    peek = type(dbm._rng)(seed=None).set_state(json.loads(json.dumps(dbm._rng.get_state())))
-    peek.randint(2 ** 31 - 1)
-    AIS['seed'], AIS['k'] = int(peek.randint(2 ** 31 - 1)), 2
-    log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=20, n_runs=6, n_gibbs_steps=2)
-    rec['log_Z'] = {'n_betas': 20, 'n_runs': 6, 'n_gibbs_steps': 2, 'log_mean': float(log_mean), 'log_low': float(log_low),
-                    'log_high': float(log_high), 'values': tolist(values)}
+    if variant == 'bernoulli_2layer':
+        rec['log_proba'] = tolist(dbm.log_proba(X_val, log_Z=0.0))
+        # the mirror's log_Z draws the call seed and then a dedicated AIS seed from the model's RNG
+        peek = type(dbm._rng)(seed=None).set_state(json.loads(json.dumps(dbm._rng.get_state())))
+        peek.randint(2 ** 31 - 1)
+        AIS['seed'], AIS['k'] = int(peek.randint(2 ** 31 - 1)), 2
+        log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=20, n_runs=6, n_gibbs_steps=2)
+        rec['log_Z'] = {'n_betas': 20, 'n_runs': 6, 'n_gibbs_steps': 2, 'log_mean': float(log_mean), 'log_low': float(log_low),
+                        'log_high': float(log_high), 'values': tolist(values)}
     rec['after_queries'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()}
                             for sc in ('weights', 'negative_particles')}
     return rec
@@ -324,7 +347,7 @@ def main():
     try:
         os.chdir(work)
         recs = [run_case(ref.rbm, c, work) for c in cases()]
-        dbm_rec = run_dbm_case(ref, work)
+        dbm_recs = {v: run_dbm_case(ref, work, v) for v in ('bernoulli_2layer', 'gaussian_visible_2layer', 'bernoulli_3layer')}
     finally:
         os.chdir(cwd)
         shutil.rmtree(work, ignore_errors=True)
@@ -335,11 +358,13 @@ def main():
     with open(path, 'w') as fh:
         json.dump(out, fh)
     print('wrote', path, os.path.getsize(path), 'bytes;', len(recs), 'cases')
-    dpath = os.path.join(HERE, 'reference_dbm_case.json')
+    dpath = os.path.join(HERE, 'reference_dbm_cases.json')
     with open(dpath, 'w') as fh:
         json.dump({'source': out['source'].replace('boltzmann_machines/rbm, layers.py', 'boltzmann_machines/dbm.py, rbm, layers.py'),
-                   'case': dbm_rec}, fh)
-    print('wrote', dpath, os.path.getsize(dpath), 'bytes; dbm log', dbm_rec['log'], 'log_Z', dbm_rec['log_Z']['log_mean'])
+                   'cases': dbm_recs}, fh)
+    print('wrote', dpath, os.path.getsize(dpath), 'bytes')
+    for v, r in dbm_recs.items():
+        print(' ', v, 'log', r['log'], 'log_Z', r.get('log_Z', {}).get('log_mean'))
     for r in recs:
         print(' ', r['name'], 'iter_', r['iter_'], 'train log', r['log']['train'][-1:] , 'feg', r['log']['feg'])
 

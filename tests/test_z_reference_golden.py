@@ -134,7 +134,7 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
 # DBM: greedy pre-training, DBM.fit, transform, reconstruct, sample_v, log_proba, log_Z -- the reference's dbm.py
 # (mean-field with its stale-mu start, PCD particles, sparsity quirk, max-norm, AIS) executed on the shim
 # ---------------------------------------------------------------------------------------------------------
-DBM_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_case.json')))['case']
+DBM_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_cases.json')))['cases']
 
 
 @pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
@@ -152,10 +152,13 @@ def both_engines(request, monkeypatch):
     set_engine_factory('dbm', old[1])
 
 
-def test_dbm_scenario_matches_the_reference(both_engines, workdir):
+@pytest.mark.parametrize('variant', sorted(DBM_GOLD))
+def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
+    """bernoulli_2layer: the whole query surface incl. AIS; gaussian_visible_2layer: a GaussianRBM bottom layer
+    (dbm_cifar*.py); bernoulli_3layer: the intermediate-layer Gibbs update and the halving of the middle RBM."""
     from boltzmann_machines import DBM
-    from boltzmann_machines.rbm import BernoulliRBM
-    g = DBM_GOLD
+    from boltzmann_machines import rbm as R
+    g = DBM_GOLD[variant]
     tol = 2e-5 if both_engines == 'oracle' else 2e-4
     X, X_val = np.asarray(g['X'], dtype=np.float32), np.asarray(g['X_val'], dtype=np.float32)
     rbms = []
@@ -163,11 +166,12 @@ def test_dbm_scenario_matches_the_reference(both_engines, workdir):
     for i, kw in enumerate(g['rbm_kw']):
         kw = dict(kw)
         kw['W_init'] = np.asarray(kw['W_init'], dtype=np.float32)
-        r = BernoulliRBM(model_path=os.path.join(str(workdir), 'rbm%d' % i) + '/', **kw)
+        r = getattr(R, g['rbm_cls'][i])(model_path=os.path.join(str(workdir), 'rbm%d' % i) + '/', **kw)
         r.fit(inp)
-        if i == 0:
-            inp = r.transform(X)
-            close(inp, g['Q'], tol * 5, 'rbm1.transform')
+        if i < len(g['rbm_kw']) - 1:
+            inp = r.transform(inp)
+            if i == 0:
+                close(inp, g['Q'], tol * 5, 'rbm1.transform')
         rbms.append(r)
     dbm = DBM(rbms=rbms, model_path=os.path.join(str(workdir), 'dbm') + '/', **g['dbm_kw'])
     log = {'train': [], 'val': []}
@@ -196,6 +200,9 @@ def test_dbm_scenario_matches_the_reference(both_engines, workdir):
     close(dbm.transform(X[:16]), g['transform'], 5 * tol, 'transform')
     close(dbm.reconstruct(X[:8]), g['reconstruct'], 5 * tol, 'reconstruct')
     close(dbm.sample_v(n_gibbs_steps=2), g['sample_v'], 5 * tol, 'sample_v')
+    if 'log_Z' not in g:
+        check_after_queries(dbm, g, tol)
+        return
     close(dbm.log_proba(X_val, log_Z=0.0), g['log_proba'], 2e-4, 'log_proba')
     z = g['log_Z']
     log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=z['n_betas'], n_runs=z['n_runs'], n_gibbs_steps=z['n_gibbs_steps'])
@@ -203,6 +210,10 @@ def test_dbm_scenario_matches_the_reference(both_engines, workdir):
     np.testing.assert_allclose(values, z['values'], rtol=0, atol=2e-4 if both_engines == 'oracle' else 2e-3, err_msg='AIS log-weights')
     np.testing.assert_allclose([log_mean, log_low, log_high], [z['log_mean'], z['log_low'], z['log_high']], rtol=0, atol=1e-3 if both_engines == 'oracle' else 5e-3,
                                err_msg='log_Z summary')
+    check_after_queries(dbm, g, tol)
+
+
+def check_after_queries(dbm, g, tol):
     for scope, want in g['after_queries'].items():
         got = dbm.get_tf_params(scope=scope)
         for k, v in want.items():
