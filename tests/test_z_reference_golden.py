@@ -16,12 +16,41 @@ GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '
 CASES = {c['name']: c for c in GOLD['cases']}
 
 
-@pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
+def epoch_oracle_factory(cfg):
+    """The oracle behind the interface of the CUDA engine's whole-epoch entry points (`train_epoch`, `pin`), so that the
+    host code path BaseRBM takes with libbm.so -- one native call per epoch, byte-valued pinned data, per-iteration metric
+    lists -- is exercised on CPU as well."""
+    from boltzmann_machines import _native
+    from oracle.rbm import OracleRBM
+
+    class EpochOracle(OracleRBM):
+        def pin(self, X):
+            Xb = _native.as_bytes(np.ascontiguousarray(X))
+            return Xb if Xb is not None else np.ascontiguousarray(X)
+
+        def unpin(self, P):
+            pass
+
+        def train_epoch(self, X, batch, lr, momentum, k, seed, tick0, metrics=(), every=0, iter0=0):
+            X = np.asarray(X, dtype=self.dt)              # bytes are widened exactly, like bm_rbm_train_epoch_u8
+            out = {m: [] for m in metrics}
+            for i, lo in enumerate(range(0, len(X), batch)):
+                report = metrics if (every and (iter0 + i + 1) % every == 0) else ()
+                got = self.train_step(X[lo:lo + batch], lr, momentum, k, seed, tick0 + i, metrics=report)
+                for m in report:
+                    out[m].append(got[m])
+            return out
+    return EpochOracle(cfg)
+
+
+@pytest.fixture(params=['oracle', 'oracle-epoch', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
 def engine_kind(request, monkeypatch):
     from boltzmann_machines.base import set_engine_factory
     if request.param == 'oracle':
         from oracle.rbm import rbm_factory
         old = set_engine_factory('rbm', rbm_factory)
+    elif request.param == 'oracle-epoch':
+        old = set_engine_factory('rbm', epoch_oracle_factory)
     else:
         monkeypatch.setenv('BM_COMPUTE', 'fp32')
         old = set_engine_factory('rbm', None)
@@ -78,7 +107,7 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
     case = CASES[name]
     model, log, dt = build(case, workdir)
     # float32: the same formulas in float32 with different summation orders; a Bernoulli draw is u < p on the SAME u
-    tol = 1e-9 if dt == 'float64' else (2e-5 if engine_kind == 'oracle' else 2e-4)
+    tol = 1e-9 if dt == 'float64' else (2e-5 if engine_kind.startswith('oracle') else 2e-4)
     if case['X'] is None:
         model.init()
     else:
