@@ -180,6 +180,13 @@ def cases():
                     kw=dict(n_visible=20, n_hidden=12, W_init=W20, n_gibbs_steps=[1, 1, 2], learning_rate=[0.05, 0.04, 0.03, 0.02],
                             momentum=[0.5, 0.6, 0.7], max_epoch=2, batch_size=10, l2=1e-3, sparsity_cost=0.02, random_seed=77,
                             metrics_config=dict(mc), verbose=False, save_after_each_epoch=True)))
+    out.append(dict(name='bernoulli_init_from_another_rbm', cls='BernoulliRBM', X=Xb, X_val=None, transform_rows=5,
+                    pre_kw=dict(n_visible=20, n_hidden=12, W_init=W20, n_gibbs_steps=1, learning_rate=0.05, momentum=0.5,
+                                max_epoch=2, batch_size=10, l2=1e-3, random_seed=31, verbose=False, save_after_each_epoch=False),
+                    kw=dict(n_visible=20, n_hidden=12, n_gibbs_steps=2, learning_rate=0.02, momentum=0.9, max_epoch=4,
+                            batch_size=8, l2=1e-4, sparsity_cost=0.01, random_seed=32,
+                            metrics_config=dict(msre=True, train_metrics_every_iter=3), verbose=False,
+                            save_after_each_epoch=False)))
     out.append(dict(name='init_from_seed', cls='BernoulliRBM', X=None, X_val=None, transform_rows=0,
                     kw=dict(n_visible=20, n_hidden=12, W_init=0.01, vb_init=0.25, random_seed=1337, verbose=False)))
     return out
@@ -279,6 +286,15 @@ def run_case(ref_rbm, case, workdir):
     kw = dict(case['kw'])
     kw['model_path'] = os.path.join(workdir, case['name']) + '/'
     model = cls(**kw)
+    if case.get('pre_kw'):                           # momentum accumulators and weights carried over (base_rbm.py:657-678)
+        pre_kw = dict(case['pre_kw'])
+        pre_kw['model_path'] = os.path.join(workdir, case['name'] + '_pre') + '/'
+        pre = cls(**pre_kw)
+        pre.fit(case['X'])
+        model.init_from(pre)
+        # init_from also copies `initialized_` (base_rbm.py:675-678), after which the reference would try to restore a
+        # graph that was never saved under the new model_path; a user has to clear the flag (the host mirror does so itself)
+        model.initialized_ = False
     log = {'train': [], 'val': [], 'feg': []}
     for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val'), ('_run_feg', 'feg')):
         orig = getattr(model, meth)
@@ -290,7 +306,8 @@ def run_case(ref_rbm, case, workdir):
         setattr(model, meth, wrapped)
     rec = {'name': case['name'], 'cls': case['cls'], 'kw': {k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in case['kw'].items()},
            'X': tolist(case['X']), 'X_val': tolist(case['X_val']), 'transform_rows': case['transform_rows'],
-           'resume_max_epoch': case.get('resume_max_epoch')}
+           'resume_max_epoch': case.get('resume_max_epoch'),
+           'pre_kw': None if not case.get('pre_kw') else {k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in case['pre_kw'].items()}}
     if case['X'] is None:
         model.init()
     else:

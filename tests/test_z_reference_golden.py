@@ -67,6 +67,13 @@ def build(case, workdir):
             kw[k] = np.asarray(kw[k], dtype=dt)
     kw['model_path'] = os.path.join(str(workdir), case['name']) + '/'
     model = getattr(R, case['cls'])(**kw)
+    if case.get('pre_kw'):
+        pre_kw = dict(case['pre_kw'])
+        pre_kw['W_init'] = np.asarray(pre_kw['W_init'], dtype=dt)
+        pre_kw['model_path'] = os.path.join(str(workdir), case['name'] + '_pre') + '/'
+        pre = getattr(R, case['cls'])(**pre_kw)
+        pre.fit(np.asarray(case['X'], dtype=dt))
+        model.init_from(pre)
     log = {'train': [], 'val': [], 'feg': []}
     for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val'), ('_run_feg', 'feg')):
         orig = getattr(model, meth)
