@@ -440,7 +440,13 @@ class CudaDBM(object):
         c.n_hiddens, c.h_kinds, c.h_n_samples, c.sample_h, c.sparsity_target, c.sparsity_cost = self._keep
         c.v_kind = UNIT_KINDS[cfg.get('v_kind', 'bernoulli')]
         c.dtype = DTYPES[self.dt.name]
-        c.compute = COMPUTE['fp32']
+        # The DBM's default engine is the storage-precision CUDA-core one.  compute='bf16' (or BM_DBM_COMPUTE=bf16)
+        # opts a float32 model with Bernoulli hidden layers into the tensor-core engine (csrc/bm_dbm_tc.cuh).
+        compute = 'fp32'
+        if self.dt == np.float32:
+            compute = cfg.get('compute') or os.environ.get('BM_DBM_COMPUTE') or 'fp32'
+        self.compute = compute
+        c.compute = COMPUTE[compute]
         c.n_particles, c.batch_size = self.M, self.B
         c.max_mf_updates = int(cfg.get('max_mf_updates', 10))
         c.sample_v = int(cfg.get('sample_v', True))

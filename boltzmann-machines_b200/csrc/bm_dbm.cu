@@ -600,6 +600,8 @@ struct Dbm : DbmBase {
 
 }  // namespace bm
 
+#include "bm_dbm_tc.cuh"     // DbmTC: the same engine with every GEMM on the tensor cores (opt-in)
+
 using namespace bm;
 
 extern "C" {
@@ -613,8 +615,13 @@ int bm_dbm_create(bm_ctx* hctx, const bm_dbm_cfg* cfg, bm_dbm** out) {
     BM_REQUIRE(cfg->n_particles > 0 && cfg->batch_size > 0, "n_particles and batch_size must be positive");
     BM_REQUIRE(cfg->v_kind != BM_UNIT_GAUSSIAN || cfg->sigma, "gaussian visible layer needs sigma");
     BM_CUDA(cudaSetDevice(ctx->device));
-    DbmBase* d = cfg->dtype == BM_DTYPE_F64 ? static_cast<DbmBase*>(new Dbm<double>(ctx, *cfg))
-                                            : static_cast<DbmBase*>(new Dbm<float>(ctx, *cfg));
+    // BM_COMPUTE_BF16 (opt-in): float32 models with Bernoulli hidden layers run their GEMMs on tcgen05; every other
+    // combination keeps the storage-precision CUDA-core engine (as bm_rbm_create does for unit kinds the
+    // tensor-core epilogue does not implement)
+    DbmBase* d;
+    if (cfg->dtype == BM_DTYPE_F64) d = new Dbm<double>(ctx, *cfg);
+    else if (cfg->compute == BM_COMPUTE_BF16 && DbmTC::supports(*cfg)) d = new DbmTC(ctx, *cfg);
+    else d = new Dbm<float>(ctx, *cfg);
     *out = reinterpret_cast<bm_dbm*>(d);
     BM_API_END
 }

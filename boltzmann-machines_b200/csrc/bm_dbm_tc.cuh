@@ -1,0 +1,494 @@
+// Tensor-core DBM engine (BM_COMPUTE_BF16, float32 models): included by bm_dbm.cu after Dbm<T>.
+//
+// Same state, same update kernels and same control flow as Dbm<float> (the reference's dbm.py, see the
+// header of bm_dbm.cu); every GEMM -- the layer-wise Gibbs step with its two-sided input
+// H_{i-1} W_i + H_{i+1} W_{i+1}^T (dbm.py:385-427) as ONE two-pair tcgen05 op, the mean-field sweeps
+// (:429-478), the particle sweeps (:480-509), the gradients pos^T mu - neg^T h (:558-568, split over the
+// batch rows), the pre-activations of the AIS ladder (:650-736) -- runs on the fused tensor-core layer op
+// of bm_tc.cu (bf16 operands, fp32 accumulation in TMEM, bias + beta scaling + sigmoid + Philox draw in
+// the epilogue).  Variables stay fp32 as in the reference; activations (variational parameters, particles,
+// AIS states) are kept as bf16 operands, binary samples being exact in bf16.  AIS pre-activations leave the
+// kernel in fp32 and the importance weights are accumulated in fp64 from differences
+//   softplus(b z) - softplus(a z) = log1p(sigmoid(a z) * expm1((b - a) z)),
+// which is exact to fp32 rounding of a SMALL quantity (no cancellation between two O(1) softplus values).
+//
+// STATUS: opt-in (bm_dbm_cfg.compute = BM_COMPUTE_BF16; the Python mirror passes it only when asked:
+// DBM(..., compute='bf16') or BM_DBM_COMPUTE=bf16).  The default DBM engine is the fp32 CUDA-core one.
+#pragma once
+
+namespace bm {
+
+typedef __nv_bfloat16 bf16_t;
+
+static inline int dbm_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// max |a - b| over a [rows, cols] window of two bf16 matrices (leading dimensions lda / ldb)
+__global__ void max_abs_diff_bf16_kernel(const bf16_t* __restrict__ a, int lda, const bf16_t* __restrict__ b, int ldb,
+                                         int rows, int cols, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    const size_t total = (size_t)rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        m = fmaxf(m, fabsf(__bfloat162float(a[(size_t)r * lda + c]) - __bfloat162float(b[(size_t)r * ldb + c])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// G = (sum of `sp` positive slices) / n_div - (sum of `sn` negative slices) / m_div      (dbm.py:558-568)
+__global__ void dbm_grad_combine_kernel(const float* __restrict__ pos, int sp, const float* __restrict__ neg, int sn,
+                                        size_t stride, float inv_n, float inv_m, float* __restrict__ G, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int s = 0; s < sp; ++s) a += pos[(size_t)s * stride + i];
+        for (int s = 0; s < sn; ++s) b += neg[(size_t)s * stride + i];
+        G[i] = a * inv_n - b * inv_m;
+    }
+}
+
+// AIS unit update from fp32 pre-activations: out = sample ? (u < sigmoid(beta * pre)) : sigmoid(beta * pre), bf16.
+// pre == nullptr: pre-activation 0 (the uniform base-rate draw x_0 ~ Ber(1/2), dbm.py:700-702).
+// ldo % 4 == 0 (buffers are padded to 64 columns): the four columns of a Philox block leave as one 8-byte store.
+__global__ void ais_unit_bf16_kernel(const float* __restrict__ pre, int ldp, float beta, bf16_t* __restrict__ out, int ldo,
+                                     int rows, int cols, int sample, RngKey rng) {
+    const int cb = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (cb * 4 >= cols || r >= rows) return;
+    U4 w{0, 0, 0, 0};
+    if (sample) w = site_block(rng, (uint32_t)r, (uint32_t)cb);
+    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = cb * 4 + j;
+        const float z = (pre && c < cols) ? beta * pre[(size_t)r * ldp + c] : 0.f;
+        const float p = 1.0f / (1.0f + expf(-z));
+        o[j] = (c < cols) ? (sample ? ((u32_to_unit_float(words[j]) < p) ? 1.0f : 0.0f) : p) : 0.f;
+    }
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + (size_t)r * ldo + cb * 4) = pk;       // columns >= cols land in the padding
+}
+
+// softplus(b z) - softplus(a z), b >= a >= 0, without cancellation
+__device__ __forceinline__ float softplus_diff(float a, float b, float z) {
+    const float s = 1.0f / (1.0f + expf(-a * z));          // sigmoid(a z)
+    return log1pf(s * expm1f((b - a) * z));
+}
+
+// logw[r] += log p*_b(x_r) - log p*_a(x_r),  log p*_beta(x) = beta x.c1 + sum softplus(beta pa) + sum softplus(beta pb)
+// (dbm.py:650-668); one warp per chain, fp64 accumulation
+__global__ void ais_accum2_bf16_kernel(double* __restrict__ logw, float a, float b, const bf16_t* __restrict__ x, int ldx, int H0,
+                                       const float* __restrict__ hb0, const float* __restrict__ pa, int V,
+                                       const float* __restrict__ pb, int H1, int rows) {
+    const int r = blockIdx.x * blockDim.y + threadIdx.y;
+    if (r >= rows) return;
+    double acc = 0.0;
+    float lin = 0.f;
+    for (int j = threadIdx.x; j < H0; j += 32) lin += __bfloat162float(x[(size_t)r * ldx + j]) * hb0[j];
+    acc += ((double)b - (double)a) * (double)lin;
+    float part = 0.f;
+    int n = 0;
+    for (int j = threadIdx.x; j < V; j += 32) {
+        part += softplus_diff(a, b, pa[(size_t)r * V + j]);
+        if (++n == 8) { acc += (double)part; part = 0.f; n = 0; }
+    }
+    for (int j = threadIdx.x; j < H1; j += 32) {
+        part += softplus_diff(a, b, pb[(size_t)r * H1 + j]);
+        if (++n == 8) { acc += (double)part; part = 0.f; n = 0; }
+    }
+    acc += (double)part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) logw[r] += acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DbmTC : Dbm<float> {
+    std::vector<int> ldn;                        // leading dimension of a bf16 activation of layer idx (0 = visible)
+    std::vector<DevBuf<bf16_t>> Wb;              // bf16 shadows of W_i: [size(i), ldn[i+1]]
+    DevBuf<bf16_t> Xb, recon_b, v_b, v2_b, v3_b;
+    std::vector<DevBuf<bf16_t>> mu_b, mu2_b, h_b, h2_b, h3_b;
+    std::vector<DevBuf<float>> Gp;               // split-K slices of the gradient GEMMs
+    bool particles_f32_stale = false;            // the bf16 particles are newer than the fp32 copies get_param reads
+
+    static bool supports(const bm_dbm_cfg& f) {
+        if (f.dtype != BM_DTYPE_F32) return false;
+        if (!(f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN)) return false;
+        for (int i = 0; i < f.n_layers; ++i) if (f.h_kinds[i] != BM_UNIT_BERNOULLI) return false;
+        return true;
+    }
+
+    DbmTC(Ctx* c, const bm_dbm_cfg& f) : Dbm<float>(c, f) {
+        ldn.push_back(dbm_round_up(V, 64));
+        for (int i = 0; i < L; ++i) ldn.push_back(dbm_round_up(Hs[i], 64));
+        Wb.resize(L); mu_b.resize(L); mu2_b.resize(L); h_b.resize(L); h2_b.resize(L); h3_b.resize(L); Gp.resize(L);
+        Xb.ensure((size_t)B * ldn[0]); recon_b.ensure((size_t)B * ldn[0]);
+        v_b.ensure((size_t)M * ldn[0]); v2_b.ensure((size_t)M * ldn[0]);
+        for (DevBuf<bf16_t>* b : {&Xb, &recon_b, &v_b, &v2_b}) b->zero(ctx->stream);
+        for (int i = 0; i < L; ++i) {
+            Wb[i].ensure((size_t)size_of(i, V, Hs) * ldn[i + 1]);
+            mu_b[i].ensure((size_t)B * ldn[i + 1]); mu2_b[i].ensure((size_t)B * ldn[i + 1]);
+            h_b[i].ensure((size_t)M * ldn[i + 1]); h2_b[i].ensure((size_t)M * ldn[i + 1]);
+            for (DevBuf<bf16_t>* b : {&Wb[i], &mu_b[i], &mu2_b[i], &h_b[i], &h2_b[i]}) b->zero(ctx->stream);
+        }
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    static TcMat mat(const bf16_t* p, int rows, int cols, int ld) { TcMat m; m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; return m; }
+
+    // ---- fp32 <-> bf16 coherence ---------------------------------------------------------------------------
+    void refresh_shadow(int i) { launch_f32_to_bf16(ctx, W[i].p, Hs[i], Wb[i].p, ldn[i + 1], size_of(i, V, Hs), Hs[i]); }
+    void narrow_state() {          // fp32 variables (as set by the caller / initialised) -> bf16 operands
+        launch_f32_to_bf16(ctx, v.p, V, v_b.p, ldn[0], M, V);
+        for (int i = 0; i < L; ++i) {
+            launch_f32_to_bf16(ctx, h[i].p, Hs[i], h_b[i].p, ldn[i + 1], M, Hs[i]);
+            launch_f32_to_bf16(ctx, mu[i].p, Hs[i], mu_b[i].p, ldn[i + 1], B, Hs[i]);
+            refresh_shadow(i);
+        }
+        // the bf16 operands are what the engine computes with: get_param reports them (widened), not the unrounded input
+        widen_mu(B);
+        particles_f32_stale = true;
+    }
+    void widen_particles() {
+        if (!particles_f32_stale) return;
+        launch_bf16_to_f32(ctx, v_b.p, ldn[0], v.p, V, M, V);
+        for (int i = 0; i < L; ++i) launch_bf16_to_f32(ctx, h_b[i].p, ldn[i + 1], h[i].p, Hs[i], M, Hs[i]);
+        particles_f32_stale = false;
+    }
+    void widen_mu(int rows) { for (int i = 0; i < L; ++i) launch_bf16_to_f32(ctx, mu_b[i].p, ldn[i + 1], mu[i].p, Hs[i], rows, Hs[i]); }
+
+    void set_param(const char* name, const void* host, size_t bytes) override {
+        widen_particles();                         // the fp32 copies become the truth for one moment
+        Dbm<float>::set_param(name, host, bytes);
+        narrow_state();
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void get_param(const char* name, void* host, size_t bytes) override {
+        widen_particles();
+        Dbm<float>::get_param(name, host, bytes);
+    }
+    void init_particles(uint64_t seed) override {
+        widen_particles();
+        Dbm<float>::init_particles(seed);
+        narrow_state();
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // ---- one fused conditional on the tensor cores -----------------------------------------------------------
+    // act(acc_scale * (below W_i [+ above W_{i+1}^T]) + bias_scale * b_i): means XOR sampled states (bf16)
+    void hidden_tc(int i, const bf16_t* below, const bf16_t* above, bf16_t* out, bool sample, int rows,
+                   float acc_scale, float bias_scale, RngKey rng) {
+        const int in = size_of(i, V, Hs), H = Hs[i];
+        TcGemm g;
+        g.M = rows; g.N = H;
+        g.A[0] = mat(below, rows, in, ldn[i]); g.K[0] = in;
+        g.B[0] = mat(Wb[i].p, in, H, ldn[i + 1]); g.b_t[0] = true;           // x W_i: W_i stored [K, N]
+        if (above) {
+            const int Hn = Hs[i + 1];
+            g.n_pairs = 2;
+            g.A[1] = mat(above, rows, Hn, ldn[i + 2]); g.K[1] = Hn;
+            g.B[1] = mat(Wb[i + 1].p, H, Hn, ldn[i + 2]); g.b_t[1] = false;   // y W_{i+1}^T: W_{i+1} stored [N, K]
+        }
+        g.acc_scale = acc_scale; g.bias_scale = bias_scale; g.bias = hb[i].p;
+        g.act = ACT_SIGMOID; g.rng = rng;
+        if (sample) { g.sample = SMP_BERNOULLI; g.out_state_bf = out; g.ld_state_bf = ldn[i + 1]; }
+        else { g.out_mean_bf = out; g.ld_mean_bf = ldn[i + 1]; }
+        launch_tc_gemm(ctx, g);
+    }
+    void visible_tc(const bf16_t* h0, bf16_t* out, bool sample, int rows, RngKey rng) {
+        TcGemm g;
+        g.M = rows; g.N = V;
+        g.A[0] = mat(h0, rows, Hs[0], ldn[1]); g.K[0] = Hs[0];
+        g.B[0] = mat(Wb[0].p, V, Hs[0], ldn[1]); g.b_t[0] = false;            // h W_0^T: W_0 stored [N, K]
+        g.bias = vb.p; g.rng = rng;
+        if (v_kind == BM_UNIT_BERNOULLI) {
+            g.act = ACT_SIGMOID;
+            if (sample) g.sample = SMP_BERNOULLI;
+        } else {                                                               // layers.py:84-89
+            g.act = ACT_LINEAR; g.sigma = sigma.p;
+            if (sample) { g.sample = SMP_GAUSSIAN; g.noise_sigma = sigma.p; }
+        }
+        if (sample) { g.out_state_bf = out; g.ld_state_bf = ldn[0]; }
+        else { g.out_mean_bf = out; g.ld_mean_bf = ldn[0]; }
+        launch_tc_gemm(ctx, g);
+    }
+    // raw fp32 product A W_i (+ bias): the bound's t-terms and the AIS pre-activations
+    void linear_tc(const bf16_t* A, int lda, int rows, int K, const bf16_t* Wsh, int w_rows, int w_cols, int ldw, bool b_t,
+                   int N, const float* bias, float* out) {
+        TcGemm g;
+        g.M = rows; g.N = N;
+        g.A[0] = mat(A, rows, K, lda); g.K[0] = K;
+        g.B[0] = mat(Wsh, w_rows, w_cols, ldw); g.b_t[0] = b_t;
+        g.bias = bias; g.act = ACT_LINEAR;
+        g.out_f32 = out; g.ld_f32 = N;
+        launch_tc_gemm(ctx, g);
+    }
+
+    // dbm.py:385-427 on bf16 operands.  Hn[i] receive the new hidden values (states when sampled, else means)
+    void gibbs_tc(const bf16_t* vin, const std::vector<const bf16_t*>& Hin, const std::vector<bf16_t*>& Hn, bf16_t* v_new,
+                  bool update_v, bool sample, int rows, uint64_t seed, uint32_t tstep, uint32_t tick) {
+        for (int i = 0; i < L; ++i) {
+            const bf16_t* below = i == 0 ? vin : Hn[i - 1];
+            const bf16_t* above = (i + 1 < L) ? Hin[i + 1] : nullptr;
+            hidden_tc(i, below, above, Hn[i], sample && sample_h[i], rows, 1.f, 1.f, make_rng(seed, SITE_DBM_H + i, tstep, tick, 0));
+        }
+        if (update_v) visible_tc(Hn[0], v_new, sample && sample_vis, rows, make_rng(seed, SITE_DBM_V, tstep, tick, 0));
+    }
+
+    const float* upload_tc(const void* Xh, int rows) {
+        const float* X = upload(Xh, rows);
+        launch_f32_to_bf16(ctx, X, V, Xb.p, ldn[0], rows, V);
+        return X;
+    }
+
+    // ---- E-step (dbm.py:429-478) ------------------------------------------------------------------------------
+    int mean_field_tc(int rows) {
+        for (int i = 0; i < L; ++i) {
+            const bf16_t* below = i == 0 ? Xb.p : mu2_b[i - 1].p;
+            const float sc = (i == 0 || i < L - 1) ? 2.f : 1.f;              // :438, :441-442
+            hidden_tc(i, below, nullptr, mu2_b[i].p, false, rows, sc, 1.f, RngKey{});
+        }
+        std::vector<bf16_t*> cur(L), nxt(L);
+        for (int i = 0; i < L; ++i) { cur[i] = mu_b[i].p; nxt[i] = mu2_b[i].p; }
+        int step = 0;
+        while (step < max_mf) {
+            BM_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(unsigned int), ctx->stream));
+            for (int i = 0; i < L; ++i) {
+                max_abs_diff_bf16_kernel<<<148, 256, 0, ctx->stream>>>(cur[i], ldn[i + 1], nxt[i], ldn[i + 1], rows, Hs[i], flag.p);
+                count_launch(ctx);
+            }
+            unsigned int bits = 0;
+            BM_CUDA(cudaMemcpyAsync(&bits, flag.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+            BM_CUDA(cudaStreamSynchronize(ctx->stream));
+            float diff; memcpy(&diff, &bits, sizeof(diff));
+            if (!(diff > (float)mf_tol)) break;                               // :451-452
+            std::vector<const bf16_t*> Hin(cur.begin(), cur.end());
+            gibbs_tc(Xb.p, Hin, nxt, nullptr, false, false, rows, 0, 0, 0);
+            std::swap(cur, nxt);                                              // :457
+            ++step;
+        }
+        for (int i = 0; i < L; ++i)
+            if (cur[i] != mu_b[i].p)
+                BM_CUDA(cudaMemcpyAsync(mu_b[i].p, cur[i], (size_t)rows * ldn[i + 1] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        widen_mu(rows);                        // get_param('mu'), transform and the bound read the fp32 variables
+        return step;
+    }
+
+    // ---- PCD particle update (dbm.py:480-509) -----------------------------------------------------------------
+    void particles_tc(int n_steps, bool sample, uint64_t seed, uint32_t tick, int t0, bool commit, bf16_t** v_final) {
+        std::vector<bf16_t*> cur(L), nxt(L), spare(L);
+        for (int i = 0; i < L; ++i) { cur[i] = h_b[i].p; nxt[i] = h2_b[i].p; spare[i] = nullptr; }
+        bf16_t* vc = v_b.p; bf16_t* vn = v2_b.p; bf16_t* vspare = nullptr;
+        if (!commit) {      // an uncommitted run must never write the persistent particles: ping-pong on scratch
+            v3_b.ensure((size_t)M * ldn[0]); vspare = v3_b.p;
+            for (int i = 0; i < L; ++i) { h3_b[i].ensure((size_t)M * ldn[i + 1]); spare[i] = h3_b[i].p; }
+        }
+        for (int s = 0; s < n_steps; ++s) {
+            std::vector<const bf16_t*> Hin(cur.begin(), cur.end());
+            gibbs_tc(vc, Hin, nxt, vn, true, sample, M, seed, (uint32_t)(t0 + s + 1), tick);
+            if (!commit && s == 0) { cur = nxt; nxt = spare; vc = vn; vn = vspare; }
+            else { std::swap(cur, nxt); std::swap(vc, vn); }
+        }
+        if (commit) {
+            for (int i = 0; i < L; ++i)
+                if (cur[i] != h_b[i].p)
+                    BM_CUDA(cudaMemcpyAsync(h_b[i].p, cur[i], (size_t)M * ldn[i + 1] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (vc != v_b.p) BM_CUDA(cudaMemcpyAsync(v_b.p, vc, (size_t)M * ldn[0] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (n_steps > 0) particles_f32_stale = true;
+            if (v_final) *v_final = v_b.p;
+        } else if (v_final) *v_final = vc;
+    }
+
+    void reconstruction_tc(int rows) {                                        // :626-628; fp32 copy in `recon`
+        visible_tc(mu_b[0].p, recon_b.p, false, rows, RngKey{});
+        launch_bf16_to_f32(ctx, recon_b.p, ldn[0], recon.p, V, rows, V);
+    }
+    double msre_tc(const float* X, int rows) {
+        reconstruction_tc(rows);
+        launch_sqdiff_mean<float>(ctx, X, V, recon.p, V, rows, V, (double)rows * V, scal.p);
+        double hval = 0.0;
+        BM_CUDA(cudaMemcpyAsync(&hval, scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        return hval;
+    }
+
+    // G_i = pos^T mu_i / N - neg^T h_i / M (dbm.py:558-568): two split-K tensor-core GEMMs over the rows
+    void gradient_tc(int i, const bf16_t* pos, int pos_rows, const bf16_t* neg, float n_div, float m_div) {
+        const int in = size_of(i, V, Hs), H = Hs[i];
+        const int total_pairs = ctx->sm_count / 2;
+        const int pair_tiles = ((in + 255) / 256) * ((H + 255) / 256);
+        auto splits_for = [&](int rows) { return std::max(1, std::min(total_pairs / std::max(pair_tiles, 1), (rows + 63) / 64)); };
+        const int sp = splits_for(pos_rows), sn = splits_for(M);
+        const size_t stride = (size_t)in * H;
+        Gp[i].ensure((size_t)(sp + sn) * stride);
+        auto half = [&](const bf16_t* a, const bf16_t* b, int rows, int splits, float* out) {
+            TcGemm g;
+            g.M = in; g.N = H;
+            g.A[0] = mat(a, rows, in, ldn[i]); g.a_t[0] = true;               // stored [K = rows, M = in]
+            g.B[0] = mat(b, rows, H, ldn[i + 1]); g.b_t[0] = true;            // stored [K = rows, N = H]
+            g.K[0] = rows;
+            g.splits = splits; g.split_stride = stride;
+            g.out_f32 = out; g.ld_f32 = H;
+            launch_tc_gemm(ctx, g);
+        };
+        half(pos, mu_b[i].p, pos_rows, sp, Gp[i].p);
+        half(neg, h_b[i].p, M, sn, Gp[i].p + (size_t)sp * stride);
+        dbm_grad_combine_kernel<<<592, 256, 0, ctx->stream>>>(Gp[i].p, sp, Gp[i].p + (size_t)sp * stride, sn, stride,
+                                                              1.0f / n_div, 1.0f / m_div, G[i].p, stride);
+        count_launch(ctx);
+    }
+
+    void train_step(const void* Xh, int rows, double lr, double mom, int k, uint64_t seed, uint32_t tick, int want, double* out) override {
+        BM_REQUIRE(rows >= 1, "empty batch");
+        const float* X = upload_tc(Xh, rows);
+        const int n_mf = mean_field_tc(rows);
+        particles_tc(k, true, seed, tick, 0, true, nullptr);
+        if (want) { BM_REQUIRE(out, "metrics requested without a buffer"); out[0] = msre_tc(X, rows); out[1] = (double)n_mf; }
+        const float N = (float)B, Mp = (float)M;                // configured sizes, as the reference (dbm.py:254-255)
+        for (int i = 0; i < L; ++i) {
+            const int H = Hs[i];
+            gradient_tc(i, i == 0 ? Xb.p : mu_b[i - 1].p, rows, i == 0 ? v_b.p : h_b[i - 1].p, N, Mp);
+            launch_colsum_bf16(ctx, mu_b[i].p, ldn[i + 1], nullptr, 0, rows, H, 1.f, 0.f, musum[i].p);
+            launch_colsum_bf16(ctx, h_b[i].p, ldn[i + 1], nullptr, 0, M, H, 1.f, 0.f, hsum[i].p);
+        }
+        launch_colsum<float>(ctx, X, V, (const float*)nullptr, 0, rows, V, 1.f, 0.f, xsum.p);
+        launch_colsum_bf16(ctx, v_b.p, ldn[0], nullptr, 0, M, V, 1.f, 0.f, vsum.p);
+        dbm_vbias_kernel<float><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, (float)rows, Mp, vb.p, dvb.p, (float)lr, (float)mom);
+        count_launch(ctx);
+        for (int i = 0; i < L; ++i) {
+            const int in = size_of(i, V, Hs), H = Hs[i];
+            BM_REQUIRE(i < H, "the reference's sparsity update indexes element i of layer i's unit vector");
+            dbm_sparsity_bias_kernel<float><<<(H + 255) / 256, 256, 0, ctx->stream>>>(
+                H, i, musum[i].p, hsum[i].p, (float)rows, Mp, qm[i].p, mm[i].p, pen[i].p, hb[i].p, dhb[i].p,
+                (float)damping, (float)sp_cost[i], (float)sp_target[i], (float)lr, (float)mom);
+            count_launch(ctx);
+            launch_weight_update<float>(ctx, G[i].p, H, 1.f, W[i].p, dW[i].p, in, H, pen[i].p, (float)l2, (float)lr, (float)mom, nullptr, 0);
+            colnorm_kernel<float><<<(H + 31) / 32, dim3(32, 8), 0, ctx->stream>>>(W[i].p, in, H, norm[i].p);       // :511-513
+            count_launch(ctx);
+            max_norm_scale_kernel<float><<<dim3((H + 255) / 256, in), 256, 0, ctx->stream>>>(W[i].p, in, H, norm[i].p, (float)max_norm);
+            count_launch(ctx);
+            refresh_shadow(i);
+        }
+    }
+
+    void val_metrics(const void* Xh, int rows, int k, uint64_t seed, uint32_t tick, double* out) override {
+        const float* X = upload_tc(Xh, rows);
+        const int n_mf = mean_field_tc(rows);
+        particles_tc(k, true, seed, tick, 0, true, nullptr);                  // dbm.py:523 control dependencies
+        out[0] = msre_tc(X, rows); out[1] = (double)n_mf;
+    }
+    void transform(const void* Xh, int rows, void* out) override {
+        upload_tc(Xh, rows);
+        mean_field_tc(rows);
+        BM_CUDA(cudaMemcpyAsync(out, mu[L - 1].p, (size_t)rows * Hs[L - 1] * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void reconstruct(const void* Xh, int rows, void* out) override {
+        upload_tc(Xh, rows);
+        mean_field_tc(rows);
+        reconstruction_tc(rows);
+        BM_CUDA(cudaMemcpyAsync(out, recon.p, (size_t)rows * V * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void log_proba(const void* Xh, int rows, double* out) override {
+        BM_REQUIRE(L == 2, "log_proba is defined for 2 hidden layers");
+        const float* X = upload_tc(Xh, rows);
+        mean_field_tc(rows);
+        linear_tc(Xb.p, ldn[0], rows, V, Wb[0].p, V, Hs[0], ldn[1], true, Hs[0], nullptr, t[0].p);              // t1 = X W_0
+        linear_tc(mu_b[0].p, ldn[1], rows, Hs[0], Wb[1].p, Hs[0], Hs[1], ldn[2], true, Hs[1], nullptr, t[1].p); // t2 = mu_0 W_1
+        dbm_bound_rows_kernel<float><<<(rows + 7) / 8, dim3(32, 8), 0, ctx->stream>>>(X, V, mu[0].p, Hs[0], mu[1].p, Hs[1], t[0].p, t[1].p,
+                                                                                     vb.p, hb[0].p, hb[1].p, rows, rowd.p);
+        count_launch(ctx);
+        BM_CUDA(cudaMemcpyAsync(out, rowd.p, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void sample_v(int k, uint64_t seed, uint32_t tick, void* out) override {
+        // dbm.py:641-648: k sampled sweeps (committed), k more without sampling; v <- their visible means
+        particles_tc(k, true, seed, tick, 0, true, nullptr);
+        bf16_t* vf = nullptr;
+        particles_tc(k, false, seed, tick, k, false, &vf);
+        if (vf != v_b.p) BM_CUDA(cudaMemcpyAsync(v_b.p, vf, (size_t)M * ldn[0] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        particles_f32_stale = true;
+        widen_particles();
+        BM_CUDA(cudaMemcpyAsync(out, v.p, (size_t)M * V * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // ---- AIS (dbm.py:650-736) -------------------------------------------------------------------------------------
+    // Per temperature: 2 tensor-core GEMMs for the shared pre-activations (x W_0^T + b, x W_1 + c_2; fp32 out),
+    // one pass that adds log p*_{i+1}(x) - log p*_i(x) of the same x to the chain's fp64 log-weight, two unit
+    // kernels (v, h2) and ONE two-pair tensor-core op for x' = act(beta (v W_0 + h2 W_1^T) + beta c_1) with the
+    // Bernoulli draw in its epilogue.
+    void ais(int R, int n_betas, int k, uint64_t seed, double* out) override {
+        BM_REQUIRE(L == 2 && v_kind == BM_UNIT_BERNOULLI, "AIS is defined for a 2-layer binary DBM");
+        BM_REQUIRE(R >= 1 && R <= 65535 && n_betas >= 2 && k >= 1, "bad AIS arguments (at most 65535 runs per call)");
+        const int H0 = Hs[0], H1 = Hs[1];
+        const int ld0 = ldn[1], ldv = ldn[0], ld1 = ldn[2];
+        DevBuf<bf16_t> x, xn, va, hc;
+        DevBuf<float> pa, pb;
+        DevBuf<double> logw;
+        x.ensure((size_t)R * ld0); xn.ensure((size_t)R * ld0); va.ensure((size_t)R * ldv); hc.ensure((size_t)R * ld1);
+        pa.ensure((size_t)R * V); pb.ensure((size_t)R * H1); logw.ensure(R);
+        for (DevBuf<bf16_t>* b : {&x, &xn, &va, &hc}) b->zero(ctx->stream);
+        logw.zero(ctx->stream);
+        const dim3 rgrid((R + 7) / 8), rblock(32, 8);
+        auto pre = [&](const bf16_t* xs) {          // pa = x W_0^T + b ; pb = x W_1 + c_2   (beta-free, shared)
+            linear_tc(xs, ld0, R, H0, Wb[0].p, V, H0, ld0, false, V, vb.p, pa.p);
+            linear_tc(xs, ld0, R, H0, Wb[1].p, H0, H1, ld1, true, H1, hb[1].p, pb.p);
+        };
+        auto accum2 = [&](const bf16_t* xs, float a, float b) {
+            ais_accum2_bf16_kernel<<<rgrid, rblock, 0, ctx->stream>>>(logw.p, a, b, xs, ld0, H0, hb[0].p, pa.p, V, pb.p, H1, R);
+            count_launch(ctx);
+        };
+        bf16_t* xc = x.p; bf16_t* xo = xn.p;
+        int it = 0;
+        auto transition = [&](float beta, bool have_pre) {
+            for (int s = 0; s < k; ++s) {
+                const uint32_t tick = (uint32_t)(it * k + s);
+                if (!(have_pre && s == 0)) pre(xc);
+                dim3 gv(((V + 3) / 4 + 127) / 128, R), gh(((H1 + 3) / 4 + 127) / 128, R);
+                ais_unit_bf16_kernel<<<gv, 128, 0, ctx->stream>>>(pa.p, V, beta, va.p, ldv, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, 0));
+                ais_unit_bf16_kernel<<<gh, 128, 0, ctx->stream>>>(pb.p, H1, beta, hc.p, ld1, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, 0));
+                count_launch(ctx); count_launch(ctx);
+                TcGemm o;                     // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
+                o.M = R; o.N = H0; o.n_pairs = 2;
+                o.A[0] = mat(va.p, R, V, ldv); o.K[0] = V; o.B[0] = mat(Wb[0].p, V, H0, ld0); o.b_t[0] = true;
+                o.A[1] = mat(hc.p, R, H1, ld1); o.K[1] = H1; o.B[1] = mat(Wb[1].p, H0, H1, ld1); o.b_t[1] = false;
+                o.acc_scale = beta; o.bias_scale = beta; o.bias = hb[0].p; o.act = ACT_SIGMOID;
+                o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, 0);
+                if (sample_h[0]) { o.sample = SMP_BERNOULLI; o.out_state_bf = xo; o.ld_state_bf = ld0; }
+                else { o.out_mean_bf = xo; o.ld_mean_bf = ld0; }
+                launch_tc_gemm(ctx, o);
+                std::swap(xc, xo);
+            }
+            ++it;
+        };
+        {   // x_0 ~ Ber(1/2)   (:700-702)
+            dim3 g(((H0 + 3) / 4 + 127) / 128, R);
+            ais_unit_bf16_kernel<<<g, 128, 0, ctx->stream>>>(nullptr, 0, 0.f, xc, ld0, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, 0));
+            count_launch(ctx);
+        }
+        const float delta = (float)(1.0 / n_betas);
+        transition(delta, false);                               // x_1 ~ T_1(x_1 | x_0)            :705
+        pre(xc);
+        float beta = delta, prev = 0.f;                         // - log p_0(x_1) pairs with + log p_1(x_1) :708
+        while (beta < 1.f - delta + 1e-5f) {                    // :710-711 (beta accumulates in the storage dtype)
+            accum2(xc, prev, beta);                             // + log p_i(x_i) - log p_{i-1}(x_i)
+            transition(beta + delta, true);                     // x_{i+1} ~ T_{i+1}
+            pre(xc);
+            prev = beta;
+            beta = beta + delta;
+        }
+        accum2(xc, prev, 1.0f);                                 // + log p_M(x_M) - log p_{M-1}(x_M)   :728
+        std::vector<double> hw(R);
+        BM_CUDA(cudaMemcpyAsync(hw.data(), logw.p, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double logZ0 = (double)(V + H0 + H1) * 0.6931471805599453;     // :731-734
+        for (int r = 0; r < R; ++r) out[r] = hw[r] + logZ0;
+    }
+};
+
+}  // namespace bm

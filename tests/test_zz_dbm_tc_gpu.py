@@ -1,0 +1,166 @@
+"""Tensor-core DBM engine (compute='bf16', csrc/bm_dbm_tc.cuh) against its bf16-operand emulation
+(oracle/dbm_bf16.py), the pinned fp32 oracle and exact enumeration.
+
+OPT-IN: the engine was written after the round's GPU budget was spent and has not run on a B200 yet, so these tests
+only run with BM_EXPERIMENTAL=1 (first thing to do on the next GPU visit:
+`BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q`).  The default DBM engine (fp32
+CUDA cores) and its tests are unaffected."""
+import os
+
+import numpy as np
+import pytest
+
+from boltzmann_machines import _native
+from oracle.dbm import OracleDBM
+from oracle.dbm_bf16 import OracleDBMbf16
+from oracle.rbm import bf16_round
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('BM_EXPERIMENTAL') != '1', reason='opt-in engine: set BM_EXPERIMENTAL=1')]
+
+
+def make_cfg(V=30, Hs=(18, 11), **kw):
+    cfg = dict(n_visible=V, n_hiddens=list(Hs), v_kind='bernoulli', h_kinds=['bernoulli'] * len(Hs),
+               h_n_samples=[100.] * len(Hs), dtype='float32', compute='bf16', n_particles=12, batch_size=10,
+               max_mf_updates=6, mf_tol=1e-6, l2=1e-4, max_norm=3.0, sample_v=True, sample_h=[True] * len(Hs),
+               sparsity_target=[0.2] * len(Hs), sparsity_cost=[0.01] * len(Hs), sparsity_damping=0.9)
+    cfg.update(kw)
+    return cfg
+
+
+def init(cfg, engines, seed=0, scale=0.3):
+    rng = np.random.RandomState(seed)
+    sizes = [cfg['n_visible']] + cfg['n_hiddens']
+    d = {'vb': (0.1 * rng.randn(sizes[0])).astype(np.float32)}
+    for i in range(len(cfg['n_hiddens'])):
+        s = '' if i == 0 else '_%d' % i
+        d['W' + s] = (scale * rng.randn(sizes[i], sizes[i + 1])).astype(np.float32)
+        d['hb' + s] = (0.1 * rng.randn(sizes[i + 1])).astype(np.float32)
+    for e in engines:
+        e.set_params(d)
+        e.init_particles(4242)
+    return d
+
+
+def batch(cfg, rows, seed=1):
+    return (np.random.RandomState(seed).rand(rows, cfg['n_visible']) < 0.3).astype(np.float32)
+
+
+def close_bf16(got, want, name, frac=0.1):
+    """bf16-stored means: equal up to one bf16 ulp almost everywhere (the kernel's sigmoid is ex2/rcp based)."""
+    np.testing.assert_allclose(got, want, rtol=2.0 ** -6, atol=1e-3, err_msg=name)
+    assert np.mean(got != want) <= frac, name
+
+
+def test_state_roundtrip_is_bf16_for_activations_and_fp32_for_variables():
+    cfg = make_cfg()
+    eng = _native.CudaDBM(cfg)
+    assert eng.compute == 'bf16'
+    d = init(cfg, (eng,))
+    g = eng.get_params()
+    for k in ('W', 'W_1', 'vb', 'hb', 'hb_1'):
+        np.testing.assert_array_equal(g[k], d[k])
+    emu = OracleDBMbf16(cfg); init(cfg, (emu,))
+    w = emu.get_params()
+    for k in ('v', 'h', 'h_1'):
+        np.testing.assert_array_equal(g[k], w[k])
+    eng.close()
+
+
+@pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7), (70, 130)])
+def test_mean_field_and_queries(Hs):
+    cfg = make_cfg(Hs=Hs)
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    init(cfg, (eng, emu))
+    Xq = batch(cfg, 7, seed=9)
+    close_bf16(eng.transform(Xq), emu.transform(Xq), 'transform')
+    close_bf16(eng.reconstruct(Xq), emu.reconstruct(Xq), 'reconstruct')
+    if len(Hs) == 2:
+        np.testing.assert_allclose(eng.log_proba(Xq), emu.log_proba(Xq), atol=0.05)
+    g, w = eng.get_params(['mu']), emu.get_params(['mu'])
+    close_bf16(g['mu'][:7], w['mu'][:7], 'mu')
+    eng.close()
+
+
+@pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7)])
+def test_training_steps_track_the_emulation(Hs):
+    cfg = make_cfg(Hs=Hs)
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    init(cfg, (eng, emu))
+    for it in range(3):
+        X = batch(cfg, 10, seed=it)
+        got = eng.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        want = emu.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        assert got['msre'] == pytest.approx(want['msre'], rel=0.05)
+        assert abs(got['n_mf_updates'] - want['n_mf_updates']) <= 1
+    g, w = eng.get_params(), emu.get_params()
+    for k in w:
+        if k.startswith(('W', 'dW', 'vb', 'hb', 'dvb', 'dhb')):
+            np.testing.assert_allclose(g[k], w[k], atol=2e-2, err_msg=k)
+    assert set(np.unique(g['h'])) <= {0.0, 1.0}
+    # a Bernoulli draw may differ only where u is within rounding of p: particles agree almost everywhere
+    assert np.mean(g['h'] != w['h']) < 0.1
+    eng.close()
+
+
+def test_first_gibbs_sweep_is_the_philox_draw():
+    """One sampled sweep from identical particles: states equal the emulation's except at rounding-level ties."""
+    cfg = make_cfg(V=784, Hs=(512, 256), n_particles=256, batch_size=16)
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    init(cfg, (eng, emu), scale=0.05)
+    X = batch(cfg, 16)
+    eng.val_metrics(X, 1, 77, 3); emu.val_metrics(X, 1, 77, 3)
+    g, w = eng.get_params(['v', 'h', 'h_1']), emu.get_params(['v', 'h', 'h_1'])
+    for k in w:
+        assert set(np.unique(g[k])) <= {0.0, 1.0}, k
+        assert np.mean(g[k] != w[k]) < 0.01, (k, np.mean(g[k] != w[k]))
+    eng.close()
+
+
+def test_ais_matches_exact_enumeration():
+    cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    init(cfg, (eng, emu))
+    a = eng.ais(32, 500, 1, 2222)
+    b = emu.ais(32, 500, 1, 2222)
+    lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
+    assert abs(lm(a) - lm(b)) < 0.1
+    p = emu.get_params()
+    W0, W1 = bf16_round(p['W']).astype(np.float64), bf16_round(p['W_1']).astype(np.float64)
+    terms = []
+    for s in range(2 ** 5):
+        x = np.array([(s >> i) & 1 for i in range(5)], dtype=np.float64)
+        terms.append(x @ p['hb'] + np.logaddexp(0, W0 @ x + p['vb']).sum() + np.logaddexp(0, x @ W1 + p['hb_1']).sum())
+    exact = np.logaddexp.reduce(terms)
+    assert abs(lm(a) - exact) < 0.15, (lm(a), exact)
+    eng.close()
+
+
+def test_ais_is_within_one_nat_of_the_pinned_oracle():
+    """BASELINE.json: AIS log Z within +-1.0 of the reference path (784-64-32, 64 runs x 200 betas)."""
+    cfg = make_cfg(V=784, Hs=(64, 32), n_particles=4, batch_size=4)
+    eng, ref = _native.CudaDBM(cfg), OracleDBM(dict(cfg, compute='fp32'))
+    init(cfg, (eng, ref), scale=0.05)
+    a = eng.ais(64, 200, 1, 1)
+    b = ref.ais(64, 200, 1, 1)
+    lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
+    assert abs(lm(a) - lm(b)) < 1.0
+    eng.close()
+
+
+def test_cfg4_shape_step_agrees_with_the_fp32_engine():
+    """BASELINE.json configs[3] shape: DBM 784-512-1024, 1024 particles, batch 1024, 25 mean-field updates."""
+    base = make_cfg(V=784, Hs=(512, 1024), n_particles=1024, batch_size=1024, max_mf_updates=25, mf_tol=1e-7,
+                    max_norm=6.0, sparsity_cost=[0., 0.])
+    tc, simt = _native.CudaDBM(base), _native.CudaDBM(dict(base, compute='fp32'))
+    assert tc.compute == 'bf16' and simt.compute == 'fp32'
+    init(base, (tc, simt), scale=0.02)
+    X = batch(base, 1024)
+    a = tc.train_step(X, 2e-3, 0.5, 1, 7, 0, metrics=('msre', 'n_mf_updates'))
+    b = simt.train_step(X, 2e-3, 0.5, 1, 7, 0, metrics=('msre', 'n_mf_updates'))
+    assert a['msre'] == pytest.approx(b['msre'], rel=0.02)
+    ga, gb = tc.get_params(['W', 'W_1', 'vb', 'hb', 'hb_1']), simt.get_params(['W', 'W_1', 'vb', 'hb', 'hb_1'])
+    for k in ga:
+        rel = np.linalg.norm(ga[k] - gb[k]) / max(np.linalg.norm(gb[k]), 1e-12)
+        assert rel < 0.02, (k, rel)
+    tc.close(); simt.close()
