@@ -29,7 +29,7 @@ EXPORTS = (
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
     'bm_dbm_create', 'bm_dbm_destroy', 'bm_dbm_set_param', 'bm_dbm_get_param', 'bm_dbm_init_particles',
     'bm_dbm_train_step', 'bm_dbm_val_metrics', 'bm_dbm_transform', 'bm_dbm_reconstruct', 'bm_dbm_log_proba',
-    'bm_dbm_sample_v', 'bm_dbm_ais',
+    'bm_dbm_sample_v', 'bm_dbm_ais', 'bm_dbm_ais_rows',
 )
 
 
@@ -111,6 +111,7 @@ def load_library(path=None):
         'bm_dbm_transform': [vp, vp, i32, vp], 'bm_dbm_reconstruct': [vp, vp, i32, vp],
         'bm_dbm_log_proba': [vp, vp, i32, vp], 'bm_dbm_sample_v': [vp, i32, u64, u32, vp],
         'bm_dbm_ais': [vp, i32, i32, i32, u64, vp],
+        'bm_dbm_ais_rows': [vp, i32, i32, i32, u64, u32, vp],
     }
     for name, argtypes in protos.items():
         fn = getattr(lib, name)
@@ -529,9 +530,15 @@ class CudaDBM(object):
         check(self._lib.bm_dbm_sample_v(self.handle, int(k), int(seed), int(tick), out.ctypes.data))
         return out
 
-    def ais(self, n_runs, n_betas, k, seed):
+    def ais(self, n_runs, n_betas, k, seed, first_run=None):
+        """log Z estimates of ``n_runs`` AIS runs.  ``first_run=None``: the whole ladder (sharded over the ranks of
+        the context's communicator, if any); an integer: runs [first_run, first_run + n_runs) of it, computed here."""
         out = np.empty(int(n_runs), dtype=np.float64)
-        check(self._lib.bm_dbm_ais(self.handle, int(n_runs), int(n_betas), int(k), int(seed), out.ctypes.data))
+        if first_run is None:
+            check(self._lib.bm_dbm_ais(self.handle, int(n_runs), int(n_betas), int(k), int(seed), out.ctypes.data))
+        else:
+            check(self._lib.bm_dbm_ais_rows(self.handle, int(n_runs), int(n_betas), int(k), int(seed), int(first_run),
+                                            out.ctypes.data))
         return out
 
     def close(self):

@@ -189,6 +189,7 @@ struct DbmBase {
     virtual void log_proba(const void* X, int rows, double* out) = 0;
     virtual void sample_v(int k, uint64_t seed, uint32_t tick, void* out) = 0;
     virtual void ais(int n_runs, int n_betas, int k, uint64_t seed, double* out) = 0;
+    virtual void ais_rows(int n_runs, int n_betas, int k, uint64_t seed, uint32_t first_run, double* out) = 0;
 };
 
 template <typename T>
@@ -527,16 +528,44 @@ struct Dbm : DbmBase {
     }
 
     // ---- AIS (dbm.py:650-736) ---------------------------------------------------------------------------------
-    void ais(int R, int n_betas, int k, uint64_t seed, double* out) override {
+    // The runs are independent chains: run r draws from row r of the AIS sites whichever rank or call computes it
+    // (row0 = first_run), so a ladder sharded over ranks, or cut into several calls, reproduces the unsharded one.
+    void ais_check(int R, int n_betas, int k) const {
         BM_REQUIRE(L == 2 && v_kind == BM_UNIT_BERNOULLI && h_kinds[0] == BM_UNIT_BERNOULLI && h_kinds[1] == BM_UNIT_BERNOULLI,
                    "AIS is defined for a 2-layer binary DBM");
         BM_REQUIRE(R >= 1 && n_betas >= 2 && k >= 1, "bad AIS arguments");
+    }
+    // runs [first, first + n) of a ladder of `total` runs -> out[0..n)
+    void ais_slice(int n, uint32_t first, int n_betas, int k, uint64_t seed, double* out, bool reduce, int total, int offset) {
+        DevBuf<double> all;
+        all.ensure(total);
+        all.zero(ctx->stream);
+        if (n > 0) ais_local(n, first, n_betas, k, seed, all.p + offset);
+        if (reduce) allreduce_sum(ctx, all.p, (size_t)total, true);        // every rank ends with every run
+        std::vector<double> hw(total);
+        BM_CUDA(cudaMemcpyAsync(hw.data(), all.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double logZ0 = (double)(V + Hs[0] + Hs[1]) * 0.6931471805599453;     // :731-734
+        for (int r = 0; r < total; ++r) out[r] = hw[r] + logZ0;
+    }
+    void ais(int R, int n_betas, int k, uint64_t seed, double* out) override {
+        ais_check(R, n_betas, k);
+        // with a communicator the runs are sharded over the ranks and gathered by one sum-allreduce of R doubles
+        const int nr = ctx->nranks > 1 ? ctx->nranks : 1, rk = ctx->nranks > 1 ? ctx->rank : 0;
+        const int lo = (int)((long long)R * rk / nr), hi = (int)((long long)R * (rk + 1) / nr);
+        ais_slice(hi - lo, (uint32_t)lo, n_betas, k, seed, out, nr > 1, R, lo);
+    }
+    void ais_rows(int R, int n_betas, int k, uint64_t seed, uint32_t first_run, double* out) override {
+        ais_check(R, n_betas, k);
+        ais_slice(R, first_run, n_betas, k, seed, out, false, R, 0);
+    }
+    // R chains starting at global run `row0`; their log-weights (without log Z_0) are ADDED to logw_out[0..R) (device, zeroed)
+    virtual void ais_local(int R, uint32_t row0, int n_betas, int k, uint64_t seed, double* logw_out) {
         const int H0 = Hs[0], H1 = Hs[1];
         DevBuf<T> x, xn, va, hc, pa, pb;
-        DevBuf<double> logw;
+        struct { double* p; } logw{logw_out};
         x.ensure((size_t)R * H0); xn.ensure((size_t)R * H0); va.ensure((size_t)R * V); hc.ensure((size_t)R * H1);
-        pa.ensure((size_t)R * V); pb.ensure((size_t)R * H1); logw.ensure(R);
-        logw.zero(ctx->stream);
+        pa.ensure((size_t)R * V); pb.ensure((size_t)R * H1);
         const dim3 rgrid((R + 7) / 8), rblock(32, 8);
         auto pre = [&](const T* xs) {          // pa = x W_0^T + b ; pb = x W_1 + c_2   (beta-free, shared)
             LayerOp<T> a; a.M = R; a.N = V; a.A1 = xs; a.lda1 = H0; a.K1 = H0; a.B1 = W[0].p; a.ldb1 = H0; a.b1_trans = 1;
@@ -557,14 +586,14 @@ struct Dbm : DbmBase {
                 const uint32_t tick = (uint32_t)(it * k + s);
                 if (!(have_pre && s == 0)) pre(xc);
                 dim3 gv(((V + 3) / 4 + 127) / 128, R), gh(((H1 + 3) / 4 + 127) / 128, R);
-                ais_unit_kernel<T><<<gv, 128, 0, ctx->stream>>>(pa.p, beta, va.p, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, 0));
-                ais_unit_kernel<T><<<gh, 128, 0, ctx->stream>>>(pb.p, beta, hc.p, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, 0));
+                ais_unit_kernel<T><<<gv, 128, 0, ctx->stream>>>(pa.p, beta, va.p, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, row0));
+                ais_unit_kernel<T><<<gh, 128, 0, ctx->stream>>>(pb.p, beta, hc.p, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, row0));
                 count_launch(ctx); count_launch(ctx);
                 LayerOp<T> o;                 // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
                 o.M = R; o.N = H0; o.A1 = va.p; o.lda1 = V; o.K1 = V; o.B1 = W[0].p; o.ldb1 = H0;
                 o.A2 = hc.p; o.lda2 = H1; o.K2 = H1; o.B2 = W[1].p; o.ldb2 = H1; o.b2_trans = 1;
                 o.acc_scale = beta; o.bias_scale = beta; o.bias = hb[0].p; o.act = ACT_SIGMOID;
-                o.means = xo; o.ldm = H0; o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, 0);
+                o.means = xo; o.ldm = H0; o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, row0);
                 if (sample_h[0]) { o.sample = SMP_BERNOULLI; o.states = xo; o.lds = H0; }
                 launch_layer_op<T>(ctx, o);
                 std::swap(xc, xo);
@@ -576,7 +605,7 @@ struct Dbm : DbmBase {
             dim3 g(((H0 + 3) / 4 + 127) / 128, R);
             launch_fill<T>(ctx, pb.p, (size_t)R * H1, T(0));
             launch_fill<T>(ctx, xo, (size_t)R * H0, T(0));          // pre-activation 0 -> p = 1/2
-            ais_unit_kernel<T><<<g, 128, 0, ctx->stream>>>(xo, T(0), xc, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, 0));
+            ais_unit_kernel<T><<<g, 128, 0, ctx->stream>>>(xo, T(0), xc, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, row0));
             count_launch(ctx);
         }
         const T delta = (T)(1.0 / n_betas);
@@ -590,11 +619,7 @@ struct Dbm : DbmBase {
             beta = (T)(beta + delta);
         }
         accum(xc, +1.0, 1.0);                                   // + log p_M(x_M)                 :728
-        std::vector<double> hw(R);
-        BM_CUDA(cudaMemcpyAsync(hw.data(), logw.p, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        BM_CUDA(cudaStreamSynchronize(ctx->stream));
-        const double logZ0 = (double)(V + H0 + H1) * 0.6931471805599453;     // :731-734
-        for (int r = 0; r < R; ++r) out[r] = hw[r] + logZ0;
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));            // the workspaces above are released on return
     }
 };
 
@@ -665,6 +690,9 @@ int bm_dbm_sample_v(bm_dbm* h, int32_t k, uint64_t seed, uint32_t tick, void* ou
 }
 int bm_dbm_ais(bm_dbm* h, int32_t n_runs, int32_t n_betas, int32_t k, uint64_t seed, double* logZ) {
     BM_API_BEGIN DBM_ENTER(h) BM_REQUIRE(logZ, "null argument"); DBM(h)->ais(n_runs, n_betas, k, seed, logZ); BM_API_END
+}
+int bm_dbm_ais_rows(bm_dbm* h, int32_t n_runs, int32_t n_betas, int32_t k, uint64_t seed, uint32_t first_run, double* logZ) {
+    BM_API_BEGIN DBM_ENTER(h) BM_REQUIRE(logZ, "null argument"); DBM(h)->ais_rows(n_runs, n_betas, k, seed, first_run, logZ); BM_API_END
 }
 
 }  // extern "C"

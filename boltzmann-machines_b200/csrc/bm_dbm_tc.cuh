@@ -422,18 +422,17 @@ struct DbmTC : Dbm<float> {
     // one pass that adds log p*_{i+1}(x) - log p*_i(x) of the same x to the chain's fp64 log-weight, two unit
     // kernels (v, h2) and ONE two-pair tensor-core op for x' = act(beta (v W_0 + h2 W_1^T) + beta c_1) with the
     // Bernoulli draw in its epilogue.
-    void ais(int R, int n_betas, int k, uint64_t seed, double* out) override {
-        BM_REQUIRE(L == 2 && v_kind == BM_UNIT_BERNOULLI, "AIS is defined for a 2-layer binary DBM");
-        BM_REQUIRE(R >= 1 && R <= 65535 && n_betas >= 2 && k >= 1, "bad AIS arguments (at most 65535 runs per call)");
+    // (sharding over ranks / calls: Dbm<float>::ais, ais_rows; run r draws from row row0 + r of the AIS sites)
+    void ais_local(int R, uint32_t row0, int n_betas, int k, uint64_t seed, double* logw_out) override {
+        BM_REQUIRE(R <= 65535, "at most 65535 AIS runs per rank and call");
         const int H0 = Hs[0], H1 = Hs[1];
         const int ld0 = ldn[1], ldv = ldn[0], ld1 = ldn[2];
         DevBuf<bf16_t> x, xn, va, hc;
         DevBuf<float> pa, pb;
-        DevBuf<double> logw;
+        struct { double* p; } logw{logw_out};
         x.ensure((size_t)R * ld0); xn.ensure((size_t)R * ld0); va.ensure((size_t)R * ldv); hc.ensure((size_t)R * ld1);
-        pa.ensure((size_t)R * V); pb.ensure((size_t)R * H1); logw.ensure(R);
+        pa.ensure((size_t)R * V); pb.ensure((size_t)R * H1);
         for (DevBuf<bf16_t>* b : {&x, &xn, &va, &hc}) b->zero(ctx->stream);
-        logw.zero(ctx->stream);
         const dim3 rgrid((R + 7) / 8), rblock(32, 8);
         auto pre = [&](const bf16_t* xs) {          // pa = x W_0^T + b ; pb = x W_1 + c_2   (beta-free, shared)
             linear_tc(xs, ld0, R, H0, Wb[0].p, V, H0, ld0, false, V, vb.p, pa.p);
@@ -450,15 +449,15 @@ struct DbmTC : Dbm<float> {
                 const uint32_t tick = (uint32_t)(it * k + s);
                 if (!(have_pre && s == 0)) pre(xc);
                 dim3 gv(((V + 3) / 4 + 127) / 128, R), gh(((H1 + 3) / 4 + 127) / 128, R);
-                ais_unit_bf16_kernel<<<gv, 128, 0, ctx->stream>>>(pa.p, V, beta, va.p, ldv, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, 0));
-                ais_unit_bf16_kernel<<<gh, 128, 0, ctx->stream>>>(pb.p, H1, beta, hc.p, ld1, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, 0));
+                ais_unit_bf16_kernel<<<gv, 128, 0, ctx->stream>>>(pa.p, V, beta, va.p, ldv, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, row0));
+                ais_unit_bf16_kernel<<<gh, 128, 0, ctx->stream>>>(pb.p, H1, beta, hc.p, ld1, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, row0));
                 count_launch(ctx); count_launch(ctx);
                 TcGemm o;                     // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
                 o.M = R; o.N = H0; o.n_pairs = 2;
                 o.A[0] = mat(va.p, R, V, ldv); o.K[0] = V; o.B[0] = mat(Wb[0].p, V, H0, ld0); o.b_t[0] = true;
                 o.A[1] = mat(hc.p, R, H1, ld1); o.K[1] = H1; o.B[1] = mat(Wb[1].p, H0, H1, ld1); o.b_t[1] = false;
                 o.acc_scale = beta; o.bias_scale = beta; o.bias = hb[0].p; o.act = ACT_SIGMOID;
-                o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, 0);
+                o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, row0);
                 if (sample_h[0]) { o.sample = SMP_BERNOULLI; o.out_state_bf = xo; o.ld_state_bf = ld0; }
                 else { o.out_mean_bf = xo; o.ld_mean_bf = ld0; }
                 launch_tc_gemm(ctx, o);
@@ -468,7 +467,7 @@ struct DbmTC : Dbm<float> {
         };
         {   // x_0 ~ Ber(1/2)   (:700-702)
             dim3 g(((H0 + 3) / 4 + 127) / 128, R);
-            ais_unit_bf16_kernel<<<g, 128, 0, ctx->stream>>>(nullptr, 0, 0.f, xc, ld0, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, 0));
+            ais_unit_bf16_kernel<<<g, 128, 0, ctx->stream>>>(nullptr, 0, 0.f, xc, ld0, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, row0));
             count_launch(ctx);
         }
         const float delta = (float)(1.0 / n_betas);
@@ -483,11 +482,7 @@ struct DbmTC : Dbm<float> {
             beta = beta + delta;
         }
         accum2(xc, prev, 1.0f);                                 // + log p_M(x_M) - log p_{M-1}(x_M)   :728
-        std::vector<double> hw(R);
-        BM_CUDA(cudaMemcpyAsync(hw.data(), logw.p, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        BM_CUDA(cudaStreamSynchronize(ctx->stream));
-        const double logZ0 = (double)(V + H0 + H1) * 0.6931471805599453;     // :731-734
-        for (int r = 0; r < R; ++r) out[r] = hw[r] + logZ0;
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));            // the workspaces above are released on return
     }
 };
 

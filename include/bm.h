@@ -147,7 +147,7 @@ typedef struct bm_dbm_cfg {
     int32_t v_kind;                  /* BM_UNIT_*                                          */
     const int32_t* h_kinds;
     const double*  h_n_samples;      /* MultinomialLayer.n_samples per layer (nullable)    */
-    int32_t dtype, compute;
+    int32_t dtype, compute;          /* BM_COMPUTE_BF16: tensor-core engine (F32 models, Bernoulli hidden layers); opt-in */
     int32_t n_particles, batch_size, max_mf_updates;
     int32_t sample_v;
     const int32_t* sample_h;
@@ -176,8 +176,15 @@ int  bm_dbm_transform(bm_dbm* dbm, const void* X, int32_t rows, void* out);     
 int  bm_dbm_reconstruct(bm_dbm* dbm, const void* X, int32_t rows, void* out);     /* dbm.py:626-632, 874-885 */
 int  bm_dbm_log_proba(bm_dbm* dbm, const void* X, int32_t rows, double* out);     /* variational bound + log Z, dbm.py:738-759 */
 int  bm_dbm_sample_v(bm_dbm* dbm, int32_t n_gibbs_steps, uint64_t seed, uint32_t tick, void* out);  /* dbm.py:641-648 */
-/* AIS estimates of log Z, one per run (dbm.py:650-736, 899-939) */
+/* AIS estimates of log Z, one per run (dbm.py:650-736, 899-939).  The runs are independent chains and run r always draws
+ * from row r of the AIS sites: on a context with a communicator (bm_ctx_comm_init) the n_runs runs are sharded over the
+ * ranks and gathered with one sum-allreduce of n_runs doubles -- every rank calls with the same arguments and receives all
+ * n_runs values, identical to a single-GPU call. */
 int  bm_dbm_ais(bm_dbm* dbm, int32_t n_runs, int32_t n_betas, int32_t n_gibbs_steps, uint64_t seed, double* logZ);
+/* runs [first_run, first_run + n_runs) of the same ladder, no communication: for callers that shard or chunk the runs
+ * themselves (one process driving several GPUs; more runs than fit in memory at once) */
+int  bm_dbm_ais_rows(bm_dbm* dbm, int32_t n_runs, int32_t n_betas, int32_t n_gibbs_steps, uint64_t seed, uint32_t first_run,
+                     double* logZ);
 
 /* ---- test hook: the raw tensor-core GEMM (no counterpart in the reference) -----------------
  * C[M,N] (fp32) = A * B^T (+/- A2 * B2^T), operands given as host fp32 and rounded to bf16.

@@ -110,7 +110,7 @@ class OracleDBM(object):
     def _sample(self, kind, means, n_samples, seed, site, t, tick):
         rows, n = means.shape
         if kind == 'bernoulli':
-            u = P.uniform_at(rows, n, seed, site, t, tick)
+            u = P.uniform_at(rows, n, seed, site, t, tick, getattr(self, '_row0', 0))
             return (u.astype(self.dt) < means).astype(self.dt)
         if kind == 'multinomial':
             probs = (means / means.sum(axis=1, keepdims=True)).astype(np.float32)
@@ -307,11 +307,20 @@ class OracleDBM(object):
                 x = self._sample(self.h_kinds[0], x, 100., seed, P.SITE_AIS_H1, 0, tick)
         return x
 
-    def ais(self, n_runs, n_betas, k, seed):
+    def ais(self, n_runs, n_betas, k, seed, first_run=0):
+        """``first_run``: these are runs [first_run, first_run + n_runs) of a longer ladder (the runs are independent
+        chains; run r draws from row r of the AIS sites), which is how the engine shards them over GPUs."""
         assert self.L == 2
+        self._row0 = int(first_run)
+        try:
+            return self._ais(n_runs, n_betas, k, seed)
+        finally:
+            self._row0 = 0
+
+    def _ais(self, n_runs, n_betas, k, seed):
         dt = self.dt
         delta = dt.type(1. / n_betas)
-        u = P.uniform_at(int(n_runs), self.Hs[0], seed, P.SITE_AIS_INIT, 0, 0)
+        u = P.uniform_at(int(n_runs), self.Hs[0], seed, P.SITE_AIS_INIT, 0, 0, self._row0)
         x = (u < np.float32(0.5)).astype(dt)                                        # :700-702
         it = 0
         x = self._ais_transition(x, delta, k, seed, it); it += 1                     # :705

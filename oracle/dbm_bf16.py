@@ -71,7 +71,7 @@ class OracleDBMbf16(OracleDBM):
         pre = (np.float32(acc_scale) * T + np.float32(bias_scale) * self.hb(i)).astype(np.float32)
         m = sigmoid(pre)
         if sample:
-            u = P.uniform_at(m.shape[0], m.shape[1], seed, site, t, tick)
+            u = P.uniform_at(m.shape[0], m.shape[1], seed, site, t, tick, getattr(self, '_row0', 0))
             return (u < m).astype(np.float32)
         return _r(m)
 
@@ -206,17 +206,17 @@ class OracleDBMbf16(OracleDBM):
         with np.errstate(over='ignore'):
             p = np.float32(1.) / (np.float32(1.) + np.exp(-(np.float32(beta) * pre)))
         if sample:
-            u = P.uniform_at(pre.shape[0], pre.shape[1], seed, site, 0, tick)
+            u = P.uniform_at(pre.shape[0], pre.shape[1], seed, site, 0, tick, getattr(self, '_row0', 0))
             return (u < p).astype(np.float32)
         return _r(p)
 
-    def ais(self, n_runs, n_betas, k, seed):
+    def _ais(self, n_runs, n_betas, k, seed):
         assert self.L == 2 and self.v_kind == 'bernoulli'
         f = np.float32
         sh = self.cfg.get('sample_h', [True] * self.L)
         sv = self.cfg.get('sample_v', True)
         delta = f(1. / n_betas)
-        u = P.uniform_at(int(n_runs), self.Hs[0], seed, P.SITE_AIS_INIT, 0, 0)
+        u = P.uniform_at(int(n_runs), self.Hs[0], seed, P.SITE_AIS_INIT, 0, 0, self._row0)
         x = (u < f(0.5)).astype(f)
         state = {'it': 0}
 

@@ -104,3 +104,17 @@ def test_ais_paper_scale_is_within_one_nat_of_the_oracle():
     lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
     assert abs(lm(a) - lm(b)) < 1.0
     eng.close()
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+def test_ais_runs_shard_by_first_run(dtype):
+    """bm_dbm_ais_rows: runs [first, first + n) of the ladder, computed alone, equal those runs of the whole ladder
+    (what lets bm_dbm_ais shard n_runs over the ranks of a communicator) -- and the oracle's."""
+    cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4, dtype=dtype)
+    eng, ora = make_pair(cfg)
+    full = eng.ais(13, 40, 2, 99)
+    parts = np.concatenate([eng.ais(5, 40, 2, 99, first_run=0), eng.ais(1, 40, 2, 99, first_run=5),
+                            eng.ais(7, 40, 2, 99, first_run=6)])
+    np.testing.assert_allclose(full, parts, rtol=0, atol=1e-6)    # same chains; a different chain would differ by ~0.1
+    np.testing.assert_allclose(eng.ais(7, 40, 2, 99, first_run=6), ora.ais(7, 40, 2, 99, first_run=6), atol=5e-3)
+    eng.close()

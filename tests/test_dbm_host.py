@@ -108,3 +108,21 @@ def test_log_Z_small_model_close_to_exact(engines, workdir):
     assert values.shape == (64,)
     assert abs(log_mean - exact) < 0.05, (log_mean, exact)
     assert lo <= log_mean <= hi
+
+
+def test_ais_runs_shard_by_first_run():
+    """AIS runs are independent chains -- run r draws from row r of the AIS sites, so any split of the
+    ladder over ranks / calls reproduces the unsharded runs exactly (the engine's bm_dbm_ais / bm_dbm_ais_rows)."""
+    from oracle.dbm import OracleDBM
+    from oracle.dbm_bf16 import OracleDBMbf16
+    for cls in (OracleDBM, OracleDBMbf16):
+        cfg = dict(n_visible=7, n_hiddens=[5, 4], dtype='float32', n_particles=4, batch_size=4)
+        ora = cls(cfg)
+        rng = np.random.RandomState(0)
+        ora.set_params({'W': 0.3 * rng.randn(7, 5), 'W_1': 0.3 * rng.randn(5, 4), 'vb': 0.1 * rng.randn(7),
+                        'hb': 0.1 * rng.randn(5), 'hb_1': 0.1 * rng.randn(4)})
+        full = ora.ais(13, 40, 2, 99)
+        parts = np.concatenate([ora.ais(5, 40, 2, 99, first_run=0), ora.ais(1, 40, 2, 99, first_run=5),
+                                ora.ais(7, 40, 2, 99, first_run=6)])
+        np.testing.assert_allclose(full, parts, rtol=0, atol=1e-6)    # same chains; a different chain would differ by ~0.1
+        assert ora.ais(13, 40, 2, 99).tolist() == full.tolist()          # first_run does not leak into later calls

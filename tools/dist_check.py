@@ -46,6 +46,23 @@ def main():
             rank, compute, err, identical), flush=True)
         ok = ok and err < tol and identical
         eng.close()
+    # AIS: the runs shard over the ranks inside bm_dbm_ais (one sum-allreduce of n_runs doubles gathers them);
+    # every rank must receive the ladder a single GPU computes (run r draws from row r whichever rank owns it)
+    from oracle.dbm import OracleDBM
+    dcfg = dict(n_visible=20, n_hiddens=[12, 8], dtype='float32', n_particles=4, batch_size=4)
+    dparams = {'W': (0.3 * rng.randn(20, 12)).astype(np.float32), 'W_1': (0.3 * rng.randn(12, 8)).astype(np.float32),
+               'vb': (0.1 * rng.randn(20)).astype(np.float32), 'hb': (0.1 * rng.randn(12)).astype(np.float32),
+               'hb_1': (0.1 * rng.randn(8)).astype(np.float32)}
+    dbm, dora = _native.CudaDBM(dcfg, ctx=ctx), OracleDBM(dcfg)
+    dbm.set_params(dparams); dora.set_params(dparams)
+    n_runs = 13                                    # does not divide evenly
+    sharded = dbm.ais(n_runs, 50, 1, 4321)         # collective: every rank calls it
+    alone = dbm.ais(n_runs, 50, 1, 4321, first_run=0)      # the same ladder computed entirely on this GPU
+    want = dora.ais(n_runs, 50, 1, 4321)
+    e1, e2 = float(np.max(np.abs(sharded - alone))), float(np.max(np.abs(sharded - want)))
+    print('rank {0} AIS: max |sharded - single GPU| = {1:.3e}, max |sharded - oracle| = {2:.3e}'.format(rank, e1, e2), flush=True)
+    ok = ok and e1 < 1e-6 and e2 < 5e-3
+    dbm.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
