@@ -4,7 +4,8 @@ there, tests/test_full_size_gpu.py).  One JSON object per configuration on stdou
     python tools/bench_configs.py [cfg3] [cfg4] [cfg4-ais] [cfg5]
 
 cfg3: GaussianRBM 3072-5000, batch 2048, CD-1            (bf16 tensor-core program)
-cfg4: DBM 784-512-1024, batch = particles = 1024, 25 mean-field updates, 1 Gibbs step per PCD update (fp32 CUDA-core path)
+cfg4: DBM 784-512-1024, batch = particles = 1024, 25 mean-field updates, 1 Gibbs step per PCD update
+      (--dbm-compute fp32: CUDA-core engine, default; bf16: the opt-in tensor-core engine)
 cfg4-ais: AIS on that DBM, 20000 runs (or --ais-runs) x 1000 betas
 cfg5: the per-GPU shard of BernoulliRBM 784-4096, 4096 particles, 25 Gibbs steps per update
 FLOP counts follow SURVEY.md section 8(d).  Times: CUDA events on the engine's stream after warm-up.
@@ -57,9 +58,9 @@ def rbm_case(name, kind, V, H, B, k, steps, warmup, lr):
     return out
 
 
-def dbm(ctx):
+def dbm(ctx, compute='fp32'):
     V, Hs, B = 784, [512, 1024], 1024
-    cfg = dict(n_visible=V, n_hiddens=Hs, v_kind='bernoulli', h_kinds=['bernoulli'] * 2, h_n_samples=[100.] * 2,
+    cfg = dict(compute=compute, n_visible=V, n_hiddens=Hs, v_kind='bernoulli', h_kinds=['bernoulli'] * 2, h_n_samples=[100.] * 2,
                dtype='float32', n_particles=B, batch_size=B, max_mf_updates=25, mf_tol=1e-7, l2=1e-7, max_norm=6.0,
                sample_v=True, sample_h=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[1e-4, 5e-5],
                sparsity_damping=0.9)
@@ -72,9 +73,9 @@ def dbm(ctx):
     return eng, cfg
 
 
-def cfg4(steps, warmup):
+def cfg4(steps, warmup, compute='fp32'):
     ctx = _native.Context.default()
-    eng, cfg = dbm(ctx)
+    eng, cfg = dbm(ctx, compute)
     B, V, (H1, H2) = 1024, 784, cfg['n_hiddens']
     X = (np.random.RandomState(3).rand(B, V) < 0.13).astype(np.float32)
     n_mf = [0.0]
@@ -86,15 +87,15 @@ def cfg4(steps, warmup):
     mf = 2.0 * B * (V * H1 + 2 * H1 * H2) * 25 + 2.0 * B * (V * H1 + H1 * H2)
     pcd = 2.0 * B * (2 * V * H1 + 2 * H1 * H2)
     grads = 2.0 * B * 2 * (V * H1 + H1 * H2)
-    out = dict(config='cfg4 DBM 784-512-1024 step', ms_per_step=ms, n_mf_updates=n_mf[0],
+    out = dict(config='cfg4 DBM 784-512-1024 step', engine=eng.compute, ms_per_step=ms, n_mf_updates=n_mf[0],
                tflops=(mf + pcd + grads) / (ms * 1e-3) / 1e12, flop_per_step=mf + pcd + grads, steps=steps)
     eng.close()
     return out
 
 
-def cfg4_ais(n_runs, n_betas):
+def cfg4_ais(n_runs, n_betas, compute='fp32'):
     ctx = _native.Context.default()
-    eng, cfg = dbm(ctx)
+    eng, cfg = dbm(ctx, compute)
     V, (H1, H2) = 784, cfg['n_hiddens']
     eng.ais(256, 20, 1, 1)          # warm-up
     ctx.sync()
@@ -103,7 +104,7 @@ def cfg4_ais(n_runs, n_betas):
     ms = ctx.timer_stop()
     flop = float(n_runs) * (n_betas - 1) * (4.0 * H1 * V + 4.0 * H1 * H2)      # fused count, SURVEY 8(d)
     lm = float(np.logaddexp.reduce(vals) - np.log(len(vals)))
-    out = dict(config='cfg4 AIS {0} runs x {1} betas'.format(n_runs, n_betas), ms=ms, tflops=flop / (ms * 1e-3) / 1e12,
+    out = dict(config='cfg4 AIS {0} runs x {1} betas'.format(n_runs, n_betas), engine=eng.compute, ms=ms, tflops=flop / (ms * 1e-3) / 1e12,
                chain_transitions_per_s=n_runs * (n_betas - 1) / (ms * 1e-3), log_Z=lm)
     eng.close()
     return out
@@ -116,6 +117,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--ais-runs', type=int, default=20000)
     ap.add_argument('--ais-betas', type=int, default=1000)
+    ap.add_argument('--dbm-compute', default='fp32', choices=['fp32', 'bf16'],
+                    help="DBM engine of cfg4 / cfg4-ais: fp32 CUDA cores (default) or the opt-in tensor-core engine")
     a = ap.parse_args()
     for w in a.which:
         if w == 'cfg3':
@@ -123,9 +126,9 @@ def main():
         elif w == 'cfg5':
             r = rbm_case('cfg5 shard BernoulliRBM 784-4096 batch 4096 k=25', 'bernoulli', 784, 4096, 4096, 25, a.steps, a.warmup, 0.01)
         elif w == 'cfg4':
-            r = cfg4(a.steps, a.warmup)
+            r = cfg4(a.steps, a.warmup, a.dbm_compute)
         elif w == 'cfg4-ais':
-            r = cfg4_ais(a.ais_runs, a.ais_betas)
+            r = cfg4_ais(a.ais_runs, a.ais_betas, a.dbm_compute)
         else:
             raise SystemExit('unknown configuration ' + w)
         print(json.dumps(r), flush=True)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU visit of the opt-in tensor-core DBM engine (csrc/bm_dbm_tc.cuh): its gated parity tests under a short timeout
+# (a deadlocked tcgen05 kernel must not hold the box), then cfg4 / cfg4-ais timings of both engines side by side.
+# usage: tools/gpu_dbm_tc_first_visit.sh [tag]      -> gpurun_out/<tag>_dbm_tc_*.{log,json}
+TAG=${1:-r02_a}
+OUT=gpurun_out
+mkdir -p $OUT
+BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q > $OUT/${TAG}_dbm_tc_pytest.log 2>&1
+echo "pytest exit $?" >> $OUT/${TAG}_dbm_tc_pytest.log
+tail -15 $OUT/${TAG}_dbm_tc_pytest.log
+for c in fp32 bf16; do
+  timeout 600 python tools/bench_configs.py cfg4 cfg4-ais --dbm-compute $c --steps 20 --ais-runs 20000 --ais-betas 1000 \
+    > $OUT/${TAG}_dbm_tc_bench_$c.json 2> $OUT/${TAG}_dbm_tc_bench_$c.err
+  echo "bench_configs($c) exit $?"; cat $OUT/${TAG}_dbm_tc_bench_$c.json
+done
