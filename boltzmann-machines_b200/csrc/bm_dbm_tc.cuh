@@ -15,6 +15,10 @@
 // STATUS: opt-in (bm_dbm_cfg.compute = BM_COMPUTE_BF16; the Python mirror passes it only when asked:
 // DBM(..., compute='bf16') or BM_DBM_COMPUTE=bf16).  The default DBM engine is the fp32 CUDA-core one.
 #pragma once
+#include <map>
+#include <memory>
+#include <utility>
+#include <stdlib.h>
 
 namespace bm {
 
@@ -34,6 +38,24 @@ __global__ void max_abs_diff_bf16_kernel(const bf16_t* __restrict__ a, int lda, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// Convergence tests of a speculated chunk of mean-field sweeps: `hist` holds slots 0..n_tests of one layer's variational
+// parameters ([slot][rows_cap, ld]); flags[j] = max(flags[j], max |slot j+1 - slot j|) over the [rows, cols] window.
+__global__ void mf_chunk_diffs_kernel(const bf16_t* __restrict__ hist, size_t slot_stride, int ld, int rows, int cols,
+                                      unsigned int* __restrict__ flags) {
+    const int j = blockIdx.y;
+    const bf16_t* a = hist + (size_t)(j + 1) * slot_stride;
+    const bf16_t* b = hist + (size_t)j * slot_stride;
+    float m = 0.f;
+    const size_t total = (size_t)rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        m = fmaxf(m, fabsf(__bfloat162float(a[(size_t)r * ld + c]) - __bfloat162float(b[(size_t)r * ld + c])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(flags + j, __float_as_uint(m));
 }
 
 // G = (sum of `sp` positive slices) / n_div - (sum of `sn` negative slices) / m_div      (dbm.py:558-568)
@@ -113,6 +135,11 @@ struct DbmTC : Dbm<float> {
     std::vector<DevBuf<bf16_t>> mu_b, mu2_b, h_b, h2_b, h3_b;
     std::vector<DevBuf<float>> Gp;               // split-K slices of the gradient GEMMs
     bool particles_f32_stale = false;            // the bf16 particles are newer than the fp32 copies get_param reads
+    // mean-field as persistent dataflow programs (opt-in, BM_DBM_MF_CHUNK = sweeps per launch): slot history + programs
+    int mf_chunk = 0;
+    std::vector<DevBuf<bf16_t>> hist;            // per layer: (mf_chunk + 2) slots of [B, ldn[i+1]]
+    DevBuf<unsigned int> mf_flags;
+    std::map<std::pair<int, int>, std::unique_ptr<TcProgram>> mf_progs;      // keyed by (rows, sweeps in the chunk)
 
     static bool supports(const bm_dbm_cfg& f) {
         if (f.dtype != BM_DTYPE_F32) return false;
@@ -133,6 +160,14 @@ struct DbmTC : Dbm<float> {
             mu_b[i].ensure((size_t)B * ldn[i + 1]); mu2_b[i].ensure((size_t)B * ldn[i + 1]);
             h_b[i].ensure((size_t)M * ldn[i + 1]); h2_b[i].ensure((size_t)M * ldn[i + 1]);
             for (DevBuf<bf16_t>* b : {&Wb[i], &mu_b[i], &mu2_b[i], &h_b[i], &h2_b[i]}) b->zero(ctx->stream);
+        }
+        { const char* e = getenv("BM_DBM_MF_CHUNK"); mf_chunk = e ? atoi(e) : 0; }
+        if (mf_chunk > max_mf) mf_chunk = max_mf;
+        if (mf_chunk * L > 90) mf_chunk = 90 / L;              // a program holds at most 96 ops
+        if (mf_chunk > 0) {
+            hist.resize(L);
+            for (int i = 0; i < L; ++i) { hist[i].ensure((size_t)(mf_chunk + 2) * B * ldn[i + 1]); hist[i].zero(ctx->stream); }
+            mf_flags.ensure(mf_chunk);
         }
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -181,6 +216,10 @@ struct DbmTC : Dbm<float> {
     // act(acc_scale * (below W_i [+ above W_{i+1}^T]) + bias_scale * b_i): means XOR sampled states (bf16)
     void hidden_tc(int i, const bf16_t* below, const bf16_t* above, bf16_t* out, bool sample, int rows,
                    float acc_scale, float bias_scale, RngKey rng) {
+        launch_tc_gemm(ctx, hidden_gemm(i, below, above, out, sample, rows, acc_scale, bias_scale, rng));
+    }
+    TcGemm hidden_gemm(int i, const bf16_t* below, const bf16_t* above, bf16_t* out, bool sample, int rows,
+                       float acc_scale, float bias_scale, RngKey rng) {
         const int in = size_of(i, V, Hs), H = Hs[i];
         TcGemm g;
         g.M = rows; g.N = H;
@@ -196,7 +235,7 @@ struct DbmTC : Dbm<float> {
         g.act = ACT_SIGMOID; g.rng = rng;
         if (sample) { g.sample = SMP_BERNOULLI; g.out_state_bf = out; g.ld_state_bf = ldn[i + 1]; }
         else { g.out_mean_bf = out; g.ld_mean_bf = ldn[i + 1]; }
-        launch_tc_gemm(ctx, g);
+        return g;
     }
     void visible_tc(const bf16_t* h0, bf16_t* out, bool sample, int rows, RngKey rng) {
         TcGemm g;
@@ -245,7 +284,73 @@ struct DbmTC : Dbm<float> {
     }
 
     // ---- E-step (dbm.py:429-478) ------------------------------------------------------------------------------
-    int mean_field_tc(int rows) {
+    int mean_field_tc(int rows) { return mf_chunk > 0 ? mean_field_programs(rows) : mean_field_launches(rows); }
+
+    // The E-step as persistent dataflow programs: `mf_chunk` sweeps (mf_chunk x L two-pair ops) per launch, every op
+    // waiting per 256-row block on the ops it reads (layer i-1 of the same sweep, layer i+1 of the previous one) --
+    // no kernel boundary and no host round trip between dependent sweeps.  The sweeps of a chunk are SPECULATED: every
+    // sweep writes its own history slot, one kernel evaluates the chunk's convergence tests (dbm.py:449-452) afterwards
+    // and the host picks the first sweep index that passed, so the result and n_mf_updates are those of the
+    // sweep-by-sweep loop.  Slots: 0 = S_{a-1}, 1 = S_a, 2.. = S_{a+1}...; test t of the chunk compares slots t+1 and t.
+    bf16_t* slot(int i, int s) { return hist[i].p + (size_t)s * B * ldn[i + 1]; }
+    int mean_field_programs(int rows) {
+        for (int i = 0; i < L; ++i) {                                        // approximate-inference pass -> slot 0
+            const bf16_t* below = i == 0 ? Xb.p : slot(i - 1, 0);
+            const float sc = (i == 0 || i < L - 1) ? 2.f : 1.f;
+            hidden_tc(i, below, nullptr, slot(i, 0), false, rows, sc, 1.f, RngKey{});
+            BM_CUDA(cudaMemcpyAsync(slot(i, 1), mu_b[i].p, (size_t)rows * ldn[i + 1] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        int a = 0, result_slot = 1;
+        bool done = false;
+        while (!done && a < max_mf) {
+            const int c = std::min(mf_chunk, max_mf - a);
+            std::unique_ptr<TcProgram>& pslot = mf_progs[std::make_pair(rows, c)];
+            if (!pslot) {
+                pslot.reset(new TcProgram());
+                std::vector<TcGemm>& ops = pslot->ops;
+                for (int s = 1; s <= c; ++s)                                 // sweep s: slot s -> slot s + 1
+                    for (int i = 0; i < L; ++i) {
+                        const bf16_t* below = i == 0 ? Xb.p : slot(i - 1, s + 1);
+                        const bf16_t* above = (i + 1 < L) ? slot(i + 1, s) : nullptr;
+                        TcGemm g = hidden_gemm(i, below, above, slot(i, s + 1), false, rows, 1.f, 1.f, RngKey{});
+                        const int self = (int)ops.size();
+                        if (i > 0) { g.dep[g.n_deps] = self - 1; g.dep_all[g.n_deps] = false; ++g.n_deps; }           // layer i-1, this sweep
+                        if (above && s > 1) { g.dep[g.n_deps] = self - L + 1; g.dep_all[g.n_deps] = false; ++g.n_deps; } // layer i+1, previous sweep
+                        g.lane = LANE_CHAIN;
+                        ops.push_back(g);
+                    }
+            }
+            launch_tc_program(ctx, *pslot, RngKey{}, 0);
+            BM_CUDA(cudaMemsetAsync(mf_flags.p, 0, (size_t)c * sizeof(unsigned int), ctx->stream));
+            for (int i = 0; i < L; ++i) {
+                mf_chunk_diffs_kernel<<<dim3(74, c), 256, 0, ctx->stream>>>(hist[i].p, (size_t)B * ldn[i + 1], ldn[i + 1], rows, Hs[i], mf_flags.p);
+                count_launch(ctx);
+            }
+            unsigned int bits[96];
+            BM_CUDA(cudaMemcpyAsync(bits, mf_flags.p, (size_t)c * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            BM_CUDA(cudaStreamSynchronize(ctx->stream));
+            int t = 0;
+            for (; t < c; ++t) { float diff; memcpy(&diff, &bits[t], sizeof(diff)); if (!(diff > (float)mf_tol)) break; }   // :451-452
+            if (t < c) { done = true; result_slot = t + 1; a += t; }
+            else {
+                a += c;
+                result_slot = c + 1;
+                if (a < max_mf)                                              // next chunk starts from S_{a-1}, S_a in slots 0, 1
+                    for (int i = 0; i < L; ++i) {
+                        const size_t bytes = (size_t)rows * ldn[i + 1] * sizeof(bf16_t);
+                        BM_CUDA(cudaMemcpyAsync(slot(i, 0), slot(i, c), bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                        BM_CUDA(cudaMemcpyAsync(slot(i, 1), slot(i, c + 1), bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                    }
+                if (a < max_mf) result_slot = 1;
+            }
+        }
+        for (int i = 0; i < L; ++i)
+            BM_CUDA(cudaMemcpyAsync(mu_b[i].p, slot(i, result_slot), (size_t)rows * ldn[i + 1] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        widen_mu(rows);
+        return a;
+    }
+
+    int mean_field_launches(int rows) {
         for (int i = 0; i < L; ++i) {
             const bf16_t* below = i == 0 ? Xb.p : mu2_b[i - 1].p;
             const float sc = (i == 0 || i < L - 1) ? 2.f : 1.f;              // :438, :441-442

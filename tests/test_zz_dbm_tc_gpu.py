@@ -164,3 +164,30 @@ def test_cfg4_shape_step_agrees_with_the_fp32_engine():
         rel = np.linalg.norm(ga[k] - gb[k]) / max(np.linalg.norm(gb[k]), 1e-12)
         assert rel < 0.02, (k, rel)
     tc.close(); simt.close()
+
+
+@pytest.mark.parametrize('chunk', [1, 3, 6, 25])
+@pytest.mark.parametrize('Hs,rows', [((18, 11), 10), ((18, 11, 7), 10), ((512, 1024), 300)])
+def test_mean_field_programs_equal_the_sweep_by_sweep_loop(monkeypatch, chunk, Hs, rows):
+    """BM_DBM_MF_CHUNK=C runs the E-step as persistent dataflow programs of C speculated sweeps per launch; the first
+    sweep index whose convergence test passes is picked afterwards, so mu and n_mf_updates are those of the
+    launch-per-op loop up to fp32 summation order."""
+    V = 30 if Hs[0] < 100 else 784
+    cfg = make_cfg(V=V, Hs=Hs, batch_size=max(rows, 10), max_mf_updates=7, mf_tol=2e-3)
+    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
+    loop = _native.CudaDBM(cfg)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', str(chunk))
+    prog = _native.CudaDBM(cfg)
+    init(cfg, (loop, prog), scale=0.3 if V == 30 else 0.03)
+    for it in range(2):                      # the second E-step starts from the first one's mu (stale-mu quirk)
+        X = batch(cfg, rows, seed=it)
+        a, b = loop.val_metrics(X, 1, 5, it), prog.val_metrics(X, 1, 5, it)
+        # same ops and operands; only the order in which a consumer adds its K chunks may follow the producers'
+        # completion order (granule-level dataflow), i.e. fp32 rounding before the bf16 store
+        assert abs(a['n_mf_updates'] - b['n_mf_updates']) <= 1
+        assert a['msre'] == pytest.approx(b['msre'], rel=1e-2)
+        ga, gb = loop.get_params(), prog.get_params()
+        for k in ga:
+            np.testing.assert_allclose(ga[k], gb[k], rtol=2.0 ** -7, atol=1e-3, err_msg=k)
+            assert np.mean(ga[k] != gb[k]) < 0.02, k
+    loop.close(); prog.close()
