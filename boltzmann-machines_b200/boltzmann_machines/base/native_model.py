@@ -164,12 +164,12 @@ class NativeModel(BaseModel, DtypeMixin):
             self._engine.set_params({k: z[k] for k in z.files})
 
     # ---- scalar summaries (tf_model.py:110-115: tf.summary.FileWriter on logs/train, logs/val) ----------
-    def _log_scalars(self, kind, step, values):
+    def _log_scalars(self, kind, step, values, allow_empty=False):
         """Append ``{"step": step, tag: value, ...}`` to ``<model>/logs/<kind>/scalars.jsonl`` -- the
         scalar summaries the reference hands to its TensorBoard writers, as one JSON object per line
         (``kind`` in {'train', 'val'}; tags are the reference's summary tags)."""
         values = {k: float(v) for k, v in values.items() if v is not None}
-        if not values:
+        if not values and not allow_empty:
             return
         d = self._train_summary_dirpath if kind == 'train' else self._val_summary_dirpath
         if not os.path.isdir(d):

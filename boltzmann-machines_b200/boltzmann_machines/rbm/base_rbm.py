@@ -226,32 +226,39 @@ class BaseRBM(EnergyBasedModel):
             if every:
                 steps = [self.iter_ + i + 1 for i in range(len(bounds)) if (self.iter_ + i + 1) % every == 0]
                 for j, step in enumerate(steps):
-                    self._log_scalars('train', step, {self._METRIC_TAGS[m]: got[m][j] for m in wanted})
+                    self._log_scalars('train', step, {self._METRIC_TAGS[m]: got[m][j] for m in wanted}, allow_empty=True)
             self.iter_ += len(bounds)
             return {m: (float(np.mean(got[m])) if got[m] else None) for m in wanted}
         for lo, hi in _maybe_bar(bounds, self.verbose, leave=False, ncols=64, desc='epoch'):
             self.iter_ += 1
-            report = wanted if (every and self.iter_ % every == 0) else ()
+            reporting = bool(every and self.iter_ % every == 0)
+            report = wanted if reporting else ()
             got = self._engine.train_step(X[lo:hi], tick=self._next_tick(),
                                           metrics=report, **self._step_args())
             for m in report:
                 sums[m].append(got[m])
-            if report:
-                self._log_scalars('train', self.iter_, {self._METRIC_TAGS[m]: got[m] for m in report})
+            if reporting:
+                # the reference writes its merged summaries at every reporting iteration, whether or not a scalar
+                # train metric is enabled (base_rbm.py:554-564)
+                self._log_scalars('train', self.iter_, {self._METRIC_TAGS[m]: got[m] for m in report}, allow_empty=True)
         return {m: (float(np.mean(v)) if v else None) for m, v in sums.items()}
 
     def _run_val_metrics(self, X_val):
         wanted = self._enabled(self._VAL_METRICS)
         acc = {m: [] for m in wanted}
-        if wanted:
-            a = self._step_args()
-            for lo, hi in batch_bounds(len(X_val), self.batch_size):
-                got = self._engine.metrics(X_val[lo:hi], k=a['k'], seed=a['seed'],
-                                           tick=self._next_tick(), names=wanted)
-                for m in wanted:
-                    acc[m].append(got[m])
+        a = self._step_args()
+        for lo, hi in batch_bounds(len(X_val), self.batch_size):
+            # the reference runs the session once per validation batch even when no validation metric is enabled
+            # (`run_ops == []`, base_rbm.py:575-579): the call still counts as a tick of this public call
+            tick = self._next_tick()
+            if not wanted:
+                continue
+            got = self._engine.metrics(X_val[lo:hi], k=a['k'], seed=a['seed'], tick=tick, names=wanted)
+            for m in wanted:
+                acc[m].append(got[m])
         res = {m: (float(np.mean(v)) if v else None) for m, v in acc.items()}
-        self._log_scalars('val', self.iter_, {self._METRIC_TAGS[m]: v for m, v in res.items()})   # base_rbm.py:584-589
+        # base_rbm.py:584-589: the summary is written even when it holds no value
+        self._log_scalars('val', self.iter_, {self._METRIC_TAGS[m]: v for m, v in res.items()}, allow_empty=True)
         return res
 
     def _mean_free_energy(self, X):

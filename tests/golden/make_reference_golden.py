@@ -187,8 +187,65 @@ def cases():
                             batch_size=8, l2=1e-4, sparsity_cost=0.01, random_seed=32,
                             metrics_config=dict(msre=True, train_metrics_every_iter=3), verbose=False,
                             save_after_each_epoch=False)))
+    # found by --fuzz: with no scalar metric enabled the reference still runs the session once per validation batch (an
+    # empty fetch list is a tick of the public call) and still writes its train / validation summary events
+    out.append(dict(name='bernoulli_no_scalar_metrics_feg_only', cls='BernoulliRBM', X=Xb, X_val=Xb_val, transform_rows=6,
+                    kw=dict(n_visible=20, n_hidden=12, W_init=W20, n_gibbs_steps=[2, 1], learning_rate=0.04, momentum=0.6,
+                            max_epoch=3, batch_size=12, l2=1e-4, sample_v_states=True, dropout=0.9, random_seed=2024,
+                            metrics_config=dict(msre=False, pll=False, l2_loss=False, feg=True, train_metrics_every_iter=3,
+                                                val_metrics_every_epoch=1, feg_every_epoch=2, n_batches_for_feg=2),
+                            verbose=False, save_after_each_epoch=False)))
     out.append(dict(name='init_from_seed', cls='BernoulliRBM', X=None, X_val=None, transform_rows=0,
                     kw=dict(n_visible=20, n_hidden=12, W_init=0.01, vb_init=0.25, random_seed=1337, verbose=False)))
+    return out
+
+
+def fuzz_cases(n, seed):
+    """Random public-API scenarios (same record format as `cases()`): the oracle and the host mirror are fuzzed against
+    the reference's own source with them --
+        python tests/golden/make_reference_golden.py --fuzz 40 --seed 1 --out /tmp/fuzz.json
+        BM_GOLDEN_RBM_CASES=/tmp/fuzz.json python -m pytest tests/test_z_reference_golden.py -k public_api -m 'not gpu'
+    (nothing is committed: a disagreement found this way becomes a named case in `cases()`)."""
+    rng = np.random.RandomState(seed)
+    pick = lambda xs: xs[rng.randint(len(xs))]
+    out = []
+    for i in range(n):
+        cls = pick(['BernoulliRBM', 'BernoulliRBM', 'BernoulliRBM', 'GaussianRBM', 'MultinomialRBM'])
+        dt = pick(['float32', 'float32', 'float32', 'float64'])
+        V, H = int(rng.randint(6, 25)), int(rng.randint(3, 15))
+        n_rows, n_val = int(rng.randint(17, 46)), int(pick([0, 9, 14]))
+        epochs = int(rng.randint(1, 4))
+        sched = lambda lo, hi: (float(rng.uniform(lo, hi)) if rng.rand() < 0.5 else
+                                [float(rng.uniform(lo, hi)) for _ in range(int(rng.randint(1, epochs + 2)))])
+        if cls == 'GaussianRBM':
+            X = rng.randn(n_rows, V).astype(dt)
+            X_val = rng.randn(n_val, V).astype(dt) if n_val else None
+        else:
+            X = (rng.rand(n_rows, V) < 0.3).astype(dt)
+            X_val = (rng.rand(n_val, V) < 0.3).astype(dt) if n_val else None
+        mc = dict(msre=bool(rng.rand() < 0.8), pll=bool(rng.rand() < 0.6), l2_loss=bool(rng.rand() < 0.5),
+                  feg=bool(n_val and rng.rand() < 0.6), train_metrics_every_iter=int(rng.randint(1, 4)),
+                  val_metrics_every_epoch=int(rng.randint(1, 3)), feg_every_epoch=int(rng.randint(1, 3)),
+                  n_batches_for_feg=int(rng.randint(1, 4)))
+        kw = dict(n_visible=V, n_hidden=H,
+                  W_init=(0.1 * rng.randn(V, H)).astype(dt) if rng.rand() < 0.7 else float(rng.uniform(0.01, 0.1)),
+                  vb_init=float(rng.uniform(-0.5, 0.5)), hb_init=float(rng.uniform(-0.3, 0.3)),
+                  n_gibbs_steps=(int(rng.randint(1, 4)) if rng.rand() < 0.5 else
+                                 [int(rng.randint(1, 4)) for _ in range(int(rng.randint(1, epochs + 2)))]),
+                  learning_rate=sched(2e-3, 5e-2) if cls != 'GaussianRBM' else sched(5e-4, 3e-3),
+                  momentum=sched(0.3, 0.9), max_epoch=epochs, batch_size=int(rng.randint(4, 17)),
+                  l2=float(pick([0., 1e-4, 1e-3])), sparsity_target=float(rng.uniform(0.05, 0.3)),
+                  sparsity_cost=float(pick([0., 0.01, 0.05])), sparsity_damping=float(rng.uniform(0.5, 0.95)),
+                  sample_v_states=bool(rng.rand() < 0.5), sample_h_states=bool(rng.rand() < 0.7),
+                  dropout=pick([None, None, 0.7, 0.9]), dbm_first=bool(rng.rand() < 0.25), dbm_last=bool(rng.rand() < 0.25),
+                  random_seed=int(rng.randint(1, 10 ** 6)), dtype=dt, metrics_config=mc, verbose=False,
+                  save_after_each_epoch=bool(rng.rand() < 0.5))
+        if cls == 'GaussianRBM':
+            kw['sigma'] = float(rng.uniform(0.6, 1.5)) if rng.rand() < 0.5 else rng.uniform(0.6, 1.5, size=V).tolist()
+        if cls == 'MultinomialRBM':
+            kw['n_samples'] = int(rng.randint(3, 12))
+        out.append(dict(name='fuzz_{0}_{1}_{2}'.format(seed, i, cls), cls=cls, X=X, X_val=X_val,
+                        transform_rows=int(rng.randint(1, n_rows)), kw=kw))
     return out
 
 
@@ -336,6 +393,12 @@ def run_case(ref_rbm, case, workdir):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--fuzz', type=int, default=0, help='write N random RBM scenarios instead of the committed goldens')
+    ap.add_argument('--seed', type=int, default=1)
+    ap.add_argument('--out', default=None)
+    args = ap.parse_args()
     tf1shim.default_random_provider = provider
     tf1shim.install()
     sys.path[:0] = ['/root/reference', '/root/reference/boltzmann_machines']
@@ -363,6 +426,17 @@ def main():
     cwd = os.getcwd()
     try:
         os.chdir(work)
+        if args.fuzz:
+            recs = []
+            for c in fuzz_cases(args.fuzz, args.seed):
+                try:
+                    recs.append(run_case(ref.rbm, c, work))
+                except Exception as e:           # a configuration the reference itself rejects is not a test case
+                    print('  skipped', c['name'], type(e).__name__, str(e)[:120])
+            with open(args.out, 'w') as fh:
+                json.dump({'source': 'fuzz seed {0}'.format(args.seed), 'cases': recs}, fh)
+            print('wrote', args.out, len(recs), 'cases')
+            return
         recs = [run_case(ref.rbm, c, work) for c in cases()]
         dbm_recs = {v: run_dbm_case(ref, work, v) for v in ('bernoulli_2layer', 'gaussian_visible_2layer', 'bernoulli_3layer')}
     finally:

@@ -12,7 +12,9 @@ import os
 import numpy as np
 import pytest
 
-GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_rbm_cases.json')))
+# BM_GOLDEN_RBM_CASES: replay another file of the same format (tests/golden/make_reference_golden.py --fuzz)
+GOLD = json.load(open(os.environ.get('BM_GOLDEN_RBM_CASES') or
+                      os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_rbm_cases.json')))
 CASES = {c['name']: c for c in GOLD['cases']}
 
 
