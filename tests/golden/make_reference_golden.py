@@ -48,7 +48,7 @@ def gibbs_index(req):
     return False, 0
 
 
-AIS = {'seed': None, 'k': 1}     # set around DBM.log_Z: the mirror draws a dedicated AIS seed per call (dbm.py:701)
+AIS = {'seed': None, 'k': 1, 'sites': [P.SITE_AIS_V, P.SITE_AIS_H2, P.SITE_AIS_H1]}     # set around DBM.log_Z: the mirror draws a dedicated AIS seed per call (dbm.py:701)
 
 
 def dbm_provider(req, seed, tick, shape):
@@ -75,8 +75,9 @@ def dbm_provider(req, seed, tick, shape):
             return (u < np.float32(0.5)).astype(np.int32)
         stack = req.loop_stack
         it, s = (0, stack[0]) if len(stack) == 1 else (stack[0] + 1, stack[1])
-        leaf = req.name.split('/')[-1].split(':')[0]          # sample, sample_1, sample_2: v, h2, x_hat (creation order)
-        site = {'sample': P.SITE_AIS_V, 'sample_1': P.SITE_AIS_H2, 'sample_2': P.SITE_AIS_H1}[leaf]
+        # sample, sample_1, sample_2 in creation order: v, h2, x_hat -- those of them the model samples (dbm.py:669-684)
+        leaf = req.name.split('/')[-1].split(':')[0]
+        site = AIS['sites'][0 if leaf == 'sample' else int(leaf.split('_')[-1])]
         u = P.uniform_at(shape[0], shape[1], AIS['seed'], site, 0, it * AIS['k'] + s)
         return (u.astype(p.dtype) < p).astype(np.int32)
     assert 'gibbs_chain' in parts, (req.scope, req.kind)
@@ -249,11 +250,10 @@ def fuzz_cases(n, seed):
     return out
 
 
-def run_dbm_case(ref, workdir, variant):
-    """Greedy pre-training of the RBM stack, then DBM.fit / transform / reconstruct / sample_v (/ log_proba / log_Z for
-    the 2-layer binary model, the only one the reference implements them for) -- dbm_mnist.py's sequence in miniature --
-    all through the reference's public API.  Variants: 2 binary layers; Gaussian visibles (dbm_cifar*.py); 3 layers."""
-    rng = np.random.RandomState({'bernoulli_2layer': 21, 'gaussian_visible_2layer': 22, 'bernoulli_3layer': 23}[variant])
+def dbm_spec(variant):
+    """(X, X_val, rbm_cls, rbm_kw, dbm_kw, with_ais) of the three committed variants."""
+    rng = np.random.RandomState({'bernoulli_2layer': 21, 'gaussian_visible_2layer': 22, 'bernoulli_3layer': 23,
+                                 'bernoulli_2layer_partial_sampling': 24}[variant])
     V = 16
     sizes = [V, 10, 6] if variant != 'bernoulli_3layer' else [V, 10, 8, 5]
     L = len(sizes) - 1
@@ -281,6 +281,64 @@ def run_dbm_case(ref, workdir, variant):
                   save_after_each_epoch=True, random_seed=303)
     if variant == 'gaussian_visible_2layer':
         dbm_kw.update(learning_rate=[2e-3, 1e-3], max_norm=1.5)
+    if variant == 'bernoulli_2layer_partial_sampling':      # found by --fuzz: fewer sample ops in the AIS transition; no max-norm
+        dbm_kw.update(sample_v_states=False, sample_h_states=[True, False], max_norm=np.inf, n_gibbs_steps=2, mf_tol=1e-2)
+    return X, X_val, rbm_cls, rbm_kw, dbm_kw, variant.startswith('bernoulli_2layer')
+
+
+def fuzz_dbm_spec(seed, i):
+    """A random DBM scenario of the same shape (see fuzz_cases): 2 or 3 layers, binary or Gaussian visibles, random
+    schedules / particle counts / mean-field limits / sparsity / max-norm / sampling flags."""
+    rng = np.random.RandomState(100003 * seed + i)
+    pick = lambda xs: xs[rng.randint(len(xs))]
+    L = int(pick([2, 2, 3]))
+    gaussian = bool(rng.rand() < 0.25)
+    V = int(rng.randint(8, 20))
+    sizes = [V] + [int(rng.randint(4, 12)) for _ in range(L)]
+    # the reference's variational parameters are a [batch_size, H] variable: every batch it sees (training, validation,
+    # the 16 / 8 rows of the queries) must be full
+    dbm_batch = int(pick([4, 8]))
+    n_rows, n_val = int(pick([16, 24, 32])), 16
+    if gaussian:
+        X, X_val = rng.randn(n_rows, V).astype(np.float32), rng.randn(n_val, V).astype(np.float32)
+    else:
+        X, X_val = (rng.rand(n_rows, V) < 0.3).astype(np.float32), (rng.rand(n_val, V) < 0.3).astype(np.float32)
+    rbm_cls, rbm_kw = [], []
+    for j in range(L):
+        kw = dict(n_visible=sizes[j], n_hidden=sizes[j + 1], W_init=(0.1 * rng.randn(sizes[j], sizes[j + 1])).astype(np.float32),
+                  n_gibbs_steps=int(rng.randint(1, 3)), learning_rate=float(rng.uniform(0.01, 0.05)), momentum=float(rng.uniform(0.3, 0.9)),
+                  max_epoch=int(rng.randint(1, 3)), batch_size=int(rng.randint(5, 13)), l2=float(pick([0., 1e-3])),
+                  dbm_first=(j == 0), dbm_last=(j == L - 1), random_seed=int(rng.randint(1, 10 ** 6)), verbose=False,
+                  save_after_each_epoch=False)
+        cls = 'BernoulliRBM'
+        if j == 0 and gaussian:
+            cls = 'GaussianRBM'
+            kw.update(sigma=rng.uniform(0.7, 1.3, size=V).tolist(), learning_rate=5e-3, sample_v_states=True)
+        rbm_cls.append(cls)
+        rbm_kw.append(kw)
+    epochs = int(rng.randint(1, 4))
+    sched = lambda lo, hi: (float(rng.uniform(lo, hi)) if rng.rand() < 0.5 else
+                            [float(rng.uniform(lo, hi)) for _ in range(int(rng.randint(1, epochs + 2)))])
+    dbm_kw = dict(n_particles=int(rng.randint(3, 13)),
+                  n_gibbs_steps=(int(rng.randint(1, 4)) if rng.rand() < 0.5 else [int(rng.randint(1, 4)) for _ in range(int(rng.randint(1, epochs + 2)))]),
+                  max_mf_updates=int(rng.randint(1, 8)), mf_tol=float(pick([1e-7, 1e-5, 1e-2])),
+                  learning_rate=sched(1e-3, 2e-2) if not gaussian else sched(5e-4, 2e-3), momentum=sched(0.3, 0.9),
+                  max_epoch=epochs, batch_size=dbm_batch, l2=float(pick([0., 1e-4])),
+                  max_norm=float(pick([0.6, 1.5, np.inf])), sample_v_states=bool(rng.rand() < 0.7),
+                  sample_h_states=[bool(rng.rand() < 0.8) for _ in range(L)],
+                  sparsity_target=[float(rng.uniform(0.05, 0.3)) for _ in range(L)],
+                  sparsity_cost=[float(pick([0., 1e-2, 5e-3])) for _ in range(L)], sparsity_damping=float(rng.uniform(0.5, 0.95)),
+                  train_metrics_every_iter=int(rng.randint(1, 4)), val_metrics_every_epoch=int(rng.randint(1, 3)), verbose=False,
+                  save_after_each_epoch=bool(rng.rand() < 0.5), random_seed=int(rng.randint(1, 10 ** 6)))
+    return X, X_val, rbm_cls, rbm_kw, dbm_kw, (L == 2 and not gaussian)
+
+
+def run_dbm_case(ref, workdir, variant, spec=None):
+    """Greedy pre-training of the RBM stack, then DBM.fit / transform / reconstruct / sample_v (/ log_proba / log_Z for
+    the 2-layer binary model, the only one the reference implements them for) -- dbm_mnist.py's sequence in miniature --
+    all through the reference's public API.  Variants: 2 binary layers; Gaussian visibles (dbm_cifar*.py); 3 layers."""
+    X, X_val, rbm_cls, rbm_kw, dbm_kw, with_ais = spec if spec is not None else dbm_spec(variant)
+    L = len(rbm_kw)
     rbms, inp, Q = [], X, None
     for i in range(L):
         r = getattr(ref.rbm, rbm_cls[i])(model_path=os.path.join(workdir, variant, 'rbm%d' % i) + '/', **rbm_kw[i])
@@ -304,19 +362,21 @@ def run_dbm_case(ref, workdir, variant):
     dbm_summaries = summaries_of(dbm)
     rec = {'summaries': dbm_summaries, 'variant': variant, 'rbm_cls': rbm_cls,
            'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
-           'dbm_kw': dbm_kw, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
+           'dbm_kw': {k: ('inf' if isinstance(v, float) and np.isinf(v) else v) for k, v in dbm_kw.items()}, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
            'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_)}
     scopes = ('weights', 'grads_accumulators', 'variational_params', 'hidden_means_accumulators', 'negative_particles')
     rec['after_fit'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()} for sc in scopes}
     rec['transform'] = tolist(dbm.transform(X[:16]))
     rec['reconstruct'] = tolist(dbm.reconstruct(X[:8]))
     rec['sample_v'] = tolist(dbm.sample_v(n_gibbs_steps=2))
-    if variant == 'bernoulli_2layer':
+    if with_ais:
         rec['log_proba'] = tolist(dbm.log_proba(X_val, log_Z=0.0))
         # the mirror's log_Z draws the call seed and then a dedicated AIS seed from the model's RNG
         peek = type(dbm._rng)(seed=None).set_state(json.loads(json.dumps(dbm._rng.get_state())))
         peek.randint(2 ** 31 - 1)
         AIS['seed'], AIS['k'] = int(peek.randint(2 ** 31 - 1)), 2
+        AIS['sites'] = ([P.SITE_AIS_V] if dbm_kw['sample_v_states'] else []) + \
+                       ([P.SITE_AIS_H2] if dbm_kw['sample_h_states'][1] else []) + ([P.SITE_AIS_H1] if dbm_kw['sample_h_states'][0] else [])
         log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=20, n_runs=6, n_gibbs_steps=2)
         rec['log_Z'] = {'n_betas': 20, 'n_runs': 6, 'n_gibbs_steps': 2, 'log_mean': float(log_mean), 'log_low': float(log_low),
                         'log_high': float(log_high), 'values': tolist(values)}
@@ -398,6 +458,8 @@ def main():
     ap.add_argument('--fuzz', type=int, default=0, help='write N random RBM scenarios instead of the committed goldens')
     ap.add_argument('--seed', type=int, default=1)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--fuzz-dbm', type=int, default=10)
+    ap.add_argument('--out-dbm', default=None, help='also write --fuzz-dbm random DBM scenarios (BM_GOLDEN_DBM_CASES)')
     args = ap.parse_args()
     tf1shim.default_random_provider = provider
     tf1shim.install()
@@ -436,9 +498,21 @@ def main():
             with open(args.out, 'w') as fh:
                 json.dump({'source': 'fuzz seed {0}'.format(args.seed), 'cases': recs}, fh)
             print('wrote', args.out, len(recs), 'cases')
+            if args.out_dbm:
+                drecs = {}
+                for i in range(args.fuzz_dbm):
+                    name = 'fuzz_{0}_{1}'.format(args.seed, i)
+                    try:
+                        drecs[name] = run_dbm_case(ref, work, name, spec=fuzz_dbm_spec(args.seed, i))
+                    except Exception as e:
+                        print('  skipped DBM', name, type(e).__name__, str(e)[:160])
+                with open(args.out_dbm, 'w') as fh:
+                    json.dump({'source': 'fuzz seed {0}'.format(args.seed), 'cases': drecs}, fh)
+                print('wrote', args.out_dbm, len(drecs), 'DBM cases')
             return
         recs = [run_case(ref.rbm, c, work) for c in cases()]
-        dbm_recs = {v: run_dbm_case(ref, work, v) for v in ('bernoulli_2layer', 'gaussian_visible_2layer', 'bernoulli_3layer')}
+        dbm_recs = {v: run_dbm_case(ref, work, v) for v in ('bernoulli_2layer', 'gaussian_visible_2layer', 'bernoulli_3layer',
+                                                                  'bernoulli_2layer_partial_sampling')}
     finally:
         os.chdir(cwd)
         shutil.rmtree(work, ignore_errors=True)

@@ -172,7 +172,8 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
 # DBM: greedy pre-training, DBM.fit, transform, reconstruct, sample_v, log_proba, log_Z -- the reference's dbm.py
 # (mean-field with its stale-mu start, PCD particles, sparsity quirk, max-norm, AIS) executed on the shim
 # ---------------------------------------------------------------------------------------------------------
-DBM_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_cases.json')))['cases']
+DBM_GOLD = json.load(open(os.environ.get('BM_GOLDEN_DBM_CASES') or
+                          os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_cases.json')))['cases']
 
 
 @pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
@@ -211,7 +212,8 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
             if i == 0:
                 close(inp, g['Q'], tol * 5, 'rbm1.transform')
         rbms.append(r)
-    dbm = DBM(rbms=rbms, model_path=os.path.join(str(workdir), 'dbm') + '/', **g['dbm_kw'])
+    dbm_kw = {k: (np.inf if v == 'inf' else v) for k, v in g['dbm_kw'].items()}
+    dbm = DBM(rbms=rbms, model_path=os.path.join(str(workdir), 'dbm') + '/', **dbm_kw)
     log = {'train': [], 'val': []}
     for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
         orig = getattr(dbm, meth)
@@ -246,8 +248,13 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
     log_mean, (log_low, log_high), values = dbm.log_Z(n_betas=z['n_betas'], n_runs=z['n_runs'], n_gibbs_steps=z['n_gibbs_steps'])
     # the reference accumulates the importance weights in float32, the engines in float64
     np.testing.assert_allclose(values, z['values'], rtol=0, atol=2e-4 if both_engines == 'oracle' else 2e-3, err_msg='AIS log-weights')
-    np.testing.assert_allclose([log_mean, log_low, log_high], [z['log_mean'], z['log_low'], z['log_high']], rtol=0, atol=1e-3 if both_engines == 'oracle' else 5e-3,
-                               err_msg='log_Z summary')
+    # log(mean +- std): with float32 estimates whose spread is below float32 resolution (chains that sample nothing) the
+    # reference's log_std_exp takes the log of a rounding-negative variance and returns NaN; the engines hand float64
+    # estimates to the same formulas and get a finite value there -- compared wherever the reference's is finite
+    got3, want3 = np.array([log_mean, log_low, log_high], dtype=np.float64), np.array([z['log_mean'], z['log_low'], z['log_high']], dtype=np.float64)
+    fin = np.isfinite(want3)
+    assert fin[0] and np.all(np.isfinite(got3))
+    np.testing.assert_allclose(got3[fin], want3[fin], rtol=0, atol=1e-3 if both_engines == 'oracle' else 5e-3, err_msg='log_Z summary')
     check_after_queries(dbm, g, tol)
 
 
