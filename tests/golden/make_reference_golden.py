@@ -245,8 +245,19 @@ def fuzz_cases(n, seed):
             kw['sigma'] = float(rng.uniform(0.6, 1.5)) if rng.rand() < 0.5 else rng.uniform(0.6, 1.5, size=V).tolist()
         if cls == 'MultinomialRBM':
             kw['n_samples'] = int(rng.randint(3, 12))
-        out.append(dict(name='fuzz_{0}_{1}_{2}'.format(seed, i, cls), cls=cls, X=X, X_val=X_val,
-                        transform_rows=int(rng.randint(1, n_rows)), kw=kw))
+        case = dict(name='fuzz_{0}_{1}_{2}'.format(seed, i, cls), cls=cls, X=X, X_val=X_val,
+                    transform_rows=int(rng.randint(1, n_rows)), kw=kw)
+        r = rng.rand()
+        if r < 0.2:                                  # load_model + more epochs in a "new process"
+            case['resume_max_epoch'] = epochs + int(rng.randint(1, 3))
+        elif r < 0.35 and isinstance(kw['W_init'], np.ndarray):      # init_from a briefly trained model of the same class
+            pre = dict(kw)
+            pre.update(max_epoch=1, random_seed=int(rng.randint(1, 10 ** 6)), metrics_config=dict(mc), save_after_each_epoch=False)
+            case['pre_kw'] = pre
+            case['kw'] = {k: v for k, v in kw.items() if k not in ('W_init', 'vb_init', 'hb_init')}
+            if case['X_val'] is not None and rng.rand() < 0.5:
+                case['X_val'] = None
+        out.append(case)
     return out
 
 

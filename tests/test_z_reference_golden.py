@@ -18,6 +18,24 @@ GOLD = json.load(open(os.environ.get('BM_GOLDEN_RBM_CASES') or
 CASES = {c['name']: c for c in GOLD['cases']}
 
 
+def _corpus(name):
+    """Random scenarios generated like the committed goldens (make_reference_golden.py --fuzz 48 --seed 2026): replayed on
+    the oracle everywhere; on the CUDA engine only with BM_EXPERIMENTAL=1 until they have passed on a B200 once."""
+    import gzip
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)
+    with gzip.open(p, 'rt') as fh:
+        return json.load(fh)['cases']
+
+
+def _skip_unverified_corpus(name, engine):
+    if name.startswith('fuzz_') and engine.startswith('cuda') and os.environ.get('BM_EXPERIMENTAL') != '1':
+        pytest.skip('fuzz corpus on the CUDA engine: set BM_EXPERIMENTAL=1 (not yet run on a B200)')
+
+
+if not os.environ.get('BM_GOLDEN_RBM_CASES'):
+    CASES.update({c['name']: c for c in _corpus('fuzz_corpus_rbm.json.gz')})
+
+
 def epoch_oracle_factory(cfg):
     """The oracle behind the interface of the CUDA engine's whole-epoch entry points (`train_epoch`, `pin`), so that the
     host code path BaseRBM takes with libbm.so -- one native call per epoch, byte-valued pinned data, per-iteration metric
@@ -113,6 +131,7 @@ def close(got, want, tol, what):
 
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
+    _skip_unverified_corpus(name, engine_kind)
     case = CASES[name]
     model, log, dt = build(case, workdir)
     # float32: the same formulas in float32 with different summation orders; a Bernoulli draw is u < p on the SAME u
@@ -174,6 +193,8 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
 # ---------------------------------------------------------------------------------------------------------
 DBM_GOLD = json.load(open(os.environ.get('BM_GOLDEN_DBM_CASES') or
                           os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dbm_cases.json')))['cases']
+if not os.environ.get('BM_GOLDEN_DBM_CASES'):
+    DBM_GOLD.update(_corpus('fuzz_corpus_dbm.json.gz'))
 
 
 @pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
@@ -195,6 +216,7 @@ def both_engines(request, monkeypatch):
 def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
     """bernoulli_2layer: the whole query surface incl. AIS; gaussian_visible_2layer: a GaussianRBM bottom layer
     (dbm_cifar*.py); bernoulli_3layer: the intermediate-layer Gibbs update and the halving of the middle RBM."""
+    _skip_unverified_corpus(variant, both_engines)
     from boltzmann_machines import DBM
     from boltzmann_machines import rbm as R
     g = DBM_GOLD[variant]

@@ -8,6 +8,10 @@ mkdir -p $OUT
 BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q > $OUT/${TAG}_dbm_tc_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${TAG}_dbm_tc_pytest.log
 tail -15 $OUT/${TAG}_dbm_tc_pytest.log
+# the fuzz corpus (68 random reference scenarios, CPU-verified on the oracle) on the CUDA fp32 engines
+BM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_z_reference_golden.py -k 'fuzz_ and cuda' -q > $OUT/${TAG}_fuzz_corpus_pytest.log 2>&1
+echo "fuzz corpus pytest exit $?" >> $OUT/${TAG}_fuzz_corpus_pytest.log
+tail -8 $OUT/${TAG}_fuzz_corpus_pytest.log
 for c in fp32 bf16; do
   timeout 600 python tools/bench_configs.py cfg4 cfg4-ais --dbm-compute $c --steps 20 --ais-runs 20000 --ais-betas 1000 \
     > $OUT/${TAG}_dbm_tc_bench_$c.json 2> $OUT/${TAG}_dbm_tc_bench_$c.err
