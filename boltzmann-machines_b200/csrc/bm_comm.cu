@@ -60,6 +60,16 @@ void allreduce_sum(Ctx* ctx, void* buf, size_t count, bool is_double) {
     count_launch(ctx);
 }
 
+// max-allreduce of unsigned 32-bit words in place (bit patterns of non-negative floats order like the floats):
+// the DBM's mean-field convergence test over row-sharded variational parameters
+void allreduce_max_u32(Ctx* ctx, unsigned int* buf, size_t count) {
+    if (ctx->nranks <= 1) return;
+    NcclApi* a = nccl_api();
+    // ncclUint32 = 3, ncclMax = 2
+    nccl_check(a->AllReduce(buf, buf, count, 3, 2, ctx->nccl_comm, ctx->stream), "ncclAllReduce(max)");
+    count_launch(ctx);
+}
+
 cudaEvent_t profile_event(Ctx* c) {
     if (c->prof_used == c->prof_events.size()) {
         if (c->prof_events.size() >= 16384) profile_drain(c);

@@ -7,6 +7,13 @@
 //   pre-activations x W_0^T + b and x W_1 + c_2 are computed once per temperature and shared by the
 //   importance weight and by the transition), variational bound :738-759.
 // Storage-precision (float32 / float64) CUDA-core path: the shared fused LayerOp of bm_simt.cu.
+//
+// Data parallelism (not in the reference, which is single-device): on a context with a communicator every
+// rank holds batch_size rows of the batch (and of mu) and n_particles persistent particles -- the global model has
+// nranks times as many of each.  Rows are independent given the weights: the sampling sites are keyed by the GLOBAL
+// particle index (row0 = rank * n_particles), the mean-field convergence test takes the max over all ranks, and the
+// row sums that enter the update (pos^T mu - neg^T h per layer, the column sums of mu, h, X, v) are sum-allreduced
+// in one buffer before every rank applies the identical update.  With one rank nothing below changes.
 #include "bm_rbm.h"
 #include <vector>
 #include <string>
@@ -206,8 +213,39 @@ struct Dbm : DbmBase {
     DevBuf<unsigned int> flag;
     DevBuf<double> scal, rowd;
     int xcap = 0;
+    DevBuf<T> dpbuf;        // data parallelism: the step's statistics packed for ONE sum-allreduce
 
     static int size_of(int idx, int V, const std::vector<int>& Hs) { return idx == 0 ? V : Hs[idx - 1]; }
+    int nranks() const { return ctx->nranks > 1 ? ctx->nranks : 1; }
+    uint32_t particle_row0() const { return ctx->nranks > 1 ? (uint32_t)ctx->rank * (uint32_t)M : 0u; }   // global index of local particle 0
+
+    // [G_0 | ... | musum_0 | hsum_0 | ... | xsum | vsum] -> one allreduce -> back (no-op on a single rank)
+    void allreduce_step_statistics() {
+        if (ctx->nranks <= 1) return;
+        std::vector<std::pair<T*, size_t>> parts;
+        int in = V;
+        for (int i = 0; i < L; ++i) { parts.push_back({G[i].p, (size_t)in * Hs[i]}); in = Hs[i]; }
+        for (int i = 0; i < L; ++i) { parts.push_back({musum[i].p, (size_t)Hs[i]}); parts.push_back({hsum[i].p, (size_t)Hs[i]}); }
+        parts.push_back({xsum.p, (size_t)V}); parts.push_back({vsum.p, (size_t)V});
+        size_t total = 0;
+        for (auto& p : parts) total += p.second;
+        dpbuf.ensure(total);
+        size_t off = 0;
+        for (auto& p : parts) { BM_CUDA(cudaMemcpyAsync(dpbuf.p + off, p.first, p.second * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream)); off += p.second; }
+        allreduce_sum(ctx, dpbuf.p, total, sizeof(T) == 8);
+        off = 0;
+        for (auto& p : parts) { BM_CUDA(cudaMemcpyAsync(p.first, dpbuf.p + off, p.second * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream)); off += p.second; }
+    }
+    // mean of a per-rank mean over equally sized shards
+    double allreduce_mean(double local) {
+        if (ctx->nranks <= 1) return local;
+        BM_CUDA(cudaMemcpyAsync(scal.p + 2, &local, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        allreduce_sum(ctx, scal.p + 2, 1, true);
+        double out = 0.0;
+        BM_CUDA(cudaMemcpyAsync(&out, scal.p + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));
+        return out / ctx->nranks;
+    }
 
     Dbm(Ctx* c, const bm_dbm_cfg& f) {
         ctx = c; L = f.n_layers; V = f.n_visible; M = f.n_particles; B = f.batch_size;
@@ -295,8 +333,9 @@ struct Dbm : DbmBase {
             const int kind = idx == 0 ? v_kind : h_kinds[idx - 1];
             T* dst = idx == 0 ? v.p : h[idx - 1].p;
             dim3 grid(((n + 3) / 4 + 127) / 128, M);
-            particle_init_kernel<T><<<grid, 128, 0, ctx->stream>>>(dst, M, n, kind, sigma.p, make_rng(seed, SITE_PARTICLE_INIT, idx, 0, 0));
+            particle_init_kernel<T><<<grid, 128, 0, ctx->stream>>>(dst, M, n, kind, sigma.p, make_rng(seed, SITE_PARTICLE_INIT, idx, 0, particle_row0()));
             count_launch(ctx);
+            BM_REQUIRE(kind != BM_UNIT_MULTINOMIAL || ctx->nranks <= 1, "multinomial layers are not supported with sharded particles");
             if (kind == BM_UNIT_MULTINOMIAL) {       // t /= reduce_sum(t) over the whole tensor
                 launch_mean_combine<T>(ctx, dst, (const T*)nullptr, 0.0, (int)((size_t)M * n), scal.p);   // mean
                 // total = mean * count: fold the count into the divisor on the host side of the kernel
@@ -358,11 +397,11 @@ struct Dbm : DbmBase {
             const T* above = (i + 1 < L) ? Hin[i + 1] : nullptr;
             const bool smp = sample && sample_h[i];
             // when sampling, means go to the scratch t[] (rows <= M may exceed xcap: use h2 as mean target)
-            hidden_op(i, below, above, Hn[i], Hn[i], smp, rows, T(1), T(1), make_rng(seed, SITE_DBM_H + i, tstep, tick, 0));
+            hidden_op(i, below, above, Hn[i], Hn[i], smp, rows, T(1), T(1), make_rng(seed, SITE_DBM_H + i, tstep, tick, particle_row0()));
         }
         if (update_v) {
             const bool smp = sample && sample_vis;
-            visible_op(Hn[0], v_new, v_new, smp, rows, make_rng(seed, SITE_DBM_V, tstep, tick, 0));
+            visible_op(Hn[0], v_new, v_new, smp, rows, make_rng(seed, SITE_DBM_V, tstep, tick, particle_row0()));
         }
     }
 
@@ -390,6 +429,7 @@ struct Dbm : DbmBase {
                 max_abs_diff_kernel<T><<<148, 256, 0, ctx->stream>>>(cur[i], nxt[i], n, flag.p);
                 count_launch(ctx);
             }
+            allreduce_max_u32(ctx, flag.p, 1);           // sharded rows: every rank runs the same number of sweeps
             unsigned int bits = 0;
             BM_CUDA(cudaMemcpyAsync(&bits, flag.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
             BM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -439,7 +479,7 @@ struct Dbm : DbmBase {
         double hval = 0.0;
         BM_CUDA(cudaMemcpyAsync(&hval, scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
-        return hval;
+        return allreduce_mean(hval);
     }
 
     void train_step(const void* Xh, int rows, double lr, double mom, int k, uint64_t seed, uint32_t tick, int want, double* out) override {
@@ -448,7 +488,9 @@ struct Dbm : DbmBase {
         const int n_mf = mean_field(X, rows);
         particles_update(k, true, seed, tick, 0, true, nullptr);
         if (want) { BM_REQUIRE(out, "metrics requested without a buffer"); out[0] = msre(X, rows); out[1] = (double)n_mf; }
-        const T N = (T)B, Mp = (T)M;                        // configured sizes, as the reference (dbm.py:254-255)
+        const int nr = nranks();
+        const T N = (T)((double)B * nr), Mp = (T)((double)M * nr);      // configured (global) sizes, as the reference (dbm.py:254-255)
+        const T rows_g = (T)((double)rows * nr);                         // rows present in this step on all ranks
         // gradients (dbm.py:558-568): G_i = pos/N - neg/M
         for (int i = 0; i < L; ++i) {
             LayerOp<T> g;
@@ -464,14 +506,15 @@ struct Dbm : DbmBase {
         }
         launch_colsum<T>(ctx, X, V, (const T*)nullptr, 0, rows, V, T(1), T(0), xsum.p);
         launch_colsum<T>(ctx, v.p, V, (const T*)nullptr, 0, M, V, T(1), T(0), vsum.p);
-        dbm_vbias_kernel<T><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, (T)rows, Mp, vb.p, dvb.p, (T)lr, (T)mom);
+        allreduce_step_statistics();
+        dbm_vbias_kernel<T><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, rows_g, Mp, vb.p, dvb.p, (T)lr, (T)mom);
         count_launch(ctx);
         for (int i = 0; i < L; ++i) {
             const int in = size_of(i, V, Hs), H = Hs[i];
             BM_REQUIRE(i < H, "the reference's sparsity update indexes element i of layer i's unit vector");
             // dhb uses reduce_mean over the rows present (mu) and over the particles (H)
             dbm_sparsity_bias_kernel<T><<<(H + 255) / 256, 256, 0, ctx->stream>>>(
-                H, i, musum[i].p, hsum[i].p, (T)rows, Mp, qm[i].p, mm[i].p, pen[i].p, hb[i].p, dhb[i].p,
+                H, i, musum[i].p, hsum[i].p, rows_g, Mp, qm[i].p, mm[i].p, pen[i].p, hb[i].p, dhb[i].p,
                 (T)damping, (T)sp_cost[i], (T)sp_target[i], (T)lr, (T)mom);
             count_launch(ctx);
             launch_weight_update<T>(ctx, G[i].p, H, T(1), W[i].p, dW[i].p, in, H, pen[i].p, (T)l2, (T)lr, (T)mom, nullptr, 0);

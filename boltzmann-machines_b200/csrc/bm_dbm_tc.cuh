@@ -272,9 +272,9 @@ struct DbmTC : Dbm<float> {
         for (int i = 0; i < L; ++i) {
             const bf16_t* below = i == 0 ? vin : Hn[i - 1];
             const bf16_t* above = (i + 1 < L) ? Hin[i + 1] : nullptr;
-            hidden_tc(i, below, above, Hn[i], sample && sample_h[i], rows, 1.f, 1.f, make_rng(seed, SITE_DBM_H + i, tstep, tick, 0));
+            hidden_tc(i, below, above, Hn[i], sample && sample_h[i], rows, 1.f, 1.f, make_rng(seed, SITE_DBM_H + i, tstep, tick, particle_row0()));
         }
-        if (update_v) visible_tc(Hn[0], v_new, sample && sample_vis, rows, make_rng(seed, SITE_DBM_V, tstep, tick, 0));
+        if (update_v) visible_tc(Hn[0], v_new, sample && sample_vis, rows, make_rng(seed, SITE_DBM_V, tstep, tick, particle_row0()));
     }
 
     const float* upload_tc(const void* Xh, int rows) {
@@ -326,6 +326,7 @@ struct DbmTC : Dbm<float> {
                 mf_chunk_diffs_kernel<<<dim3(74, c), 256, 0, ctx->stream>>>(hist[i].p, (size_t)B * ldn[i + 1], ldn[i + 1], rows, Hs[i], mf_flags.p);
                 count_launch(ctx);
             }
+            allreduce_max_u32(ctx, mf_flags.p, (size_t)c);       // sharded rows: the same sweep index on every rank
             unsigned int bits[96];
             BM_CUDA(cudaMemcpyAsync(bits, mf_flags.p, (size_t)c * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
             BM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -365,6 +366,7 @@ struct DbmTC : Dbm<float> {
                 max_abs_diff_bf16_kernel<<<148, 256, 0, ctx->stream>>>(cur[i], ldn[i + 1], nxt[i], ldn[i + 1], rows, Hs[i], flag.p);
                 count_launch(ctx);
             }
+            allreduce_max_u32(ctx, flag.p, 1);
             unsigned int bits = 0;
             BM_CUDA(cudaMemcpyAsync(&bits, flag.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
             BM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -417,7 +419,7 @@ struct DbmTC : Dbm<float> {
         double hval = 0.0;
         BM_CUDA(cudaMemcpyAsync(&hval, scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
-        return hval;
+        return allreduce_mean(hval);
     }
 
     // G_i = pos^T mu_i / N - neg^T h_i / M (dbm.py:558-568): two split-K tensor-core GEMMs over the rows
@@ -452,7 +454,9 @@ struct DbmTC : Dbm<float> {
         const int n_mf = mean_field_tc(rows);
         particles_tc(k, true, seed, tick, 0, true, nullptr);
         if (want) { BM_REQUIRE(out, "metrics requested without a buffer"); out[0] = msre_tc(X, rows); out[1] = (double)n_mf; }
-        const float N = (float)B, Mp = (float)M;                // configured sizes, as the reference (dbm.py:254-255)
+        const int nr = nranks();                               // data parallelism: see the header of bm_dbm.cu
+        const float N = (float)((double)B * nr), Mp = (float)((double)M * nr);      // configured (global) sizes (dbm.py:254-255)
+        const float rows_g = (float)((double)rows * nr);
         for (int i = 0; i < L; ++i) {
             const int H = Hs[i];
             gradient_tc(i, i == 0 ? Xb.p : mu_b[i - 1].p, rows, i == 0 ? v_b.p : h_b[i - 1].p, N, Mp);
@@ -461,13 +465,14 @@ struct DbmTC : Dbm<float> {
         }
         launch_colsum<float>(ctx, X, V, (const float*)nullptr, 0, rows, V, 1.f, 0.f, xsum.p);
         launch_colsum_bf16(ctx, v_b.p, ldn[0], nullptr, 0, M, V, 1.f, 0.f, vsum.p);
-        dbm_vbias_kernel<float><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, (float)rows, Mp, vb.p, dvb.p, (float)lr, (float)mom);
+        allreduce_step_statistics();
+        dbm_vbias_kernel<float><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, rows_g, Mp, vb.p, dvb.p, (float)lr, (float)mom);
         count_launch(ctx);
         for (int i = 0; i < L; ++i) {
             const int in = size_of(i, V, Hs), H = Hs[i];
             BM_REQUIRE(i < H, "the reference's sparsity update indexes element i of layer i's unit vector");
             dbm_sparsity_bias_kernel<float><<<(H + 255) / 256, 256, 0, ctx->stream>>>(
-                H, i, musum[i].p, hsum[i].p, (float)rows, Mp, qm[i].p, mm[i].p, pen[i].p, hb[i].p, dhb[i].p,
+                H, i, musum[i].p, hsum[i].p, rows_g, Mp, qm[i].p, mm[i].p, pen[i].p, hb[i].p, dhb[i].p,
                 (float)damping, (float)sp_cost[i], (float)sp_target[i], (float)lr, (float)mom);
             count_launch(ctx);
             launch_weight_update<float>(ctx, G[i].p, H, 1.f, W[i].p, dW[i].p, in, H, pen[i].p, (float)l2, (float)lr, (float)mom, nullptr, 0);

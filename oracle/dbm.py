@@ -76,17 +76,29 @@ class OracleDBM(object):
         names = list(self.p) if names is None else list(names)
         return {k: self.p[k].copy() for k in names}
 
+    # -- data parallelism (the engine's contract, csrc/bm_dbm.cu; the reference is single-device) ----------------
+    def set_shard(self, rank, world, allreduce_sum, allreduce_max):
+        """This oracle holds shard `rank` of `world`: batch_size rows of every batch / of mu and n_particles particles
+        (the global model has `world` times as many).  Sampling sites are keyed by the global particle index, the
+        mean-field test takes the max over the shards, the statistics of the update are summed over them."""
+        self.shard = (int(rank), int(world), allreduce_sum, allreduce_max)
+
+    def _particle_row0(self):
+        sh = getattr(self, 'shard', None)
+        return 0 if sh is None else sh[0] * self.M
+
     def init_particles(self, seed):
         """layer.init(batch_size=n_particles) for every layer (dbm.py:362-383; layers.py:43-45,
         59-63,78-82): Bernoulli -> U[0,1), Multinomial -> U[0,1)/sum, Gaussian -> sigma*N(0,1)."""
         kinds = [self.v_kind] + self.h_kinds
         sizes = [self.V] + self.Hs
         names = ['v'] + ['h' + self._sfx(i) for i in range(self.L)]
+        r0 = self._particle_row0()
         for idx, (kind, n, name) in enumerate(zip(kinds, sizes, names)):
             if kind == 'gaussian':
-                t = P.normal_at(self.M, n, seed, P.SITE_PARTICLE_INIT, idx, 0) * self.sigma[None, :]
+                t = P.normal_at(self.M, n, seed, P.SITE_PARTICLE_INIT, idx, 0, r0) * self.sigma[None, :]
             else:
-                t = P.uniform_at(self.M, n, seed, P.SITE_PARTICLE_INIT, idx, 0)
+                t = P.uniform_at(self.M, n, seed, P.SITE_PARTICLE_INIT, idx, 0, r0)
                 if kind == 'multinomial':
                     t = t / t.sum(dtype=np.float64)
             self.p[name] = t.astype(self.dt)
@@ -115,7 +127,7 @@ class OracleDBM(object):
         if kind == 'multinomial':
             probs = (means / means.sum(axis=1, keepdims=True)).astype(np.float32)
             return multinomial_counts(probs, int(n_samples), seed, site, t, tick).astype(self.dt)
-        eps = P.normal_at(rows, n, seed, site, t, tick).astype(self.dt)
+        eps = P.normal_at(rows, n, seed, site, t, tick, getattr(self, '_row0', 0)).astype(self.dt)
         return (means + self.sigma * eps).astype(self.dt)
 
     def gibbs_step(self, v, H, update_v, sample, seed, t, tick):
@@ -165,8 +177,11 @@ class OracleDBM(object):
             mu_new.append(T)
         step = 0
         tol = self.dt.type(self.cfg.get('mf_tol', 1e-7))
-        while step < int(self.cfg.get('max_mf_updates', 10)) and \
-                max(np.max(np.abs(a - b)) for a, b in zip(mu, mu_new)) > tol:      # :449-452
+        def spread(mu, mu_new):
+            d = max(np.max(np.abs(a - b)) for a, b in zip(mu, mu_new))
+            sh = getattr(self, 'shard', None)
+            return d if sh is None else self.dt.type(sh[3](np.array([d], dtype=np.float64))[0])
+        while step < int(self.cfg.get('max_mf_updates', 10)) and spread(mu, mu_new) > tol:      # :449-452
             _, Hn = self.gibbs_step(X, mu, update_v=False, sample=False, seed=0, t=0, tick=0)
             mu, mu_new = Hn, mu                                                    # :455-457 (swap)
             step += 1
@@ -179,8 +194,12 @@ class OracleDBM(object):
         """dbm.py:480-509.  Returns (v, H) after n_steps; commits them to the persistent particles."""
         v = self.p['v']
         H = [self.p['h' + self._sfx(i)] for i in range(self.L)]
-        for s in range(int(n_steps)):
-            v, H = self.gibbs_step(v, H, update_v=True, sample=sample, seed=seed, t=t0 + s + 1, tick=tick)
+        self._row0 = self._particle_row0()
+        try:
+            for s in range(int(n_steps)):
+                v, H = self.gibbs_step(v, H, update_v=True, sample=sample, seed=seed, t=t0 + s + 1, tick=tick)
+        finally:
+            self._row0 = 0
         if commit:
             self.p['v'] = v
             for i in range(self.L):
@@ -214,19 +233,41 @@ class OracleDBM(object):
         mu = [p['mu' + self._sfx(i)][:rows] for i in range(L)]
         Hp = [p['h' + self._sfx(i)] for i in range(L)]
         l2 = dt.type(c.get('l2', 0.))
-        dvb = X.mean(axis=0) - p['v'].mean(axis=0)                                   # :553
-        dW = [(X.T @ mu[0]) / N - (p['v'].T @ Hp[0]) / Mp - l2 * self.W(0)]          # :558-560
-        for i in range(1, L):
-            dW.append((mu[i - 1].T @ mu[i]) / N - (Hp[i - 1].T @ Hp[i]) / Mp - l2 * self.W(i))   # :566-568
-        dhb = [mu[i].mean(axis=0) - Hp[i].mean(axis=0) for i in range(L)]            # :575
+        shard = getattr(self, 'shard', None)
+        if shard is None:
+            dvb = X.mean(axis=0) - p['v'].mean(axis=0)                                   # :553
+            dW = [(X.T @ mu[0]) / N - (p['v'].T @ Hp[0]) / Mp - l2 * self.W(0)]          # :558-560
+            for i in range(1, L):
+                dW.append((mu[i - 1].T @ mu[i]) / N - (Hp[i - 1].T @ Hp[i]) / Mp - l2 * self.W(i))   # :566-568
+            dhb = [mu[i].mean(axis=0) - Hp[i].mean(axis=0) for i in range(L)]            # :575
+            q_sums, mu_sums = [Hp[i].sum(axis=0) for i in range(L)], [mu[i].sum(axis=0) for i in range(L)]
+        else:
+            # the same quantities from sums over the shards: global sizes, one sum-allreduce (csrc/bm_dbm.cu)
+            world, allsum = shard[1], shard[2]
+            N, Mp, rows_g = dt.type(self.B * world), dt.type(self.M * world), dt.type(rows * world)
+            pos, neg = [X] + mu[:-1], [p['v']] + Hp[:-1]
+            parts = [(pos[i].T @ mu[i]) / N - (neg[i].T @ Hp[i]) / Mp for i in range(L)]
+            parts += [mu[i].sum(axis=0) for i in range(L)] + [Hp[i].sum(axis=0) for i in range(L)]
+            parts += [X.sum(axis=0), p['v'].sum(axis=0)]
+            flat = allsum(np.concatenate([np.ravel(a) for a in parts]).astype(dt))
+            out_parts, off = [], 0
+            for a in parts:
+                out_parts.append(flat[off:off + a.size].reshape(a.shape)); off += a.size
+            G, mu_sums, q_sums = out_parts[:L], out_parts[L:2 * L], out_parts[2 * L:3 * L]
+            x_sum, v_sum = out_parts[3 * L], out_parts[3 * L + 1]
+            dvb = x_sum / rows_g - v_sum / Mp
+            dW = [G[i] - l2 * self.W(i) for i in range(L)]
+            dhb = [mu_sums[i] / rows_g - q_sums[i] / Mp for i in range(L)]
+            if out is not None and 'msre' in out:
+                out['msre'] = float(allsum(np.array([out['msre']], dtype=np.float64))[0] / world)
         damp = dt.type(c.get('sparsity_damping', 0.9))
         targets = c.get('sparsity_target', [0.1] * L)
         costs = c.get('sparsity_cost', [0.] * L)
         for i in range(L):                                                           # :580-590 (element i: sic)
             s = self._sfx(i)
-            qv = Hp[i].sum(axis=0)
+            qv = q_sums[i]
             p['q_means' + s] = (damp * p['q_means' + s] + (dt.type(1) - damp) * qv[i]).astype(dt)
-            mv = mu[i].sum(axis=0)
+            mv = mu_sums[i]
             p['mu_means' + s] = (damp * p['mu_means' + s] + (dt.type(1) - damp) * mv[i]).astype(dt)
             pen = dt.type(costs[i]) * (p['q_means' + s] - dt.type(targets[i]))
             pen = pen + dt.type(costs[i]) * (p['mu_means' + s] - dt.type(targets[i]))

@@ -63,6 +63,36 @@ def main():
     print('rank {0} AIS: max |sharded - single GPU| = {1:.3e}, max |sharded - oracle| = {2:.3e}'.format(rank, e1, e2), flush=True)
     ok = ok and e1 < 1e-6 and e2 < 5e-3
     dbm.close()
+    # DBM training step, data parallel: batch rows and persistent particles sharded over the ranks (global particle
+    # index in the draws, max over ranks in the mean-field test, one sum-allreduce of the statistics) must reproduce
+    # the single-process oracle with `world` times the batch and the particles
+    Bd, Md = 8, 6
+    def dcfg2(B, M):
+        return dict(n_visible=20, n_hiddens=[12, 8], v_kind='bernoulli', h_kinds=['bernoulli'] * 2, dtype='float32',
+                    n_particles=M, batch_size=B, max_mf_updates=6, mf_tol=1e-3, l2=1e-4, max_norm=1.2, sample_v=True,
+                    sample_h=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[0.01, 0.005], sparsity_damping=0.8)
+    Xd = (rng.rand(3, Bd * world, 20) < 0.3).astype(np.float32)
+    deng, dref = _native.CudaDBM(dcfg2(Bd, Md), ctx=ctx), OracleDBM(dcfg2(Bd * world, Md * world))
+    for e in (deng, dref):
+        e.set_params(dparams)
+        e.init_particles(4242)
+    dok = True
+    for it in range(3):
+        g = deng.train_step(Xd[it, rank * Bd:(rank + 1) * Bd], 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        w = dref.train_step(Xd[it], 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        dok = dok and g['n_mf_updates'] == w['n_mf_updates'] and abs(g['msre'] - w['msre']) < 1e-4 * max(w['msre'], 1e-9)
+    got, want = deng.get_params(), dref.get_params()
+    derr = 0.0
+    for k in want:
+        ref = want[k]
+        if k in ('v', 'h', 'h_1'):
+            ref = ref[rank * Md:(rank + 1) * Md]
+        elif k.startswith('mu') and not k.startswith('mu_means'):
+            ref = ref[rank * Bd:(rank + 1) * Bd]
+        derr = max(derr, float(np.max(np.abs(got[k] - ref))))
+    print('rank {0} DBM data parallel: max |engine - oracle(global)| = {1:.3e}, metrics agree: {2}'.format(rank, derr, dok), flush=True)
+    ok = ok and dok and derr < 5e-5
+    deng.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
