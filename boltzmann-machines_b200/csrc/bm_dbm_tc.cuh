@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <utility>
+#include <tuple>
 #include <stdlib.h>
 
 namespace bm {
@@ -140,6 +141,9 @@ struct DbmTC : Dbm<float> {
     std::vector<DevBuf<bf16_t>> hist;            // per layer: (mf_chunk + 2) slots of [B, ldn[i+1]]
     DevBuf<unsigned int> mf_flags;
     std::map<std::pair<int, int>, std::unique_ptr<TcProgram>> mf_progs;      // keyed by (rows, sweeps in the chunk)
+    // committed particle sweeps as ONE persistent program (opt-in, BM_DBM_PCD_PROGRAM=1): keyed by (sweeps, sampled, t0)
+    bool pcd_program = false;
+    std::map<std::tuple<int, int, int>, std::unique_ptr<TcProgram>> pcd_progs;
 
     static bool supports(const bm_dbm_cfg& f) {
         if (f.dtype != BM_DTYPE_F32) return false;
@@ -162,6 +166,7 @@ struct DbmTC : Dbm<float> {
             for (DevBuf<bf16_t>* b : {&Wb[i], &mu_b[i], &mu2_b[i], &h_b[i], &h2_b[i]}) b->zero(ctx->stream);
         }
         { const char* e = getenv("BM_DBM_MF_CHUNK"); mf_chunk = e ? atoi(e) : 0; }
+        { const char* e = getenv("BM_DBM_PCD_PROGRAM"); pcd_program = e && atoi(e) != 0; }
         if (mf_chunk > max_mf) mf_chunk = max_mf;
         if (mf_chunk * L > 90) mf_chunk = 90 / L;              // a program holds at most 96 ops
         if (mf_chunk > 0) {
@@ -237,7 +242,8 @@ struct DbmTC : Dbm<float> {
         else { g.out_mean_bf = out; g.ld_mean_bf = ldn[i + 1]; }
         return g;
     }
-    void visible_tc(const bf16_t* h0, bf16_t* out, bool sample, int rows, RngKey rng) {
+    void visible_tc(const bf16_t* h0, bf16_t* out, bool sample, int rows, RngKey rng) { launch_tc_gemm(ctx, visible_gemm(h0, out, sample, rows, rng)); }
+    TcGemm visible_gemm(const bf16_t* h0, bf16_t* out, bool sample, int rows, RngKey rng) {
         TcGemm g;
         g.M = rows; g.N = V;
         g.A[0] = mat(h0, rows, Hs[0], ldn[1]); g.K[0] = Hs[0];
@@ -252,7 +258,7 @@ struct DbmTC : Dbm<float> {
         }
         if (sample) { g.out_state_bf = out; g.ld_state_bf = ldn[0]; }
         else { g.out_mean_bf = out; g.ld_mean_bf = ldn[0]; }
-        launch_tc_gemm(ctx, g);
+        return g;
     }
     // raw fp32 product A W_i (+ bias): the bound's t-terms and the AIS pre-activations
     void linear_tc(const bf16_t* A, int lda, int rows, int K, const bf16_t* Wsh, int w_rows, int w_cols, int ldw, bool b_t,
@@ -385,7 +391,57 @@ struct DbmTC : Dbm<float> {
     }
 
     // ---- PCD particle update (dbm.py:480-509) -----------------------------------------------------------------
+    // k committed sweeps of the persistent chains as one dataflow program: per sweep L hidden ops and the visible op,
+    // each waiting per 256-row block on the ops it reads (for a single hidden layer this is the RBM chain of bm_rbm_tc.cu:
+    // PCD-k on an RBM is the reference's DBM with one layer).  Ping-pong buffers: a buffer is overwritten two sweeps
+    // after it was written, and every reader of the old value precedes the writer in the dependency chain.
+    void particles_program(int n_steps, bool sample, uint64_t seed, uint32_t tick, int t0) {
+        std::unique_ptr<TcProgram>& pslot = pcd_progs[std::make_tuple(n_steps, sample ? 1 : 0, t0)];
+        std::vector<bf16_t*> cur(L), nxt(L);
+        for (int i = 0; i < L; ++i) { cur[i] = h_b[i].p; nxt[i] = h2_b[i].p; }
+        bf16_t* vc = v_b.p; bf16_t* vn = v2_b.p;
+        const bool build = !pslot;
+        if (build) pslot.reset(new TcProgram());
+        std::vector<TcGemm>& ops = pslot->ops;
+        int last_vis = -1;
+        std::vector<int> last_h(L, -1), this_h(L, -1);
+        for (int s = 0; s < n_steps; ++s) {
+            if (build) {
+                const uint32_t tstep = (uint32_t)(t0 + s + 1);
+                for (int i = 0; i < L; ++i) {
+                    const bf16_t* below = i == 0 ? vc : nxt[i - 1];
+                    const bf16_t* above = (i + 1 < L) ? cur[i + 1] : nullptr;
+                    TcGemm g = hidden_gemm(i, below, above, nxt[i], sample && sample_h[i], M, 1.f, 1.f, make_rng(0, SITE_DBM_H + i, tstep, 0, 0));
+                    const int below_op = i == 0 ? last_vis : this_h[i - 1];
+                    if (below_op >= 0) { g.dep[g.n_deps] = below_op; g.dep_all[g.n_deps] = false; ++g.n_deps; }
+                    if (above && last_h[i + 1] >= 0) { g.dep[g.n_deps] = last_h[i + 1]; g.dep_all[g.n_deps] = false; ++g.n_deps; }
+                    g.lane = LANE_CHAIN;
+                    this_h[i] = (int)ops.size();
+                    ops.push_back(g);
+                }
+                TcGemm gv = visible_gemm(nxt[0], vn, sample && sample_vis, M, make_rng(0, SITE_DBM_V, tstep, 0, 0));
+                gv.dep[0] = this_h[0]; gv.dep_all[0] = false; gv.n_deps = 1;
+                gv.lane = LANE_CHAIN;
+                last_vis = (int)ops.size();
+                ops.push_back(gv);
+                last_h = this_h;
+            }
+            std::swap(cur, nxt); std::swap(vc, vn);
+        }
+        launch_tc_program(ctx, *pslot, make_rng(seed, 0, 0, tick, particle_row0()), 0);
+        for (int i = 0; i < L; ++i)
+            if (cur[i] != h_b[i].p)
+                BM_CUDA(cudaMemcpyAsync(h_b[i].p, cur[i], (size_t)M * ldn[i + 1] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (vc != v_b.p) BM_CUDA(cudaMemcpyAsync(v_b.p, vc, (size_t)M * ldn[0] * sizeof(bf16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        particles_f32_stale = true;
+    }
+
     void particles_tc(int n_steps, bool sample, uint64_t seed, uint32_t tick, int t0, bool commit, bf16_t** v_final) {
+        if (pcd_program && commit && n_steps >= 1 && n_steps * (L + 1) <= 90) {
+            particles_program(n_steps, sample, seed, tick, t0);
+            if (v_final) *v_final = v_b.p;
+            return;
+        }
         std::vector<bf16_t*> cur(L), nxt(L), spare(L);
         for (int i = 0; i < L; ++i) { cur[i] = h_b[i].p; nxt[i] = h2_b[i].p; spare[i] = nullptr; }
         bf16_t* vc = v_b.p; bf16_t* vn = v2_b.p; bf16_t* vspare = nullptr;

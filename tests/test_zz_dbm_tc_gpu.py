@@ -191,3 +191,25 @@ def test_mean_field_programs_equal_the_sweep_by_sweep_loop(monkeypatch, chunk, H
             np.testing.assert_allclose(ga[k], gb[k], rtol=2.0 ** -7, atol=1e-3, err_msg=k)
             assert np.mean(ga[k] != gb[k]) < 0.02, k
     loop.close(); prog.close()
+
+
+@pytest.mark.parametrize('Hs,k', [((18,), 3), ((18, 11), 1), ((18, 11, 7), 2), ((512,), 5), ((512, 256), 2)])
+def test_particle_sweep_program_equals_the_launch_per_op_sweeps(monkeypatch, Hs, k):
+    """BM_DBM_PCD_PROGRAM=1: the k committed sweeps of the persistent chains (k x (L + 1) ops) run as ONE persistent
+    dataflow program; same ops, same Philox sites -> the same particles up to draws at rounding-level ties."""
+    V = 30 if Hs[0] < 100 else 784
+    cfg = make_cfg(V=V, Hs=Hs, n_particles=12 if V == 30 else 300, batch_size=10)
+    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    loop = _native.CudaDBM(cfg)
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
+    prog = _native.CudaDBM(cfg)
+    init(cfg, (loop, prog), scale=0.3 if V == 30 else 0.03)
+    X = batch(cfg, 10)
+    for it in range(2):
+        loop.val_metrics(X, k, 5, it), prog.val_metrics(X, k, 5, it)
+        names = ['v'] + ['h' + ('' if i == 0 else '_%d' % i) for i in range(len(Hs))]
+        ga, gb = loop.get_params(names), prog.get_params(names)
+        for n in names:
+            assert set(np.unique(gb[n])) <= {0.0, 1.0}, n
+            assert np.mean(ga[n] != gb[n]) < 0.05, (n, np.mean(ga[n] != gb[n]))
+    loop.close(); prog.close()
