@@ -7,7 +7,8 @@ cfg3: GaussianRBM 3072-5000, batch 2048, CD-1            (bf16 tensor-core progr
 cfg4: DBM 784-512-1024, batch = particles = 1024, 25 mean-field updates, 1 Gibbs step per PCD update
       (--dbm-compute fp32: CUDA-core engine, default; bf16: the opt-in tensor-core engine)
 cfg4-ais: AIS on that DBM, 20000 runs (or --ais-runs) x 1000 betas
-cfg5: the per-GPU shard of BernoulliRBM 784-4096, 4096 particles, 25 Gibbs steps per update
+cfg5: the per-GPU shard of BernoulliRBM 784-4096, 4096 particles, 25 Gibbs steps per update (CD chain of the RBM engine)
+cfg5-dbm: the same shard as the reference would run PCD: its DBM class with one hidden layer (--dbm-compute, BM_DBM_PCD_PROGRAM)
 FLOP counts follow SURVEY.md section 8(d).  Times: CUDA events on the engine's stream after warm-up.
 """
 import argparse
@@ -110,6 +111,28 @@ def cfg4_ais(n_runs, n_betas, compute='fp32'):
     return out
 
 
+def cfg5_dbm(steps, warmup, compute):
+    """BASELINE.json configs[4] as the reference would run it: PCD-25 on a single RBM = its DBM class with ONE hidden layer
+    (README.md:96), 4096 persistent particles and 4096 batch rows per GPU."""
+    ctx = _native.Context.default()
+    V, H, B, k = 784, 4096, 4096, 25
+    cfg = dict(compute=compute, n_visible=V, n_hiddens=[H], v_kind='bernoulli', h_kinds=['bernoulli'], h_n_samples=[100.],
+               dtype='float32', n_particles=B, batch_size=B, max_mf_updates=1, mf_tol=1e-7, l2=1e-5, max_norm=1e9,
+               sample_v=False, sample_h=[True], sparsity_target=[0.1], sparsity_cost=[0.], sparsity_damping=0.9)
+    rng = np.random.RandomState(4)
+    eng = _native.CudaDBM(cfg)
+    eng.set_params({'vb': np.zeros(V, np.float32), 'W': (0.01 * rng.randn(V, H)).astype(np.float32), 'hb': np.zeros(H, np.float32)})
+    eng.init_particles(4242)
+    X = (rng.rand(B, V) < 0.13).astype(np.float32)
+    ms = timed(ctx, lambda i: eng.train_step(X, 0.01, 0.5, k, 99, i), steps, warmup)
+    flop = 2.0 * B * V * H * (2 * k + 3 + 1)          # k sweeps, positive pass + its init pass, two gradient GEMMs
+    out = dict(config='cfg5 as a 1-layer DBM (PCD-25) 784-4096, 4096 particles', engine=eng.compute, ms_per_step=ms,
+               gibbs_updates_per_s=B * k / (ms * 1e-3), tflops=flop / (ms * 1e-3) / 1e12, steps=steps,
+               env={k_: os.environ.get(k_) for k_ in ('BM_DBM_PCD_PROGRAM', 'BM_DBM_MF_CHUNK')})
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('which', nargs='*', default=['cfg3', 'cfg4', 'cfg4-ais', 'cfg5'])
@@ -127,6 +150,8 @@ def main():
             r = rbm_case('cfg5 shard BernoulliRBM 784-4096 batch 4096 k=25', 'bernoulli', 784, 4096, 4096, 25, a.steps, a.warmup, 0.01)
         elif w == 'cfg4':
             r = cfg4(a.steps, a.warmup, a.dbm_compute)
+        elif w == 'cfg5-dbm':
+            r = cfg5_dbm(a.steps, a.warmup, a.dbm_compute)
         elif w == 'cfg4-ais':
             r = cfg4_ais(a.ais_runs, a.ais_betas, a.dbm_compute)
         else:

@@ -17,3 +17,6 @@ for c in fp32 bf16; do
     > $OUT/${TAG}_dbm_tc_bench_$c.json 2> $OUT/${TAG}_dbm_tc_bench_$c.err
   echo "bench_configs($c) exit $?"; cat $OUT/${TAG}_dbm_tc_bench_$c.json
 done
+BM_DBM_PCD_PROGRAM=1 BM_DBM_MF_CHUNK=5 timeout 600 python tools/bench_configs.py cfg4 cfg5-dbm --dbm-compute bf16 --steps 20 \
+  > $OUT/${TAG}_dbm_tc_bench_programs.json 2> $OUT/${TAG}_dbm_tc_bench_programs.err
+echo "bench_configs(programs) exit $?"; cat $OUT/${TAG}_dbm_tc_bench_programs.json
