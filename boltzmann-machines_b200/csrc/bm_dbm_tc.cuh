@@ -128,6 +128,55 @@ __global__ void ais_accum2_bf16_kernel(double* __restrict__ logw, float a, float
     if (threadIdx.x == 0) logw[r] += acc;
 }
 
+// One pass over the shared pre-activations of a temperature step: the importance-weight increment of ais_accum2_bf16_kernel
+// AND the first unit updates of the next transition (v ~ sigmoid(beta_next pa), h2 ~ sigmoid(beta_next pb), exactly the
+// expressions of ais_unit_bf16_kernel) -- pa / pb are read once instead of three times.  One warp per chain; a lane owns
+// whole Philox blocks (4 consecutive columns).  emit == 0: weights only (the last increment of the ladder).
+__device__ __forceinline__ float ais_fused_row(const float* __restrict__ pre, int n, float a, float b, float beta_next, int emit,
+                                               int sample, bf16_t* __restrict__ out, const RngKey& rng, int r, int lane) {
+    float part = 0.f;
+    for (int cb = lane; cb * 4 < n; cb += 32) {
+        float z[4], o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = (cb * 4 + j < n) ? pre[cb * 4 + j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (cb * 4 + j < n) part += softplus_diff(a, b, z[j]);
+        if (emit) {
+            U4 w{0, 0, 0, 0};
+            if (sample) w = site_block(rng, (uint32_t)r, (uint32_t)cb);
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float zz = (cb * 4 + j < n) ? beta_next * z[j] : 0.f;
+                const float p = 1.0f / (1.0f + expf(-zz));
+                o[j] = (cb * 4 + j < n) ? (sample ? ((u32_to_unit_float(words[j]) < p) ? 1.0f : 0.0f) : p) : 0.f;
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(out + cb * 4) = pk;
+        }
+    }
+    return part;
+}
+__global__ void ais_fused_step_kernel(double* __restrict__ logw, float a, float b, float beta_next, int emit,
+                                      const bf16_t* __restrict__ x, int ldx, int H0, const float* __restrict__ hb0,
+                                      const float* __restrict__ pa, int V, bf16_t* __restrict__ va, int ldv, int sample_v, RngKey rng_v,
+                                      const float* __restrict__ pb, int H1, bf16_t* __restrict__ hc, int ldh, int sample_h2, RngKey rng_h2,
+                                      int rows) {
+    const int r = blockIdx.x * blockDim.y + threadIdx.y;
+    if (r >= rows) return;
+    const int lane = threadIdx.x;
+    float lin = 0.f;
+    for (int j = lane; j < H0; j += 32) lin += __bfloat162float(x[(size_t)r * ldx + j]) * hb0[j];
+    double acc = ((double)b - (double)a) * (double)lin;
+    acc += (double)ais_fused_row(pa + (size_t)r * V, V, a, b, beta_next, emit, sample_v, va + (size_t)r * ldv, rng_v, r, lane);
+    acc += (double)ais_fused_row(pb + (size_t)r * H1, H1, a, b, beta_next, emit, sample_h2, hc + (size_t)r * ldh, rng_h2, r, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) logw[r] += acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 struct DbmTC : Dbm<float> {
     std::vector<int> ldn;                        // leading dimension of a bf16 activation of layer idx (0 = visible)
@@ -610,14 +659,20 @@ struct DbmTC : Dbm<float> {
         };
         bf16_t* xc = x.p; bf16_t* xo = xn.p;
         int it = 0;
-        auto transition = [&](float beta, bool have_pre) {
+        // BM_DBM_AIS_FUSED=0: weight increment and unit updates as three separate passes over pa / pb
+        bool fused = true;
+        { const char* e = getenv("BM_DBM_AIS_FUSED"); if (e && !atoi(e)) fused = false; }
+        // `units_done`: the fused pass of this temperature step has already produced va / hc of sweep 0
+        auto transition = [&](float beta, bool have_pre, bool units_done) {
             for (int s = 0; s < k; ++s) {
                 const uint32_t tick = (uint32_t)(it * k + s);
                 if (!(have_pre && s == 0)) pre(xc);
-                dim3 gv(((V + 3) / 4 + 127) / 128, R), gh(((H1 + 3) / 4 + 127) / 128, R);
-                ais_unit_bf16_kernel<<<gv, 128, 0, ctx->stream>>>(pa.p, V, beta, va.p, ldv, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, row0));
-                ais_unit_bf16_kernel<<<gh, 128, 0, ctx->stream>>>(pb.p, H1, beta, hc.p, ld1, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, row0));
-                count_launch(ctx); count_launch(ctx);
+                if (!(units_done && s == 0)) {
+                    dim3 gv(((V + 3) / 4 + 127) / 128, R), gh(((H1 + 3) / 4 + 127) / 128, R);
+                    ais_unit_bf16_kernel<<<gv, 128, 0, ctx->stream>>>(pa.p, V, beta, va.p, ldv, R, V, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, row0));
+                    ais_unit_bf16_kernel<<<gh, 128, 0, ctx->stream>>>(pb.p, H1, beta, hc.p, ld1, R, H1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, row0));
+                    count_launch(ctx); count_launch(ctx);
+                }
                 TcGemm o;                     // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
                 o.M = R; o.N = H0; o.n_pairs = 2;
                 o.A[0] = mat(va.p, R, V, ldv); o.K[0] = V; o.B[0] = mat(Wb[0].p, V, H0, ld0); o.b_t[0] = true;
@@ -636,13 +691,23 @@ struct DbmTC : Dbm<float> {
             ais_unit_bf16_kernel<<<g, 128, 0, ctx->stream>>>(nullptr, 0, 0.f, xc, ld0, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, row0));
             count_launch(ctx);
         }
+        // increment of the log-weights on the current x (pa / pb current) and, fused, sweep 0's unit updates at beta_next
+        auto step = [&](float prev, float beta, float beta_next) {
+            if (!fused) { accum2(xc, prev, beta); return; }
+            const uint32_t tick = (uint32_t)(it * k);            // sweep 0 of the transition that follows
+            ais_fused_step_kernel<<<rgrid, rblock, 0, ctx->stream>>>(
+                logw.p, prev, beta, beta_next, 1, xc, ld0, H0, hb[0].p,
+                pa.p, V, va.p, ldv, sample_vis, make_rng(seed, SITE_AIS_V, 0, tick, row0),
+                pb.p, H1, hc.p, ld1, sample_h[1], make_rng(seed, SITE_AIS_H2, 0, tick, row0), R);
+            count_launch(ctx);
+        };
         const float delta = (float)(1.0 / n_betas);
-        transition(delta, false);                               // x_1 ~ T_1(x_1 | x_0)            :705
+        transition(delta, false, false);                        // x_1 ~ T_1(x_1 | x_0)            :705
         pre(xc);
         float beta = delta, prev = 0.f;                         // - log p_0(x_1) pairs with + log p_1(x_1) :708
         while (beta < 1.f - delta + 1e-5f) {                    // :710-711 (beta accumulates in the storage dtype)
-            accum2(xc, prev, beta);                             // + log p_i(x_i) - log p_{i-1}(x_i)
-            transition(beta + delta, true);                     // x_{i+1} ~ T_{i+1}
+            step(prev, beta, beta + delta);                     // + log p_i(x_i) - log p_{i-1}(x_i)  [+ v, h2 of T_{i+1}]
+            transition(beta + delta, true, fused);              // x_{i+1} ~ T_{i+1}
             pre(xc);
             prev = beta;
             beta = beta + delta;

@@ -117,12 +117,16 @@ def test_first_gibbs_sweep_is_the_philox_draw():
     eng.close()
 
 
-def test_ais_matches_exact_enumeration():
+@pytest.mark.parametrize('fused,k', [('1', 1), ('0', 1), ('1', 3), ('0', 3)])
+def test_ais_matches_exact_enumeration(monkeypatch, fused, k):
+    """fused: one pass over the pre-activations per temperature (weight increment + the next transition's first unit
+    updates); BM_DBM_AIS_FUSED=0: three passes.  Same expressions, same Philox sites."""
+    monkeypatch.setenv('BM_DBM_AIS_FUSED', fused)
     cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
     eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
     init(cfg, (eng, emu))
-    a = eng.ais(32, 500, 1, 2222)
-    b = emu.ais(32, 500, 1, 2222)
+    a = eng.ais(32, 500, k, 2222)
+    b = emu.ais(32, 500, k, 2222)
     lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
     assert abs(lm(a) - lm(b)) < 0.1
     p = emu.get_params()
