@@ -84,12 +84,13 @@ def test_bf16_queries_track_the_pinned_oracle():
     assert v.shape == (cfg['n_particles'], cfg['n_visible']) and np.all((v >= 0) & (v <= 1))
 
 
-def test_bf16_ais_matches_exact_enumeration_and_the_pinned_oracle():
+@pytest.mark.parametrize('k', [1, 3])
+def test_bf16_ais_matches_exact_enumeration_and_the_pinned_oracle(k):
     cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
     ref, emu = OracleDBM(cfg), OracleDBMbf16(cfg)
     init(cfg, (ref, emu))
-    a = emu.ais(32, 500, 1, 2222)
-    b = ref.ais(32, 500, 1, 2222)
+    a = emu.ais(32, 500, k, 2222)
+    b = ref.ais(32, 500, k, 2222)
     lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
     assert abs(lm(a) - lm(b)) < 0.1
     # exact log Z of the model the bf16 engine actually evaluates (weights rounded to bf16)
