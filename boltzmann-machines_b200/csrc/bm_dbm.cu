@@ -588,7 +588,8 @@ struct Dbm : DbmBase {
         std::vector<double> hw(total);
         BM_CUDA(cudaMemcpyAsync(hw.data(), all.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
-        const double logZ0 = (double)(V + Hs[0] + Hs[1]) * 0.6931471805599453;     // :731-734
+        // :731-734 -- the reference multiplies by `tf.cast(tf.log(2.), dtype)`: the FLOAT32 value of log 2 in every dtype
+        const double logZ0 = (double)(V + Hs[0] + Hs[1]) * 0.693147182464599609375;
         for (int r = 0; r < total; ++r) out[r] = hw[r] + logZ0;
     }
     void ais(int R, int n_betas, int k, uint64_t seed, double* out) override {

@@ -373,7 +373,8 @@ class OracleDBM(object):
             log_Z = log_Z - self._log_p_star(x, beta)                                # :719
             beta = dt.type(beta + delta)
         log_Z = log_Z + self._log_p_star(x, dt.type(1.))                             # :728
-        log_Z = log_Z + (self.V + self.Hs[0] + self.Hs[1]) * np.log(2.)              # :731-734
+        # :731-734 -- `tf.cast(tf.log(2.), dtype)`: the float32 value of log 2, also in a float64 model
+        log_Z = log_Z + (self.V + self.Hs[0] + self.Hs[1]) * float(np.float32(np.log(2.)))
         return log_Z
 
     def close(self):

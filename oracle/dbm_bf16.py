@@ -241,7 +241,7 @@ class OracleDBMbf16(OracleDBM):
             prev = beta
             beta = f(beta + delta)
         logw += self._accum2(x, pre[0], pre[1], prev, f(1.))
-        return logw + (self.V + self.Hs[0] + self.Hs[1]) * np.log(2.)
+        return logw + (self.V + self.Hs[0] + self.Hs[1]) * float(np.float32(np.log(2.)))
 
 
 def dbm_bf16_factory(cfg):

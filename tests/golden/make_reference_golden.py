@@ -303,6 +303,7 @@ def fuzz_dbm_spec(seed, i):
     rng = np.random.RandomState(100003 * seed + i)
     pick = lambda xs: xs[rng.randint(len(xs))]
     L = int(pick([2, 2, 3]))
+    dt = pick(['float32', 'float32', 'float32', 'float64'])
     gaussian = bool(rng.rand() < 0.25)
     V = int(rng.randint(8, 20))
     sizes = [V] + [int(rng.randint(4, 12)) for _ in range(L)]
@@ -311,12 +312,12 @@ def fuzz_dbm_spec(seed, i):
     dbm_batch = int(pick([4, 8]))
     n_rows, n_val = int(pick([16, 24, 32])), 16
     if gaussian:
-        X, X_val = rng.randn(n_rows, V).astype(np.float32), rng.randn(n_val, V).astype(np.float32)
+        X, X_val = rng.randn(n_rows, V).astype(dt), rng.randn(n_val, V).astype(dt)
     else:
-        X, X_val = (rng.rand(n_rows, V) < 0.3).astype(np.float32), (rng.rand(n_val, V) < 0.3).astype(np.float32)
+        X, X_val = (rng.rand(n_rows, V) < 0.3).astype(dt), (rng.rand(n_val, V) < 0.3).astype(dt)
     rbm_cls, rbm_kw = [], []
     for j in range(L):
-        kw = dict(n_visible=sizes[j], n_hidden=sizes[j + 1], W_init=(0.1 * rng.randn(sizes[j], sizes[j + 1])).astype(np.float32),
+        kw = dict(n_visible=sizes[j], n_hidden=sizes[j + 1], W_init=(0.1 * rng.randn(sizes[j], sizes[j + 1])).astype(dt), dtype=dt,
                   n_gibbs_steps=int(rng.randint(1, 3)), learning_rate=float(rng.uniform(0.01, 0.05)), momentum=float(rng.uniform(0.3, 0.9)),
                   max_epoch=int(rng.randint(1, 3)), batch_size=int(rng.randint(5, 13)), l2=float(pick([0., 1e-3])),
                   dbm_first=(j == 0), dbm_last=(j == L - 1), random_seed=int(rng.randint(1, 10 ** 6)), verbose=False,
@@ -340,7 +341,7 @@ def fuzz_dbm_spec(seed, i):
                   sparsity_target=[float(rng.uniform(0.05, 0.3)) for _ in range(L)],
                   sparsity_cost=[float(pick([0., 1e-2, 5e-3])) for _ in range(L)], sparsity_damping=float(rng.uniform(0.5, 0.95)),
                   train_metrics_every_iter=int(rng.randint(1, 4)), val_metrics_every_epoch=int(rng.randint(1, 3)), verbose=False,
-                  save_after_each_epoch=bool(rng.rand() < 0.5), random_seed=int(rng.randint(1, 10 ** 6)))
+                  save_after_each_epoch=bool(rng.rand() < 0.5), random_seed=int(rng.randint(1, 10 ** 6)), dtype=dt)
     return X, X_val, rbm_cls, rbm_kw, dbm_kw, (L == 2 and not gaussian)
 
 
