@@ -342,14 +342,17 @@ def fuzz_dbm_spec(seed, i):
                   sparsity_cost=[float(pick([0., 1e-2, 5e-3])) for _ in range(L)], sparsity_damping=float(rng.uniform(0.5, 0.95)),
                   train_metrics_every_iter=int(rng.randint(1, 4)), val_metrics_every_epoch=int(rng.randint(1, 3)), verbose=False,
                   save_after_each_epoch=bool(rng.rand() < 0.5), random_seed=int(rng.randint(1, 10 ** 6)), dtype=dt)
-    return X, X_val, rbm_cls, rbm_kw, dbm_kw, (L == 2 and not gaussian)
+    resume = epochs + int(rng.randint(1, 3)) if rng.rand() < 0.3 else None     # load_model + load_rbms + more epochs
+    return X, X_val, rbm_cls, rbm_kw, dbm_kw, (L == 2 and not gaussian), resume
 
 
 def run_dbm_case(ref, workdir, variant, spec=None):
     """Greedy pre-training of the RBM stack, then DBM.fit / transform / reconstruct / sample_v (/ log_proba / log_Z for
     the 2-layer binary model, the only one the reference implements them for) -- dbm_mnist.py's sequence in miniature --
     all through the reference's public API.  Variants: 2 binary layers; Gaussian visibles (dbm_cifar*.py); 3 layers."""
-    X, X_val, rbm_cls, rbm_kw, dbm_kw, with_ais = spec if spec is not None else dbm_spec(variant)
+    spec = tuple(spec if spec is not None else dbm_spec(variant))
+    X, X_val, rbm_cls, rbm_kw, dbm_kw, with_ais = spec[:6]
+    resume_max_epoch = spec[6] if len(spec) > 6 else None
     L = len(rbm_kw)
     rbms, inp, Q = [], X, None
     for i in range(L):
@@ -372,10 +375,24 @@ def run_dbm_case(ref, workdir, variant, spec=None):
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
     dbm_summaries = summaries_of(dbm)
+    if resume_max_epoch:
+        # what dbm_mnist.py does in a new process: DBM.load_model(path), load_rbms(rbms), then more epochs
+        dbm = ref.DBM.load_model(os.path.join(workdir, variant, 'dbm') + '/')
+        dbm.load_rbms(rbms)
+        dbm.set_params(max_epoch=resume_max_epoch)
+        for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
+            orig = getattr(dbm, meth)
+
+            def wrapped2(*a, _orig=orig, _key=key, **k):
+                r = _orig(*a, **k)
+                log[_key].append([None if v is None else float(v) for v in r])
+                return r
+            setattr(dbm, meth, wrapped2)
+        dbm.fit(X, X_val)
     rec = {'summaries': dbm_summaries, 'variant': variant, 'rbm_cls': rbm_cls,
            'rbm_kw': [{k: (tolist(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in rbm_kw],
            'dbm_kw': {k: ('inf' if isinstance(v, float) and np.isinf(v) else v) for k, v in dbm_kw.items()}, 'X': tolist(X), 'X_val': tolist(X_val), 'Q': tolist(Q), 'log': log,
-           'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_)}
+           'epoch_': int(dbm.epoch_), 'iter_': int(dbm.iter_), 'resume_max_epoch': resume_max_epoch}
     scopes = ('weights', 'grads_accumulators', 'variational_params', 'hidden_means_accumulators', 'negative_particles')
     rec['after_fit'] = {sc: {k: tolist(v) for k, v in dbm.get_tf_params(scope=sc).items()} for sc in scopes}
     rec['transform'] = tolist(dbm.transform(X[:16]))

@@ -248,6 +248,21 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
     check_summaries(dbm, g['summaries'], tol)
+    if g.get('resume_max_epoch'):
+        path = dbm._model_dirpath
+        dbm.close()
+        dbm = DBM.load_model(path)
+        dbm.load_rbms(rbms)
+        dbm.set_params(max_epoch=g['resume_max_epoch'])
+        for meth, key in (('_train_epoch', 'train'), ('_run_val_metrics', 'val')):
+            orig = getattr(dbm, meth)
+
+            def wrapped2(*a, _orig=orig, _key=key, **k):
+                r = _orig(*a, **k)
+                log[_key].append(list(r))
+                return r
+            setattr(dbm, meth, wrapped2)
+        dbm.fit(X, X_val)
     assert (int(dbm.epoch_), int(dbm.iter_)) == (g['epoch_'], g['iter_'])
     for key in ('train', 'val'):
         assert len(log[key]) == len(g['log'][key])
