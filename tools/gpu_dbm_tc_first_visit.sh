@@ -12,6 +12,10 @@ tail -15 $OUT/${TAG}_dbm_tc_pytest.log
 BM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_z_reference_golden.py -k 'fuzz_ and cuda' -q > $OUT/${TAG}_fuzz_corpus_pytest.log 2>&1
 echo "fuzz corpus pytest exit $?" >> $OUT/${TAG}_fuzz_corpus_pytest.log
 tail -8 $OUT/${TAG}_fuzz_corpus_pytest.log
+# random-shape fuzz of the verified engines (fp32 / bf16 RBM, fp32 DBM) against the oracles
+BM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_engine_fuzz_gpu.py -q > $OUT/${TAG}_engine_fuzz_pytest.log 2>&1
+echo "engine fuzz pytest exit $?" >> $OUT/${TAG}_engine_fuzz_pytest.log
+tail -8 $OUT/${TAG}_engine_fuzz_pytest.log
 for c in fp32 bf16; do
   timeout 600 python tools/bench_configs.py cfg4 cfg4-ais --dbm-compute $c --steps 20 --ais-runs 20000 --ais-betas 1000 \
     > $OUT/${TAG}_dbm_tc_bench_$c.json 2> $OUT/${TAG}_dbm_tc_bench_$c.err
