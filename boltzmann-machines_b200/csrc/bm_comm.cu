@@ -7,11 +7,20 @@
 #include "bm_internal.h"
 #include <dlfcn.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
+#include <nvtx3/nvToolsExt.h>
 
 namespace bm {
 
 thread_local std::string g_last_error;
+
+static bool nvtx_enabled() {
+    static const bool on = [] { const char* e = getenv("BM_NVTX"); return e && atoi(e) != 0; }();
+    return on;
+}
+NvtxRange::NvtxRange(const char* name) : on(nvtx_enabled()) { if (on) nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { if (on) nvtxRangePop(); }
 
 struct NcclId { char internal[128]; };
 struct NcclApi {

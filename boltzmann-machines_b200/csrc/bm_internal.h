@@ -33,7 +33,14 @@ struct Error : std::runtime_error {
 
 extern thread_local std::string g_last_error;
 
-#define BM_API_BEGIN try {
+// Every C-ABI entry point is an NVTX range named after the function when BM_NVTX=1 (ncu --nvtx --nvtx-include "bm_rbm_train_step/",
+// timeline tools): header-only NVTX v3, a no-op unless a tool injects itself.
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define BM_API_BEGIN try { ::bm::NvtxRange nvtx_range__(__func__);
 #define BM_API_END                                                                   \
     return BM_OK;                                                                    \
     }                                                                                \
