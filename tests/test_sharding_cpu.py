@@ -11,7 +11,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, X, init, out_dir):
+def _rbm_cfg(kind, V, H):
+    cfg = dict(n_visible=V, n_hidden=H, sample_v=True, sample_h=True, dropout=0.9, l2=1e-4, sparsity_cost=0.01)
+    if kind == 'gaussian':
+        cfg.update(v_kind='gaussian', h_kind='bernoulli', sigma=np.linspace(0.7, 1.3, V))
+    elif kind == 'multinomial':
+        cfg.update(v_kind='bernoulli', h_kind='multinomial', h_n_samples=7)
+    return cfg
+
+
+def _worker(rank, world, port, X, init, out_dir, kind='bernoulli'):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -25,9 +34,7 @@ def _worker(rank, world, port, X, init, out_dir):
         dist.all_reduce(t)
         return t.numpy()
 
-    cfg = dict(n_visible=X.shape[1], n_hidden=init['W'].shape[1], sample_v=True, sample_h=True, dropout=0.9, l2=1e-4,
-               sparsity_cost=0.01)
-    ora = OracleRBM(cfg)
+    ora = OracleRBM(_rbm_cfg(kind, X.shape[1], init['W'].shape[1]))
     ora.set_params(init)
     rows = X.shape[0] // world
     for it in range(3):
@@ -36,16 +43,17 @@ def _worker(rank, world, port, X, init, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_oracle_equals_single_process(tmp_path):
+@pytest.mark.parametrize('kind', ['bernoulli', 'gaussian', 'multinomial'])
+def test_two_rank_oracle_equals_single_process(tmp_path, kind):
     torch = pytest.importorskip('torch')
     import torch.multiprocessing as mp
     from oracle.rbm import OracleRBM
     rng = np.random.RandomState(0)
-    X = (rng.rand(16, 24) < 0.3).astype(np.float32)
+    X = (rng.randn(16, 24) if kind == 'gaussian' else (rng.rand(16, 24) < 0.3)).astype(np.float32)
     init = dict(W=(0.1 * rng.randn(24, 10)).astype(np.float32), vb=np.zeros(24, np.float32), hb=np.zeros(10, np.float32))
-    port = 29500 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, X, init, str(tmp_path)), nprocs=2, join=True)
-    single = OracleRBM(dict(n_visible=24, n_hidden=10, sample_v=True, sample_h=True, dropout=0.9, l2=1e-4, sparsity_cost=0.01))
+    port = 29500 + (os.getpid() % 1000) + {'bernoulli': 0, 'gaussian': 11, 'multinomial': 23}[kind]
+    mp.spawn(_worker, args=(2, port, X, init, str(tmp_path), kind), nprocs=2, join=True)
+    single = OracleRBM(_rbm_cfg(kind, 24, 10))
     single.set_params(init)
     for it in range(3):
         single.train_step(X, 0.05, 0.5, 2, 77, it)
