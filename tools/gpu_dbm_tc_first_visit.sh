@@ -24,3 +24,10 @@ done
 BM_DBM_PCD_PROGRAM=1 BM_DBM_MF_CHUNK=5 timeout 600 python tools/bench_configs.py cfg4 cfg5-dbm --dbm-compute bf16 --steps 20 \
   > $OUT/${TAG}_dbm_tc_bench_programs.json 2> $OUT/${TAG}_dbm_tc_bench_programs.err
 echo "bench_configs(programs) exit $?"; cat $OUT/${TAG}_dbm_tc_bench_programs.json
+# micro-benchmarks for the cluster-resident chain: DSMEM push latency / throughput, and cta_group::2 pairs +
+# commit multicast + a DSMEM-fed A tile inside one 8-CTA cluster
+for u in dsmem_push cluster8_pair_mma; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/$u tools/ubench/$u.cu > $OUT/${TAG}_ubench_$u.log 2>&1 \
+    && timeout 60 /tmp/$u >> $OUT/${TAG}_ubench_$u.log 2>&1
+  echo "$u exit $?" >> $OUT/${TAG}_ubench_$u.log; cat $OUT/${TAG}_ubench_$u.log
+done
