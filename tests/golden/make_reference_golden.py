@@ -481,6 +481,40 @@ def run_case(ref_rbm, case, workdir):
     return rec
 
 
+def write_layer_goldens(ref):
+    """tests/golden/reference_layers.json: the reference's layers.py plug-ins (layers.py:39-89) evaluated on the shim --
+    `activation(x, b)` of the three unit types in both dtypes and the shape / dtype of `init` -- for the host mirror's
+    layers.py, which keeps that surface with numpy semantics."""
+    tf = sys.modules['tensorflow']
+    L = ref.layers
+    rng = np.random.RandomState(11)
+    recs = []
+    for dt in ('float32', 'float64'):
+        for name, make in (('BernoulliLayer', lambda n: L.BernoulliLayer(n_units=n, dtype=dt)),
+                           ('MultinomialLayer', lambda n: L.MultinomialLayer(n_samples=7, n_units=n, dtype=dt)),
+                           ('GaussianLayer', lambda n: L.GaussianLayer(sigma=np.linspace(0.5, 1.5, n), n_units=n, dtype=dt))):
+            n = 6
+            layer = make(n)
+            x = (2.0 * rng.randn(5, n)).astype(dt)
+            b = (0.5 * rng.randn(n)).astype(dt)
+            saved = tf1shim.default_random_provider          # `init` draws: only its shape / dtype are recorded
+            tf1shim.default_random_provider = lambda req: np.zeros(tuple(int(v) for v in req.shape), dtype=req.dtype)
+            try:
+                tf.reset_default_graph()                     # a graph takes its provider when it is created
+                with tf.Session() as sess:
+                    act = sess.run(layer.activation(tf.constant(x), tf.constant(b)))
+                    init = sess.run(layer.init(batch_size=4, random_seed=5))
+            finally:
+                tf1shim.default_random_provider = saved
+            recs.append({'cls': name, 'dtype': dt, 'x': x.tolist(), 'b': b.tolist(), 'activation': np.asarray(act).tolist(),
+                         'activation_dtype': str(np.asarray(act).dtype), 'init_shape': list(np.asarray(init).shape),
+                         'init_dtype': str(np.asarray(init).dtype)})
+    path = os.path.join(HERE, 'reference_layers.json')
+    with open(path, 'w') as fh:
+        json.dump({'source': 'yell/boltzmann-machines boltzmann_machines/layers.py on oracle/tf1shim.py', 'cases': recs}, fh)
+    print('wrote', path, len(recs), 'cases')
+
+
 def main():
     import argparse
     ap = argparse.ArgumentParser()
@@ -513,6 +547,8 @@ def main():
     sys.meta_path.insert(0, _LayersAlias())
     import boltzmann_machines as ref                     # the reference package, unmodified
     assert ref.__file__.startswith('/root/reference/'), ref.__file__
+    if not args.fuzz:
+        write_layer_goldens(ref)
     work = tempfile.mkdtemp(prefix='bm_golden_')
     cwd = os.getcwd()
     try:

@@ -60,3 +60,32 @@ def test_host_rng_matches_the_reference():
         m = M(random_seed=rec['seed'])
         m._rng.rand(3)
         assert [m.make_random_seed() for _ in range(3)] == rec['make_random_seed']
+
+
+def test_layer_plugins_match_the_reference_layers():
+    """layers.py plug-in surface (north_star): `activation(x, b)` of the three unit types in both dtypes and the shape /
+    dtype contract of `init`, against the reference's own layers.py evaluated on the shim
+    (tests/golden/reference_layers.json, written by make_reference_golden.py)."""
+    import json
+    import os
+    import numpy as np
+    from boltzmann_machines import layers as L
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_layers.json')
+    cases = json.load(open(path))['cases']
+    assert len(cases) == 6
+    for c in cases:
+        n = len(c['b'])
+        kw = dict(n_units=n, dtype=c['dtype'])
+        if c['cls'] == 'MultinomialLayer':
+            kw['n_samples'] = 7
+        if c['cls'] == 'GaussianLayer':
+            kw['sigma'] = np.linspace(0.5, 1.5, n)
+        layer = getattr(L, c['cls'])(**kw)
+        x, b = np.asarray(c['x'], dtype=c['dtype']), np.asarray(c['b'], dtype=c['dtype'])
+        got = np.asarray(layer.activation(x, b))
+        np.testing.assert_allclose(got, np.asarray(c['activation']), rtol=2e-6 if c['dtype'] == 'float32' else 1e-12,
+                                   atol=1e-7 if c['dtype'] == 'float32' else 1e-14, err_msg=c['cls'] + ' ' + c['dtype'])
+        init = layer.init(batch_size=4, random_seed=5)
+        assert list(init.shape) == c['init_shape'] and str(init.dtype) == c['init_dtype'], c['cls']
+        s = layer.sample(got)
+        assert s.shape == got.shape and str(s.dtype) == c['dtype']
