@@ -1,0 +1,253 @@
+// TEST INFRASTRUCTURE ONLY -- a stand-in for the CUDA runtime that lets the HOST side of libbm.so run without a GPU.
+//
+// tests/hostsim/build.sh links the library's own object files (the ones build.sh compiles for sm_100a) against this file
+// instead of libcudart: device memory becomes host memory, kernel launches are recorded and skipped, and everything the host
+// code asks the runtime or the driver to check is checked here --
+//   * every cudaMemcpy* / cudaMemset* range must lie inside one live allocation when it touches "device" memory;
+//   * cuTensorMapEncodeTiled (reached through cudaGetDriverEntryPoint, as bm_tc.cu does) validates its arguments the way the
+//     driver does (16-byte aligned base, strides multiples of 16 bytes, box dimensions 1..256, 128-byte swizzle span) AND that
+//     the whole tensor view (rows, leading dimension) lies inside one live allocation -- a wrong TcMat is a failure here,
+//     not a corrupted tile on the GPU;
+//   * frees of unknown pointers and leaks at exit are reported.
+// What the run proves: argument validation (every BM_REQUIRE), buffer sizing, pointer arithmetic, program construction and
+// the control flow around the kernels.  What it cannot prove: anything a kernel computes (results are whatever the zeroed
+// buffers hold).  It never ships: the product library links the real runtime and refuses to start without a B200.
+#include <cuda_runtime_api.h>
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+// Construct-on-first-use: the nvcc-generated registration constructors of the library's objects call into this file
+// while the shared object is still being initialised, possibly before this translation unit's own globals exist.
+struct State {
+    std::mutex mu;
+    std::map<uintptr_t, size_t> alloc;               // live "device" allocations
+    std::map<const void*, std::string> kernels;      // host stub -> device (mangled) name
+    std::map<std::string, long> launches;            // per kernel name
+    std::string violation;                           // first violation (sticky)
+    long encodes = 0;
+};
+State& st() { static State* s = new State(); return *s; }
+#define g_mu (st().mu)
+#define g_alloc (st().alloc)
+#define g_kernels (st().kernels)
+#define g_launches (st().launches)
+#define g_violation (st().violation)
+#define g_encodes (st().encodes)
+struct CallCfg { dim3 grid, block; size_t smem; cudaStream_t stream; };
+std::vector<CallCfg>& cfg_stack() { thread_local std::vector<CallCfg>* v = new std::vector<CallCfg>(); return *v; }
+#define t_cfg (cfg_stack())
+
+void violation(const std::string& m) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_violation.empty()) g_violation = m;
+    fprintf(stderr, "[fake_cudart] VIOLATION: %s\n", m.c_str());
+}
+// the live allocation containing [p, p + n), or 0
+bool inside_one_allocation(const void* p, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_alloc.upper_bound(a);
+    if (it == g_alloc.begin()) return false;
+    --it;
+    return a >= it->first && a + n <= it->first + it->second;
+}
+bool touches_device(const void* p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_alloc.upper_bound(a);
+    if (it == g_alloc.begin()) return false;
+    --it;
+    return a >= it->first && a < it->first + it->second;
+}
+void check_range(const void* p, size_t n, const char* what) {
+    if (n == 0 || !touches_device(p)) return;          // host buffers of the caller are not tracked
+    if (!inside_one_allocation(p, n)) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "%s: %zu bytes at %p run past the end of their device allocation", what, n, p);
+        violation(buf);
+    }
+}
+
+CUresult fake_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
+                           const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                           CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    ++g_encodes;
+    char buf[256];
+    auto bad = [&](const char* why) { snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled: %s", why); violation(buf); return CUDA_ERROR_INVALID_VALUE; };
+    if (!tm || !base || !gdim || !box || !estr) return bad("null argument");
+    if (rank < 1 || rank > 5) return bad("rank out of range");
+    if (dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) return bad("this library only maps bf16 tensors");
+    const size_t esz = 2;
+    if (((uintptr_t)base & 15) != 0) return bad("global address not 16-byte aligned");
+    for (cuuint32_t i = 0; i < rank; ++i) {
+        if (gdim[i] == 0 || gdim[i] > (1ull << 32)) return bad("global dimension out of range");
+        if (box[i] == 0 || box[i] > 256) return bad("box dimension must be 1..256");
+        if (estr[i] == 0 || estr[i] > 8) return bad("element stride must be 1..8");
+    }
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) {
+        if (gstride[i] % 16 != 0 || gstride[i] >= (1ull << 40)) return bad("global stride must be a multiple of 16 bytes below 2^40");
+        if (i == 0 && gstride[0] < gdim[0] * esz) return bad("row stride smaller than a row");
+    }
+    if (il == CU_TENSOR_MAP_INTERLEAVE_NONE && sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * esz > 128) return bad("inner box dimension exceeds the 128-byte swizzle span");
+    if (il == CU_TENSOR_MAP_INTERLEAVE_NONE && (box[0] * esz) % 16 != 0) return bad("inner box dimension must be a multiple of 16 bytes");
+    // the whole view must be backed by one allocation: last row start + one row
+    size_t span = gdim[0] * esz;
+    for (cuuint32_t i = 1; i < rank; ++i) span += (size_t)(gdim[i] - 1) * gstride[i - 1];
+    if (!inside_one_allocation(base, span)) {
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled: tensor view of %zu bytes at %p (dims %llu x %llu, row stride %llu B) is not inside one device allocation",
+                 span, base, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 1), (unsigned long long)(rank > 1 ? gstride[0] : 0));
+        violation(buf);
+        return CUDA_ERROR_INVALID_VALUE;
+    }
+    memset(tm, 0, sizeof(*tm));
+    memcpy(tm, &base, sizeof(base));
+    return CUDA_SUCCESS;
+}
+
+void record_launch(const void* func) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_kernels.find(func);
+    g_launches[it == g_kernels.end() ? std::string("<unregistered>") : it->second]++;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- inspection hooks for the tests --------------------------------------------------------------------------------
+const char* fakecuda_violation(void) { std::lock_guard<std::mutex> lk(g_mu); static std::string s; s = g_violation; return s.c_str(); }
+void fakecuda_reset(void) { std::lock_guard<std::mutex> lk(g_mu); g_violation.clear(); g_launches.clear(); g_encodes = 0; }
+long fakecuda_launches(const char* substr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    long n = 0;
+    for (auto& kv : g_launches) if (!substr || !*substr || kv.first.find(substr) != std::string::npos) n += kv.second;
+    return n;
+}
+long fakecuda_tensor_maps(void) { return g_encodes; }
+long fakecuda_live_allocations(void) { std::lock_guard<std::mutex> lk(g_mu); return (long)g_alloc.size(); }
+
+// ---- registration (called by the nvcc-generated host stubs at load time) ------------------------------------------------
+void** __cudaRegisterFatBinary(void*) { static void* handle = nullptr; return &handle; }
+void __cudaRegisterFatBinaryEnd(void**) {}
+void __cudaUnregisterFatBinary(void**) {}
+void __cudaRegisterFunction(void**, const char* hostFun, char*, const char* deviceName, int, uint3*, uint3*, dim3*, dim3*, int*) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_kernels[(const void*)hostFun] = deviceName ? deviceName : "?";
+}
+void __cudaRegisterVar(void**, char*, char*, const char*, int, size_t, int, int) {}
+unsigned __cudaPushCallConfiguration(dim3 grid, dim3 block, size_t smem, struct CUstream_st* stream) {
+    t_cfg.push_back(CallCfg{grid, block, smem, stream});
+    return 0;
+}
+cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, void* stream) {
+    if (t_cfg.empty()) return cudaErrorInvalidConfiguration;
+    const CallCfg c = t_cfg.back(); t_cfg.pop_back();
+    *grid = c.grid; *block = c.block; *smem = c.smem; *(cudaStream_t*)stream = c.stream;
+    return cudaSuccess;
+}
+
+// ---- devices ----------------------------------------------------------------------------------------------------------
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) {
+    memset(p, 0, sizeof(*p));
+    snprintf(p->name, sizeof(p->name), "fake B200 (host simulation)");
+    p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
+    p->sharedMemPerBlockOptin = 232448; p->totalGlobalMem = (size_t)180 << 30;
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "fake_cudart error"; }
+cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* st) {
+    if (symbol && !strcmp(symbol, "cuTensorMapEncodeTiled")) { *fn = (void*)&fake_encode_tiled; if (st) *st = cudaDriverEntryPointSuccess; return cudaSuccess; }
+    *fn = nullptr; if (st) *st = cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}
+
+// ---- memory -------------------------------------------------------------------------------------------------------------
+cudaError_t cudaMalloc(void** p, size_t n) {
+    void* q = nullptr;
+    if (n == 0) n = 1;
+    if (posix_memalign(&q, 256, n) != 0) return cudaErrorMemoryAllocation;
+    memset(q, 0xCD, n);                                  // device memory is NOT zero-initialised
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_alloc[(uintptr_t)q] = n;
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_alloc.find((uintptr_t)p);
+        if (it == g_alloc.end()) { if (g_violation.empty()) g_violation = "cudaFree of a pointer that is not a live allocation"; return cudaErrorInvalidValue; }
+        g_alloc.erase(it);
+    }
+    free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) {
+    check_range(d, n, "cudaMemcpy destination"); check_range(s, n, "cudaMemcpy source");
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t) {
+    if (h) { check_range(d, (h - 1) * dp + w, "cudaMemcpy2D destination"); check_range(s, (h - 1) * sp + w, "cudaMemcpy2D source"); }
+    for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { check_range(d, n, "cudaMemset"); memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpyToSymbolAsync(const void* sym, const void* s, size_t n, size_t off, enum cudaMemcpyKind, cudaStream_t) {
+    memcpy((char*)sym + off, s, n);                       // the host shadow of the __constant__ array
+    return cudaSuccess;
+}
+
+// ---- streams / events -------------------------------------------------------------------------------------------------------
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1e-3f; return cudaSuccess; }
+
+// ---- launches: recorded, not executed --------------------------------------------------------------------------------------
+cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void**, size_t smem, cudaStream_t) {
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024 ||
+        grid.y > 65535 || grid.z > 65535 || smem > 232448) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "invalid launch configuration: grid (%u,%u,%u) block (%u,%u,%u) smem %zu", grid.x, grid.y, grid.z, block.x, block.y, block.z, smem);
+        violation(buf);
+        return cudaErrorInvalidConfiguration;
+    }
+    record_launch(func);
+    return cudaSuccess;
+}
+cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* func, void** args) {
+    for (unsigned i = 0; i < c->numAttrs; ++i)
+        if (c->attrs[i].id == cudaLaunchAttributeClusterDimension) {
+            const unsigned cx = c->attrs[i].val.clusterDim.x, cy = c->attrs[i].val.clusterDim.y, cz = c->attrs[i].val.clusterDim.z;
+            if (cx == 0 || cy == 0 || cz == 0 || cx * cy * cz > 8 || c->gridDim.x % cx || c->gridDim.y % cy || c->gridDim.z % cz) {
+                violation("cluster launch: the grid is not a whole number of (portable-size) clusters");
+                return cudaErrorInvalidConfiguration;
+            }
+        }
+    return cudaLaunchKernel(func, c->gridDim, c->blockDim, args, c->dynamicSmemBytes, c->stream);
+}
+
+}  // extern "C"
