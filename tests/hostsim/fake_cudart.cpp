@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+namespace fakecuda { bool execute(const std::string& name, dim3 grid, dim3 block, void** args); }
+
 namespace {
 
 // Construct-on-first-use: the nvcc-generated registration constructors of the library's objects call into this file
@@ -33,6 +35,8 @@ struct State {
     std::map<std::string, long> launches;            // per kernel name
     std::string violation;                           // first violation (sticky)
     long encodes = 0;
+    bool execute = false;                            // interpret launches on the CPU (kernels_cpu.cpp) instead of skipping them
+    std::map<std::string, long> skipped;             // launches without a CPU restatement while `execute` was on
 };
 State& st() { static State* s = new State(); return *s; }
 #define g_mu (st().mu)
@@ -107,15 +111,21 @@ CUresult fake_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dt, cuuint32_t r
         violation(buf);
         return CUDA_ERROR_INVALID_VALUE;
     }
+    struct MapView { const void* base; unsigned long long cols, rows, ld_bytes; unsigned box0, box1; unsigned magic; } mv;   // read by kernels_cpu.cpp
+    memset(&mv, 0, sizeof(mv));
+    mv.base = base; mv.cols = gdim[0]; mv.rows = rank > 1 ? gdim[1] : 1; mv.ld_bytes = rank > 1 ? gstride[0] : gdim[0] * esz;
+    mv.box0 = box[0]; mv.box1 = rank > 1 ? box[1] : 1; mv.magic = 0xB200C0DEu;
     memset(tm, 0, sizeof(*tm));
-    memcpy(tm, &base, sizeof(base));
+    memcpy(tm, &mv, sizeof(mv));
     return CUDA_SUCCESS;
 }
 
-void record_launch(const void* func) {
+std::string record_launch(const void* func) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_kernels.find(func);
-    g_launches[it == g_kernels.end() ? std::string("<unregistered>") : it->second]++;
+    const std::string name = it == g_kernels.end() ? std::string("<unregistered>") : it->second;
+    g_launches[name]++;
+    return name;
 }
 
 }  // namespace
@@ -124,7 +134,7 @@ extern "C" {
 
 // ---- inspection hooks for the tests --------------------------------------------------------------------------------
 const char* fakecuda_violation(void) { std::lock_guard<std::mutex> lk(g_mu); static std::string s; s = g_violation; return s.c_str(); }
-void fakecuda_reset(void) { std::lock_guard<std::mutex> lk(g_mu); g_violation.clear(); g_launches.clear(); g_encodes = 0; }
+void fakecuda_reset(void) { std::lock_guard<std::mutex> lk(g_mu); g_violation.clear(); g_launches.clear(); g_encodes = 0; st().skipped.clear(); }
 long fakecuda_launches(const char* substr) {
     std::lock_guard<std::mutex> lk(g_mu);
     long n = 0;
@@ -132,6 +142,14 @@ long fakecuda_launches(const char* substr) {
     return n;
 }
 long fakecuda_tensor_maps(void) { return g_encodes; }
+void fakecuda_set_execute(int on) { st().execute = on != 0; }
+// kernels that were launched while executing but have no CPU restatement: "name xN; ..." ("" if none)
+const char* fakecuda_skipped(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    static std::string s; s.clear();
+    for (auto& kv : st().skipped) s += kv.first + " x" + std::to_string(kv.second) + "; ";
+    return s.c_str();
+}
 long fakecuda_live_allocations(void) { std::lock_guard<std::mutex> lk(g_mu); return (long)g_alloc.size(); }
 
 // ---- registration (called by the nvcc-generated host stubs at load time) ------------------------------------------------
@@ -227,7 +245,7 @@ cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1e-3f; return cudaSuccess; }
 
 // ---- launches: recorded, not executed --------------------------------------------------------------------------------------
-cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void**, size_t smem, cudaStream_t) {
+cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024 ||
         grid.y > 65535 || grid.z > 65535 || smem > 232448) {
         char buf[160];
@@ -235,7 +253,8 @@ cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void**, si
         violation(buf);
         return cudaErrorInvalidConfiguration;
     }
-    record_launch(func);
+    const std::string name = record_launch(func);
+    if (st().execute && !fakecuda::execute(name, grid, block, args)) { std::lock_guard<std::mutex> lk(g_mu); st().skipped[name]++; }
     return cudaSuccess;
 }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* func, void** args) {

@@ -162,3 +162,145 @@ def test_the_simulation_catches_a_tensor_view_past_its_allocation(sim):
     rc = C.CDLL(SIM).cudaFree(C.c_void_p(12345678))
     assert rc != 0 and b'not a live allocation' in lib.fakecuda_violation()
     lib.fakecuda_reset()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Numerics of the tensor-core DBM engine with its kernels INTERPRETED on the CPU (tests/hostsim/kernels_cpu.cpp: the program
+# kernel from its descriptors, the small kernels restated from their sources) against the bf16 oracle emulation.  This is the
+# check of the engine's wiring -- operand orientations, scales, sites, buffers, program dependencies -- that does not need a GPU.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def executing(sim):
+    sim.fakecuda_skipped.restype = C.c_char_p
+    sim.fakecuda_reset()
+    sim.fakecuda_set_execute(1)
+    yield sim
+    sim.fakecuda_set_execute(0)
+
+
+def tc_pair(cfg, scale=0.3, seed=0):
+    from boltzmann_machines import _native
+    from oracle.dbm_bf16 import OracleDBMbf16
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    assert eng.compute == 'bf16'
+    rng = np.random.RandomState(seed)
+    sizes = [cfg['n_visible']] + cfg['n_hiddens']
+    d = {'vb': (0.1 * rng.randn(sizes[0])).astype(np.float32)}
+    for i in range(len(cfg['n_hiddens'])):
+        s = '' if i == 0 else '_%d' % i
+        d['W' + s] = (scale * rng.randn(sizes[i], sizes[i + 1])).astype(np.float32)
+        d['hb' + s] = (0.1 * rng.randn(sizes[i + 1])).astype(np.float32)
+    for e in (eng, emu):
+        e.set_params(d)
+        e.init_particles(4242)
+    return eng, emu
+
+
+def small_cfg(Hs=(18, 11), V=30, gaussian=False, **kw):
+    cfg = dbm_cfg(V, Hs, 10, 12, 'bf16', gaussian, 6)
+    cfg['mf_tol'] = 1e-6
+    if gaussian:
+        cfg['sigma'] = np.linspace(0.7, 1.3, V)
+    cfg.update(kw)
+    return cfg
+
+
+def no_skips(sim):
+    clean(sim)
+    assert sim.fakecuda_skipped() == b'', sim.fakecuda_skipped()
+
+
+@pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7), (70, 130)])
+@pytest.mark.parametrize('programs', [False, True])
+def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, programs):
+    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
+    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    if programs:
+        monkeypatch.setenv('BM_DBM_MF_CHUNK', '4')
+        monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
+    cfg = small_cfg(Hs)
+    eng, emu = tc_pair(cfg)
+    g, w = eng.get_params(), emu.get_params()
+    for k in ('v', 'h'):
+        np.testing.assert_array_equal(g[k], w[k], err_msg='initial ' + k)
+    X = (np.random.RandomState(9).rand(7, cfg['n_visible']) < 0.3).astype(np.float32)
+    tol = dict(rtol=2.0 ** -7, atol=1e-6)
+    np.testing.assert_allclose(eng.transform(X), emu.transform(X), err_msg='transform', **tol)
+    np.testing.assert_allclose(eng.reconstruct(X), emu.reconstruct(X), err_msg='reconstruct', **tol)
+    if len(Hs) == 2:
+        np.testing.assert_allclose(eng.log_proba(X), emu.log_proba(X), rtol=1e-3, atol=2e-2)
+    a, b = eng.val_metrics(X, 2, 7, 3), emu.val_metrics(X, 2, 7, 3)
+    assert a['n_mf_updates'] == b['n_mf_updates'] and a['msre'] == pytest.approx(b['msre'], rel=1e-3)
+    np.testing.assert_allclose(eng.sample_v(3, 11, 4), emu.sample_v(3, 11, 4), err_msg='sample_v', **tol)
+    g, w = eng.get_params(), emu.get_params()
+    for k in w:
+        if k.startswith(('v', 'h', 'mu')) and not k.startswith(('hb', 'vb', 'mu_means')):
+            np.testing.assert_allclose(g[k], w[k], err_msg=k, **tol)
+    no_skips(executing)
+    eng.close()
+
+
+@pytest.mark.parametrize('Hs,gaussian', [((18,), False), ((18, 11), False), ((18, 11, 7), False), ((18, 11), True)])
+@pytest.mark.parametrize('programs', [False, True])
+def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, Hs, gaussian, programs):
+    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
+    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    if programs:
+        monkeypatch.setenv('BM_DBM_MF_CHUNK', '3')
+        monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
+    cfg = small_cfg(Hs, gaussian=gaussian)
+    eng, emu = tc_pair(cfg)
+    rng = np.random.RandomState(5)
+    for it in range(3):
+        X = rng.randn(10, cfg['n_visible']).astype(np.float32) if gaussian else (rng.rand(10, cfg['n_visible']) < 0.3).astype(np.float32)
+        a = eng.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        b = emu.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        assert a['n_mf_updates'] == b['n_mf_updates'], it
+        assert a['msre'] == pytest.approx(b['msre'], rel=1e-3), it
+    g, w = eng.get_params(), emu.get_params()
+    for k in w:
+        np.testing.assert_allclose(g[k], w[k], rtol=2.0 ** -7, atol=2e-5, err_msg=k)
+    no_skips(executing)
+    eng.close()
+
+
+@pytest.mark.parametrize('k,fused', [(1, '1'), (1, '0'), (3, '1')])
+def test_tc_dbm_ais_equals_the_bf16_emulation(executing, monkeypatch, k, fused):
+    monkeypatch.setenv('BM_DBM_AIS_FUSED', fused)
+    cfg = small_cfg((5, 4), V=7, n_particles=4, batch_size=4)
+    eng, emu = tc_pair(cfg)
+    a = eng.ais(16, 60, k, 2222)
+    b = emu.ais(16, 60, k, 2222)
+    np.testing.assert_allclose(a, b, rtol=0, atol=2e-4)                 # same chains: a different one would differ by ~0.1
+    np.testing.assert_allclose(eng.ais(5, 60, k, 2222, first_run=9), b[9:14], rtol=0, atol=2e-4)
+    no_skips(executing)
+    eng.close()
+
+
+@pytest.mark.parametrize('kind', ['bernoulli', 'gaussian'])
+@pytest.mark.parametrize('V,H,B,k', [(37, 29, 19, 2), (130, 72, 65, 1), (784, 16, 32, 3)])
+def test_the_interpreter_reproduces_the_gpu_verified_rbm_program(executing, kind, V, H, B, k):
+    """Credential of the interpreter: the RBM tensor-core path is verified on the GPU against the bf16-rounding oracle
+    (tests/test_tc_gpu.py); run through the interpreter instead of the GPU it must land on the same oracle -- whole CD-k
+    programs with their split-K dW ops, spare-lane scheduling and both weight-update variants included."""
+    from boltzmann_machines import _native
+    from oracle.rbm import OracleRBM
+    cfg = dict(n_visible=V, n_hidden=H, dtype='float32', compute='bf16', l2=1e-4, max_batch=B, sample_v=False, sample_h=True,
+               sparsity_cost=0.01, sparsity_target=0.2, v_kind=kind, h_kind='bernoulli', dropout=0.9)
+    if kind == 'gaussian':
+        cfg['sigma'] = np.linspace(0.5, 1.5, V)
+    rng = np.random.RandomState(0)
+    init = dict(W=(0.1 * rng.randn(V, H)).astype(np.float32), vb=(0.1 * rng.randn(V)).astype(np.float32), hb=(0.1 * rng.randn(H)).astype(np.float32))
+    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg)
+    eng.set_params(init), ora.set_params(init)
+    for it in range(3):
+        X = rng.randn(B, V).astype(np.float32) if kind == 'gaussian' else (rng.rand(B, V) < 0.3).astype(np.float32)
+        a = eng.train_step(X, 0.05, 0.5, k, 0xABCDEF, it, metrics=('msre',))
+        b = ora.train_step(X, 0.05, 0.5, k, 0xABCDEF, it, metrics=('msre',))
+        assert a['msre'] == pytest.approx(b['msre'], rel=2e-3)
+    g, w = eng.get_params(), ora.get_params()
+    for name in ('W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'):
+        np.testing.assert_allclose(g[name], w[name], atol=2e-3, err_msg=name)
+    np.testing.assert_allclose(eng.transform(X, k, 5, 9), ora.transform(X, k, 5, 9), atol=2e-2)
+    no_skips(executing)
+    eng.close()
