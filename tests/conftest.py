@@ -57,3 +57,45 @@ def engines(request, monkeypatch):
 def workdir(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     return tmp_path
+
+
+@pytest.fixture(scope='session')
+def hostsim_library():
+    """tests/hostsim: libbm's own objects linked against the stand-in CUDA runtime, kernels interpreted on the CPU."""
+    import ctypes as C
+    import subprocess
+    obj = os.path.join(ROOT, 'boltzmann-machines_b200', 'build')
+    if not (os.path.isdir(obj) and any(f.endswith('.o') for f in os.listdir(obj))):
+        pytest.skip('library objects not built (run build.sh / __graft_entry__.build())')
+    subprocess.check_call(['bash', os.path.join(ROOT, 'tests', 'hostsim', 'build.sh')], stdout=subprocess.DEVNULL)
+    from boltzmann_machines import _native
+    lib = _native.load_library(os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'))
+    lib.fakecuda_violation.restype = C.c_char_p
+    lib.fakecuda_skipped.restype = C.c_char_p
+    return lib
+
+
+@pytest.fixture
+def hostsim_engines(hostsim_library, monkeypatch):
+    """Route the package's CUDA engines to the host simulation (fp32 compute, launches interpreted); checks on exit that
+    nothing was skipped and no runtime rule was violated."""
+    from boltzmann_machines import _native
+    from boltzmann_machines.base import set_engine_factory
+    lib = hostsim_library
+    old_lib, old_ctx = _native._lib, dict(_native.Context._default)
+    _native._lib = lib
+    _native.Context._default.clear()
+    lib.fakecuda_reset()
+    lib.fakecuda_set_execute(1)
+    monkeypatch.setenv('BM_COMPUTE', 'fp32')
+    old = set_engine_factory('rbm', None), set_engine_factory('dbm', None)
+    yield lib
+    set_engine_factory('rbm', old[0])
+    set_engine_factory('dbm', old[1])
+    lib.fakecuda_set_execute(0)
+    violation, skipped = lib.fakecuda_violation().decode(), lib.fakecuda_skipped().decode()
+    _native.Context._default.clear()
+    _native.Context._default.update(old_ctx)
+    _native._lib = old_lib
+    assert violation == '', violation
+    assert skipped == '', skipped

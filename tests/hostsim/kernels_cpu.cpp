@@ -16,12 +16,12 @@
 #include <string>
 #include <vector>
 
+#include <cuda_runtime.h>
 #undef __host__
 #undef __device__
 #undef __forceinline__
-#include "../../boltzmann-machines_b200/csrc/bm_rng.cuh"      // host build: defines the three qualifiers away
+#include "../../boltzmann-machines_b200/csrc/bm_internal.h"   // LayerOp<T>, BiasUpdate<T>, RngKey (bm_rng.cuh defines the qualifiers away on the host)
 #include "../../boltzmann-machines_b200/csrc/bm_tc_desc.h"
-#include "../../include/bm.h"
 
 namespace fakecuda {
 
@@ -48,8 +48,7 @@ static View view_of(const CUtensorMap& tm) {
     return v;
 }
 
-static const int ACT_LINEAR = 0, ACT_SIGMOID = 1, ACT_SOFTPLUS = 2;
-static const int SMP_NONE = 0, SMP_BERNOULLI = 1, SMP_GAUSSIAN = 2;
+using bm::ACT_LINEAR; using bm::ACT_SIGMOID; using bm::ACT_SOFTPLUS; using bm::SMP_NONE; using bm::SMP_BERNOULLI; using bm::SMP_GAUSSIAN;
 
 // ---- the program kernel, from its descriptors ------------------------------------------------------------------------------
 static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L) {
@@ -194,60 +193,90 @@ static void k_u8_to_bf16(void** a) {
     for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) dst[(size_t)r * ldd + c] = f2bf((float)src[(size_t)r * lds + c]);
 }
 
-// ---- bm_simt.cu (float instantiations) --------------------------------------------------------------------------------------
-template <typename T> struct BiasUpdateT {            // bm_internal.h::BiasUpdate<T>
-    int V, H;
-    const T* dvb_raw; const T* dhb_raw; const T* qsum;
-    T *vb, *hb, *dvb, *dhb, *q_means, *pen;
-    T n_div;
-    T lr, mom, damp, cost, target;
-};
-static void k_bias_update_f32(void** a) {
-    const BiasUpdateT<float>& u = *reinterpret_cast<const BiasUpdateT<float>*>(a[0]);
-    for (int i = 0; i < u.H; ++i) {
-        const float q = u.damp * u.q_means[i] + (1.f - u.damp) * u.qsum[i];
-        u.q_means[i] = q;
-        const float pen = u.cost * (q - u.target);
-        u.pen[i] = pen;
-        const float g = u.dhb_raw[i] / u.n_div - pen;
-        const float d = u.lr * (u.mom * u.dhb[i] + g);
-        u.dhb[i] = d; u.hb[i] += d;
-    }
-    for (int i = 0; i < u.V; ++i) { const float d = u.lr * (u.mom * u.dvb[i] + u.dvb_raw[i] / u.n_div); u.dvb[i] = d; u.vb[i] += d; }
+// ---- bm_simt.cu and bm_dbm.cu, templated on the storage type like the kernels ------------------------------------------------
+template <typename T> static inline T sigmoid_t(T x) { return T(1) / (T(1) + (T)std::exp(-x)); }
+template <> inline float sigmoid_t<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
+template <typename T> static inline T softplus_t(T x) { return std::fmax(x, T(0)) + (T)std::log1p(std::exp(-std::fabs(x))); }
+template <> inline float softplus_t<float>(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+static inline void box_muller_f(uint32_t x0, uint32_t x1, float& n0, float& n1) {
+    const float u1 = fmaxf(bm::u32_to_unit_float(x0), 1.0e-7f), v1 = 6.2831853071795864769f * bm::u32_to_unit_float(x1), u2 = sqrtf(-2.0f * logf(u1));
+    n0 = sinf(v1) * u2; n1 = cosf(v1) * u2;
 }
-static void k_prepare_input_f32(void** a) {
-    const float* X = arg<const float*>(a, 0); const int ldx = arg<int>(a, 1); float* Xp = arg<float*>(a, 2); const int ldxp = arg<int>(a, 3);
-    const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); const float* sigma = arg<const float*>(a, 6); const float keep = arg<float>(a, 7);
-    const int do_dropout = arg<int>(a, 8); const bm::RngKey rng = arg<bm::RngKey>(a, 9);
-    for (int r = 0; r < rows; ++r)
-        for (int cb = 0; cb * 4 < cols; ++cb) {
+
+// layer_op_kernel<T>: C = s1 op(A1) op(B1) + s2 op(A2) op(B2), then the fused epilogue
+template <typename T> static void k_layer_op(void** a) {
+    const bm::LayerOp<T>& op = *reinterpret_cast<const bm::LayerOp<T>*>(a[0]);
+    for (int m = 0; m < op.M; ++m)
+        for (int nb = 0; nb < op.N; nb += 4) {
             bm::U4 w{0, 0, 0, 0};
-            if (do_dropout) w = bm::site_block(rng, (uint32_t)r, (uint32_t)cb);
+            if (op.sample != SMP_NONE) w = bm::site_block(op.rng, (uint32_t)m, (uint32_t)(nb >> 2));
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-            for (int j = 0; j < 4 && cb * 4 + j < cols; ++j) {
-                const int c = cb * 4 + j;
-                float x = X[(size_t)r * ldx + c];
-                if (sigma) x = x / sigma[c];
-                if (do_dropout) { const float m = floorf(keep + bm::u32_to_unit_float(words[j])); x = x / keep * m; }
-                Xp[(size_t)r * ldxp + c] = x;
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (op.sample == SMP_GAUSSIAN) { box_muller_f(w.x, w.y, g[0], g[1]); box_muller_f(w.z, w.w, g[2], g[3]); }
+            for (int j = 0; j < 4 && nb + j < op.N; ++j) {
+                const int n = nb + j;
+                T acc[2] = {T(0), T(0)};
+                for (int pair = 0; pair < 2; ++pair) {
+                    const T* A = pair ? op.A2 : op.A1; const T* B = pair ? op.B2 : op.B1;
+                    const int K = pair ? op.K2 : op.K1, lda = pair ? op.lda2 : op.lda1, ldb = pair ? op.ldb2 : op.ldb1, bt = pair ? op.b2_trans : op.b1_trans;
+                    if (K <= 0 || !A) continue;
+                    T s = T(0);
+                    for (int k = 0; k < K; ++k)
+                        s = (T)std::fma(op.a_trans ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k], bt ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n], s);
+                    acc[pair] = s;
+                }
+                T pre = op.acc_scale * (op.s1 * acc[0] + op.s2 * acc[1]);
+                if (op.sigma) pre = pre * op.sigma[n];
+                if (op.bias) pre = pre + op.bias_scale * op.bias[n];
+                T mean = pre;
+                if (op.act == ACT_SIGMOID) mean = sigmoid_t<T>(pre);
+                else if (op.act == ACT_SOFTPLUS) mean = softplus_t<T>(pre);
+                if (op.means) op.means[(size_t)m * op.ldm + n] = mean;
+                if (op.states) {
+                    T st = mean;
+                    if (op.sample == SMP_BERNOULLI) st = (T(bm::u32_to_unit_float(words[j])) < mean) ? T(1) : T(0);
+                    else if (op.sample == SMP_GAUSSIAN) st = mean + (op.noise_sigma ? op.noise_sigma[n] : T(1)) * T(g[j]);
+                    op.states[(size_t)m * op.lds + n] = st;
+                }
             }
         }
 }
-static void k_colsum_f32(void** a) {
-    const float* P = arg<const float*>(a, 0); const int ldp = arg<int>(a, 1); const float* Q = arg<const float*>(a, 2); const int ldq = arg<int>(a, 3);
-    const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); const float s1 = arg<float>(a, 6), s2 = arg<float>(a, 7); float* out = arg<float*>(a, 8);
+template <typename T> static void k_colsum(void** a) {
+    const T* P = arg<const T*>(a, 0); const int ldp = arg<int>(a, 1); const T* Q = arg<const T*>(a, 2); const int ldq = arg<int>(a, 3);
+    const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); const T s1 = arg<T>(a, 6), s2 = arg<T>(a, 7); T* out = arg<T*>(a, 8);
     for (int c = 0; c < cols; ++c) {
         double s = 0.0;
-        for (int r = 0; r < rows; ++r) { s += (double)s1 * P[(size_t)r * ldp + c]; if (Q) s += (double)s2 * Q[(size_t)r * ldq + c]; }
-        out[c] = (float)s;
+        for (int r = 0; r < rows; ++r) { double v = (double)s1 * (double)P[(size_t)r * ldp + c]; if (Q) v += (double)s2 * (double)Q[(size_t)r * ldq + c]; s += v; }
+        out[c] = (T)s;
     }
 }
-static double g_sq_sum = 0.0;                                   // sqdiff_partial -> finish_sum travel through the partial buffer
-static void k_sqdiff_partial_f32(void** a, dim3 grid) {
-    const float* P = arg<const float*>(a, 0); const int ldp = arg<int>(a, 1); const float* Q = arg<const float*>(a, 2); const int ldq = arg<int>(a, 3);
+template <typename T> static void k_rowdot(void** a) {
+    const T* P = arg<const T*>(a, 0); const int ldp = arg<int>(a, 1); const T* w = arg<const T*>(a, 2); const int rows = arg<int>(a, 3), cols = arg<int>(a, 4); T* out = arg<T*>(a, 5);
+    for (int r = 0; r < rows; ++r) { double s = 0.0; for (int c = 0; c < cols; ++c) { double v = (double)P[(size_t)r * ldp + c]; if (w) v *= (double)w[c]; s += v; } out[r] = (T)s; }
+}
+template <typename T> static void k_fe_visible(void** a) {
+    const T* X = arg<const T*>(a, 0); const int ldx = arg<int>(a, 1); const T* vb = arg<const T*>(a, 2); const T* sigma = arg<const T*>(a, 3);
+    const int kind = arg<int>(a, 4), rows = arg<int>(a, 5), cols = arg<int>(a, 6); T* out = arg<T*>(a, 7);
+    for (int r = 0; r < rows; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < cols; ++c) {
+            const T x = X[(size_t)r * ldx + c];
+            if (kind == BM_UNIT_GAUSSIAN) { const T d = x - vb[c] / sigma[c]; s += 0.5 * (double)(d * d); } else s -= (double)(x * vb[c]);
+        }
+        out[r] = (T)s;
+    }
+}
+template <typename T> static void k_mean_combine(void** a) {
+    const T* x = arg<const T*>(a, 0); const T* y = arg<const T*>(a, 1); const double b_sign = arg<double>(a, 2); const int n = arg<int>(a, 3); double* out = arg<double*>(a, 4);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) { double v = (double)x[i]; if (y) v += b_sign * (double)y[i]; s += v; }
+    *out = s / (double)n;
+}
+template <typename T> static void k_sqdiff_partial(void** a, dim3 grid) {
+    const T* P = arg<const T*>(a, 0); const int ldp = arg<int>(a, 1); const T* Q = arg<const T*>(a, 2); const int ldq = arg<int>(a, 3);
     const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); double* partial = arg<double*>(a, 6);
     double s = 0.0;
-    for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) { double d = P[(size_t)r * ldp + c]; if (Q) d -= Q[(size_t)r * ldq + c]; s += d * d; }
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) { double d = (double)P[(size_t)r * ldp + c]; if (Q) d -= (double)Q[(size_t)r * ldq + c]; s += d * d; }
     for (unsigned i = 0; i < grid.x; ++i) partial[i] = 0.0;
     partial[0] = s;
 }
@@ -256,101 +285,218 @@ static void k_finish_sum(void** a) {
     double s = 0.0; for (int i = 0; i < n; ++i) s += partial[i];
     *out = s / denom;
 }
-static void k_weight_update_f32(void** a) {
-    const float* G = arg<const float*>(a, 0); const int ldg = arg<int>(a, 1); const float g_div = arg<float>(a, 2);
-    float* W = arg<float*>(a, 3); float* dW = arg<float*>(a, 4); const int V = arg<int>(a, 5), H = arg<int>(a, 6);
-    const float* pen = arg<const float*>(a, 7); const float l2 = arg<float>(a, 8), lr = arg<float>(a, 9), mom = arg<float>(a, 10);
+template <typename T> static void k_prepare_input(void** a) {
+    const T* X = arg<const T*>(a, 0); const int ldx = arg<int>(a, 1); T* Xp = arg<T*>(a, 2); const int ldxp = arg<int>(a, 3);
+    const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); const T* sigma = arg<const T*>(a, 6); const T keep = arg<T>(a, 7);
+    const int do_dropout = arg<int>(a, 8); const bm::RngKey rng = arg<bm::RngKey>(a, 9);
+    for (int r = 0; r < rows; ++r)
+        for (int cb = 0; cb * 4 < cols; ++cb) {
+            bm::U4 w{0, 0, 0, 0};
+            if (do_dropout) w = bm::site_block(rng, (uint32_t)r, (uint32_t)cb);
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            for (int j = 0; j < 4 && cb * 4 + j < cols; ++j) {
+                const int c = cb * 4 + j;
+                T x = X[(size_t)r * ldx + c];
+                if (sigma) x = x / sigma[c];
+                if (do_dropout) { const float m = floorf((float)keep + bm::u32_to_unit_float(words[j])); x = x / keep * T(m); }
+                Xp[(size_t)r * ldxp + c] = x;
+            }
+        }
+}
+template <typename T> static void k_pll_corrupt(void** a) {
+    const T* X = arg<const T*>(a, 0); const int ldx = arg<int>(a, 1); T* Xc = arg<T*>(a, 2); const int ldxc = arg<int>(a, 3);
+    const int rows = arg<int>(a, 4), cols = arg<int>(a, 5); const bm::RngKey rng = arg<bm::RngKey>(a, 6);
+    for (int r = 0; r < rows; ++r) {
+        const uint32_t idx = bm::site_block(rng, (uint32_t)r, 0).x % (uint32_t)cols;
+        for (int c = 0; c < cols; ++c) { const T x = X[(size_t)r * ldx + c]; Xc[(size_t)r * ldxc + c] = ((uint32_t)c == idx) ? T(1) - x : x; }
+    }
+}
+template <typename T> static void k_bias_update(void** a) {
+    const bm::BiasUpdate<T>& u = *reinterpret_cast<const bm::BiasUpdate<T>*>(a[0]);
+    for (int i = 0; i < u.H; ++i) {
+        const T q = u.damp * u.q_means[i] + (T(1) - u.damp) * u.qsum[i];
+        u.q_means[i] = q;
+        const T pen = u.cost * (q - u.target);
+        u.pen[i] = pen;
+        const T g = u.dhb_raw[i] / u.n_div - pen;
+        const T d = u.lr * (u.mom * u.dhb[i] + g);
+        u.dhb[i] = d; u.hb[i] += d;
+    }
+    for (int i = 0; i < u.V; ++i) { const T d = u.lr * (u.mom * u.dvb[i] + u.dvb_raw[i] / u.n_div); u.dvb[i] = d; u.vb[i] += d; }
+}
+template <typename T> static void k_weight_update(void** a) {
+    const T* G = arg<const T*>(a, 0); const int ldg = arg<int>(a, 1); const T g_div = arg<T>(a, 2);
+    T* W = arg<T*>(a, 3); T* dW = arg<T*>(a, 4); const int V = arg<int>(a, 5), H = arg<int>(a, 6);
+    const T* pen = arg<const T*>(a, 7); const T l2 = arg<T>(a, 8), lr = arg<T>(a, 9), mom = arg<T>(a, 10);
     __nv_bfloat16* Wb = arg<__nv_bfloat16*>(a, 11); const int ldwb = arg<int>(a, 12);
     for (int v = 0; v < V; ++v)
         for (int h = 0; h < H; ++h) {
             const size_t i = (size_t)v * H + h;
-            const float w = W[i];
-            float g = G[(size_t)v * ldg + h] / g_div - l2 * w;
+            const T w = W[i];
+            T g = G[(size_t)v * ldg + h] / g_div - l2 * w;
             g = g - pen[h];
-            const float d = lr * (mom * dW[i] + g);
+            const T d = lr * (mom * dW[i] + g);
             dW[i] = d; W[i] = w + d;
-            if (Wb) Wb[(size_t)v * ldwb + h] = f2bf(w + d);
+            if (Wb) Wb[(size_t)v * ldwb + h] = f2bf((float)(w + d));
         }
 }
-static void k_fill_f32(void** a) { float* p = arg<float*>(a, 0); const size_t n = arg<size_t>(a, 1); const float v = arg<float>(a, 2); for (size_t i = 0; i < n; ++i) p[i] = v; }
+template <typename T> static void k_softmax_rows(void** a) {
+    T* X = arg<T*>(a, 0); const int ldx = arg<int>(a, 1), rows = arg<int>(a, 2), cols = arg<int>(a, 3); const T scale = arg<T>(a, 4);
+    for (int r = 0; r < rows; ++r) {
+        T* x = X + (size_t)r * ldx;
+        double mx = -1e300; for (int c = 0; c < cols; ++c) mx = std::fmax(mx, (double)x[c]);
+        const T m = (T)mx;
+        double s = 0.0;
+        for (int c = 0; c < cols; ++c) { T e = sizeof(T) == 4 ? (T)expf((float)(x[c] - m)) : (T)std::exp((double)(x[c] - m)); x[c] = e; s += (double)e; }
+        const T tot = (T)s;
+        for (int c = 0; c < cols; ++c) x[c] = scale * x[c] / tot;
+    }
+}
+template <typename T> static void k_multinomial_rows(void** a) {
+    const T* means = arg<const T*>(a, 0); const int ldm = arg<int>(a, 1), rows = arg<int>(a, 2), cols = arg<int>(a, 3), n_draws = arg<int>(a, 4);
+    T* counts = arg<T*>(a, 5); const int ldc = arg<int>(a, 6); const bm::RngKey rng = arg<bm::RngKey>(a, 7);
+    std::vector<double> cdf(cols); std::vector<int> cnt(cols);
+    for (int r = 0; r < rows; ++r) {
+        const T* mrow = means + (size_t)r * ldm;
+        double tot = 0.0; for (int c = 0; c < cols; ++c) tot += (double)mrow[c];
+        double run = 0.0;
+        for (int c = 0; c < cols; ++c) { const float pr = (float)((double)mrow[c] / tot); run += (double)pr; cdf[c] = run; }
+        const double last = cdf[cols - 1];
+        for (int c = 0; c < cols; ++c) { cdf[c] = cdf[c] / last; cnt[c] = 0; }
+        for (int d = 0; d < n_draws; ++d) {
+            const bm::U4 w = bm::site_block(rng, (uint32_t)r, (uint32_t)(d >> 2));
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            const double u = (double)bm::u32_to_unit_float(words[d & 3]);
+            int lo = 0, hi = cols;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] > u) hi = mid; else lo = mid + 1; }
+            if (lo > cols - 1) lo = cols - 1;
+            cnt[lo]++;
+        }
+        for (int c = 0; c < cols; ++c) counts[(size_t)r * ldc + c] = (T)cnt[c];
+    }
+}
+static void k_tf_normal_fill_f32(void** a) {
+    float* W = arg<float*>(a, 0); const size_t n = arg<size_t>(a, 1); const float stddev = arg<float>(a, 2);
+    const uint32_t k0 = arg<uint32_t>(a, 3), k1 = arg<uint32_t>(a, 4), s2lo = arg<uint32_t>(a, 5), s2hi = arg<uint32_t>(a, 6);
+    for (size_t blk = 0; blk * 4 < n; ++blk) {
+        const bm::U4 w = bm::philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), s2lo, s2hi, k0, k1);
+        float g[4]; box_muller_f(w.x, w.y, g[0], g[1]); box_muller_f(w.z, w.w, g[2], g[3]);
+        for (int j = 0; j < 4 && blk * 4 + j < n; ++j) W[blk * 4 + j] = g[j] * stddev;
+    }
+}
+static void k_tf_normal_fill_f64(void** a) {
+    double* W = arg<double*>(a, 0); const size_t n = arg<size_t>(a, 1); const double stddev = arg<double>(a, 2);
+    const uint32_t k0 = arg<uint32_t>(a, 3), k1 = arg<uint32_t>(a, 4), s2lo = arg<uint32_t>(a, 5), s2hi = arg<uint32_t>(a, 6);
+    for (size_t blk = 0; blk * 2 < n; ++blk) {
+        const bm::U4 w = bm::philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), s2lo, s2hi, k0, k1);
+        const double u1 = std::fmax(bm::u64_to_unit_double(w.x, w.y), 1.0e-7), v1 = 6.283185307179586476925286766559 * bm::u64_to_unit_double(w.z, w.w);
+        const double u2 = std::sqrt(-2.0 * std::log(u1));
+        W[blk * 2] = std::sin(v1) * u2 * stddev;
+        if (blk * 2 + 1 < n) W[blk * 2 + 1] = std::cos(v1) * u2 * stddev;
+    }
+}
+template <typename T> static void k_fill(void** a) { T* p = arg<T*>(a, 0); const size_t n = arg<size_t>(a, 1); const T v = arg<T>(a, 2); for (size_t i = 0; i < n; ++i) p[i] = v; }
+template <typename T> static void k_u8_to_real(void** a) { const uint8_t* src = arg<const uint8_t*>(a, 0); T* dst = arg<T*>(a, 1); const size_t n = arg<size_t>(a, 2); for (size_t i = 0; i < n; ++i) dst[i] = (T)src[i]; }
 
-// ---- bm_dbm.cu (float instantiations) ----------------------------------------------------------------------------------------
-static void k_particle_init_f32(void** a) {
-    float* out = arg<float*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2), kind = arg<int>(a, 3);
-    const float* sigma = arg<const float*>(a, 4); const bm::RngKey rng = arg<bm::RngKey>(a, 5);
+// ---- bm_dbm.cu ------------------------------------------------------------------------------------------------------------------
+template <typename T> static void k_max_abs_diff(void** a) {
+    const T* x = arg<const T*>(a, 0); const T* y = arg<const T*>(a, 1); const size_t n = arg<size_t>(a, 2); unsigned* out = arg<unsigned*>(a, 3);
+    float m = 0.f;
+    for (size_t i = 0; i < n; ++i) m = fmaxf(m, (float)std::fabs((double)x[i] - (double)y[i]));
+    unsigned bits; memcpy(&bits, &m, 4);
+    if (bits > *out) *out = bits;
+}
+template <typename T> static void k_particle_init(void** a) {
+    T* out = arg<T*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2), kind = arg<int>(a, 3);
+    const T* sigma = arg<const T*>(a, 4); const bm::RngKey rng = arg<bm::RngKey>(a, 5);
     for (int r = 0; r < rows; ++r)
         for (int cb = 0; cb * 4 < cols; ++cb) {
             const bm::U4 w = bm::site_block(rng, (uint32_t)r, (uint32_t)cb);
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
             float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (kind == BM_UNIT_GAUSSIAN) {
-                float u1 = fmaxf(bm::u32_to_unit_float(w.x), 1.0e-7f), v1 = 6.2831853071795864769f * bm::u32_to_unit_float(w.y);
-                float u2 = sqrtf(-2.0f * logf(u1)); g[0] = sinf(v1) * u2; g[1] = cosf(v1) * u2;
-                u1 = fmaxf(bm::u32_to_unit_float(w.z), 1.0e-7f); v1 = 6.2831853071795864769f * bm::u32_to_unit_float(w.w);
-                u2 = sqrtf(-2.0f * logf(u1)); g[2] = sinf(v1) * u2; g[3] = cosf(v1) * u2;
-            }
+            if (kind == BM_UNIT_GAUSSIAN) { box_muller_f(w.x, w.y, g[0], g[1]); box_muller_f(w.z, w.w, g[2], g[3]); }
             for (int j = 0; j < 4 && cb * 4 + j < cols; ++j) {
                 const int c = cb * 4 + j;
-                out[(size_t)r * cols + c] = kind == BM_UNIT_GAUSSIAN ? g[j] * sigma[c] : bm::u32_to_unit_float(words[j]);
+                out[(size_t)r * cols + c] = kind == BM_UNIT_GAUSSIAN ? (T)g[j] * sigma[c] : (T)bm::u32_to_unit_float(words[j]);
             }
         }
 }
-static void k_dbm_vbias_f32(void** a) {
-    const int V = arg<int>(a, 0); const float* x_sum = arg<const float*>(a, 1); const float* v_sum = arg<const float*>(a, 2);
-    const float n_rows = arg<float>(a, 3), m_div = arg<float>(a, 4); float* vb = arg<float*>(a, 5); float* dvb = arg<float*>(a, 6);
-    const float lr = arg<float>(a, 7), mom = arg<float>(a, 8);
-    for (int j = 0; j < V; ++j) { const float g = x_sum[j] / n_rows - v_sum[j] / m_div; const float d = lr * (mom * dvb[j] + g); dvb[j] = d; vb[j] += d; }
+template <typename T> static void k_scale_all(void** a) { T* p = arg<T*>(a, 0); const size_t n = arg<size_t>(a, 1); const double* total = arg<const double*>(a, 2); for (size_t i = 0; i < n; ++i) p[i] = (T)((double)p[i] / *total); }
+template <typename T> static void k_dbm_vbias(void** a) {
+    const int V = arg<int>(a, 0); const T* x_sum = arg<const T*>(a, 1); const T* v_sum = arg<const T*>(a, 2);
+    const T n_rows = arg<T>(a, 3), m_div = arg<T>(a, 4); T* vb = arg<T*>(a, 5); T* dvb = arg<T*>(a, 6); const T lr = arg<T>(a, 7), mom = arg<T>(a, 8);
+    for (int j = 0; j < V; ++j) { const T g = x_sum[j] / n_rows - v_sum[j] / m_div; const T d = lr * (mom * dvb[j] + g); dvb[j] = d; vb[j] += d; }
 }
-static void k_dbm_sparsity_bias_f32(void** a) {
-    const int H = arg<int>(a, 0), layer = arg<int>(a, 1); const float* mu_sum = arg<const float*>(a, 2); const float* h_sum = arg<const float*>(a, 3);
-    const float n_div = arg<float>(a, 4), m_div = arg<float>(a, 5); float* q_means = arg<float*>(a, 6); float* mu_means = arg<float*>(a, 7);
-    float* pen = arg<float*>(a, 8); float* hb = arg<float*>(a, 9); float* dhb = arg<float*>(a, 10);
-    const float damp = arg<float>(a, 11), cost = arg<float>(a, 12), target = arg<float>(a, 13), lr = arg<float>(a, 14), mom = arg<float>(a, 15);
+template <typename T> static void k_dbm_sparsity_bias(void** a) {
+    const int H = arg<int>(a, 0), layer = arg<int>(a, 1); const T* mu_sum = arg<const T*>(a, 2); const T* h_sum = arg<const T*>(a, 3);
+    const T n_div = arg<T>(a, 4), m_div = arg<T>(a, 5); T* q_means = arg<T*>(a, 6); T* mu_means = arg<T*>(a, 7);
+    T* pen = arg<T*>(a, 8); T* hb = arg<T*>(a, 9); T* dhb = arg<T*>(a, 10);
+    const T damp = arg<T>(a, 11), cost = arg<T>(a, 12), target = arg<T>(a, 13), lr = arg<T>(a, 14), mom = arg<T>(a, 15);
+    const T hs = h_sum[layer], ms = mu_sum[layer];                       // element `layer` of the unit vectors (sic, dbm.py:581-586)
     for (int j = 0; j < H; ++j) {
-        const float q = damp * q_means[j] + (1.f - damp) * h_sum[layer];
-        const float mm = damp * mu_means[j] + (1.f - damp) * mu_sum[layer];
+        const T q = damp * q_means[j] + (T(1) - damp) * hs;
+        const T mm = damp * mu_means[j] + (T(1) - damp) * ms;
         q_means[j] = q; mu_means[j] = mm;
-        const float pn = cost * (q - target) + cost * (mm - target);
+        const T pn = cost * (q - target) + cost * (mm - target);
         pen[j] = pn;
-        const float g = mu_sum[j] / n_div - h_sum[j] / m_div - pn;
-        const float d = lr * (mom * dhb[j] + g);
+        const T g = mu_sum[j] / n_div - h_sum[j] / m_div - pn;
+        const T d = lr * (mom * dhb[j] + g);
         dhb[j] = d; hb[j] += d;
     }
 }
-static void k_colnorm_f32(void** a) {
-    const float* W = arg<const float*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2); float* norm = arg<float*>(a, 3);
-    for (int c = 0; c < cols; ++c) { double s = 0.0; for (int r = 0; r < rows; ++r) { const double w = W[(size_t)r * cols + c]; s += w * w; } norm[c] = (float)sqrt(s); }
+template <typename T> static void k_colnorm(void** a) {
+    const T* W = arg<const T*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2); T* norm = arg<T*>(a, 3);
+    for (int c = 0; c < cols; ++c) { double s = 0.0; for (int r = 0; r < rows; ++r) { const double w = (double)W[(size_t)r * cols + c]; s += w * w; } norm[c] = (T)std::sqrt(s); }
 }
-static void k_max_norm_scale_f32(void** a) {
-    float* W = arg<float*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2); const float* norm = arg<const float*>(a, 3); const float max_norm = arg<float>(a, 4);
+template <typename T> static void k_max_norm_scale(void** a) {
+    T* W = arg<T*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2); const T* norm = arg<const T*>(a, 3); const T max_norm = arg<T>(a, 4);
     for (int r = 0; r < rows; ++r)
         for (int c = 0; c < cols; ++c) {
-            const float n = norm[c]; const float num = n < max_norm ? n : max_norm; const float den = n > 1e-8f ? n : 1e-8f;
+            const T n = norm[c]; const T num = n < max_norm ? n : max_norm; const T den = n > T(1e-8) ? n : T(1e-8);
             W[(size_t)r * cols + c] = W[(size_t)r * cols + c] * num / den;
         }
 }
-static void k_dbm_bound_rows_f32(void** a) {
-    const float* X = arg<const float*>(a, 0); const int V = arg<int>(a, 1); const float* mu0 = arg<const float*>(a, 2); const int H0 = arg<int>(a, 3);
-    const float* mu1 = arg<const float*>(a, 4); const int H1 = arg<int>(a, 5); const float* t1 = arg<const float*>(a, 6); const float* t2 = arg<const float*>(a, 7);
-    const float* vb = arg<const float*>(a, 8); const float* hb0 = arg<const float*>(a, 9); const float* hb1 = arg<const float*>(a, 10);
+template <typename T> static void k_dbm_bound_rows(void** a) {
+    const T* X = arg<const T*>(a, 0); const int V = arg<int>(a, 1); const T* mu0 = arg<const T*>(a, 2); const int H0 = arg<int>(a, 3);
+    const T* mu1 = arg<const T*>(a, 4); const int H1 = arg<int>(a, 5); const T* t1 = arg<const T*>(a, 6); const T* t2 = arg<const T*>(a, 7);
+    const T* vb = arg<const T*>(a, 8); const T* hb0 = arg<const T*>(a, 9); const T* hb1 = arg<const T*>(a, 10);
     const int rows = arg<int>(a, 11); double* out = arg<double*>(a, 12);
+    auto clip = [](double m) { return sizeof(T) == 4 ? (double)fminf(fmaxf((float)m, 1e-7f), 1.0f - 1e-7f) : std::fmin(std::fmax(m, 1e-7), 1.0 - 1e-7); };
     for (int r = 0; r < rows; ++r) {
         double acc = 0.0;
-        for (int j = 0; j < H0; ++j) {
-            const double m = mu0[(size_t)r * H0 + j];
-            acc += (double)t1[(size_t)r * H0 + j] * m + m * (double)hb0[j];
-            const double s = (double)fminf(fmaxf((float)m, 1e-7f), 1.0f - 1e-7f);
-            acc += -s * log(s) - (1.0 - s) * log(1.0 - s);
-        }
-        for (int j = 0; j < H1; ++j) {
-            const double m = mu1[(size_t)r * H1 + j];
-            acc += (double)t2[(size_t)r * H1 + j] * m + m * (double)hb1[j];
-            const double s = (double)fminf(fmaxf((float)m, 1e-7f), 1.0f - 1e-7f);
-            acc += -s * log(s) - (1.0 - s) * log(1.0 - s);
-        }
+        for (int j = 0; j < H0; ++j) { const double m = (double)mu0[(size_t)r * H0 + j]; acc += (double)t1[(size_t)r * H0 + j] * m + m * (double)hb0[j]; const double s = clip(m); acc += -s * std::log(s) - (1.0 - s) * std::log(1.0 - s); }
+        for (int j = 0; j < H1; ++j) { const double m = (double)mu1[(size_t)r * H1 + j]; acc += (double)t2[(size_t)r * H1 + j] * m + m * (double)hb1[j]; const double s = clip(m); acc += -s * std::log(s) - (1.0 - s) * std::log(1.0 - s); }
         for (int j = 0; j < V; ++j) acc += (double)X[(size_t)r * V + j] * (double)vb[j];
         out[r] = acc;
     }
+}
+template <typename T> static void k_ais_accum(void** a) {
+    double* logw = arg<double*>(a, 0); const double sign = arg<double>(a, 1), beta = arg<double>(a, 2); const T* x = arg<const T*>(a, 3);
+    const int H0 = arg<int>(a, 4); const T* hb0 = arg<const T*>(a, 5); const T* pa = arg<const T*>(a, 6); const int V = arg<int>(a, 7);
+    const T* pb = arg<const T*>(a, 8); const int H1 = arg<int>(a, 9), rows = arg<int>(a, 10);
+    for (int r = 0; r < rows; ++r) {
+        double acc = 0.0;
+        for (int j = 0; j < H0; ++j) acc += beta * (double)x[(size_t)r * H0 + j] * (double)hb0[j];
+        for (int j = 0; j < V; ++j) { const double z = beta * (double)pa[(size_t)r * V + j]; acc += std::fmax(z, 0.0) + std::log1p(std::exp(-std::fabs(z))); }
+        for (int j = 0; j < H1; ++j) { const double z = beta * (double)pb[(size_t)r * H1 + j]; acc += std::fmax(z, 0.0) + std::log1p(std::exp(-std::fabs(z))); }
+        logw[r] += sign * acc;
+    }
+}
+template <typename T> static void k_ais_unit(void** a) {
+    const T* pre = arg<const T*>(a, 0); const T beta = arg<T>(a, 1); T* out = arg<T*>(a, 2);
+    const int rows = arg<int>(a, 3), cols = arg<int>(a, 4), sample = arg<int>(a, 5); const bm::RngKey rng = arg<bm::RngKey>(a, 6);
+    for (int r = 0; r < rows; ++r)
+        for (int cb = 0; cb * 4 < cols; ++cb) {
+            bm::U4 w{0, 0, 0, 0};
+            if (sample) w = bm::site_block(rng, (uint32_t)r, (uint32_t)cb);
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            for (int j = 0; j < 4 && cb * 4 + j < cols; ++j) {
+                const int c = cb * 4 + j;
+                const T z = beta * pre[(size_t)r * cols + c];
+                const T pr = T(1) / (T(1) + (sizeof(T) == 4 ? (T)expf(-(float)z) : (T)std::exp(-(double)z)));
+                out[(size_t)r * cols + c] = sample ? ((T(bm::u32_to_unit_float(words[j])) < pr) ? T(1) : T(0)) : pr;
+            }
+        }
 }
 
 // ---- bm_dbm_tc.cuh ----------------------------------------------------------------------------------------------------------
@@ -432,6 +578,8 @@ static void k_ais_fused_step(void** a) {
 // ---- dispatch ---------------------------------------------------------------------------------------------------------------
 bool execute(const std::string& name, dim3 grid, dim3, void** args) {
     auto has = [&](const char* s) { return name.find(s) != std::string::npos; };
+    // templated kernels: "<name>I f|d E" in the mangled name selects the instantiation
+#define BOTH(fn, kname, ...) do { if (has(kname "IfE")) { fn<float>(__VA_ARGS__); return true; } if (has(kname "IdE")) { fn<double>(__VA_ARGS__); return true; } } while (0)
     if (has("tc_program_kernel")) { k_tc_program(args); return true; }
     if (has("f32_to_bf16_kernel")) { k_f32_to_bf16(args); return true; }
     if (has("bf16_to_f32_kernel")) { k_bf16_to_f32(args); return true; }
@@ -440,27 +588,42 @@ bool execute(const std::string& name, dim3 grid, dim3, void** args) {
     if (has("sqdiff_bf16_partial_kernel")) { k_sqdiff_bf16_partial(args, grid); return true; }
     if (has("sqdiff_bf16_finish_kernel")) { k_finish_sum(args); return true; }
     if (has("u8_to_bf16_kernel")) { k_u8_to_bf16(args); return true; }
-    if (has("bias_update_kernelIfE")) { k_bias_update_f32(args); return true; }
-    if (has("prepare_input_kernelIfE")) { k_prepare_input_f32(args); return true; }
     if (has("colsum_bf16_partial_kernel")) return true;                    // folded into the finish kernel's restatement
     if (has("colsum_bf16_finish_kernel")) { k_colsum_bf16_finish(args); return true; }
-    if (has("colsum_kernelIfE")) { k_colsum_f32(args); return true; }
-    if (has("sqdiff_partial_kernelIfE")) { k_sqdiff_partial_f32(args, grid); return true; }
+    BOTH(k_layer_op, "layer_op_kernel", args);
+    BOTH(k_colsum, "colsum_kernel", args);
+    BOTH(k_rowdot, "rowdot_kernel", args);
+    BOTH(k_fe_visible, "fe_visible_kernel", args);
+    BOTH(k_mean_combine, "mean_combine_kernel", args);
+    BOTH(k_sqdiff_partial, "sqdiff_partial_kernel", args, grid);
     if (has("finish_sum_kernel")) { k_finish_sum(args); return true; }
-    if (has("weight_update_kernelIfE")) { k_weight_update_f32(args); return true; }
-    if (has("fill_kernelIfE")) { k_fill_f32(args); return true; }
-    if (has("particle_init_kernelIfE")) { k_particle_init_f32(args); return true; }
-    if (has("dbm_vbias_kernelIfE")) { k_dbm_vbias_f32(args); return true; }
-    if (has("dbm_sparsity_bias_kernelIfE")) { k_dbm_sparsity_bias_f32(args); return true; }
-    if (has("colnorm_kernelIfE")) { k_colnorm_f32(args); return true; }
-    if (has("max_norm_scale_kernelIfE")) { k_max_norm_scale_f32(args); return true; }
-    if (has("dbm_bound_rows_kernelIfE")) { k_dbm_bound_rows_f32(args); return true; }
+    BOTH(k_prepare_input, "prepare_input_kernel", args);
+    BOTH(k_pll_corrupt, "pll_corrupt_kernel", args);
+    BOTH(k_bias_update, "bias_update_kernel", args);
+    BOTH(k_weight_update, "weight_update_kernel", args);
+    BOTH(k_softmax_rows, "softmax_rows_kernel", args);
+    BOTH(k_multinomial_rows, "multinomial_rows_kernel", args);
+    if (has("tf_normal_fill_f32")) { k_tf_normal_fill_f32(args); return true; }
+    if (has("tf_normal_fill_f64")) { k_tf_normal_fill_f64(args); return true; }
+    BOTH(k_fill, "fill_kernel", args);
+    BOTH(k_u8_to_real, "u8_to_real_kernel", args);
+    BOTH(k_max_abs_diff, "max_abs_diff_kernel", args);
+    BOTH(k_particle_init, "particle_init_kernel", args);
+    BOTH(k_scale_all, "scale_all_kernel", args);
+    BOTH(k_dbm_vbias, "dbm_vbias_kernel", args);
+    BOTH(k_dbm_sparsity_bias, "dbm_sparsity_bias_kernel", args);
+    BOTH(k_colnorm, "colnorm_kernel", args);
+    BOTH(k_max_norm_scale, "max_norm_scale_kernel", args);
+    BOTH(k_dbm_bound_rows, "dbm_bound_rows_kernel", args);
+    BOTH(k_ais_accum, "ais_accum_kernel", args);
+    BOTH(k_ais_unit, "ais_unit_kernel", args);
     if (has("max_abs_diff_bf16_kernel")) { k_max_abs_diff_bf16(args); return true; }
     if (has("mf_chunk_diffs_kernel")) { k_mf_chunk_diffs(args, grid); return true; }
     if (has("dbm_grad_combine_kernel")) { k_dbm_grad_combine(args); return true; }
     if (has("ais_unit_bf16_kernel")) { k_ais_unit_bf16(args); return true; }
     if (has("ais_accum2_bf16_kernel")) { k_ais_accum2_bf16(args); return true; }
     if (has("ais_fused_step_kernel")) { k_ais_fused_step(args); return true; }
+#undef BOTH
     return false;
 }
 

@@ -304,3 +304,45 @@ def test_the_interpreter_reproduces_the_gpu_verified_rbm_program(executing, kind
     np.testing.assert_allclose(eng.transform(X, k, 5, 9), ora.transform(X, k, 5, 9), atol=2e-2)
     no_skips(executing)
     eng.close()
+
+
+@pytest.mark.parametrize('Hs,gaussian', [((18,), False), ((18, 11), False), ((18, 11, 7), False), ((18, 11), True)])
+def test_fp32_dbm_engine_equals_the_pinned_oracle_under_the_interpreter(executing, Hs, gaussian):
+    """The default (storage-precision) DBM engine, whose AIS was re-cut into slices and whose step became shard-aware in this
+    round, against oracle/dbm.py with its kernels interpreted on the CPU -- the same comparison tests/test_dbm_gpu.py makes
+    on the GPU, available before the GPU is."""
+    from boltzmann_machines import _native
+    from oracle.dbm import OracleDBM
+    cfg = small_cfg(Hs, gaussian=gaussian, compute='fp32')
+    eng, ora = _native.CudaDBM(cfg), OracleDBM(cfg)
+    assert eng.compute == 'fp32'
+    rng = np.random.RandomState(0)
+    sizes = [cfg['n_visible']] + cfg['n_hiddens']
+    d = {'vb': (0.1 * rng.randn(sizes[0])).astype(np.float32)}
+    for i in range(len(Hs)):
+        s = '' if i == 0 else '_%d' % i
+        d['W' + s] = (0.3 * rng.randn(sizes[i], sizes[i + 1])).astype(np.float32)
+        d['hb' + s] = (0.1 * rng.randn(sizes[i + 1])).astype(np.float32)
+    for e in (eng, ora):
+        e.set_params(d)
+        e.init_particles(4242)
+    for it in range(3):
+        X = rng.randn(10, cfg['n_visible']).astype(np.float32) if gaussian else (rng.rand(10, cfg['n_visible']) < 0.3).astype(np.float32)
+        a = eng.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        b = ora.train_step(X, 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        assert a['n_mf_updates'] == b['n_mf_updates'] and a['msre'] == pytest.approx(b['msre'], rel=1e-4)
+    g, w = eng.get_params(), ora.get_params()
+    for k in w:
+        np.testing.assert_allclose(g[k], w[k], atol=5e-5, err_msg=k)
+    Xq = X[:7]
+    np.testing.assert_allclose(eng.transform(Xq), ora.transform(Xq), atol=2e-5)
+    np.testing.assert_allclose(eng.reconstruct(Xq), ora.reconstruct(Xq), atol=2e-5)
+    np.testing.assert_allclose(eng.sample_v(3, 11, 4), ora.sample_v(3, 11, 4), atol=2e-5)
+    if len(Hs) == 2 and not gaussian:
+        np.testing.assert_allclose(eng.log_proba(Xq), ora.log_proba(Xq), rtol=1e-5, atol=1e-4)
+        full = eng.ais(13, 40, 2, 99)
+        np.testing.assert_allclose(full, ora.ais(13, 40, 2, 99), atol=5e-3)
+        parts = np.concatenate([eng.ais(5, 40, 2, 99, first_run=0), eng.ais(1, 40, 2, 99, first_run=5), eng.ais(7, 40, 2, 99, first_run=6)])
+        np.testing.assert_allclose(full, parts, rtol=0, atol=1e-6)
+    no_skips(executing)
+    eng.close()

@@ -63,9 +63,14 @@ def epoch_oracle_factory(cfg):
     return EpochOracle(cfg)
 
 
-@pytest.fixture(params=['oracle', 'oracle-epoch', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
+@pytest.fixture(params=['oracle', 'oracle-epoch', 'hostsim-fp32', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
 def engine_kind(request, monkeypatch):
     from boltzmann_machines.base import set_engine_factory
+    if request.param == 'hostsim-fp32':
+        # the CUDA engines' own host code (libbm's objects) with their kernels interpreted on the CPU: tests/hostsim
+        request.getfixturevalue('hostsim_engines')
+        yield request.param
+        return
     if request.param == 'oracle':
         from oracle.rbm import rbm_factory
         old = set_engine_factory('rbm', rbm_factory)
@@ -106,8 +111,9 @@ def build(case, workdir):
     return model, log, dt
 
 
-def check_summaries(model, want, tol):
-    """logs/{train,val}/scalars.jsonl against what the reference gave its TensorBoard writers."""
+def check_summaries(model, want, tol, sweeps_slack=0.0):
+    """logs/{train,val}/scalars.jsonl against what the reference gave its TensorBoard writers.  `sweeps_slack`: allowed
+    difference of a (batch-averaged) n_mf_updates value -- see the DBM test."""
     def read(d):
         p = os.path.join(d, 'scalars.jsonl')
         return [json.loads(l) for l in open(p)] if os.path.isfile(p) else []
@@ -117,8 +123,10 @@ def check_summaries(model, want, tol):
     for rec, (_, tags) in zip(val, want['val']):
         assert sorted(k for k in rec if k != 'step') == sorted(tags)
         for k, v in tags.items():
-            np.testing.assert_allclose(rec[k], v, rtol=0, atol=max(tol, 2e-3) if 'loglik' in k or 'free_energy' in k else 10 * tol,
-                                       err_msg='summary ' + k)
+            atol = max(tol, 2e-3) if 'loglik' in k or 'free_energy' in k else 10 * tol
+            if 'n_mf_updates' in k:
+                atol = max(atol, sweeps_slack)
+            np.testing.assert_allclose(rec[k], v, rtol=0, atol=atol, err_msg='summary ' + k)
 
 
 def close(got, want, tol, what):
@@ -136,6 +144,8 @@ def test_public_api_scenario_matches_the_reference(name, engine_kind, workdir):
     model, log, dt = build(case, workdir)
     # float32: the same formulas in float32 with different summation orders; a Bernoulli draw is u < p on the SAME u
     tol = 1e-9 if dt == 'float64' else (2e-5 if engine_kind.startswith('oracle') else 2e-4)
+    if dt == 'float64' and case['cls'] == 'GaussianRBM' and not engine_kind.startswith('oracle'):
+        tol = 5e-6      # float64 Gaussian units draw float32 Box-Muller noise: libm / libdevice sinf, cosf, logf differ by ulps
     if case['X'] is None:
         model.init()
     else:
@@ -197,9 +207,13 @@ if not os.environ.get('BM_GOLDEN_DBM_CASES'):
     DBM_GOLD.update(_corpus('fuzz_corpus_dbm.json.gz'))
 
 
-@pytest.fixture(params=['oracle', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
+@pytest.fixture(params=['oracle', 'hostsim-fp32', pytest.param('cuda-fp32', marks=pytest.mark.gpu)])
 def both_engines(request, monkeypatch):
     from boltzmann_machines.base import set_engine_factory
+    if request.param == 'hostsim-fp32':
+        request.getfixturevalue('hostsim_engines')
+        yield request.param
+        return
     if request.param == 'oracle':
         from oracle.rbm import rbm_factory
         from oracle.dbm import dbm_factory
@@ -222,6 +236,8 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
     g = DBM_GOLD[variant]
     dt = g['dbm_kw'].get('dtype', 'float32')
     tol = 1e-9 if dt == 'float64' else (2e-5 if both_engines == 'oracle' else 2e-4)
+    if dt == 'float64' and 'GaussianRBM' in g['rbm_cls'] and both_engines != 'oracle':
+        tol = 5e-6      # float32 Box-Muller noise inside a float64 model (see the RBM test)
     X, X_val = np.asarray(g['X'], dtype=dt), np.asarray(g['X_val'], dtype=dt)
     rbms = []
     inp = X
@@ -247,7 +263,11 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
             return r
         setattr(dbm, meth, wrapped)
     dbm.fit(X, X_val)
-    check_summaries(dbm, g['summaries'], tol)
+    # A mean-field tolerance at or below float32 resolution (1e-7 against values of ~0.5) makes the stopping sweep depend on
+    # the last bit of a float32 sum: an engine whose sums run in another order than numpy's may stop one sweep apart on a
+    # batch (the variational parameters then differ by less than that tolerance).  The oracle reproduces the count exactly.
+    slack = 1.0 if (both_engines != 'oracle' and dt == 'float32' and float(g['dbm_kw'].get('mf_tol', 1e-7)) < 1e-6) else 0.0
+    check_summaries(dbm, g['summaries'], tol, sweeps_slack=slack)
     if g.get('resume_max_epoch'):
         path = dbm._model_dirpath
         dbm.close()
@@ -268,7 +288,7 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
         assert len(log[key]) == len(g['log'][key])
         for got, want in zip(log[key], g['log'][key]):
             close(got[0], want[0], 10 * tol, key + ' msre')
-            assert got[1] == want[1], key + ' n_mf_updates'
+            assert abs(got[1] - want[1]) <= slack, key + ' n_mf_updates'
     for scope, want in g['after_fit'].items():
         got = dbm.get_tf_params(scope=scope)
         for k, v in want.items():
