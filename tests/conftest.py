@@ -12,6 +12,27 @@ for p in (ROOT, PKG_PARENT):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    if os.environ.get('BM_HOSTSIM') == '1':
+        # Dry run of the GPU tests WITHOUT a GPU: the library's objects on the stand-in runtime, kernels interpreted on the
+        # CPU (tests/hostsim).  `BM_HOSTSIM=1 python -m pytest tests/test_dbm_gpu.py -m gpu` -- shapes of benchmark size
+        # take minutes per GEMM there; meant for the small-shape tests and for checking a test's own logic and tolerances.
+        import ctypes as C
+        import subprocess
+        subprocess.check_call(['bash', os.path.join(ROOT, 'tests', 'hostsim', 'build.sh')], stdout=subprocess.DEVNULL)
+        from boltzmann_machines import _native
+        lib = _native.load_library(os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'))
+        lib.fakecuda_violation.restype = C.c_char_p
+        lib.fakecuda_skipped.restype = C.c_char_p
+        lib.fakecuda_set_execute(1)
+        _native._lib = lib
+        config._bm_hostsim = lib
+
+
+def pytest_unconfigure(config):
+    lib = getattr(config, '_bm_hostsim', None)
+    if lib is not None:
+        v, sk = lib.fakecuda_violation().decode(), lib.fakecuda_skipped().decode()
+        print('\n[hostsim] runtime violations: {0}; kernels without a CPU restatement: {1}'.format(v or 'none', sk or 'none'))
 
 
 @pytest.fixture

@@ -46,7 +46,12 @@ def rbm_case(i):
 def test_rbm_two_steps_on_random_shapes(i, compute):
     cfg, k, init, X = rbm_case(i)
     cfg = dict(cfg, compute=compute)
-    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg)
+    # unit kinds the tensor-core epilogue does not implement (multinomial) run on the storage-precision kernels whatever
+    # `compute` says (bm_rbm_tc.cu: tc_kinds): the oracle that goes with them does not round to bf16
+    tc = cfg['h_kind'] == 'bernoulli' and cfg['v_kind'] in ('bernoulli', 'gaussian')
+    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg if tc else dict(cfg, compute='fp32'))
+    if not tc:
+        compute = 'fp32'                 # tolerances below
     eng.set_params(init), ora.set_params(init)
     for it in range(2):
         eng.train_step(X[it], 0.05, 0.5, k, 4242, it)
