@@ -36,8 +36,10 @@ static NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        // BM_NCCL_LIB: explicit path of the NCCL library (a pinned build; the host simulation's stand-in), else the default names
+        const char* names[] = {getenv("BM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char* n : names) {
+            if (!n || !*n) continue;
             api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (api.lib) break;
         }

@@ -11,5 +11,6 @@ ls "$OBJ"/*.o > /dev/null
 mkdir -p "$OUT"
 g++ -O1 -g -std=c++17 -fPIC -I/usr/local/cuda/include -c "$HERE/fake_cudart.cpp" -o "$OUT/fake_cudart.o"
 g++ -O2 -g -std=c++17 -fPIC -I/usr/local/cuda/include -c "$HERE/kernels_cpu.cpp" -o "$OUT/kernels_cpu.o"
-g++ -shared -o "$OUT/libbm_hostsim.so" "$OBJ"/*.o "$OUT/fake_cudart.o" "$OUT/kernels_cpu.o" -ldl -lpthread -lrt -lstdc++
+g++ -shared -Wl,-Bsymbolic -o "$OUT/libbm_hostsim.so" "$OBJ"/*.o "$OUT/fake_cudart.o" "$OUT/kernels_cpu.o" -ldl -lpthread -lrt -lstdc++
+g++ -O2 -g -std=c++17 -fPIC -shared -o "$OUT/libfakenccl.so" "$HERE/fake_nccl.cpp" -lrt -lpthread
 echo "built $OUT/libbm_hostsim.so"

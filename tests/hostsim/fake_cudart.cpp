@@ -173,8 +173,8 @@ cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, vo
 }
 
 // ---- devices ----------------------------------------------------------------------------------------------------------
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }       // one host memory behind all of them
+cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 8 ? cudaSuccess : cudaErrorInvalidDevice; }
 cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p));
     snprintf(p->name, sizeof(p->name), "fake B200 (host simulation)");

@@ -15,6 +15,13 @@ def main():
     from boltzmann_machines import _native
     from oracle.rbm import OracleRBM
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    if os.environ.get('BM_HOSTSIM') == '1':
+        # dry run without GPUs (tests/hostsim): the library's host code on the stand-in runtime, kernels interpreted on the CPU,
+        # collectives through the shared-memory stand-in for NCCL (BM_NCCL_LIB)
+        import ctypes as C
+        sim = _native.load_library(os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'))
+        sim.fakecuda_set_execute(1)
+        _native._lib = sim
     dist.init_process_group('gloo')
     ctx = _native.Context(local)
     uid = [_native.Context.comm_unique_id() if rank == 0 else None]
@@ -93,6 +100,35 @@ def main():
     print('rank {0} DBM data parallel: max |engine - oracle(global)| = {1:.3e}, metrics agree: {2}'.format(rank, derr, dok), flush=True)
     ok = ok and dok and derr < 5e-5
     deng.close()
+    # the same contract for the tensor-core DBM engine (opt-in, compute='bf16'): sharded over the ranks it must reproduce ITSELF
+    # run in one piece (a second context without communicator holds the global batch and particles on this GPU)
+    if os.environ.get('BM_EXPERIMENTAL') != '1' and os.environ.get('BM_HOSTSIM') != '1':
+        dist.barrier()                    # the engine has not run on a B200 yet: opt-in on real GPUs (BM_EXPERIMENTAL=1)
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
+    solo = _native.Context(local)
+    teng = _native.CudaDBM(dict(dcfg2(Bd, Md), compute='bf16'), ctx=ctx)
+    tref = _native.CudaDBM(dict(dcfg2(Bd * world, Md * world), compute='bf16'), ctx=solo)
+    for e in (teng, tref):
+        e.set_params(dparams)
+        e.init_particles(4242)
+    tok = True
+    for it in range(3):
+        g = teng.train_step(Xd[it, rank * Bd:(rank + 1) * Bd], 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        w = tref.train_step(Xd[it], 0.05, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        tok = tok and g['n_mf_updates'] == w['n_mf_updates'] and abs(g['msre'] - w['msre']) < 1e-3 * max(w['msre'], 1e-9)
+    got, want = teng.get_params(), tref.get_params()
+    terr = 0.0
+    for k in want:
+        ref = want[k]
+        if k in ('v', 'h', 'h_1'):
+            ref = ref[rank * Md:(rank + 1) * Md]
+        elif k.startswith('mu') and not k.startswith('mu_means'):
+            ref = ref[rank * Bd:(rank + 1) * Bd]
+        terr = max(terr, float(np.max(np.abs(got[k] - ref))))
+    print('rank {0} tensor-core DBM data parallel: max |sharded - one piece| = {1:.3e}, metrics agree: {2}'.format(rank, terr, tok), flush=True)
+    ok = ok and tok and terr < 2e-3
+    teng.close(); tref.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
