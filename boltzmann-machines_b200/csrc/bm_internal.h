@@ -67,7 +67,13 @@ struct Ctx {
     int rank = 0, nranks = 1;
 };
 
-inline void count_launch(Ctx* c) { c->launches++; }
+// called right after every kernel launch: counts it, and turns a launch the runtime refused (invalid configuration, too
+// much shared memory, ...) into an error -- unchecked, such a launch simply does not happen and its output stays stale
+inline void count_launch(Ctx* c) {
+    c->launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(BM_ECUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
 void profile_drain(Ctx* c);      // fold recorded event pairs into prof_ms (synchronises the stream)
 cudaEvent_t profile_event(Ctx* c);
 void allreduce_sum(Ctx* ctx, void* buf, size_t count, bool is_double);

@@ -19,11 +19,15 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int lds, __nv_
     else
         dst[(size_t)r * ldd + c] = __float2bfloat16_rn(a);
 }
+// grid.y carries the row index and is limited to 65535: taller matrices (a resident dataset) go in slabs
+constexpr int ROW_SLAB = 32768;
 void launch_f32_to_bf16(Ctx* ctx, const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols) {
-    if (rows <= 0) return;
-    dim3 grid(((cols + 1) / 2 + 127) / 128, rows);
-    f32_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
-    count_launch(ctx);
+    for (int r0 = 0; r0 < rows; r0 += ROW_SLAB) {
+        const int n = rows - r0 < ROW_SLAB ? rows - r0 : ROW_SLAB;
+        dim3 grid(((cols + 1) / 2 + 127) / 128, n);
+        f32_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src + (size_t)r0 * lds, lds, dst + (size_t)r0 * ldd, ldd, n, cols);
+        count_launch(ctx);
+    }
 }
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
@@ -32,10 +36,12 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld
     if (c < cols) dst[(size_t)r * ldd + c] = __bfloat162float(src[(size_t)r * lds + c]);
 }
 void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst, int ldd, int rows, int cols) {
-    if (rows <= 0) return;
-    dim3 grid((cols + 255) / 256, rows);
-    bf16_to_f32_kernel<<<grid, 256, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
-    count_launch(ctx);
+    for (int r0 = 0; r0 < rows; r0 += ROW_SLAB) {
+        const int n = rows - r0 < ROW_SLAB ? rows - r0 : ROW_SLAB;
+        dim3 grid((cols + 255) / 256, n);
+        bf16_to_f32_kernel<<<grid, 256, 0, ctx->stream>>>(src + (size_t)r0 * lds, lds, dst + (size_t)r0 * ldd, ldd, n, cols);
+        count_launch(ctx);
+    }
 }
 
 // ---- byte-valued host datasets (bm_rbm_train_epoch_u8): u8 -> bf16 / fp32 / fp64, exact for 0..255 ----
@@ -62,10 +68,12 @@ __global__ void u8_to_bf16_kernel(const uint8_t* __restrict__ src, int lds, __nv
     }
 }
 void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols) {
-    if (rows <= 0) return;
-    dim3 grid(((cols + 7) / 8 + 127) / 128, rows);
-    u8_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
-    count_launch(ctx);
+    for (int r0 = 0; r0 < rows; r0 += ROW_SLAB) {
+        const int n = rows - r0 < ROW_SLAB ? rows - r0 : ROW_SLAB;
+        dim3 grid(((cols + 7) / 8 + 127) / 128, n);
+        u8_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src + (size_t)r0 * lds, lds, dst + (size_t)r0 * ldd, ldd, n, cols);
+        count_launch(ctx);
+    }
 }
 template <typename T>
 __global__ void u8_to_real_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, size_t n) {

@@ -182,7 +182,8 @@ cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) {
     p->sharedMemPerBlockOptin = 232448; p->totalGlobalMem = (size_t)180 << 30;
     return cudaSuccess;
 }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+static thread_local cudaError_t t_last_error = cudaSuccess;
+cudaError_t cudaGetLastError(void) { const cudaError_t e = t_last_error; t_last_error = cudaSuccess; return e; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "fake_cudart error"; }
 cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* st) {
@@ -251,6 +252,7 @@ cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** arg
         char buf[160];
         snprintf(buf, sizeof(buf), "invalid launch configuration: grid (%u,%u,%u) block (%u,%u,%u) smem %zu", grid.x, grid.y, grid.z, block.x, block.y, block.z, smem);
         violation(buf);
+        t_last_error = cudaErrorInvalidConfiguration;
         return cudaErrorInvalidConfiguration;
     }
     const std::string name = record_launch(func);

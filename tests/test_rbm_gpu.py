@@ -249,3 +249,25 @@ def test_bad_arguments_are_errors_not_crashes():
     with pytest.raises(KeyError):
         eng.set_params({'nope': np.zeros(3)})
     eng.close()
+
+
+@pytest.mark.parametrize('compute', ['fp32', 'bf16'])
+def test_resident_dataset_taller_than_the_grid_limit(compute):
+    """A resident dataset with more than 65535 rows (the bench holds 163840): the conversion kernels index rows with
+    grid.y and must go in slabs -- a step on rows beyond the limit equals the same step fed from the host."""
+    V, H, B, n = 24, 16, 64, 70000
+    cfg = make_cfg('bernoulli', V, H, B, compute=compute, sample_v=False)
+    rng = np.random.RandomState(3)
+    X = (rng.rand(n, V) < 0.3).astype(np.float32)
+    init = dict(W=(0.1 * rng.randn(V, H)).astype(np.float32))
+    a, b = _native.CudaRBM(cfg), _native.CudaRBM(cfg)
+    a.set_params(init), b.set_params(init)
+    a.set_data(X)
+    first = 69000
+    a.train_step_at(first, B, 0.05, 0.5, 2, 11, 0)
+    b.train_step(X[first:first + B], 0.05, 0.5, 2, 11, 0)
+    ga, gb = a.get_params(), b.get_params()
+    for k in ga:
+        np.testing.assert_array_equal(ga[k], gb[k], err_msg=k)
+    assert np.abs(ga['dW']).max() > 0
+    a.close(); b.close()
