@@ -342,7 +342,10 @@ extern "C" int bm_debug_tc_gemm(bm_ctx* hctx, int32_t M, int32_t N, int32_t K, c
     for (int i = 0; i < 2 * g.n_pairs; ++i) {
         const int pr = i / 2; const bool isA = (i % 2) == 0;
         const int Kp = pr ? K2 : K;
-        const bool t = isA ? (a_t != 0) : (b_t != 0);
+        bool t = isA ? (a_t != 0) : (b_t != 0);
+        // BM_TC_DEBUG_BT2=0|1: the SECOND pair's B orientation, so that a two-pair op with mixed B layouts -- the DBM's
+        // x W_i + y W_{i+1}^T -- can be exercised through this hook (B2 is then given in that layout)
+        if (!isA && pr == 1) { const char* e = getenv("BM_TC_DEBUG_BT2"); if (e) t = atoi(e) != 0; }
         const int mn = isA ? M : N;
         const int rows = t ? Kp : mn, cols = t ? mn : Kp;
         const int ld = round_up(cols, 8);

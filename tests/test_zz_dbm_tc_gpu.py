@@ -217,3 +217,17 @@ def test_particle_sweep_program_equals_the_launch_per_op_sweeps(monkeypatch, Hs,
             assert set(np.unique(gb[n])) <= {0.0, 1.0}, n
             assert np.mean(ga[n] != gb[n]) < 0.05, (n, np.mean(ga[n] != gb[n]))
     loop.close(); prog.close()
+
+
+@pytest.mark.parametrize('M,N,K1,K2', [(200, 512, 784, 1024), (1024, 512, 784, 1024), (33, 18, 30, 11), (300, 130, 70, 257)])
+def test_raw_two_pair_op_with_mixed_b_layouts(monkeypatch, M, N, K1, K2):
+    """The one op shape of the tensor-core DBM engine that no other test reaches at the kernel level: ONE accumulator fed by
+    pair 0 with B stored [K, N] (x W_i) and pair 1 with B stored [N, K] (y W_{i+1}^T).  Run this first on a new box."""
+    rng = np.random.RandomState(M + N)
+    A1, B1 = rng.rand(M, K1), 0.1 * rng.randn(K1, N)          # MN-major B
+    A2, B2 = rng.rand(M, K2), 0.1 * rng.randn(N, K2)          # K-major B
+    monkeypatch.setenv('BM_TC_DEBUG_BT2', '0')
+    C = _native.debug_tc_gemm(A1, B1, a_t=False, b_t=True, A2=A2, B2=B2)
+    r = lambda x: bf16_round(x).astype(np.float64)
+    want = r(A1) @ r(B1) + r(A2) @ r(B2).T
+    np.testing.assert_allclose(C, want, atol=5e-2, rtol=1e-3)
