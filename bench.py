@@ -324,16 +324,26 @@ def main():
 
     # clock probe: when K is so small that no 100 ms sample fell inside a timed region, keep the
     # same load running (untimed) until a few samples exist -- same work, same clocks
+    # (with peers every step is a collective: rank 0 decides, every rank runs the same number of probe steps)
+    def rank0_says(flag):
+        if dist is None:
+            return flag
+        box = [bool(flag) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
     probe = 0
     if rank == 0:
         sampler.mark()
-        t_end = time.perf_counter() + 3.0
-        while sampler.n_loaded() < 5 and time.perf_counter() < t_end:
-            for i in range(50):
-                step_resident(i)
-            ctx.sync()
+    t_end = time.perf_counter() + 3.0
+    while rank0_says(rank == 0 and sampler.n_loaded() < 5 and time.perf_counter() < t_end):
+        for i in range(50):
+            step_resident(i)
+        ctx.sync()
+        if rank == 0:
             sampler.windows.append((sampler._t0, time.perf_counter()))
-            probe += 50
+        probe += 50
+    if rank == 0:
         clocks = sampler.stop()
         clocks['probe_steps_after_timed_regions'] = probe
     barrier()
