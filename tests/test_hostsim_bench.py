@@ -1,0 +1,50 @@
+"""bench.py's own control flow on the CPU: the headline benchmark script run end to end on the stand-in CUDA runtime
+(tests/hostsim, launches recorded and checked but not interpreted -- timings are meaningless there).  Checks the JSON
+contract of the line it prints and that no launch, copy or tensor map of the benchmark-sized run breaks a runtime rule
+(the run that first showed a dataset conversion launch beyond the grid limit)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RUNNER = r'''
+import sys, runpy, ctypes as C
+sys.path[:0] = [{root!r}, {pkg!r}]
+from boltzmann_machines import _native
+sim = _native.load_library({sim!r})
+sim.fakecuda_violation.restype = C.c_char_p
+_native._lib = sim
+sys.argv = ['bench.py', '--steps', '6', '--warmup', '3', '--no-cpu-baseline']
+try:
+    runpy.run_path({bench!r}, run_name='__main__')
+finally:
+    print('VIOLATIONS=' + sim.fakecuda_violation().decode())
+'''
+
+
+def test_bench_contract_on_the_host_simulation(tmp_path):
+    obj = os.path.join(ROOT, 'boltzmann-machines_b200', 'build')
+    if not (os.path.isdir(obj) and any(f.endswith('.o') for f in os.listdir(obj))):
+        pytest.skip('library objects not built (run build.sh / __graft_entry__.build())')
+    subprocess.check_call(['bash', os.path.join(ROOT, 'tests', 'hostsim', 'build.sh')], stdout=subprocess.DEVNULL)
+    code = RUNNER.format(root=ROOT, pkg=os.path.join(ROOT, 'boltzmann-machines_b200'),
+                         sim=os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'), bench=os.path.join(ROOT, 'bench.py'))
+    res = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert 'VIOLATIONS=\n' in res.stdout + '\n', res.stdout[-1500:]
+    line = [l for l in res.stdout.splitlines() if l.startswith('{"metric"')]
+    assert len(line) == 1, res.stdout[-1500:]
+    out = json.loads(line[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+                'dtype', 'data', 'config', 'gpu_launches', 'clocks', 'roofline', 'e2e'):
+        assert key in out, key
+    assert out['n_gpus'] == 1 and out['steps'] == 6 and out['higher_is_better'] is True and out['scaling'] == 'weak'
+    assert out['config']['workload'].startswith('BernoulliRBM 784-1024') and 'model' not in out['config']
+    assert set(out['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+    assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
+    assert out['e2e']['h2d_bytes_per_step'] == 4096 * 784          # one byte per visible unit and row
+    assert out['gpu_launches'] == 5 * out['steps']                  # program, 2 x column statistics, bias update, weight update
