@@ -19,8 +19,8 @@ CASES = {c['name']: c for c in GOLD['cases']}
 
 
 def _corpus(name):
-    """Random scenarios generated like the committed goldens (make_reference_golden.py --fuzz 48 --seed 2026): replayed on
-    the oracle everywhere; on the CUDA engine only with BM_EXPERIMENTAL=1 until they have passed on a B200 once."""
+    """Random scenarios generated like the committed goldens (make_reference_golden.py --fuzz 48 --seed 2026), replayed on the
+    oracle, on the CUDA engines' host code with interpreted kernels (hostsim-fp32) and on the CUDA engines themselves."""
     import gzip
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)
     with gzip.open(p, 'rt') as fh:
@@ -28,8 +28,10 @@ def _corpus(name):
 
 
 def _skip_unverified_corpus(name, engine):
-    if name.startswith('fuzz_') and engine.startswith('cuda') and os.environ.get('BM_EXPERIMENTAL') != '1':
-        pytest.skip('fuzz corpus on the CUDA engine: set BM_EXPERIMENTAL=1 (not yet run on a B200)')
+    """The corpus runs on the CUDA engines like the committed goldens do: their host code has replayed it on the
+    interpreter (hostsim-fp32) and only GPU-verified kernels are involved.  BM_SKIP_FUZZ_CORPUS=1 leaves it out."""
+    if name.startswith('fuzz_') and engine.startswith('cuda') and os.environ.get('BM_SKIP_FUZZ_CORPUS') == '1':
+        pytest.skip('fuzz corpus skipped on request')
 
 
 if not os.environ.get('BM_GOLDEN_RBM_CASES'):

@@ -11,10 +11,6 @@ echo "mixed-layout op exit $?" >> $OUT/${TAG}_dbm_tc_mixed_b.log; tail -5 $OUT/$
 BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q > $OUT/${TAG}_dbm_tc_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${TAG}_dbm_tc_pytest.log
 tail -15 $OUT/${TAG}_dbm_tc_pytest.log
-# the fuzz corpus (68 random reference scenarios, CPU-verified on the oracle) on the CUDA fp32 engines
-BM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_z_reference_golden.py -k 'fuzz_ and cuda' -q > $OUT/${TAG}_fuzz_corpus_pytest.log 2>&1
-echo "fuzz corpus pytest exit $?" >> $OUT/${TAG}_fuzz_corpus_pytest.log
-tail -8 $OUT/${TAG}_fuzz_corpus_pytest.log
 # random-shape fuzz of the verified engines (fp32 / bf16 RBM, fp32 DBM) against the oracles
 BM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_engine_fuzz_gpu.py -q > $OUT/${TAG}_engine_fuzz_pytest.log 2>&1
 echo "engine fuzz pytest exit $?" >> $OUT/${TAG}_engine_fuzz_pytest.log
