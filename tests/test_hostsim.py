@@ -346,3 +346,42 @@ def test_fp32_dbm_engine_equals_the_pinned_oracle_under_the_interpreter(executin
         np.testing.assert_allclose(full, parts, rtol=0, atol=1e-6)
     no_skips(executing)
     eng.close()
+
+
+def test_boundary_refuses_bad_arguments_without_crashing(sim):
+    """Error behaviour of the C-ABI (include/bm.h: every function returns BM_OK or a negative code and bm_last_error() says
+    why): wrong sizes, unknown names, out-of-range rows and unsupported models are refused with a message, and the handle
+    stays usable."""
+    from boltzmann_machines import _native
+    sim.fakecuda_reset()
+    cfg = dict(n_visible=12, n_hidden=8, dtype='float32', compute='bf16', max_batch=4)
+    eng = _native.CudaRBM(cfg)
+    with pytest.raises(RuntimeError, match='unknown|size'):
+        _native.check(sim.bm_rbm_set_param(eng.handle, b'nope', np.zeros(3, np.float32).ctypes.data, 12))
+    with pytest.raises(RuntimeError, match='size'):
+        _native.check(sim.bm_rbm_set_param(eng.handle, b'W', np.zeros(5, np.float32).ctypes.data, 20))
+    with pytest.raises(ValueError):
+        eng.train_step(np.zeros((4, 11), np.float32), 0.1, 0.5, 1, 1, 0)           # wrong width: refused by the binding
+    with pytest.raises(RuntimeError):
+        eng.train_step(np.zeros((4, 12), np.float32), 0.1, 0.5, 0, 1, 0)           # k = 0
+    with pytest.raises(RuntimeError, match='resident|range|data'):
+        eng.train_step_at(0, 4, 0.1, 0.5, 1, 1, 0)                                 # no resident dataset
+    eng.train_step(np.zeros((4, 12), np.float32), 0.1, 0.5, 1, 1, 0)               # still usable
+    eng.close()
+    dcfg = dbm_cfg(9, (5, 4, 3), 4, 4, 'fp32')
+    dbm = _native.CudaDBM(dcfg)
+    with pytest.raises(RuntimeError, match='batch_size'):
+        dbm.train_step(np.zeros((5, 9), np.float32), 0.1, 0.5, 1, 1, 0)            # more rows than batch_size
+    with pytest.raises(RuntimeError, match='2-layer|2 hidden'):
+        dbm.ais(4, 5, 1, 1)                                                        # AIS is defined for two hidden layers
+    with pytest.raises(RuntimeError, match='2 hidden'):
+        dbm.log_proba(np.zeros((4, 9), np.float32))
+    with pytest.raises(RuntimeError, match='unknown'):
+        _native.check(sim.bm_dbm_get_param(dbm.handle, b'W_7', np.zeros(4, np.float32).ctypes.data, 16))
+    dbm.train_step(np.zeros((4, 9), np.float32), 0.1, 0.5, 1, 1, 0)
+    dbm.close()
+    bad = dict(dbm_cfg(9, (5, 4), 4, 4, 'fp32'), h_kinds=['bernoulli', 'gaussian'])
+    with pytest.raises((RuntimeError, KeyError)):
+        d2 = _native.CudaDBM(bad)
+        d2.train_step(np.zeros((4, 9), np.float32), 0.1, 0.5, 1, 1, 0)             # gaussian hidden layers are not supported
+    clean(sim)
