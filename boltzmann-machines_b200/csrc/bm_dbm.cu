@@ -583,7 +583,11 @@ struct Dbm : DbmBase {
         DevBuf<double> all;
         all.ensure(total);
         all.zero(ctx->stream);
-        if (n > 0) ais_local(n, first, n_betas, k, seed, all.p + offset);
+        // the unit kernels index the run with grid.y (limit 65535) and the workspaces grow with the runs: long ladders go in
+        // chunks -- run r draws from row r whatever the chunking
+        const int chunk = 32768;
+        for (int done = 0; done < n; done += chunk)
+            ais_local(std::min(chunk, n - done), first + (uint32_t)done, n_betas, k, seed, all.p + offset + done);
         if (reduce) allreduce_sum(ctx, all.p, (size_t)total, true);        // every rank ends with every run
         std::vector<double> hw(total);
         BM_CUDA(cudaMemcpyAsync(hw.data(), all.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -639,7 +639,6 @@ struct DbmTC : Dbm<float> {
     // Bernoulli draw in its epilogue.
     // (sharding over ranks / calls: Dbm<float>::ais, ais_rows; run r draws from row row0 + r of the AIS sites)
     void ais_local(int R, uint32_t row0, int n_betas, int k, uint64_t seed, double* logw_out) override {
-        BM_REQUIRE(R <= 65535, "at most 65535 AIS runs per rank and call");
         const int H0 = Hs[0], H1 = Hs[1];
         const int ld0 = ldn[1], ldv = ldn[0], ld1 = ldn[2];
         DevBuf<bf16_t> x, xn, va, hc;

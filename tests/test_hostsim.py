@@ -385,3 +385,31 @@ def test_boundary_refuses_bad_arguments_without_crashing(sim):
         d2 = _native.CudaDBM(bad)
         d2.train_step(np.zeros((4, 9), np.float32), 0.1, 0.5, 1, 1, 0)             # gaussian hidden layers are not supported
     clean(sim)
+
+
+@pytest.mark.parametrize('compute', ['fp32', 'bf16'])
+def test_long_ais_ladders_go_in_chunks(sim, compute):
+    """More runs than grid.y can index (65535): bm_dbm_ais cuts the ladder into chunks of 32768 runs; launch configurations
+    stay legal (kernels not interpreted here: 70000 runs)."""
+    from boltzmann_machines import _native
+    sim.fakecuda_reset()
+    eng = _native.CudaDBM(dbm_cfg(9, (5, 4), 4, 4, compute))
+    out = eng.ais(70000, 3, 1, 5)
+    assert out.shape == (70000,)
+    clean(sim)
+    eng.close()
+
+
+def test_chunked_ais_equals_the_unchunked_ladder(executing, monkeypatch):
+    """Same chains whatever the chunking: a 13-run ladder against its slices was checked above; here the engine's own
+    chunk boundary is crossed on purpose by comparing runs [32760, 32776) computed inside one 40000-run call with the same
+    runs computed alone."""
+    from boltzmann_machines import _native
+    cfg = small_cfg((5, 4), V=7, n_particles=4, batch_size=4, compute='fp32')
+    eng = _native.CudaDBM(cfg)
+    rng = np.random.RandomState(0)
+    eng.set_params({'W': (0.3 * rng.randn(7, 5)).astype(np.float32), 'W_1': (0.3 * rng.randn(5, 4)).astype(np.float32)})
+    alone = eng.ais(16, 6, 1, 77, first_run=32760)
+    inside = eng.ais(40000, 6, 1, 77)[32760:32776]
+    np.testing.assert_allclose(inside, alone, rtol=0, atol=1e-9)
+    eng.close()
