@@ -332,9 +332,13 @@ struct Dbm : DbmBase {
             const int n = size_of(idx, V, Hs);
             const int kind = idx == 0 ? v_kind : h_kinds[idx - 1];
             T* dst = idx == 0 ? v.p : h[idx - 1].p;
-            dim3 grid(((n + 3) / 4 + 127) / 128, M);
-            particle_init_kernel<T><<<grid, 128, 0, ctx->stream>>>(dst, M, n, kind, sigma.p, make_rng(seed, SITE_PARTICLE_INIT, idx, 0, particle_row0()));
-            count_launch(ctx);
+            for (int r0 = 0; r0 < M; r0 += 32768) {          // grid.y (the particle) is limited to 65535
+                const int rows = M - r0 < 32768 ? M - r0 : 32768;
+                dim3 grid(((n + 3) / 4 + 127) / 128, rows);
+                particle_init_kernel<T><<<grid, 128, 0, ctx->stream>>>(dst + (size_t)r0 * n, rows, n, kind, sigma.p,
+                                                                       make_rng(seed, SITE_PARTICLE_INIT, idx, 0, particle_row0() + (uint32_t)r0));
+                count_launch(ctx);
+            }
             BM_REQUIRE(kind != BM_UNIT_MULTINOMIAL || ctx->nranks <= 1, "multinomial layers are not supported with sharded particles");
             if (kind == BM_UNIT_MULTINOMIAL) {       // t /= reduce_sum(t) over the whole tensor
                 launch_mean_combine<T>(ctx, dst, (const T*)nullptr, 0.0, (int)((size_t)M * n), scal.p);   // mean

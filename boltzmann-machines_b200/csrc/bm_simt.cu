@@ -404,12 +404,16 @@ __global__ void prepare_input_kernel(const T* __restrict__ X, int ldx, T* __rest
 template <typename T>
 void launch_prepare_input(Ctx* ctx, const T* X, int ldx, T* Xp, int ldxp, int rows, int cols,
                           const T* sigma, double keep, RngKey rng) {
-    if (rows <= 0) return;
     const int cbs = (cols + 3) / 4;
-    dim3 grid((cbs + 127) / 128, rows);
-    prepare_input_kernel<T><<<grid, 128, 0, ctx->stream>>>(X, ldx, Xp, ldxp, rows, cols, sigma,
-                                                           (T)(keep < 0 ? 1.0 : keep), keep >= 0 ? 1 : 0, rng);
-    count_launch(ctx);
+    for (int r0 = 0; r0 < rows; r0 += 32768) {            // grid.y (the row) is limited to 65535: tall batches go in slabs
+        const int n = rows - r0 < 32768 ? rows - r0 : 32768;
+        RngKey slab = rng;
+        slab.row0 += (uint32_t)r0;                         // the draw of a row depends on its index in the batch, not in the slab
+        dim3 grid((cbs + 127) / 128, n);
+        prepare_input_kernel<T><<<grid, 128, 0, ctx->stream>>>(X + (size_t)r0 * ldx, ldx, Xp + (size_t)r0 * ldxp, ldxp, n, cols, sigma,
+                                                               (T)(keep < 0 ? 1.0 : keep), keep >= 0 ? 1 : 0, slab);
+        count_launch(ctx);
+    }
 }
 template void launch_prepare_input<float>(Ctx*, const float*, int, float*, int, int, int, const float*, double, RngKey);
 template void launch_prepare_input<double>(Ctx*, const double*, int, double*, int, int, int, const double*, double, RngKey);

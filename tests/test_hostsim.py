@@ -413,3 +413,29 @@ def test_chunked_ais_equals_the_unchunked_ladder(executing, monkeypatch):
     inside = eng.ais(40000, 6, 1, 77)[32760:32776]
     np.testing.assert_allclose(inside, alone, rtol=0, atol=1e-9)
     eng.close()
+
+
+def test_tall_batches_and_particle_sets_draw_by_global_row(executing):
+    """Batches / particle sets with more rows than grid.y can index go in slabs of 32768 rows; a row's draws depend on its
+    index in the whole batch: rows around the slab boundary equal the same rows of a reference computed row by row."""
+    from boltzmann_machines import _native
+    from oracle import philox as P
+    n, V = 33000, 8
+    dbm = _native.CudaDBM(dbm_cfg(V, (4,), 4, n, 'fp32'))
+    dbm.init_particles(4242)
+    v = dbm.get_params(['v'])['v']
+    want = P.uniform_at(n, V, 4242, P.SITE_PARTICLE_INIT, 0, 0)
+    np.testing.assert_array_equal(v[32760:32776], want[32760:32776])
+    np.testing.assert_array_equal(v[:8], want[:8])
+    dbm.close()
+    # dropout mask of a tall batch: the prepared input is X / keep * floor(keep + u(row, col))
+    cfg = dict(n_visible=V, n_hidden=4, dtype='float32', compute='fp32', max_batch=n, dropout=0.7, sample_v=False, sample_h=False)
+    rbm = _native.CudaRBM(cfg)
+    X = np.ones((n, V), np.float32)
+    rbm.train_step(X, 0.0, 0.0, 1, 99, 3)
+    Xp = rbm.get_activation('X', n)
+    u = P.uniform_at(n, V, 99, P.SITE_DROPOUT, 0, 3)
+    want = np.float32(1.0) / np.float32(0.7) * np.floor(np.float32(0.7) + u)
+    np.testing.assert_allclose(Xp[32760:32776], want[32760:32776], rtol=1e-6)
+    rbm.close()
+    no_skips(executing)
