@@ -290,7 +290,10 @@ def test_dbm_scenario_matches_the_reference(variant, both_engines, workdir):
         assert len(log[key]) == len(g['log'][key])
         for got, want in zip(log[key], g['log'][key]):
             close(got[0], want[0], 10 * tol, key + ' msre')
-            assert abs(got[1] - want[1]) <= slack, key + ' n_mf_updates'
+            if want[1] is None or got[1] is None:       # an epoch without a reporting iteration
+                assert got[1] is None and want[1] is None, key + ' n_mf_updates'
+            else:
+                assert abs(got[1] - want[1]) <= slack, key + ' n_mf_updates'
     for scope, want in g['after_fit'].items():
         got = dbm.get_tf_params(scope=scope)
         for k, v in want.items():
