@@ -35,6 +35,8 @@ struct State {
     std::map<std::string, long> launches;            // per kernel name
     std::string violation;                           // first violation (sticky)
     long encodes = 0;
+    long syncs = 0;                                  // host-blocking calls: stream / event synchronisation, synchronous copies
+    long h2d_bytes = 0, d2h_bytes = 0;               // by the copy kind the caller states
     bool execute = false;                            // interpret launches on the CPU (kernels_cpu.cpp) instead of skipping them
     std::map<std::string, long> skipped;             // launches without a CPU restatement while `execute` was on
 };
@@ -134,7 +136,7 @@ extern "C" {
 
 // ---- inspection hooks for the tests --------------------------------------------------------------------------------
 const char* fakecuda_violation(void) { std::lock_guard<std::mutex> lk(g_mu); static std::string s; s = g_violation; return s.c_str(); }
-void fakecuda_reset(void) { std::lock_guard<std::mutex> lk(g_mu); g_violation.clear(); g_launches.clear(); g_encodes = 0; st().skipped.clear(); }
+void fakecuda_reset(void) { std::lock_guard<std::mutex> lk(g_mu); g_violation.clear(); g_launches.clear(); g_encodes = 0; st().skipped.clear(); st().syncs = 0; st().h2d_bytes = 0; st().d2h_bytes = 0; }
 long fakecuda_launches(const char* substr) {
     std::lock_guard<std::mutex> lk(g_mu);
     long n = 0;
@@ -142,6 +144,9 @@ long fakecuda_launches(const char* substr) {
     return n;
 }
 long fakecuda_tensor_maps(void) { return g_encodes; }
+long fakecuda_syncs(void) { return st().syncs; }
+long fakecuda_h2d_bytes(void) { return st().h2d_bytes; }
+long fakecuda_d2h_bytes(void) { return st().d2h_bytes; }
 void fakecuda_set_execute(int on) { st().execute = on != 0; }
 // kernels that were launched while executing but have no CPU restatement: "name xN; ..." ("" if none)
 const char* fakecuda_skipped(void) {
@@ -216,12 +221,13 @@ cudaError_t cudaFree(void* p) {
 }
 cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) {
+static void copy_checked(void* d, const void* s, size_t n, enum cudaMemcpyKind k) {
     check_range(d, n, "cudaMemcpy destination"); check_range(s, n, "cudaMemcpy source");
+    if (k == cudaMemcpyHostToDevice) st().h2d_bytes += (long)n; else if (k == cudaMemcpyDeviceToHost) st().d2h_bytes += (long)n;
     memmove(d, s, n);
-    return cudaSuccess;
 }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind k) { st().syncs++; copy_checked(d, s, n, k); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind k, cudaStream_t) { copy_checked(d, s, n, k); return cudaSuccess; }
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t) {
     if (h) { check_range(d, (h - 1) * dp + w, "cudaMemcpy2D destination"); check_range(s, (h - 1) * sp + w, "cudaMemcpy2D source"); }
     for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
@@ -236,13 +242,13 @@ cudaError_t cudaMemcpyToSymbolAsync(const void* sym, const void* s, size_t n, si
 // ---- streams / events -------------------------------------------------------------------------------------------------------
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { st().syncs++; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { st().syncs++; return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1e-3f; return cudaSuccess; }
 
 // ---- launches: recorded, not executed --------------------------------------------------------------------------------------

@@ -439,3 +439,35 @@ def test_tall_batches_and_particle_sets_draw_by_global_row(executing):
     np.testing.assert_allclose(Xp[32760:32776], want[32760:32776], rtol=1e-6)
     rbm.close()
     no_skips(executing)
+
+
+def test_structural_cost_of_the_hot_entry_points(sim):
+    """What a step costs in runtime calls, counted on the stand-in runtime at the benchmark's shape (kernels not interpreted):
+    the whole-epoch entry point blocks the host ONCE per epoch whatever the number of batches, moves exactly one byte per
+    visible unit and row to the device and 64 bytes per step back, and launches 8 kernels per batch; a dataset-resident step is 5
+    launches, no copy and no host synchronisation -- bench.py's `gpu_launches`, `h2d_bytes_per_step`, `d2h_bytes_per_step`."""
+    from boltzmann_machines import _native
+    V, H, B = 784, 1024, 4096
+    cfg = dict(n_visible=V, n_hidden=H, dtype='float32', compute='bf16', l2=1e-5, sample_v=False, sample_h=True, max_batch=B)
+    eng = _native.CudaRBM(cfg)
+    eng.init_normal_W(0.01, 1)
+    X = (np.random.RandomState(0).rand(6 * B, V) < 0.13).astype(np.float32)
+    P = eng.pin(X)
+    assert P.dtype == np.uint8
+    eng.train_epoch(P, B, 0.05, 0.5, 5, 1, 0, metrics=('msre',), every=1)            # first call: programs, staging buffers
+    for nb in (3, 6):
+        sim.fakecuda_reset()
+        eng.train_epoch(P[:nb * B], B, 0.05, 0.5, 5, 1, 100, metrics=('msre',), every=1)
+        assert sim.fakecuda_syncs() == 1, (nb, sim.fakecuda_syncs())
+        assert sim.fakecuda_launches(b'') == 8 * nb
+        assert sim.fakecuda_launches(b'tc_program_kernel') == nb
+        assert sim.fakecuda_h2d_bytes() == nb * B * V and sim.fakecuda_d2h_bytes() == 64 * nb
+    eng.unpin(P)
+    eng.set_data(X)
+    eng.train_step_at(0, B, 0.05, 0.5, 5, 1, 0)                                      # first resident step builds its program
+    sim.fakecuda_reset()
+    for i in range(6):
+        eng.train_step_at(i * B, B, 0.05, 0.5, 5, 1, 1 + i)
+    assert sim.fakecuda_launches(b'') == 5 * 6 and sim.fakecuda_syncs() == 0 and sim.fakecuda_h2d_bytes() == 0
+    clean(sim)
+    eng.close()
