@@ -562,14 +562,23 @@ struct DbmTC : Dbm<float> {
         const int nr = nranks();                               // data parallelism: see the header of bm_dbm.cu
         const float N = (float)((double)B * nr), Mp = (float)((double)M * nr);      // configured (global) sizes (dbm.py:254-255)
         const float rows_g = (float)((double)rows * nr);
-        for (int i = 0; i < L; ++i) {
-            const int H = Hs[i];
-            gradient_tc(i, i == 0 ? Xb.p : mu_b[i - 1].p, rows, i == 0 ? v_b.p : h_b[i - 1].p, N, Mp);
-            launch_colsum_bf16(ctx, mu_b[i].p, ldn[i + 1], nullptr, 0, rows, H, 1.f, 0.f, musum[i].p);
-            launch_colsum_bf16(ctx, h_b[i].p, ldn[i + 1], nullptr, 0, M, H, 1.f, 0.f, hsum[i].p);
+        for (int i = 0; i < L; ++i) gradient_tc(i, i == 0 ? Xb.p : mu_b[i - 1].p, rows, i == 0 ? v_b.p : h_b[i - 1].p, N, Mp);
+        {   // column sums of mu_i (over the batch rows) and of h_i, v (over the particles), three per pair of launches
+            std::vector<const bf16_t*> P; std::vector<int> ld, nc; std::vector<float*> out;
+            auto flush = [&](int nrows) {
+                for (size_t o = 0; o < P.size(); o += 3) {
+                    const int n = (int)std::min<size_t>(3, P.size() - o);
+                    launch_colsums_bf16(ctx, n, P.data() + o, ld.data() + o, nc.data() + o, out.data() + o, nrows);
+                }
+                P.clear(); ld.clear(); nc.clear(); out.clear();
+            };
+            for (int i = 0; i < L; ++i) { P.push_back(mu_b[i].p); ld.push_back(ldn[i + 1]); nc.push_back(Hs[i]); out.push_back(musum[i].p); }
+            flush(rows);
+            for (int i = 0; i < L; ++i) { P.push_back(h_b[i].p); ld.push_back(ldn[i + 1]); nc.push_back(Hs[i]); out.push_back(hsum[i].p); }
+            P.push_back(v_b.p); ld.push_back(ldn[0]); nc.push_back(V); out.push_back(vsum.p);
+            flush(M);
         }
         launch_colsum<float>(ctx, X, V, (const float*)nullptr, 0, rows, V, 1.f, 0.f, xsum.p);
-        launch_colsum_bf16(ctx, v_b.p, ldn[0], nullptr, 0, M, V, 1.f, 0.f, vsum.p);
         allreduce_step_statistics();
         dbm_vbias_kernel<float><<<(V + 255) / 256, 256, 0, ctx->stream>>>(V, xsum.p, vsum.p, rows_g, Mp, vb.p, dvb.p, (float)lr, (float)mom);
         count_launch(ctx);

@@ -91,6 +91,8 @@ void launch_sqdiff_mean_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __
 // out[n] = s1 * sum_r P[r,n] + s2 * sum_r Q[r,n]  (bf16 inputs, Q nullable, fp32 out)
 void launch_colsum_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq,
                         int rows, int cols, float s1, float s2, float* out);
+// up to 3 plain column sums over the same number of rows in one pair of launches: out[i][c] = sum_r P[i][r, c]
+void launch_colsums_bf16(Ctx* ctx, int n, const __nv_bfloat16* const* P, const int* ldp, const int* cols, float* const* out, int rows);
 // the three column statistics of a CD step in one pass: sum(X - v), sum(h0 - hk), sum(hk)
 void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* v, int ldv,
                                const __nv_bfloat16* h0, const __nv_bfloat16* hk, int ldh, int rows, int V, int H,

@@ -241,6 +241,14 @@ void launch_colsum_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bf
     j.rows = rows; j.n = 1;
     run_colsum_jobs(ctx, j);
 }
+// up to 3 plain column sums over the same number of rows in one pair of launches
+void launch_colsums_bf16(Ctx* ctx, int n, const __nv_bfloat16* const* P, const int* ldp, const int* cols, float* const* out, int rows) {
+    BM_REQUIRE(n >= 1 && n <= 3, "1..3 column sums per call");
+    ColsumJobs j{};
+    for (int i = 0; i < n; ++i) { j.P[i] = P[i]; j.ldp[i] = ldp[i]; j.Q[i] = nullptr; j.ldq[i] = 0; j.s1[i] = 1.f; j.s2[i] = 0.f; j.out[i] = out[i]; j.cols[i] = cols[i]; }
+    j.rows = rows; j.n = n;
+    run_colsum_jobs(ctx, j);
+}
 void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const __nv_bfloat16* v, int ldv,
                                const __nv_bfloat16* h0, const __nv_bfloat16* hk, int ldh, int rows, int V, int H,
                                float* dvb_sum, float* dhb_sum, float* q_sum) {
