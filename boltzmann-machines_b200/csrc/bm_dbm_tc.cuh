@@ -59,6 +59,21 @@ __global__ void mf_chunk_diffs_kernel(const bf16_t* __restrict__ hist, size_t sl
     if ((threadIdx.x & 31) == 0) atomicMax(flags + j, __float_as_uint(m));
 }
 
+// dst[c, r] = bf16(src[r, c]): the transposed bf16 shadow of a weight matrix (src [rows, cols] dense fp32, dst leading dimension ldd)
+__global__ void transpose_f32_to_bf16_kernel(const float* __restrict__ src, int rows, int cols, bf16_t* __restrict__ dst, int ldd) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;              // dst row = source column
+        if (c < cols && r < rows) dst[(size_t)c * ldd + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+
 // G = (sum of `sp` positive slices) / n_div - (sum of `sn` negative slices) / m_div      (dbm.py:558-568)
 __global__ void dbm_grad_combine_kernel(const float* __restrict__ pos, int sp, const float* __restrict__ neg, int sn,
                                         size_t stride, float inv_n, float inv_m, float* __restrict__ G, size_t n) {
@@ -181,6 +196,12 @@ __global__ void ais_fused_step_kernel(double* __restrict__ logw, float a, float 
 struct DbmTC : Dbm<float> {
     std::vector<int> ldn;                        // leading dimension of a bf16 activation of layer idx (0 = visible)
     std::vector<DevBuf<bf16_t>> Wb;              // bf16 shadows of W_i: [size(i), ldn[i+1]]
+    // The layer-wise conditional adds y W_{i+1}^T to x W_i in one accumulator.  Default: a second, TRANSPOSED shadow of
+    // W_{i+1} ([H_{i+1}, ld(H_i)]) so that both operand pairs read their B operand MN-major -- the layout combination the RBM
+    // program runs.  BM_DBM_TC_MIXED=1: no second shadow, pair 1 reads W_{i+1} K-major (one op, two B layouts: saves the
+    // transposes and the memory once that op shape has been verified on the hardware).
+    std::vector<DevBuf<bf16_t>> WbT;
+    bool mixed_layouts = false;
     DevBuf<bf16_t> Xb, recon_b, v_b, v2_b, v3_b;
     std::vector<DevBuf<bf16_t>> mu_b, mu2_b, h_b, h2_b, h3_b;
     std::vector<DevBuf<float>> Gp;               // split-K slices of the gradient GEMMs
@@ -216,6 +237,10 @@ struct DbmTC : Dbm<float> {
         }
         { const char* e = getenv("BM_DBM_MF_CHUNK"); mf_chunk = e ? atoi(e) : 0; }
         { const char* e = getenv("BM_DBM_PCD_PROGRAM"); pcd_program = e && atoi(e) != 0; }
+        { const char* e = getenv("BM_DBM_TC_MIXED"); mixed_layouts = e && atoi(e) != 0; }
+        WbT.resize(L);
+        if (!mixed_layouts)
+            for (int i = 1; i < L; ++i) { WbT[i].ensure((size_t)Hs[i] * ldn[i]); WbT[i].zero(ctx->stream); }
         if (mf_chunk > max_mf) mf_chunk = max_mf;
         if (mf_chunk * L > 90) mf_chunk = 90 / L;              // a program holds at most 96 ops
         if (mf_chunk > 0) {
@@ -229,7 +254,22 @@ struct DbmTC : Dbm<float> {
     static TcMat mat(const bf16_t* p, int rows, int cols, int ld) { TcMat m; m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; return m; }
 
     // ---- fp32 <-> bf16 coherence ---------------------------------------------------------------------------
-    void refresh_shadow(int i) { launch_f32_to_bf16(ctx, W[i].p, Hs[i], Wb[i].p, ldn[i + 1], size_of(i, V, Hs), Hs[i]); }
+    void refresh_shadow(int i) {
+        const int in = size_of(i, V, Hs);
+        launch_f32_to_bf16(ctx, W[i].p, Hs[i], Wb[i].p, ldn[i + 1], in, Hs[i]);
+        if (i >= 1 && !mixed_layouts) {
+            transpose_f32_to_bf16_kernel<<<dim3((Hs[i] + 31) / 32, (in + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(W[i].p, in, Hs[i], WbT[i].p, ldn[i]);
+            count_launch(ctx);
+        }
+    }
+    // second operand pair of a conditional: y W_{i+1}^T with y = `above` [rows, H_{i+1}]
+    void above_pair(TcGemm& g, int i, const bf16_t* above, int rows) {
+        const int H = Hs[i], Hn = Hs[i + 1];
+        g.n_pairs = 2;
+        g.A[1] = mat(above, rows, Hn, ldn[i + 2]); g.K[1] = Hn;
+        if (mixed_layouts) { g.B[1] = mat(Wb[i + 1].p, H, Hn, ldn[i + 2]); g.b_t[1] = false; }     // W_{i+1} stored [N, K]
+        else { g.B[1] = mat(WbT[i + 1].p, Hn, H, ldn[i + 1]); g.b_t[1] = true; }                    // W_{i+1}^T stored [K, N]
+    }
     void narrow_state() {          // fp32 variables (as set by the caller / initialised) -> bf16 operands
         launch_f32_to_bf16(ctx, v.p, V, v_b.p, ldn[0], M, V);
         for (int i = 0; i < L; ++i) {
@@ -279,12 +319,7 @@ struct DbmTC : Dbm<float> {
         g.M = rows; g.N = H;
         g.A[0] = mat(below, rows, in, ldn[i]); g.K[0] = in;
         g.B[0] = mat(Wb[i].p, in, H, ldn[i + 1]); g.b_t[0] = true;           // x W_i: W_i stored [K, N]
-        if (above) {
-            const int Hn = Hs[i + 1];
-            g.n_pairs = 2;
-            g.A[1] = mat(above, rows, Hn, ldn[i + 2]); g.K[1] = Hn;
-            g.B[1] = mat(Wb[i + 1].p, H, Hn, ldn[i + 2]); g.b_t[1] = false;   // y W_{i+1}^T: W_{i+1} stored [N, K]
-        }
+        if (above) above_pair(g, i, above, rows);
         g.acc_scale = acc_scale; g.bias_scale = bias_scale; g.bias = hb[i].p;
         g.act = ACT_SIGMOID; g.rng = rng;
         if (sample) { g.sample = SMP_BERNOULLI; g.out_state_bf = out; g.ld_state_bf = ldn[i + 1]; }
@@ -682,9 +717,9 @@ struct DbmTC : Dbm<float> {
                     count_launch(ctx); count_launch(ctx);
                 }
                 TcGemm o;                     // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
-                o.M = R; o.N = H0; o.n_pairs = 2;
+                o.M = R; o.N = H0;
                 o.A[0] = mat(va.p, R, V, ldv); o.K[0] = V; o.B[0] = mat(Wb[0].p, V, H0, ld0); o.b_t[0] = true;
-                o.A[1] = mat(hc.p, R, H1, ld1); o.K[1] = H1; o.B[1] = mat(Wb[1].p, H0, H1, ld1); o.b_t[1] = false;
+                above_pair(o, 0, hc.p, R);
                 o.acc_scale = beta; o.bias_scale = beta; o.bias = hb[0].p; o.act = ACT_SIGMOID;
                 o.rng = make_rng(seed, SITE_AIS_H1, 0, tick, row0);
                 if (sample_h[0]) { o.sample = SMP_BERNOULLI; o.out_state_bf = xo; o.ld_state_bf = ld0; }

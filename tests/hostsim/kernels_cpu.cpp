@@ -519,6 +519,10 @@ static void k_mf_chunk_diffs(void** a, dim3 grid) {
         if (bits > flags[j]) flags[j] = bits;
     }
 }
+static void k_transpose_f32_to_bf16(void** a) {
+    const float* src = arg<const float*>(a, 0); const int rows = arg<int>(a, 1), cols = arg<int>(a, 2); __nv_bfloat16* dst = arg<__nv_bfloat16*>(a, 3); const int ldd = arg<int>(a, 4);
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) dst[(size_t)c * ldd + r] = f2bf(src[(size_t)r * cols + c]);
+}
 static void k_dbm_grad_combine(void** a) {
     const float* pos = arg<const float*>(a, 0); const int sp = arg<int>(a, 1); const float* neg = arg<const float*>(a, 2); const int sn = arg<int>(a, 3);
     const size_t stride = arg<size_t>(a, 4); const float inv_n = arg<float>(a, 5), inv_m = arg<float>(a, 6); float* G = arg<float*>(a, 7); const size_t n = arg<size_t>(a, 8);
@@ -581,6 +585,7 @@ bool execute(const std::string& name, dim3 grid, dim3, void** args) {
     // templated kernels: "<name>I f|d E" in the mangled name selects the instantiation
 #define BOTH(fn, kname, ...) do { if (has(kname "IfE")) { fn<float>(__VA_ARGS__); return true; } if (has(kname "IdE")) { fn<double>(__VA_ARGS__); return true; } } while (0)
     if (has("tc_program_kernel")) { k_tc_program(args); return true; }
+    if (has("transpose_f32_to_bf16_kernel")) { k_transpose_f32_to_bf16(args); return true; }     // before its substring below
     if (has("f32_to_bf16_kernel")) { k_f32_to_bf16(args); return true; }
     if (has("bf16_to_f32_kernel")) { k_bf16_to_f32(args); return true; }
     if (has("reduce_partials_kernel")) { k_reduce_partials(args); return true; }

@@ -212,7 +212,9 @@ def no_skips(sim):
 
 @pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7), (70, 130)])
 @pytest.mark.parametrize('programs', [False, True])
-def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, programs):
+@pytest.mark.parametrize('mixed', ['0', '1'])
+def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, programs, mixed):
+    monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)        # 0: transposed second shadow (default); 1: one op, two B layouts
     monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
     monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
     if programs:
@@ -242,7 +244,9 @@ def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, pro
 
 @pytest.mark.parametrize('Hs,gaussian', [((18,), False), ((18, 11), False), ((18, 11, 7), False), ((18, 11), True)])
 @pytest.mark.parametrize('programs', [False, True])
-def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, Hs, gaussian, programs):
+@pytest.mark.parametrize('mixed', ['0', '1'])
+def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, Hs, gaussian, programs, mixed):
+    monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
     monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
     monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
     if programs:
@@ -265,7 +269,9 @@ def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, 
 
 
 @pytest.mark.parametrize('k,fused', [(1, '1'), (1, '0'), (3, '1')])
-def test_tc_dbm_ais_equals_the_bf16_emulation(executing, monkeypatch, k, fused):
+@pytest.mark.parametrize('mixed', ['0', '1'])
+def test_tc_dbm_ais_equals_the_bf16_emulation(executing, monkeypatch, k, fused, mixed):
+    monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
     monkeypatch.setenv('BM_DBM_AIS_FUSED', fused)
     cfg = small_cfg((5, 4), V=7, n_particles=4, batch_size=4)
     eng, emu = tc_pair(cfg)

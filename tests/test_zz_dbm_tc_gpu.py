@@ -68,7 +68,11 @@ def test_state_roundtrip_is_bf16_for_activations_and_fp32_for_variables():
 
 
 @pytest.mark.parametrize('Hs', [(18,), (18, 11), (18, 11, 7), (70, 130)])
-def test_mean_field_and_queries(Hs):
+@pytest.mark.parametrize('mixed', ['0', '1'])
+def test_mean_field_and_queries(monkeypatch, Hs, mixed):
+    """mixed = 0 (default): the second operand pair reads a transposed shadow of W_{i+1}, both pairs MN-major; 1: one op with
+    two B layouts and no second shadow (BM_DBM_TC_MIXED)."""
+    monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
     cfg = make_cfg(Hs=Hs)
     eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
     init(cfg, (eng, emu))
