@@ -235,3 +235,15 @@ def test_raw_two_pair_op_with_mixed_b_layouts(monkeypatch, M, N, K1, K2):
     r = lambda x: bf16_round(x).astype(np.float64)
     want = r(A1) @ r(B1) + r(A2) @ r(B2).T
     np.testing.assert_allclose(C, want, atol=5e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize('M,N,K1,K2', [(200, 512, 784, 1024), (1024, 512, 784, 1024), (33, 18, 30, 11), (300, 130, 70, 257)])
+def test_raw_two_pair_op_with_uniform_layouts(M, N, K1, K2):
+    """The op shape the tensor-core DBM engine uses by default: two pairs, both with K-major A and MN-major B
+    (x W_i + y (W_{i+1}^T) with the transposed shadow)."""
+    rng = np.random.RandomState(M + N + 1)
+    A1, B1 = rng.rand(M, K1), 0.1 * rng.randn(K1, N)
+    A2, B2 = rng.rand(M, K2), 0.1 * rng.randn(K2, N)
+    C = _native.debug_tc_gemm(A1, B1, a_t=False, b_t=True, A2=A2, B2=B2)
+    r = lambda x: bf16_round(x).astype(np.float64)
+    np.testing.assert_allclose(C, r(A1) @ r(B1) + r(A2) @ r(B2), atol=5e-2, rtol=1e-3)

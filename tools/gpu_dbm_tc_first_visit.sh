@@ -6,7 +6,7 @@ TAG=${1:-r02_a}
 OUT=gpurun_out
 mkdir -p $OUT
 # the one kernel-level question first, alone and under a short timeout: a two-pair op whose pairs have different B layouts
-BM_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q -k mixed_b > $OUT/${TAG}_dbm_tc_mixed_b.log 2>&1
+BM_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q -k raw_two_pair > $OUT/${TAG}_dbm_tc_mixed_b.log 2>&1
 echo "mixed-layout op exit $?" >> $OUT/${TAG}_dbm_tc_mixed_b.log; tail -5 $OUT/${TAG}_dbm_tc_mixed_b.log
 BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q > $OUT/${TAG}_dbm_tc_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${TAG}_dbm_tc_pytest.log
