@@ -23,7 +23,8 @@ for _p in (ROOT, os.path.join(ROOT, 'boltzmann-machines_b200')):
         sys.path.insert(0, _p)
 
 V, H, B, K_GIBBS = 784, 1024, 4096, 5
-N_BATCHES = 40                       # resident dataset: 40 x 4096 rows = 257 MB of bf16 > 126 MB L2
+N_BATCHES = int(os.environ.get('BM_BENCH_BATCHES', '40'))    # resident dataset: 40 x 4096 rows = 257 MB of bf16 > 126 MB L2
+#                                      (BM_BENCH_BATCHES: dry runs on the host simulation only -- `config.l2_policy` states the size)
 LR, MOMENTUM, L2 = 0.05, 0.5, 1e-5
 FLOP_PER_STEP = 2.0 * B * V * H * (2 * K_GIBBS + 3)      # (2k+3) GEMMs of 2BVH
 
