@@ -477,3 +477,20 @@ def test_structural_cost_of_the_hot_entry_points(sim):
     assert sim.fakecuda_launches(b'') == 5 * 6 and sim.fakecuda_syncs() == 0 and sim.fakecuda_h2d_bytes() == 0
     clean(sim)
     eng.close()
+
+
+def test_random_tc_dbm_configurations_equal_the_bf16_emulation(executing, monkeypatch):
+    """tools/fuzz_dbm_tc_hostsim.py over a fixed range of seeds: ragged widths, 1-3 hidden layers, Gaussian visibles, every
+    combination of the engine's switches; one training step at a time from identical states, then queries and AIS."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('fuzz_dbm_tc_hostsim', os.path.join(ROOT, 'tools', 'fuzz_dbm_tc_hostsim.py'))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    for k in ('BM_DBM_TC_MIXED', 'BM_DBM_AIS_FUSED', 'BM_DBM_MF_CHUNK', 'BM_DBM_PCD_PROGRAM'):
+        monkeypatch.setenv(k, '0')                       # restored afterwards (the tool sets them per configuration)
+    outcomes = {}
+    for seed in range(900000, 900150):
+        cfg, env, run = fuzz.draw(np.random.RandomState(seed))
+        r = fuzz.one(cfg, env, run, seed, executing)
+        outcomes[r] = outcomes.get(r, 0) + 1
+    assert outcomes.get('ok', 0) >= 145, outcomes        # ('mf-count': a sweep stopping within bf16 rounding of the tolerance)
