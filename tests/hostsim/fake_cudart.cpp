@@ -9,6 +9,9 @@
 //     the whole tensor view (rows, leading dimension) lies inside one live allocation -- a wrong TcMat is a failure here,
 //     not a corrupted tile on the GPU;
 //   * frees of unknown pointers and leaks at exit are reported.
+// With fakecuda_set_execute(1) the recorded launches are interpreted on the CPU (kernels_cpu.cpp), which also checks the dataflow of
+// every program launch for hazards no declared dependency covers (fakecuda_set_hazards: 0 off, 1 launches small enough to shadow
+// -- the default --, 2 always; fakecuda_drop_dependency pretends one declaration away, for tests of the checker).
 // What the run proves: argument validation (every BM_REQUIRE), buffer sizing, pointer arithmetic, program construction and
 // the control flow around the kernels.  What it cannot prove: anything a kernel computes (results are whatever the zeroed
 // buffers hold).  It never ships: the product library links the real runtime and refuses to start without a B200.
@@ -22,7 +25,11 @@
 #include <string>
 #include <vector>
 
-namespace fakecuda { bool execute(const std::string& name, dim3 grid, dim3 block, void** args); }
+namespace fakecuda {
+bool execute(const std::string& name, dim3 grid, dim3 block, void** args);
+void report_violation(const std::string& m);        // for kernels_cpu.cpp (dataflow hazards of a program launch)
+int hazard_mode();                                   // 0 off, 1 on for launches small enough to shadow, 2 always
+}
 
 namespace {
 
@@ -39,6 +46,9 @@ struct State {
     long h2d_bytes = 0, d2h_bytes = 0;               // by the copy kind the caller states
     bool execute = false;                            // interpret launches on the CPU (kernels_cpu.cpp) instead of skipping them
     std::map<std::string, long> skipped;             // launches without a CPU restatement while `execute` was on
+    int hazards = 1;                                 // check the dataflow of interpreted program launches (kernels_cpu.cpp)
+    long hazard_launches = 0;                        // program launches that were checked
+    int drop_op = -1, drop_dep = -1;                 // tests of the checker itself: pretend this dependency was not declared
 };
 State& st() { static State* s = new State(); return *s; }
 #define g_mu (st().mu)
@@ -56,6 +66,14 @@ void violation(const std::string& m) {
     if (g_violation.empty()) g_violation = m;
     fprintf(stderr, "[fake_cudart] VIOLATION: %s\n", m.c_str());
 }
+}  // namespace
+namespace fakecuda {
+void report_violation(const std::string& m) { violation(m); }
+int hazard_mode() { return st().hazards; }
+void count_hazard_launch() { st().hazard_launches++; }
+bool dropped_dependency(int op, int d) { return st().drop_op == op && st().drop_dep == d; }
+}
+namespace {
 // the live allocation containing [p, p + n), or 0
 bool inside_one_allocation(const void* p, size_t n) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -148,6 +166,9 @@ long fakecuda_syncs(void) { return st().syncs; }
 long fakecuda_h2d_bytes(void) { return st().h2d_bytes; }
 long fakecuda_d2h_bytes(void) { return st().d2h_bytes; }
 void fakecuda_set_execute(int on) { st().execute = on != 0; }
+void fakecuda_set_hazards(int mode) { st().hazards = mode; }
+long fakecuda_hazard_launches(void) { return st().hazard_launches; }
+void fakecuda_drop_dependency(int op, int d) { st().drop_op = op; st().drop_dep = d; }
 // kernels that were launched while executing but have no CPU restatement: "name xN; ..." ("" if none)
 const char* fakecuda_skipped(void) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -24,6 +25,10 @@
 #include "../../boltzmann-machines_b200/csrc/bm_tc_desc.h"
 
 namespace fakecuda {
+void report_violation(const std::string& m);
+int hazard_mode();
+void count_hazard_launch();
+bool dropped_dependency(int op, int d);
 
 // what fake_encode_tiled stores in the opaque CUtensorMap
 struct MapView { const void* base; unsigned long long cols, rows, ld_bytes; unsigned box0, box1; unsigned magic; };
@@ -40,6 +45,7 @@ template <class T> static inline T arg(void** a, int i) { return *reinterpret_ca
 struct View {
     const __nv_bfloat16* p; long cols, rows, ld;
     float at(long r, long c) const { return (r >= 0 && r < rows && c >= 0 && c < cols) ? bf2f(p[r * ld + c]) : 0.f; }   // TMA zero fill
+    const void* addr(long r, long c) const { return (r >= 0 && r < rows && c >= 0 && c < cols) ? (const void*)(p + r * ld + c) : nullptr; }
 };
 static View view_of(const CUtensorMap& tm) {
     MapView mv; memcpy(&mv, &tm, sizeof(mv));
@@ -50,8 +56,87 @@ static View view_of(const CUtensorMap& tm) {
 
 using bm::ACT_LINEAR; using bm::ACT_SIGMOID; using bm::ACT_SOFTPLUS; using bm::SMP_NONE; using bm::SMP_BERNOULLI; using bm::SMP_GAUSSIAN;
 
+
+// ---- dataflow hazards of a program launch --------------------------------------------------------------------------------------
+// On the GPU the units of a program run concurrently on the CTA pairs, ordered ONLY by the dependencies the host declared
+// (TcGemm::dep / dep_all -> dep_ctr / dep_groups); interpreting the ops one after the other in program order hides a missing one.
+// While the ops are interpreted, every element an op reads or writes is therefore looked up in a shadow of the memory this launch
+// touched: a read of something an earlier op of the launch wrote, a write over something an earlier op read or wrote, must be
+// covered by a dependency path -- row block by row block: "same row block" dependencies (dep_groups == 0) order (op j, block g)
+// before (op i, block g) only, dep_all ones order all of op j before every unit of op i.  Units of ONE op are not checked against
+// each other, and no credit is given for the order in which one CTA pair happens to walk its units.
+struct Hazards {
+    const bm::TcLaunch& L;
+    int n, G;                                         // ops; largest row-block count of any op
+    std::vector<std::vector<char>> hb;                // [i * G + g] -> [j * G + gj]: (op j, block gj) completes before unit (i, g) starts
+    struct Cell { int writer = -1; std::vector<int> readers; };      // ids: op * (G + 1) + (block + 1); block -1 = every block
+    std::unordered_map<uintptr_t, Cell> shadow;
+    int reported = 0;
+    static constexpr int ROWS = 256;                  // rows per row-block group: CTA pairs of two 128-row tiles
+
+    explicit Hazards(const bm::TcLaunch& l) : L(l), n(l.n_phases), G(1) {
+        for (int i = 0; i < n; ++i) G = std::max(G, L.phases[i].l.m_groups);
+        hb.assign((size_t)n * G, std::vector<char>((size_t)n * G, 0));
+        for (int i = 0; i < n; ++i) {
+            const bm::TcPhaseLite& p = L.phases[i].l;
+            for (int d = 0; d < p.n_deps; ++d) {
+                if (dropped_dependency(i, d)) continue;
+                int j = -1;
+                for (int q = 0; q < i; ++q) if (L.phases[q].l.done_ctr == p.dep_ctr[d]) j = q;
+                if (j < 0) { report("op " + std::to_string(i) + " waits on a counter no earlier op of the launch publishes"); continue; }
+                const bm::TcPhaseLite& pj = L.phases[j].l;
+                if (p.dep_groups[d] != 0 && p.dep_groups[d] != pj.m_groups)
+                    report("op " + std::to_string(i) + " waits for " + std::to_string(p.dep_groups[d]) + " row blocks of op " + std::to_string(j) +
+                           ", which has " + std::to_string(pj.m_groups));
+                for (int g = 0; g < p.m_groups; ++g) {
+                    std::vector<char>& me = hb[(size_t)i * G + g];
+                    for (int gj = 0; gj < pj.m_groups; ++gj) {
+                        if (p.dep_groups[d] == 0 && gj != g) continue;
+                        me[(size_t)j * G + gj] = 1;
+                        const std::vector<char>& before = hb[(size_t)j * G + gj];
+                        for (size_t x = 0; x < before.size(); ++x) me[x] |= before[x];
+                    }
+                }
+            }
+        }
+    }
+    void report(const std::string& m) { if (reported++ < 4) report_violation("tc program dataflow: " + m); }
+    int id(int op, int g) const { return op * (G + 1) + g + 1; }
+    // does the access `prev` happen before every unit (i, g) that makes the new access?  (g == -1: every block of op i)
+    bool ordered(int prev, int i, int g) const {
+        const int j = prev / (G + 1), gj = prev % (G + 1) - 1;
+        if (j == i) return true;
+        const int g0 = g < 0 ? 0 : g, g1 = g < 0 ? L.phases[i].l.m_groups : g + 1;
+        const int q0 = gj < 0 ? 0 : gj, q1 = gj < 0 ? L.phases[j].l.m_groups : gj + 1;
+        for (int a = g0; a < g1; ++a)
+            for (int b = q0; b < q1; ++b)
+                if (!hb[(size_t)i * G + a][(size_t)j * G + b]) return false;
+        return true;
+    }
+    std::string who(int x) const {
+        const int g = x % (G + 1) - 1;
+        return "op " + std::to_string(x / (G + 1)) + (g < 0 ? " (every row block)" : " (row block " + std::to_string(g) + ")");
+    }
+    void read(const void* a, int i, int g) {
+        if (!a) return;
+        Cell& c = shadow[(uintptr_t)a >> 1];
+        const int me = id(i, g);
+        if (c.writer >= 0 && !ordered(c.writer, i, g)) report(who(me) + " reads what " + who(c.writer) + " writes, without a dependency path");
+        if (c.readers.empty() || c.readers.back() != me) c.readers.push_back(me);
+    }
+    void write(const void* a, int i, int g) {
+        Cell& c = shadow[(uintptr_t)a >> 1];
+        const int me = id(i, g);
+        if (c.writer >= 0 && !ordered(c.writer, i, g)) report(who(me) + " overwrites what " + who(c.writer) + " wrote, without a dependency path");
+        for (int r : c.readers)
+            if (!ordered(r, i, g)) { report(who(me) + " overwrites what " + who(r) + " reads, without a dependency path"); break; }
+        c.writer = me;
+        c.readers.clear();
+    }
+};
+
 // ---- the program kernel, from its descriptors ------------------------------------------------------------------------------
-static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L) {
+static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L, Hazards* hz = nullptr, int op = 0) {
     const bm::TcPhaseLite& p = ph.l;
     const int shift_all = L.batch_row;
     const int total_chunks = p.chunks[0] + (p.n_pairs > 1 ? p.chunks[1] : 0);
@@ -74,6 +159,15 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L) {
             for (int n = 0; n < p.N; ++n)
                 for (int k = 0; k < 64; ++k)
                     Bt[(size_t)n * 64 + k] = p.b_mn[pr] ? B[pr].at(k0 + k, n) : B[pr].at(n, k0 + k);
+            if (hz) {
+                for (int m = 0; m < p.M; ++m)
+                    for (int k = 0; k < 64; ++k)
+                        hz->read(p.a_mn[pr] ? A[pr].addr(p.a_k0[pr] + shift + k0 + k, m) : A[pr].addr(p.a_row0[pr] + shift + m, k0 + k),
+                                 op, m / Hazards::ROWS);
+                for (int n = 0; n < p.N; ++n)             // every unit of the op reads its column block of B over the split's K range
+                    for (int k = 0; k < 64; ++k)
+                        hz->read(p.b_mn[pr] ? B[pr].addr(k0 + k, n) : B[pr].addr(n, k0 + k), op, -1);
+            }
             for (int m = 0; m < p.M; ++m) {
                 const float* a = &At[(size_t)m * 64];
                 float* out = &acc[(size_t)m * p.N];
@@ -113,6 +207,12 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L) {
                     if (p.out_mean_bf) p.out_mean_bf[(size_t)m * p.ld_mean_bf + n] = f2bf(mean);
                     if (p.out_state_bf) p.out_state_bf[(size_t)m * p.ld_state_bf + n] = f2bf(state);
                     if (p.out_f32) (p.out_f32 + (size_t)split * p.split_stride)[(size_t)m * p.ld_f32 + n] = mean;
+                    if (hz) {
+                        const int g = m / Hazards::ROWS;
+                        if (p.out_mean_bf) hz->write(p.out_mean_bf + (size_t)m * p.ld_mean_bf + n, op, g);
+                        if (p.out_state_bf) hz->write(p.out_state_bf + (size_t)m * p.ld_state_bf + n, op, g);
+                        if (p.out_f32) hz->write(p.out_f32 + (size_t)split * p.split_stride + (size_t)m * p.ld_f32 + n, op, g);
+                    }
                 }
             }
     }
@@ -120,7 +220,21 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L) {
 static void k_tc_program(void** a) {
     const bm::TcLaunch& L = *reinterpret_cast<const bm::TcLaunch*>(a[0]);
     if (L.n_phases == 0) { run_tc_op(L.inl, L); return; }
-    for (int i = 0; i < L.n_phases; ++i) run_tc_op(L.phases[i], L);      // program order is a topological order of the dependencies
+    // program order is a topological order of the dependencies; whether the declared dependencies cover every hazard between
+    // the ops is checked on the side (Hazards) -- always with mode 2, with mode 1 only for launches small enough to shadow
+    double touched = 0;
+    for (int i = 0; i < L.n_phases; ++i) {
+        const bm::TcPhaseLite& p = L.phases[i].l;
+        touched += ((double)p.M + p.N) * 64.0 * (p.chunks[0] + (p.n_pairs > 1 ? p.chunks[1] : 0)) + (double)p.M * p.N * p.splits;
+    }
+    const int mode = hazard_mode();
+    if (mode == 2 || (mode == 1 && touched < 2.0e7)) {
+        Hazards hz(L);
+        for (int i = 0; i < L.n_phases; ++i) run_tc_op(L.phases[i], L, &hz, i);
+        count_hazard_launch();
+    } else {
+        for (int i = 0; i < L.n_phases; ++i) run_tc_op(L.phases[i], L);
+    }
 }
 
 // ---- bm_tc_util.cu -----------------------------------------------------------------------------------------------------------

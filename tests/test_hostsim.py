@@ -493,4 +493,63 @@ def test_random_tc_dbm_configurations_equal_the_bf16_emulation(executing, monkey
         cfg, env, run = fuzz.draw(np.random.RandomState(seed))
         r = fuzz.one(cfg, env, run, seed, executing)
         outcomes[r] = outcomes.get(r, 0) + 1
-    assert outcomes.get('ok', 0) >= 145, outcomes        # ('mf-count': a sweep stopping within bf16 rounding of the tolerance)
+    assert outcomes.get("ok", 0) >= 145 and not outcomes.get("FAIL"), outcomes   # (mf-count, sample-flip: rounding events, see the tool)
+    assert executing.fakecuda_hazard_launches() > 100          # the programs' dataflow was checked on the way
+
+
+def test_program_dataflow_hazards_are_checked_and_a_missing_dependency_is_caught(executing, monkeypatch):
+    """On the GPU the units of a program run concurrently, ordered only by the dependencies the host declares; the interpreter
+    runs the ops in program order, so it shadows every element a launch touches and reports reads / overwrites no dependency
+    path covers (row block by row block).  Clean: the GPU-verified RBM step program and the tensor-core DBM engine's mean-field
+    and particle programs on three 256-row blocks.  The checker itself: with any one needed dependency taken away it speaks up."""
+    from boltzmann_machines import _native
+    executing.fakecuda_hazard_launches.restype = C.c_long
+    rng = np.random.RandomState(0)
+
+    def rbm_step(drop=None):
+        executing.fakecuda_reset()
+        eng = _native.CudaRBM(dict(n_visible=70, n_hidden=40, dtype='float32', compute='bf16', l2=1e-5, sample_v=False, sample_h=True,
+                                   max_batch=600))
+        eng.init_normal_W(0.01, 1)
+        X = (rng.rand(600, 70) < 0.3).astype(np.float32)
+        if drop:
+            executing.fakecuda_drop_dependency(*drop)
+        before = executing.fakecuda_hazard_launches()
+        eng.train_step(X, 0.05, 0.5, 2, 7, 0)
+        executing.fakecuda_drop_dependency(-1, -1)
+        checked, v = executing.fakecuda_hazard_launches() - before, executing.fakecuda_violation().decode()
+        eng.close()
+        return checked, v
+
+    def dbm_step(Hs, drop=None):
+        executing.fakecuda_reset()
+        cfg = dbm_cfg(70, Hs, 600, 520, 'bf16', False, 6)
+        cfg['mf_tol'] = 1e-6
+        eng = _native.CudaDBM(cfg)
+        eng.init_particles(1)
+        X = (rng.rand(600, 70) < 0.3).astype(np.float32)
+        if drop:
+            executing.fakecuda_drop_dependency(*drop)
+        before = executing.fakecuda_hazard_launches()
+        eng.train_step(X, 0.05, 0.5, 2, 7, 0)
+        executing.fakecuda_drop_dependency(-1, -1)
+        checked, v = executing.fakecuda_hazard_launches() - before, executing.fakecuda_violation().decode()
+        eng.close()
+        return checked, v
+
+    checked, v = rbm_step()
+    assert checked == 1 and v == '', v
+    for op in (1, 2, 3, 4, 5):
+        _, v = rbm_step(drop=(op, 0))
+        assert 'without a dependency path' in v, (op, v)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', '3')
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
+    for mixed in ('0', '1'):
+        monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
+        for Hs in ((40,), (40, 24), (40, 24, 16)):
+            checked, v = dbm_step(Hs)
+            assert checked >= 2 and v == '', (Hs, mixed, v)
+    for op in (1, 2, 3):
+        _, v = dbm_step((40, 24), drop=(op, 0))
+        assert 'without a dependency path' in v, (op, v)
+    executing.fakecuda_reset()

@@ -36,6 +36,10 @@ def draw(rng):
                sparsity_cost=[float(rng.choice([0., 0.01, 0.1])) for _ in range(L)], sparsity_damping=float(rng.uniform(0.5, 0.99)))
     if gaussian:
         cfg['sigma'] = rng.uniform(0.6, 1.5, V)
+    if rng.rand() < 0.1:
+        # several 256-row blocks: the programs' row-block dependencies are then checked block by block (the interpreter shadows
+        # every element a program launch touches and reports hazards no declared dependency covers)
+        cfg['batch_size'], cfg['n_particles'] = int(rng.randint(257, 700)), int(rng.randint(257, 700))
     env = dict(BM_DBM_TC_MIXED=str(rng.randint(0, 2)), BM_DBM_AIS_FUSED=str(rng.randint(0, 2)))
     if rng.rand() < 0.6:
         env['BM_DBM_MF_CHUNK'] = str(rng.randint(1, 6))
@@ -94,6 +98,9 @@ def one(cfg, env, run, seed, sim):
         # the other bf16 neighbour (float32 sums in another order) would otherwise grow step by step into percent-level
         # differences that say nothing about the wiring.
         g, w = eng.get_params(), emu.get_params()
+        flips = sum(int((np.abs(g[k] - w[k]) > 0.5).sum()) for k in w if k == 'v' or (k.startswith('h') and not k.startswith('hb')))
+        if 0 < flips <= 2:
+            return 'sample-flip'          # a uniform within float32 rounding of its probability: the chains part here
         for k in w:
             close(g[k], w[k], 'after training step {0}: {1}'.format(it, k))
         emu.set_params(g)
@@ -129,6 +136,7 @@ def main():
     sim.fakecuda_set_execute(1)
     _native._lib = sim
     counts = {}
+    sim.fakecuda_hazard_launches.restype = C.c_long
     for i in range(args.n):
         seed = args.seed * 100000 + i
         cfg, env, run = draw(np.random.RandomState(seed))
@@ -142,7 +150,7 @@ def main():
             if not isinstance(e, AssertionError):
                 traceback.print_exc()
         counts[r] = counts.get(r, 0) + 1
-    print(counts)
+    print(counts, '-- program launches checked for dataflow hazards:', sim.fakecuda_hazard_launches())
     sys.exit(1 if counts.get('FAIL') else 0)
 
 
