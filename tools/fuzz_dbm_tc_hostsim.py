@@ -22,10 +22,11 @@ for p in (ROOT, os.path.join(ROOT, 'boltzmann-machines_b200')):
 
 def draw(rng):
     L = int(rng.choice([1, 2, 2, 3]))
-    V = int(rng.choice([rng.randint(2, 40), rng.randint(40, 200)]))
+    wide = rng.rand() < 0.12                      # several column tiles / more than a handful of K chunks per op
+    V = int(rng.choice([rng.randint(2, 40), rng.randint(40, 200)]) if not wide else rng.randint(200, 640))
     # (layer i needs more than i units: the reference's sparsity update indexes element i of layer i's vector, and the engine
     # refuses narrower layers like the reference's graph does)
-    Hs = [max(i + 1, int(rng.choice([rng.randint(2, 30), rng.randint(30, 150)]))) for i in range(L)]
+    Hs = [max(i + 1, int(rng.choice([rng.randint(2, 30), rng.randint(30, 150)]) if not wide else rng.randint(100, 640))) for i in range(L)]
     gaussian = bool(rng.rand() < 0.25)
     cfg = dict(n_visible=V, n_hiddens=Hs, v_kind='gaussian' if gaussian else 'bernoulli', h_kinds=['bernoulli'] * L,
                h_n_samples=[100.] * L, dtype='float32', compute='bf16', n_particles=int(rng.randint(1, 40)),
@@ -134,6 +135,7 @@ def main():
     sim.fakecuda_violation.restype = C.c_char_p
     sim.fakecuda_skipped.restype = C.c_char_p
     sim.fakecuda_set_execute(1)
+    sim.fakecuda_set_hazards(2)               # shadow every program launch, whatever its size
     _native._lib = sim
     counts = {}
     sim.fakecuda_hazard_launches.restype = C.c_long
