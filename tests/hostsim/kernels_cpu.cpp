@@ -72,6 +72,7 @@ struct Hazards {
     struct Cell { int writer = -1; std::vector<int> readers; };      // ids: op * (G + 1) + (block + 1); block -1 = every block
     std::unordered_map<uintptr_t, Cell> shadow;
     int reported = 0;
+    std::vector<std::string> skipped_waits;           // declared dependencies the kernel's wait loop does not honour (see below)
     static constexpr int ROWS = 256;                  // rows per row-block group: CTA pairs of two 128-row tiles
 
     explicit Hazards(const bm::TcLaunch& l) : L(l), n(l.n_phases), G(1) {
@@ -85,6 +86,14 @@ struct Hazards {
                 for (int q = 0; q < i; ++q) if (L.phases[q].l.done_ctr == p.dep_ctr[d]) j = q;
                 if (j < 0) { report("op " + std::to_string(i) + " waits on a counter no earlier op of the launch publishes"); continue; }
                 const bm::TcPhaseLite& pj = L.phases[j].l;
+                // The kernel's wait loop (bm_tc.cu, "dataflow: wait until the row blocks this unit reads have been written"): an op
+                // that consumes its A operand granule by granule (dep_chunk_ctr) SKIPS the unit-level wait of every same-row-block
+                // dependency; the granule waits order it after the producer whose granule counters those are, and after nothing else.
+                if (p.dep_groups[d] == 0 && p.dep_chunk_ctr && pj.chunk_ctr != p.dep_chunk_ctr) {
+                    skipped_waits.push_back("op " + std::to_string(i) + " declares a same-row-block dependency on op " + std::to_string(j) +
+                                            " that the kernel does not wait for (the op follows the granules of another producer)");
+                    continue;
+                }
                 if (p.dep_groups[d] != 0 && p.dep_groups[d] != pj.m_groups)
                     report("op " + std::to_string(i) + " waits for " + std::to_string(p.dep_groups[d]) + " row blocks of op " + std::to_string(j) +
                            ", which has " + std::to_string(pj.m_groups));
@@ -100,7 +109,12 @@ struct Hazards {
             }
         }
     }
-    void report(const std::string& m) { if (reported++ < 4) report_violation("tc program dataflow: " + m); }
+    void report(const std::string& m) {
+        if (reported++ >= 4) return;
+        std::string extra;
+        for (const std::string& w : skipped_waits) extra += " [" + w + "]";
+        report_violation("tc program dataflow: " + m + extra);
+    }
     int id(int op, int g) const { return op * (G + 1) + g + 1; }
     // does the access `prev` happen before every unit (i, g) that makes the new access?  (g == -1: every block of op i)
     bool ordered(int prev, int i, int g) const {

@@ -115,7 +115,7 @@ def one(cfg, env, run, seed, sim):
         # (a single mean-valued unit on a rounding boundary moves one run by a few 1e-3)
         a, b = eng.ais(6, 25, run['k'], 2222), emu.ais(6, 25, run['k'], 2222)
         d = np.abs(a - b)
-        assert (d > 5e-4 + 2e-5 * np.abs(b)).sum() <= 1 and d.max() < 0.02, 'ais: {0} vs {1}'.format(a, b)
+        assert (d > 5e-4 + 2e-5 * np.abs(b)).sum() <= 1 and d.max() < 1.0, 'ais: {0} vs {1}'.format(a, b)    # (one run may take another sample)
     v = sim.fakecuda_violation().decode()
     assert v == '', v
     sk = sim.fakecuda_skipped().decode()
