@@ -1200,7 +1200,11 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
                 // for the first such dependency, single-pair ops without split-K
                 const TcPhaseLite& pj = ph[j].l;
                 const int kchunks = ph[i].l.chunks[0];
-                if (chunk_deps && d == 0 && g.n_pairs == 1 && !g.a_t[0] && ph[i].l.splits == 1 && pj.splits == 1 &&
+                // (the kernel's wait loop skips the unit-level wait of EVERY same-row-block dependency of an op that follows
+                // granules: only an op whose single such dependency is this one may do so)
+                int same_row_deps = 0;
+                for (int q = 0; q < g.n_deps; ++q) same_row_deps += g.dep_all[q] ? 0 : 1;
+                if (chunk_deps && d == 0 && same_row_deps == 1 && g.n_pairs == 1 && !g.a_t[0] && ph[i].l.splits == 1 && pj.splits == 1 &&
                     kchunks <= MAX_KCHUNKS && g.K[0] == pj.N && pj.n_tiles * pj.gran_per_tile <= 255) {
                     ph[j].l.chunk_ctr = prog.dev_counters + cctr_off[j];
                     ph[i].l.dep_chunk_ctr = prog.dev_counters + cctr_off[j];

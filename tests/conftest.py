@@ -52,7 +52,9 @@ def pytest_unconfigure(config):
     lib = getattr(config, '_bm_hostsim', None)
     if lib is not None:
         v, sk = lib.fakecuda_violation().decode(), lib.fakecuda_skipped().decode()
-        print('\n[hostsim] runtime violations: {0}; kernels without a CPU restatement: {1}'.format(v or 'none', sk or 'none'))
+        print('\n[hostsim] runtime violations: {0}; kernels without a CPU restatement: {1}; program launches checked for dataflow '
+              'hazards: {2}, declared dependencies the kernel would not wait for: {3}'.format(
+                  v or 'none', sk or 'none', lib.fakecuda_hazard_launches(), lib.fakecuda_unhonoured_dependencies()))
 
 
 @pytest.fixture

@@ -48,6 +48,7 @@ struct State {
     std::map<std::string, long> skipped;             // launches without a CPU restatement while `execute` was on
     int hazards = 1;                                 // check the dataflow of interpreted program launches (kernels_cpu.cpp)
     long hazard_launches = 0;                        // program launches that were checked
+    long unhonoured = 0;                             // declared dependencies the kernel's wait loop skips (kernels_cpu.cpp, Hazards)
     int drop_op = -1, drop_dep = -1;                 // tests of the checker itself: pretend this dependency was not declared
 };
 State& st() { static State* s = new State(); return *s; }
@@ -71,6 +72,7 @@ namespace fakecuda {
 void report_violation(const std::string& m) { violation(m); }
 int hazard_mode() { return st().hazards; }
 void count_hazard_launch() { st().hazard_launches++; }
+void count_unhonoured(long n) { st().unhonoured += n; }
 bool dropped_dependency(int op, int d) { return st().drop_op == op && st().drop_dep == d; }
 }
 namespace {
@@ -168,6 +170,7 @@ long fakecuda_d2h_bytes(void) { return st().d2h_bytes; }
 void fakecuda_set_execute(int on) { st().execute = on != 0; }
 void fakecuda_set_hazards(int mode) { st().hazards = mode; }
 long fakecuda_hazard_launches(void) { return st().hazard_launches; }
+long fakecuda_unhonoured_dependencies(void) { return st().unhonoured; }
 void fakecuda_drop_dependency(int op, int d) { st().drop_op = op; st().drop_dep = d; }
 // kernels that were launched while executing but have no CPU restatement: "name xN; ..." ("" if none)
 const char* fakecuda_skipped(void) {

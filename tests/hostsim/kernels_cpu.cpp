@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -28,6 +29,7 @@ namespace fakecuda {
 void report_violation(const std::string& m);
 int hazard_mode();
 void count_hazard_launch();
+void count_unhonoured(long n);
 bool dropped_dependency(int op, int d);
 
 // what fake_encode_tiled stores in the opaque CUtensorMap
@@ -246,6 +248,12 @@ static void k_tc_program(void** a) {
         Hazards hz(L);
         for (int i = 0; i < L.n_phases; ++i) run_tc_op(L.phases[i], L, &hz, i);
         count_hazard_launch();
+        count_unhonoured((long)hz.skipped_waits.size());
+        if (getenv("BM_HOSTSIM_TRACE_FOLLOWERS")) {
+            int f = 0;
+            for (int i = 0; i < L.n_phases; ++i) f += L.phases[i].l.dep_chunk_ctr ? 1 : 0;
+            fprintf(stderr, "[hostsim] program of %d ops, %d follow their producer granule by granule\n", L.n_phases, f);
+        }
     } else {
         for (int i = 0; i < L.n_phases; ++i) run_tc_op(L.phases[i], L);
     }

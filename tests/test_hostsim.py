@@ -552,4 +552,7 @@ def test_program_dataflow_hazards_are_checked_and_a_missing_dependency_is_caught
     for op in (1, 2, 3):
         _, v = dbm_step((40, 24), drop=(op, 0))
         assert 'without a dependency path' in v, (op, v)
+    # the kernel's wait loop skips the unit-level wait of every same-row-block dependency of an op that follows its producer
+    # granule by granule: launch_tc_program only lets an op do so when that producer is its single such dependency
+    assert executing.fakecuda_unhonoured_dependencies() == 0
     executing.fakecuda_reset()

@@ -152,7 +152,8 @@ def main():
             if not isinstance(e, AssertionError):
                 traceback.print_exc()
         counts[r] = counts.get(r, 0) + 1
-    print(counts, '-- program launches checked for dataflow hazards:', sim.fakecuda_hazard_launches())
+    print(counts, '-- program launches checked for dataflow hazards:', sim.fakecuda_hazard_launches(),
+          '; declared dependencies the kernel would not wait for:', sim.fakecuda_unhonoured_dependencies())
     sys.exit(1 if counts.get('FAIL') else 0)
 
 
