@@ -48,6 +48,18 @@ def pytest_configure(config):
         config._bm_hostsim = lib
 
 
+# GPU tests written after the last visit to a B200 (they pass on the host simulation, tests/hostsim): run them after the tests that
+# have already passed on the hardware, so that `-x` reports a surprise in one of them without hiding the rest of the suite.
+NOT_YET_RUN_ON_A_B200 = ('test_ais_runs_shard_by_first_run', 'test_resident_dataset_taller_than_the_grid_limit', '[fuzz_', '-fuzz_')
+
+
+def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if it.get_closest_marker('gpu') and any(tag in it.nodeid for tag in NOT_YET_RUN_ON_A_B200)]
+    if late:
+        ids = set(id(it) for it in late)
+        items[:] = [it for it in items if id(it) not in ids] + late
+
+
 def pytest_unconfigure(config):
     lib = getattr(config, '_bm_hostsim', None)
     if lib is not None:
