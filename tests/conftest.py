@@ -50,7 +50,8 @@ def pytest_configure(config):
 
 # GPU tests written after the last visit to a B200 (they pass on the host simulation, tests/hostsim): run them after the tests that
 # have already passed on the hardware, so that `-x` reports a surprise in one of them without hiding the rest of the suite.
-NOT_YET_RUN_ON_A_B200 = ('test_ais_runs_shard_by_first_run', 'test_resident_dataset_taller_than_the_grid_limit', '[fuzz_', '-fuzz_')
+NOT_YET_RUN_ON_A_B200 = ('test_ais_runs_shard_by_first_run', 'test_resident_dataset_taller_than_the_grid_limit', '[fuzz_', '-fuzz_',
+                         'bernoulli_no_scalar_metrics_feg_only', 'bernoulli_2layer_partial_sampling')
 
 
 def pytest_collection_modifyitems(config, items):
