@@ -31,6 +31,9 @@ struct RbmTC : RbmSimt<float> {
     // cached programs, keyed by (rows, k, with_dw, input buffer is the resident dataset)
     std::map<std::tuple<int, int, int, int>, std::unique_ptr<TcProgram>> progs;
     int dw_splits = 1;
+    // distance between two split-K slices of dW: V*H rounded up to 8 floats, so that every slice starts on a 32-byte
+    // boundary whatever the shape (the vector paths of the epilogue, reduce_partials and the fused update rely on it)
+    size_t gstride() const { return ((size_t)V * H + 7) & ~(size_t)7; }
 
     RbmTC(Ctx* c, const bm_rbm_cfg& f) : RbmSimt<float>(c, f) {
         ldw = round_up(H, 64); ldv = round_up(V, 64); ldh = round_up(H, 64);
@@ -186,7 +189,7 @@ struct RbmTC : RbmSimt<float> {
                     g.B[0] = mat(hm_b.p, rows, H, ldh); g.neg[0] = true;
                 }
                 g.b_t[0] = true; g.K[0] = rows;
-                g.split_stride = (size_t)V * H; g.ld_f32 = H;
+                g.split_stride = gstride(); g.ld_f32 = H;
                 return g;
             };
             // The positive half depends on h0 only.  When the chain leaves CTA pairs idle (cfg2: 64 units per
@@ -209,13 +212,13 @@ struct RbmTC : RbmSimt<float> {
             if (pos_splits > 0) {
                 int neg_splits = std::max(1, std::min(total_pairs / pair_tiles, row_chunks));
                 dw_splits = pos_splits + neg_splits;
-                partials.ensure((size_t)dw_splits * V * H);
+                partials.ensure((size_t)dw_splits * gstride());
                 TcGemm gp = half(false);
                 gp.splits = pos_splits; gp.out_f32 = partials.p;
                 gp.n_deps = 1; gp.dep[0] = 0; gp.dep_all[0] = true;
                 gp.lane = LANE_SPARE;
                 TcGemm gn = half(true);
-                gn.splits = neg_splits; gn.out_f32 = partials.p + (size_t)pos_splits * V * H;
+                gn.splits = neg_splits; gn.out_f32 = partials.p + (size_t)pos_splits * gstride();
                 gn.n_deps = 2; gn.dep[0] = last_v; gn.dep[1] = last_h; gn.dep_all[0] = gn.dep_all[1] = true;
                 gn.lane = LANE_ALL;
                 // program order: the positive half right after h0, so that the spare pairs meet it first
@@ -234,7 +237,7 @@ struct RbmTC : RbmSimt<float> {
                 if (splits > 2 * row_chunks) splits = 2 * row_chunks;
                 dw_splits = splits;
                 g.splits = splits;
-                partials.ensure((size_t)splits * V * H);
+                partials.ensure((size_t)splits * gstride());
                 g.out_f32 = splits > 1 ? partials.p : stats.p;
                 g.n_deps = 3;
                 g.dep[0] = 0; g.dep[1] = last_v; g.dep[2] = last_h;
@@ -266,7 +269,7 @@ struct RbmTC : RbmSimt<float> {
         // one GPU: the split-K reduction is fused into the weight update; with peers the reduced gradient is
         // needed in memory for the all-reduce
         const bool fuse_reduce = ctx->nranks == 1 && dw_splits > 1 && H % 4 == 0 && ldw % 4 == 0;
-        if (dw_splits > 1 && !fuse_reduce) launch_reduce_partials(ctx, partials.p, (size_t)V * H, dw_splits, G, (size_t)V * H);
+        if (dw_splits > 1 && !fuse_reduce) launch_reduce_partials(ctx, partials.p, gstride(), dw_splits, G, (size_t)V * H);
         launch_cd_statistics_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, h0m_b.p, hm_b.p, ldh,
                                   rows, V, H, dvb_sum, dhb_sum, q_sum);                                           // :451-457
         allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
@@ -279,7 +282,7 @@ struct RbmTC : RbmSimt<float> {
         u.damp = (float)cfg.sparsity_damping; u.cost = (float)cfg.sparsity_cost; u.target = (float)cfg.sparsity_target;
         launch_bias_update<float>(ctx, u);
         if (fuse_reduce)
-            launch_weight_update_splitk(ctx, partials.p, (size_t)V * H, dw_splits, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr,
+            launch_weight_update_splitk(ctx, partials.p, gstride(), dw_splits, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr,
                                         (float)mom, Wb.p, ldw);
         else
             launch_weight_update<float>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr, (float)mom, Wb.p, ldw);

@@ -96,23 +96,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Every wait of the kernel is bounded: a wait that has not been satisfied after HANG_NS of wall time (a lost
+// arrival, a peer that never launched, stale dataflow counters) traps -- the launch fails with an error instead
+// of holding the GPU for ever.  The clock is only read every 4096 failed attempts.
+constexpr unsigned long long HANG_NS = 4000000000ull;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void hang_guard(uint32_t& n, unsigned long long& t0) {
+    if ((++n & 0xFFFu) == 0) {
+        const unsigned long long t = gtime();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > HANG_NS) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
-    do {
+    uint32_t n = 0; unsigned long long t0 = 0;
+    for (;;) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        hang_guard(n, t0);
+    }
 }
 // for waits that are expected to be long (epilogue warps waiting for an accumulator or a staging
 // buffer): sleep between attempts instead of spinning in the issue slots of the busy roles
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
+    uint32_t n = 0; unsigned long long t0 = 0;
     for (;;) {
         asm volatile(
             "{\n\t"
@@ -122,6 +138,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) break;
         __nanosleep(ns);
+        hang_guard(n, t0);
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
@@ -182,7 +199,6 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "+r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define DBG_MARK(slot) do { if (L.dbg && blockIdx.x == 0) L.dbg[(slot)] = (unsigned long long)clock64(); } while (0)
 // per-unit marks of CTA 0: slot 64 + ord * 8 + kind (ord = ordinal of the unit within this CTA, < 24)
 #define DBG_UNIT(kind, ord) do { if (L.dbg && blockIdx.x == 0 && (ord) < 24) L.dbg[64 + (ord) * 8 + (kind)] = (unsigned long long)clock64(); } while (0)
@@ -600,15 +616,16 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             // ---- dataflow: wait until the row blocks this unit reads have been written ----------
             if (ph->n_deps > 0) {
                 if (lane == 0) {
+                    uint32_t hn = 0; unsigned long long ht0 = 0;
                     for (int d = 0; d < ph->n_deps; ++d) {
                         const int* ctr = ph->dep_ctr[d];
                         const int need = ph->dep_need[d] * L.epoch;
                         if (ph->dep_groups[d] == 0) {
                             if (ph->dep_chunk_ctr) continue;          // handled chunk by chunk below
-                            while (ld_relaxed(ctr + u.m_group) < need) __nanosleep(64);
+                            while (ld_relaxed(ctr + u.m_group) < need) { __nanosleep(64); hang_guard(hn, ht0); }
                         } else {
                             for (int gq = 0; gq < ph->dep_groups[d]; ++gq)
-                                while (ld_relaxed(ctr + gq) < need) __nanosleep(64);
+                                while (ld_relaxed(ctr + gq) < need) { __nanosleep(64); hang_guard(hn, ht0); }
                         }
                     }
                     // acquire the producers' (generic-proxy) stores, then order them before this unit's
@@ -651,6 +668,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                         int ga = 0, gb = 0;
                         if (n < u.c_end) { const int j = (int)ph->k_order[n]; ga = (int)ph->k_dep_a[j]; gb = (int)ph->k_dep_b[j]; }
                         int ready_prefix = 0;
+                        uint32_t hn = 0; unsigned long long ht0 = 0;
                         for (;;) {
                             bool ok;
                             if (L.flags & 1) ok = n < u.c_end && ld_acquire(cdep + ga) >= need && (gb == ga || ld_acquire(cdep + gb) >= need);
@@ -660,6 +678,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                             if (m == 0xffffffffu) ready_prefix = 32;
                             if (ready_prefix > 0) break;
                             __nanosleep((uint32_t)L.poll_ns);
+                            hang_guard(hn, ht0);
                         }
                         fenced_upto = ci + ready_prefix;
                         if (L.dbg && blockIdx.x == 0 && ord == 1 && lane == 0 && ci - u.c_begin < 20) { L.dbg[456 + ci - u.c_begin] = (unsigned long long)clock64(); L.dbg[480 + ci - u.c_begin] = (unsigned long long)fenced_upto; }
@@ -1244,7 +1263,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         BM_CUDA(cudaMemsetAsync(prog.dev_counters, 0, prog.n_counters * sizeof(int), ctx->stream));
         prog.epoch = 0;
     }
-    ++prog.epoch;
+    // (the epoch is only advanced once the launch has been accepted: after a refused launch the counters of the
+    //  program are re-zeroed before its next launch instead of being waited on one epoch behind)
     TcLaunch L;
     memset(&L, 0, sizeof(L));
     L.phases = reinterpret_cast<const TcPhase*>(prog.dev_phases);
@@ -1252,7 +1272,7 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     L.total_units = unit;
     L.k0 = rng.k0; L.k1 = rng.k1; L.tick = rng.tick; L.row0 = rng.row0;
     L.batch_row = batch_row;
-    L.epoch = prog.epoch;
+    L.epoch = prog.epoch + 1;
     { static int pn = -1, en = -1;
       if (pn < 0) { const char* e = getenv("BM_TC_POLL_NS"); pn = e ? atoi(e) : 64; }
       if (en < 0) { const char* e = getenv("BM_TC_EPI_NS"); en = e ? atoi(e) : 128; }
@@ -1268,10 +1288,16 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
         BM_CUDA(cudaMemsetAsync(dbg_buf, 0, 1024 * sizeof(unsigned long long), ctx->stream));
         L.dbg = dbg_buf;
     }
-    upload_ops(ctx, ph, n);
     int max_bn = 16;
     for (int i = 0; i < n; ++i) max_bn = std::max(max_bn, ph[i].l.BN);
-    do_launch(ctx, L, cluster, flops, max_bn);
+    try {
+        upload_ops(ctx, ph, n);
+        do_launch(ctx, L, cluster, flops, max_bn);
+        ++prog.epoch;
+    } catch (...) {
+        prog.epoch = 0;
+        throw;
+    }
     if (dbg) {
         --dbg_left;
         unsigned long long h[1024];

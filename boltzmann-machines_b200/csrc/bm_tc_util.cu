@@ -263,7 +263,9 @@ void launch_cd_statistics_bf16(Ctx* ctx, const __nv_bfloat16* X, int ldx, const 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t stride, int splits, float* __restrict__ G, size_t n) {
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
-    if (i + 4 <= n) {
+    // 16-byte loads need every slice and G on a 16-byte boundary (callers pad the stride; checked here all the same)
+    const bool vec = (stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+    if (vec && i + 4 <= n) {
         float4 a = *reinterpret_cast<const float4*>(partial + i);
         for (int s = 1; s < splits; ++s) {
             const float4 b = *reinterpret_cast<const float4*>(partial + s * stride + i);
@@ -271,7 +273,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t
         }
         *reinterpret_cast<float4*>(G + i) = a;
     } else {
-        for (size_t j = i; j < n; ++j) {
+        for (size_t j = i; j < n && j < i + 4; ++j) {
             float a = partial[j];
             for (int s = 1; s < splits; ++s) a += partial[s * stride + j];
             G[j] = a;
@@ -316,7 +318,7 @@ __global__ void weight_update_splitk_kernel(const float* __restrict__ partial, s
 }
 void launch_weight_update_splitk(Ctx* ctx, const float* partial, size_t stride, int splits, float g_div, float* W, float* dW,
                                  int V, int H, const float* pen, float l2, float lr, float mom, __nv_bfloat16* Wb, int ldwb) {
-    BM_REQUIRE(H % 4 == 0 && ldwb % 4 == 0, "fused weight update needs n_hidden % 4 == 0");
+    BM_REQUIRE(H % 4 == 0 && ldwb % 4 == 0 && (stride & 3) == 0, "fused weight update needs n_hidden % 4 == 0 and 16-byte aligned slices");
     const size_t n = (size_t)V * H;
     const size_t threads = n / 4;
     weight_update_splitk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(partial, stride, splits, g_div, W, dW, H, n,
