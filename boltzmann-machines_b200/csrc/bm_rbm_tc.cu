@@ -20,7 +20,8 @@ struct RbmTC : RbmSimt<float> {
     typedef __nv_bfloat16 bf16;
     int ldw, ldv, ldh;
     DevBuf<bf16> Wb, Xb, h0m_b, h0s_b, vm_b, vs_b, hm_b, hs_b, data_b;
-    DevBuf<float> partials, widen;
+    DevBuf<float> partials, vparts, tstats, widen, q_alt;
+    DevBuf<bf16> ones;             // [rows, 64] of 1.0: the B operand that turns a GEMM over the batch rows into column sums
     int tc_cap = 0;
     bool tc_kinds;
     // state of the last chain
@@ -30,15 +31,22 @@ struct RbmTC : RbmSimt<float> {
     bool last_was_tc = false;
     // cached programs, keyed by (rows, k, with_dw, input buffer is the resident dataset)
     std::map<std::tuple<int, int, int, int>, std::unique_ptr<TcProgram>> progs;
-    int dw_splits = 1;
-    // distance between two split-K slices of dW: V*H rounded up to 8 floats, so that every slice starts on a 32-byte
-    // boundary whatever the shape (the vector paths of the epilogue, reduce_partials and the fused update rely on it)
-    size_t gstride() const { return ((size_t)V * H + 7) & ~(size_t)7; }
+    int dw_splits = 1, v_splits = 1;
+    // The batch buffers (X, v_k) carry two constant columns behind their V data columns -- (1, 0) for X, (1, 1) for v_k --
+    // so that the dW GEMMs, run over V + 2 rows, also deliver sum(h0 - h_k) (row V) and -sum(h_k) (row V + 1): the
+    // column statistics of base_rbm.py:453,457 cost no pass of their own.  sum(X - v_k) (:451) is two more ops of the
+    // program ([V x 1] = X^T 1 - v_k^T 1).  Everything is summed and applied by ONE kernel (launch_cd_tail).
+    int VM() const { return V + 2; }
+    // distance between two split-K slices: rounded up to 8 floats, so that every slice starts on a 32-byte boundary
+    // whatever the shape (the vector paths of the epilogue, reduce_partials and the update rely on it)
+    size_t gstride() const { return ((size_t)VM() * H + 7) & ~(size_t)7; }
+    size_t vstride() const { return ((size_t)V + 7) & ~(size_t)7; }
 
     RbmTC(Ctx* c, const bm_rbm_cfg& f) : RbmSimt<float>(c, f) {
-        ldw = round_up(H, 64); ldv = round_up(V, 64); ldh = round_up(H, 64);
+        ldw = round_up(H, 64); ldv = round_up(V + 2, 64); ldh = round_up(H, 64);
         Wb.ensure((size_t)V * ldw);
         Wb.zero(ctx->stream);
+        q_alt.ensure(H); q_alt.zero(ctx->stream);
         tc_kinds = (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
         reserve_tc(f.max_batch > 0 ? f.max_batch : 1);
     }
@@ -51,6 +59,11 @@ struct RbmTC : RbmSimt<float> {
         h0m_b.ensure((size_t)rows * ldh); h0s_b.ensure((size_t)rows * ldh);
         hm_b.ensure((size_t)rows * ldh); hs_b.ensure((size_t)rows * ldh);
         widen.ensure((size_t)rows * (V > H ? V : H));
+        ones.ensure((size_t)rows * 64);
+        launch_fill_bf16(ctx, ones.p, (size_t)rows * 64, 1.0f);
+        launch_set_column_pair(ctx, Xb.p, ldv, (size_t)rows, V, 1.0f, 0.0f);
+        launch_set_column_pair(ctx, vm_b.p, ldv, (size_t)rows, V, 1.0f, 1.0f);
+        launch_set_column_pair(ctx, vs_b.p, ldv, (size_t)rows, V, 1.0f, 1.0f);
         progs.clear();                         // buffers moved: cached descriptors are stale
     }
 
@@ -69,6 +82,7 @@ struct RbmTC : RbmSimt<float> {
         RbmSimt<float>::set_data(X, n_rows);
         data_b.ensure((size_t)n_rows * ldv);
         launch_f32_to_bf16(ctx, data.p, V, data_b.p, ldv, (int)n_rows, V);
+        launch_set_column_pair(ctx, data_b.p, ldv, (size_t)n_rows, V, 1.0f, 0.0f);
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         progs.clear();
     }
@@ -173,28 +187,41 @@ struct RbmTC : RbmSimt<float> {
         }
         if (with_dw) {
             // dW_positive - dW_negative (base_rbm.py:447-448): G = X^T h0_means - v_k^T h_k_means, K = the batch rows,
-            // split over K so that every CTA pair gets a slice; the slices are summed by the weight update.
+            // split over K so that every CTA pair gets a slice; the slices are summed by the update kernel.  The operands'
+            // constant columns add the rows V, V + 1 (see VM()).
             const int total_pairs = ctx->sm_count / 2;
-            const int pair_tiles = ((V + 255) / 256) * ((H + 255) / 256);
+            const int pair_tiles = ((VM() + 255) / 256) * ((H + 255) / 256);
+            const int v_groups = (V + 255) / 256;
             const int row_chunks = (rows + 63) / 64;
-            auto half = [&](bool negative) {
+            auto operand_x = [&](TcGemm& g, int pr, int cols) {
+                g.A[pr] = mat(X_b, X_rows_total, cols, X_ld); g.a_t[pr] = true; g.a_batch[pr] = resident;
+                if (!resident) g.a_k0[pr] = X_row0;
+                g.K[pr] = rows;
+            };
+            auto operand_v = [&](TcGemm& g, int pr, int cols) {
+                g.A[pr] = mat(vstate_b, rows, cols, ldv); g.a_t[pr] = true; g.neg[pr] = true; g.K[pr] = rows;
+            };
+            auto dw_op = [&](bool pos, bool neg) {
                 TcGemm g;
-                g.M = V; g.N = H; g.n_pairs = 1;
-                if (!negative) {
-                    g.A[0] = mat(X_b, X_rows_total, V, X_ld); g.a_t[0] = true; g.a_batch[0] = resident;
-                    if (!resident) g.a_k0[0] = X_row0;
-                    g.B[0] = mat(h0m_b.p, rows, H, ldh);
-                } else {
-                    g.A[0] = mat(vstate_b, rows, V, ldv); g.a_t[0] = true;
-                    g.B[0] = mat(hm_b.p, rows, H, ldh); g.neg[0] = true;
-                }
-                g.b_t[0] = true; g.K[0] = rows;
+                g.M = VM(); g.N = H; g.n_pairs = (pos && neg) ? 2 : 1;
+                int pr = 0;
+                if (pos) { operand_x(g, pr, VM()); g.B[pr] = mat(h0m_b.p, rows, H, ldh); g.b_t[pr] = true; ++pr; }
+                if (neg) { operand_v(g, pr, VM()); g.B[pr] = mat(hm_b.p, rows, H, ldh); g.b_t[pr] = true; }
                 g.split_stride = gstride(); g.ld_f32 = H;
                 return g;
             };
-            // The positive half depends on h0 only.  When the chain leaves CTA pairs idle (cfg2: 64 units per
-            // half-step on 74 pairs) and is long enough to hide it, the positive half runs on those pairs BESIDE the
-            // chain and only the negative half is left for the end of the step.
+            auto colsum_op = [&](bool pos, bool neg) {            // [V x 1] = X^T 1 - v_k^T 1
+                TcGemm g;
+                g.M = V; g.N = 1; g.n_pairs = (pos && neg) ? 2 : 1;
+                int pr = 0;
+                if (pos) { operand_x(g, pr, V); g.B[pr] = mat(ones.p, rows, 64, 64); g.b_t[pr] = true; ++pr; }
+                if (neg) { operand_v(g, pr, V); g.B[pr] = mat(ones.p, rows, 64, 64); g.b_t[pr] = true; }
+                g.split_stride = vstride(); g.ld_f32 = 1;
+                return g;
+            };
+            // The positive statistics depend on the input and h0 only.  When the chain leaves CTA pairs idle (cfg2: 64 units
+            // per half-step on 74 pairs) and is long enough to hide them, they run on those pairs BESIDE the chain and only the
+            // negative ones are left for the end of the step.
             if (prog.chain_units < 0)            // shapes are fixed per cached program: plan once
                 for (const TcGemm& o : ops) prog.chain_units = std::max(prog.chain_units, tc_plan_units(ctx, o));
             const int chain_units = prog.chain_units;
@@ -210,35 +237,52 @@ struct RbmTC : RbmSimt<float> {
             { const char* e = getenv("BM_TC_DW_OVERLAP"); if (e && !atoi(e)) pos_splits = 0; }
             const int last_v = (int)ops.size() - 2, last_h = (int)ops.size() - 1;
             if (pos_splits > 0) {
-                int neg_splits = std::max(1, std::min(total_pairs / pair_tiles, row_chunks));
+                const int neg_splits = std::max(1, std::min(total_pairs / pair_tiles, row_chunks));
+                const int xs = std::max(1, std::min(spare / v_groups, row_chunks));
+                const int vs = std::max(1, std::min(2 * spare / v_groups, row_chunks));
                 dw_splits = pos_splits + neg_splits;
+                v_splits = xs + vs;
                 partials.ensure((size_t)dw_splits * gstride());
-                TcGemm gp = half(false);
+                vparts.ensure((size_t)v_splits * vstride());
+                TcGemm gx = colsum_op(true, false);                // no dependency: the input is there from the start
+                gx.splits = xs; gx.out_f32 = vparts.p; gx.lane = LANE_SPARE;
+                TcGemm gp = dw_op(true, false);
                 gp.splits = pos_splits; gp.out_f32 = partials.p;
                 gp.n_deps = 1; gp.dep[0] = 0; gp.dep_all[0] = true;
                 gp.lane = LANE_SPARE;
-                TcGemm gn = half(true);
-                gn.splits = neg_splits; gn.out_f32 = partials.p + (size_t)pos_splits * gstride();
-                gn.n_deps = 2; gn.dep[0] = last_v; gn.dep[1] = last_h; gn.dep_all[0] = gn.dep_all[1] = true;
-                gn.lane = LANE_ALL;
-                // program order: the positive half right after h0, so that the spare pairs meet it first
+                // program order: right after h0, so that the spare pairs meet them first
                 ops.insert(ops.begin() + 1, gp);
-                for (size_t i = 2; i < ops.size(); ++i)
-                    for (int d = 0; d < ops[i].n_deps; ++d) if (ops[i].dep[d] >= 1) ops[i].dep[d] += 1;
-                gn.dep[0] += 1; gn.dep[1] += 1;
+                ops.insert(ops.begin() + 1, gx);
+                for (size_t i = 3; i < ops.size(); ++i)
+                    for (int d = 0; d < ops[i].n_deps; ++d) if (ops[i].dep[d] >= 1) ops[i].dep[d] += 2;
+                TcGemm gv = colsum_op(false, true);                // beside the last hidden half-step
+                gv.splits = vs; gv.out_f32 = vparts.p + (size_t)xs * vstride();
+                gv.n_deps = 1; gv.dep[0] = last_v + 2; gv.dep_all[0] = true;
+                gv.lane = LANE_SPARE;
+                ops.push_back(gv);
+                TcGemm gn = dw_op(false, true);
+                gn.splits = neg_splits; gn.out_f32 = partials.p + (size_t)pos_splits * gstride();
+                gn.n_deps = 2; gn.dep[0] = last_v + 2; gn.dep[1] = last_h + 2; gn.dep_all[0] = gn.dep_all[1] = true;
+                gn.lane = LANE_ALL;
                 ops.push_back(gn);
             } else {
-                TcGemm g = half(false);
-                const TcGemm gneg = half(true);
-                g.n_pairs = 2;
-                g.A[1] = gneg.A[0]; g.a_t[1] = true; g.B[1] = gneg.B[0]; g.b_t[1] = true; g.K[1] = rows; g.neg[1] = true;
+                TcGemm gc = colsum_op(true, true);
+                int vs = std::max(1, std::min(total_pairs / v_groups, 2 * row_chunks));
+                v_splits = vs;
+                gc.splits = vs;
+                vparts.ensure((size_t)vs * vstride());
+                gc.out_f32 = vparts.p;
+                gc.n_deps = 1; gc.dep[0] = last_v; gc.dep_all[0] = true;
+                gc.lane = LANE_ALL;
+                ops.push_back(gc);
+                TcGemm g = dw_op(true, true);
                 int splits = total_pairs / (pair_tiles > 0 ? pair_tiles : 1);
                 if (splits < 1) splits = 1;
                 if (splits > 2 * row_chunks) splits = 2 * row_chunks;
                 dw_splits = splits;
                 g.splits = splits;
                 partials.ensure((size_t)splits * gstride());
-                g.out_f32 = splits > 1 ? partials.p : stats.p;
+                g.out_f32 = partials.p;
                 g.n_deps = 3;
                 g.dep[0] = 0; g.dep[1] = last_v; g.dep[2] = last_h;
                 g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
@@ -262,30 +306,26 @@ struct RbmTC : RbmSimt<float> {
             run_metrics(mask, rows, seed, tick, row0, out);
         }
 
-        float* G = stats.p;
-        float* dvb_sum = G + (size_t)V * H;
-        float* dhb_sum = dvb_sum + V;
-        float* q_sum = dhb_sum + H;
-        // one GPU: the split-K reduction is fused into the weight update; with peers the reduced gradient is
-        // needed in memory for the all-reduce
-        const bool fuse_reduce = ctx->nranks == 1 && dw_splits > 1 && H % 4 == 0 && ldw % 4 == 0;
-        if (dw_splits > 1 && !fuse_reduce) launch_reduce_partials(ctx, partials.p, gstride(), dw_splits, G, (size_t)V * H);
-        launch_cd_statistics_bf16(ctx, X_b + (size_t)X_row0 * X_ld, X_ld, vstate_b, ldv, h0m_b.p, hm_b.p, ldh,
-                                  rows, V, H, dvb_sum, dhb_sum, q_sum);                                           // :451-457
-        allreduce_sum(ctx, stats.p, (size_t)V * H + V + 2 * (size_t)H, false);
-        const float N = (float)((double)rows * ctx->nranks);
-
-        BiasUpdate<float> u;
-        u.V = V; u.H = H; u.dvb_raw = dvb_sum; u.dhb_raw = dhb_sum; u.qsum = q_sum;
-        u.vb = vb.p; u.hb = hb.p; u.dvb = dvb.p; u.dhb = dhb.p; u.q_means = q.p; u.pen = pen.p;
-        u.n_div = N; u.lr = (float)lr; u.mom = (float)mom;
-        u.damp = (float)cfg.sparsity_damping; u.cost = (float)cfg.sparsity_cost; u.target = (float)cfg.sparsity_target;
-        launch_bias_update<float>(ctx, u);
-        if (fuse_reduce)
-            launch_weight_update_splitk(ctx, partials.p, gstride(), dw_splits, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr,
-                                        (float)mom, Wb.p, ldw);
-        else
-            launch_weight_update<float>(ctx, G, H, N, W.p, dW.p, V, H, pen.p, (float)cfg.l2, (float)lr, (float)mom, Wb.p, ldw);
+        CdTail t{};
+        t.V = V; t.H = H;
+        t.part = partials.p; t.stride = gstride(); t.splits = dw_splits;
+        t.vpart = vparts.p; t.vstride = vstride(); t.vsplits = v_splits;
+        if (ctx->nranks > 1) {
+            // with peers: sum this rank's slices, one all-reduce over [G' | sum(X - v_k)], then the same update on every rank
+            tstats.ensure(gstride() + vstride());
+            launch_reduce_partials(ctx, partials.p, gstride(), dw_splits, tstats.p, (size_t)VM() * H);
+            launch_reduce_partials(ctx, vparts.p, vstride(), v_splits, tstats.p + gstride(), (size_t)V);
+            allreduce_sum(ctx, tstats.p, gstride() + vstride(), false);
+            t.part = tstats.p; t.splits = 1; t.vpart = tstats.p + gstride(); t.vsplits = 1;
+        }
+        t.n_div = (float)((double)rows * ctx->nranks);
+        t.lr = (float)lr; t.mom = (float)mom; t.l2 = (float)cfg.l2;
+        t.damp = (float)cfg.sparsity_damping; t.cost = (float)cfg.sparsity_cost; t.target = (float)cfg.sparsity_target;
+        t.W = W.p; t.dW = dW.p; t.vb = vb.p; t.hb = hb.p; t.dvb = dvb.p; t.dhb = dhb.p;
+        t.q_old = q.p; t.q_new = q_alt.p; t.pen = pen.p;
+        t.Wb = Wb.p; t.ldwb = ldw;
+        launch_cd_tail(ctx, t);
+        std::swap(q.p, q_alt.p);               // (same size; "q_means" names the current one)
     }
 
     void transform(const void* X_host, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) override {

@@ -3,6 +3,7 @@
 // Kernel in bm_tc.cu.
 #pragma once
 #include "bm_internal.h"
+#include "bm_tc_desc.h"
 #include <vector>
 
 namespace bm {
@@ -103,5 +104,10 @@ void launch_reduce_partials(Ctx* ctx, const float* partial, size_t stride, int s
 // W += momentum step of (sum_s partial[s]) / g_div, plus the bf16 shadow, in one pass (n_hidden % 4 == 0)
 void launch_weight_update_splitk(Ctx* ctx, const float* partial, size_t stride, int splits, float g_div, float* W, float* dW,
                                  int V, int H, const float* pen, float l2, float lr, float mom, __nv_bfloat16* Wb, int ldwb);
+
+void launch_cd_tail(Ctx* ctx, const CdTail& t);
+// buf[r, col0] = a, buf[r, col0 + 1] = b for r < rows (the two constant columns of a batch buffer)
+void launch_set_column_pair(Ctx* ctx, __nv_bfloat16* buf, int ld, size_t rows, int col0, float a, float b);
+void launch_fill_bf16(Ctx* ctx, __nv_bfloat16* buf, size_t n, float v);
 
 }  // namespace bm

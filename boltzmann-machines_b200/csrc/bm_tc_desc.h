@@ -65,4 +65,23 @@ struct TcLaunch {
     int poll_ns, epi_ns;             // back-off of the granule polls / of the epilogue's wait for an accumulator
 };
 
+// ---- the whole parameter update of a CD step in ONE launch (base_rbm.py:445-474) --------------------------------------
+// The statistics arrive as split-K slices written by the step's program:
+//   part : `splits` slices of [(V + 2) x H] fp32: rows 0..V-1  = X^T h0_means - v_k^T h_k_means   (:447-448)
+//                                                 row  V       = sum_rows (h0_means - h_k_means)     (:453)
+//                                                 row  V + 1   = - sum_rows h_k_means                (:457, negated)
+//          (rows V and V+1 come out of the same GEMMs: the batch buffers carry two constant columns behind the V data columns)
+//   vpart: `vsplits` slices of [V] fp32 whose sum is sum_rows (X - v_k)                               (:451)
+// Blocks [0, weight blocks) update W / dW / the bf16 shadow (sparsity penalty recomputed from q_old and row V+1);
+// the remaining blocks update vb, hb, their accumulators, q_means (into q_new: q_old is still being read) and `pen`.
+struct CdTail {
+    int V, H;
+    const float* part;  size_t stride;  int splits;
+    const float* vpart; size_t vstride; int vsplits;
+    float n_div, lr, mom, l2, damp, cost, target;
+    float *W, *dW, *vb, *hb, *dvb, *dhb;
+    const float* q_old; float* q_new; float* pen;
+    __nv_bfloat16* Wb; int ldwb;
+};
+
 }  // namespace bm

@@ -13,9 +13,9 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int lds, __nv_
     const int r = blockIdx.y;
     if (c >= cols) return;
     const float a = src[(size_t)r * lds + c];
-    const float b = (c + 1 < cols) ? src[(size_t)r * lds + c + 1] : 0.f;
-    if (c + 1 < cols || c + 1 < ldd)
-        *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * ldd + c) = __floats2bfloat162_rn(a, b);
+    // (columns >= cols of the destination are never written: batch buffers keep constant columns there)
+    if (c + 1 < cols)
+        *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * ldd + c) = __floats2bfloat162_rn(a, src[(size_t)r * lds + c + 1]);
     else
         dst[(size_t)r * ldd + c] = __float2bfloat16_rn(a);
 }
@@ -323,6 +323,121 @@ void launch_weight_update_splitk(Ctx* ctx, const float* partial, size_t stride, 
     const size_t threads = n / 4;
     weight_update_splitk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(partial, stride, splits, g_div, W, dW, H, n,
                                                                                            pen, l2, lr, mom, Wb, ldwb);
+    count_launch(ctx);
+}
+
+
+// ---- one launch for the whole update of a CD step (see CdTail in bm_tc.h) -----------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) cd_tail_kernel(const CdTail t, unsigned w_blocks) {
+    const int V = t.V, H = t.H;
+    if (blockIdx.x < w_blocks) {
+        // ---- weights: VEC consecutive hidden units of one visible unit per thread ----
+        const size_t n = (size_t)V * H;
+        const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+        if (i >= n) return;
+        const int h = (int)(i % (size_t)H);
+        const size_t v = i / (size_t)H;
+        float g[VEC], pen[VEC], w[VEC], d0[VEC];
+        if constexpr (VEC == 4) {
+            float4 a = *reinterpret_cast<const float4*>(t.part + i);
+            for (int s = 1; s < t.splits; ++s) {
+                const float4 b = *reinterpret_cast<const float4*>(t.part + (size_t)s * t.stride + i);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+            const float4 w4 = *reinterpret_cast<const float4*>(t.W + i), d4 = *reinterpret_cast<const float4*>(t.dW + i);
+            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w; d0[0] = d4.x; d0[1] = d4.y; d0[2] = d4.z; d0[3] = d4.w;
+        } else {
+            float a = t.part[i];
+            for (int s = 1; s < t.splits; ++s) a += t.part[(size_t)s * t.stride + i];
+            g[0] = a; w[0] = t.W[i]; d0[0] = t.dW[i];
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) pen[j] = 0.f;
+        if (t.cost != 0.f) {                                     // base_rbm.py:457-461
+            const size_t qrow = (size_t)(V + 1) * H + h;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float qs = 0.f;
+                for (int s = 0; s < t.splits; ++s) qs += t.part[(size_t)s * t.stride + qrow + j];
+                const float q = t.damp * t.q_old[h + j] + (1.0f - t.damp) * (-qs);
+                pen[j] = t.cost * (q - t.target);
+            }
+        }
+        float d[VEC], wn[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            d[j] = t.lr * (t.mom * d0[j] + (g[j] / t.n_div - t.l2 * w[j] - pen[j]));     // :449, :462, :467
+            wn[j] = w[j] + d[j];                                                           // :468
+        }
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4*>(t.dW + i) = make_float4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<float4*>(t.W + i) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(wn[0], wn[1]), hi = __floats2bfloat162_rn(wn[2], wn[3]);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(t.Wb + v * (size_t)t.ldwb + h) = pk;
+        } else {
+            t.dW[i] = d[0]; t.W[i] = wn[0];
+            t.Wb[v * (size_t)t.ldwb + h] = __float2bfloat16_rn(wn[0]);
+        }
+        return;
+    }
+    // ---- biases, sparsity statistics ----
+    const int i = (int)(blockIdx.x - w_blocks) * blockDim.x + threadIdx.x;
+    if (i < H) {
+        float ds = 0.f, qs = 0.f;
+        for (int s = 0; s < t.splits; ++s) {
+            ds += t.part[(size_t)s * t.stride + (size_t)V * H + i];
+            qs += t.part[(size_t)s * t.stride + (size_t)(V + 1) * H + i];
+        }
+        const float q = t.damp * t.q_old[i] + (1.0f - t.damp) * (-qs);                     // :457-459
+        t.q_new[i] = q;
+        const float pen = t.cost * (q - t.target);
+        t.pen[i] = pen;
+        const float g = ds / t.n_div - pen;                                                // :453, :461
+        const float d = t.lr * (t.mom * t.dhb[i] + g);                                     // :473-474
+        t.dhb[i] = d;
+        t.hb[i] += d;
+    }
+    if (i < V) {
+        float vs = 0.f;
+        for (int s = 0; s < t.vsplits; ++s) vs += t.vpart[(size_t)s * t.vstride + i];
+        const float d = t.lr * (t.mom * t.dvb[i] + vs / t.n_div);                          // :451, :470-471
+        t.dvb[i] = d;
+        t.vb[i] += d;
+    }
+}
+void launch_cd_tail(Ctx* ctx, const CdTail& t) {
+    const bool vec = t.H % 4 == 0 && t.ldwb % 4 == 0 && (t.stride & 3) == 0 && (reinterpret_cast<uintptr_t>(t.part) & 15) == 0;
+    const size_t items = ((size_t)t.V * t.H) / (vec ? 4 : 1);
+    const unsigned w_blocks = (unsigned)((items + 255) / 256);
+    const int nb = t.V > t.H ? t.V : t.H;
+    const unsigned b_blocks = (unsigned)((nb + 255) / 256);
+    if (vec) cd_tail_kernel<4><<<w_blocks + b_blocks, 256, 0, ctx->stream>>>(t, w_blocks);
+    else cd_tail_kernel<1><<<w_blocks + b_blocks, 256, 0, ctx->stream>>>(t, w_blocks);
+    count_launch(ctx);
+}
+
+__global__ void set_column_pair_kernel(__nv_bfloat16* __restrict__ buf, int ld, size_t rows, int col0, float a, float b) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    buf[r * (size_t)ld + col0] = __float2bfloat16_rn(a);
+    buf[r * (size_t)ld + col0 + 1] = __float2bfloat16_rn(b);
+}
+void launch_set_column_pair(Ctx* ctx, __nv_bfloat16* buf, int ld, size_t rows, int col0, float a, float b) {
+    if (rows == 0) return;
+    set_column_pair_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(buf, ld, rows, col0, a, b);
+    count_launch(ctx);
+}
+__global__ void fill_bf16_kernel(__nv_bfloat16* __restrict__ buf, size_t n, float v) {
+    const __nv_bfloat16 x = __float2bfloat16_rn(v);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = x;
+}
+void launch_fill_bf16(Ctx* ctx, __nv_bfloat16* buf, size_t n, float v) {
+    if (n == 0) return;
+    const size_t blocks = (n + 255) / 256;
+    fill_bf16_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, ctx->stream>>>(buf, n, v);
     count_launch(ctx);
 }
 

@@ -267,7 +267,6 @@ static void k_f32_to_bf16(void** a) {
         for (int c = 0; c < cols; c += 2) {
             dst[(size_t)r * ldd + c] = f2bf(src[(size_t)r * lds + c]);
             if (c + 1 < cols) dst[(size_t)r * ldd + c + 1] = f2bf(src[(size_t)r * lds + c + 1]);
-            else if (c + 1 < ldd) dst[(size_t)r * ldd + c + 1] = f2bf(0.f);
         }
 }
 static void k_bf16_to_f32(void** a) {
@@ -314,6 +313,50 @@ static void k_weight_update_splitk(void** a) {
         const float wn = W[i] + d;
         dW[i] = d; W[i] = wn; Wb[v * (size_t)ldwb + h] = f2bf(wn);
     }
+}
+// cd_tail_kernel (bm_tc_util.cu): slices of [(V + 2) x H] and of [V] -> the whole parameter update of a CD step
+static void k_cd_tail(void** a) {
+    const bm::CdTail& t = *reinterpret_cast<const bm::CdTail*>(a[0]);
+    const int V = t.V, H = t.H;
+    if ((t.stride & 3) != 0 && H % 4 == 0) report_violation("cd_tail: slices not 16-byte aligned although the vector path is taken");
+    auto part = [&](size_t i) { float x = t.part[i]; for (int s = 1; s < t.splits; ++s) x += t.part[(size_t)s * t.stride + i]; return x; };
+    std::vector<float> pen(H, 0.f), qn(H);
+    for (int h = 0; h < H; ++h) {
+        float qs = 0.f;
+        for (int s = 0; s < t.splits; ++s) qs += t.part[(size_t)s * t.stride + (size_t)(V + 1) * H + h];
+        qn[h] = t.damp * t.q_old[h] + (1.0f - t.damp) * (-qs);
+        pen[h] = t.cost * (qn[h] - t.target);
+    }
+    for (size_t v = 0; v < (size_t)V; ++v)
+        for (int h = 0; h < H; ++h) {
+            const size_t i = v * H + h;
+            const float p = t.cost != 0.f ? pen[h] : 0.f;
+            const float d = t.lr * (t.mom * t.dW[i] + (part(i) / t.n_div - t.l2 * t.W[i] - p));
+            const float wn = t.W[i] + d;
+            t.dW[i] = d; t.W[i] = wn; t.Wb[v * (size_t)t.ldwb + h] = f2bf(wn);
+        }
+    for (int h = 0; h < H; ++h) {
+        float ds = 0.f;
+        for (int s = 0; s < t.splits; ++s) ds += t.part[(size_t)s * t.stride + (size_t)V * H + h];
+        t.q_new[h] = qn[h]; t.pen[h] = pen[h];
+        const float d = t.lr * (t.mom * t.dhb[h] + (ds / t.n_div - pen[h]));
+        t.dhb[h] = d; t.hb[h] += d;
+    }
+    for (int v = 0; v < V; ++v) {
+        float vs = 0.f;
+        for (int s = 0; s < t.vsplits; ++s) vs += t.vpart[(size_t)s * t.vstride + v];
+        const float d = t.lr * (t.mom * t.dvb[v] + vs / t.n_div);
+        t.dvb[v] = d; t.vb[v] += d;
+    }
+}
+static void k_set_column_pair(void** a) {
+    __nv_bfloat16* buf = arg<__nv_bfloat16*>(a, 0); const int ld = arg<int>(a, 1); const size_t rows = arg<size_t>(a, 2);
+    const int col0 = arg<int>(a, 3); const float x = arg<float>(a, 4), y = arg<float>(a, 5);
+    for (size_t r = 0; r < rows; ++r) { buf[r * (size_t)ld + col0] = f2bf(x); buf[r * (size_t)ld + col0 + 1] = f2bf(y); }
+}
+static void k_fill_bf16(void** a) {
+    __nv_bfloat16* buf = arg<__nv_bfloat16*>(a, 0); const size_t n = arg<size_t>(a, 1); const float v = arg<float>(a, 2);
+    for (size_t i = 0; i < n; ++i) buf[i] = f2bf(v);
 }
 static void k_sqdiff_bf16_partial(void** a, dim3 grid) {
     const __nv_bfloat16* P = arg<const __nv_bfloat16*>(a, 0); const int ldp = arg<int>(a, 1); const __nv_bfloat16* Q = arg<const __nv_bfloat16*>(a, 2);
@@ -726,6 +769,9 @@ bool execute(const std::string& name, dim3 grid, dim3, void** args) {
     if (has("bf16_to_f32_kernel")) { k_bf16_to_f32(args); return true; }
     if (has("reduce_partials_kernel")) { k_reduce_partials(args); return true; }
     if (has("weight_update_splitk_kernel")) { k_weight_update_splitk(args); return true; }
+    if (has("cd_tail_kernel")) { k_cd_tail(args); return true; }
+    if (has("set_column_pair_kernel")) { k_set_column_pair(args); return true; }
+    if (has("fill_bf16_kernel")) { k_fill_bf16(args); return true; }
     if (has("sqdiff_bf16_partial_kernel")) { k_sqdiff_bf16_partial(args, grid); return true; }
     if (has("sqdiff_bf16_finish_kernel")) { k_finish_sum(args); return true; }
     if (has("u8_to_bf16_kernel")) { k_u8_to_bf16(args); return true; }

@@ -49,4 +49,4 @@ def test_bench_contract_on_the_host_simulation(tmp_path):
     assert set(out['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert out['e2e']['h2d_bytes_per_step'] == 4096 * 784          # one byte per visible unit and row
-    assert out['gpu_launches'] == 5 * out['steps']                  # program, 2 x column statistics, bias update, weight update
+    assert out['gpu_launches'] == 2 * out['steps']                  # the step's program and the update kernel
