@@ -441,11 +441,15 @@ class CudaDBM(object):
         c.n_hiddens, c.h_kinds, c.h_n_samples, c.sample_h, c.sparsity_target, c.sparsity_cost = self._keep
         c.v_kind = UNIT_KINDS[cfg.get('v_kind', 'bernoulli')]
         c.dtype = DTYPES[self.dt.name]
-        # The DBM's default engine is the storage-precision CUDA-core one.  compute='bf16' (or BM_DBM_COMPUTE=bf16)
-        # opts a float32 model with Bernoulli hidden layers into the tensor-core engine (csrc/bm_dbm_tc.cuh).
+        # float32 models with Bernoulli hidden layers (binary or Gaussian visibles) run on the tensor-core engine
+        # (csrc/bm_dbm_tc.cuh: bf16 operands, fp32 accumulation) -- the same rule as DbmTC::supports(); compute='fp32'
+        # (or BM_DBM_COMPUTE / BM_COMPUTE = fp32) selects the storage-precision CUDA-core engine, which every other
+        # model uses anyway.
         compute = 'fp32'
-        if self.dt == np.float32:
-            compute = cfg.get('compute') or os.environ.get('BM_DBM_COMPUTE') or 'fp32'
+        tc_ok = (self.dt == np.float32 and cfg.get('v_kind', 'bernoulli') in ('bernoulli', 'gaussian') and
+                 all(k == 'bernoulli' for k in cfg.get('h_kinds', ['bernoulli'] * self.L)))
+        if tc_ok:
+            compute = cfg.get('compute') or os.environ.get('BM_DBM_COMPUTE') or os.environ.get('BM_COMPUTE') or 'bf16'
         self.compute = compute
         c.compute = COMPUTE[compute]
         c.n_particles, c.batch_size = self.M, self.B

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def make_cfg(V=30, Hs=(18, 11), dtype='float32', **kw):
     cfg = dict(n_visible=V, n_hiddens=list(Hs), v_kind='bernoulli', h_kinds=['bernoulli'] * len(Hs),
-               h_n_samples=[100.] * len(Hs), dtype=dtype, n_particles=12, batch_size=10, max_mf_updates=6, mf_tol=1e-6,
+               h_n_samples=[100.] * len(Hs), dtype=dtype, compute='fp32', n_particles=12, batch_size=10, max_mf_updates=6, mf_tol=1e-6,
                l2=1e-4, max_norm=3.0, sample_v=True, sample_h=[True] * len(Hs),
                sparsity_target=[0.2] * len(Hs), sparsity_cost=[0.01] * len(Hs), sparsity_damping=0.9)
     cfg.update(kw)

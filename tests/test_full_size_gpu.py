@@ -142,7 +142,7 @@ def test_full_size_dbm_step_matches_the_oracle():
     runs the whole step in a few seconds, so this is a direct comparison (fp32 CUDA-core path)."""
     V, Hs, B = 784, [512, 1024], 1024
     cfg = dict(n_visible=V, n_hiddens=Hs, v_kind='bernoulli', h_kinds=['bernoulli'] * 2, h_n_samples=[100.] * 2,
-               dtype='float32', n_particles=B, batch_size=B, max_mf_updates=25, mf_tol=1e-7, l2=1e-7, max_norm=6.0,
+               dtype='float32', compute='fp32', n_particles=B, batch_size=B, max_mf_updates=25, mf_tol=1e-7, l2=1e-7, max_norm=6.0,
                sample_v=True, sample_h=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[1e-4, 5e-5],
                sparsity_damping=0.9)
     rng = np.random.RandomState(2)

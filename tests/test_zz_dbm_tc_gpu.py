@@ -1,10 +1,8 @@
 """Tensor-core DBM engine (compute='bf16', csrc/bm_dbm_tc.cuh) against its bf16-operand emulation
 (oracle/dbm_bf16.py), the pinned fp32 oracle and exact enumeration.
 
-OPT-IN: the engine was written after the round's GPU budget was spent and has not run on a B200 yet, so these tests
-only run with BM_EXPERIMENTAL=1 (first thing to do on the next GPU visit:
-`BM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_dbm_tc_gpu.py -x -q`).  The default DBM engine (fp32
-CUDA cores) and its tests are unaffected."""
+First run on a B200 in round 2 (`profiles/r02_a_*`): all green, both operand-layout variants; the engine is the default for
+float32 models with Bernoulli hidden layers since."""
 import os
 
 import numpy as np
@@ -15,8 +13,7 @@ from oracle.dbm import OracleDBM
 from oracle.dbm_bf16 import OracleDBMbf16
 from oracle.rbm import bf16_round
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('BM_EXPERIMENTAL') != '1', reason='opt-in engine: set BM_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 
 def make_cfg(V=30, Hs=(18, 11), **kw):

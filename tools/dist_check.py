@@ -60,7 +60,7 @@ def main():
     dparams = {'W': (0.3 * rng.randn(20, 12)).astype(np.float32), 'W_1': (0.3 * rng.randn(12, 8)).astype(np.float32),
                'vb': (0.1 * rng.randn(20)).astype(np.float32), 'hb': (0.1 * rng.randn(12)).astype(np.float32),
                'hb_1': (0.1 * rng.randn(8)).astype(np.float32)}
-    dbm, dora = _native.CudaDBM(dcfg, ctx=ctx), OracleDBM(dcfg)
+    dbm, dora = _native.CudaDBM(dict(dcfg, compute='fp32'), ctx=ctx), OracleDBM(dcfg)
     dbm.set_params(dparams); dora.set_params(dparams)
     n_runs = 13                                    # does not divide evenly
     sharded = dbm.ais(n_runs, 50, 1, 4321)         # collective: every rank calls it
@@ -79,7 +79,7 @@ def main():
                     n_particles=M, batch_size=B, max_mf_updates=6, mf_tol=1e-3, l2=1e-4, max_norm=1.2, sample_v=True,
                     sample_h=[True, True], sparsity_target=[0.2, 0.1], sparsity_cost=[0.01, 0.005], sparsity_damping=0.8)
     Xd = (rng.rand(3, Bd * world, 20) < 0.3).astype(np.float32)
-    deng, dref = _native.CudaDBM(dcfg2(Bd, Md), ctx=ctx), OracleDBM(dcfg2(Bd * world, Md * world))
+    deng, dref = _native.CudaDBM(dict(dcfg2(Bd, Md), compute='fp32'), ctx=ctx), OracleDBM(dcfg2(Bd * world, Md * world))
     for e in (deng, dref):
         e.set_params(dparams)
         e.init_particles(4242)
@@ -100,12 +100,8 @@ def main():
     print('rank {0} DBM data parallel: max |engine - oracle(global)| = {1:.3e}, metrics agree: {2}'.format(rank, derr, dok), flush=True)
     ok = ok and dok and derr < 5e-5
     deng.close()
-    # the same contract for the tensor-core DBM engine (opt-in, compute='bf16'): sharded over the ranks it must reproduce ITSELF
+    # the same contract for the tensor-core DBM engine (compute='bf16'): sharded over the ranks it must reproduce ITSELF
     # run in one piece (a second context without communicator holds the global batch and particles on this GPU)
-    if os.environ.get('BM_EXPERIMENTAL') != '1' and os.environ.get('BM_HOSTSIM') != '1':
-        dist.barrier()                    # the engine has not run on a B200 yet: opt-in on real GPUs (BM_EXPERIMENTAL=1)
-        dist.destroy_process_group()
-        sys.exit(0 if ok else 1)
     solo = _native.Context(local)
     teng = _native.CudaDBM(dict(dcfg2(Bd, Md), compute='bf16'), ctx=ctx)
     tref = _native.CudaDBM(dict(dcfg2(Bd * world, Md * world), compute='bf16'), ctx=solo)
