@@ -81,6 +81,14 @@ void allreduce_max_u32(Ctx* ctx, unsigned int* buf, size_t count) {
     count_launch(ctx);
 }
 
+// sum-allreduce of unsigned 32-bit words (the all-gather of small opaque tables, bm_peer.cu)
+void allreduce_sum_u32(Ctx* ctx, unsigned int* buf, size_t count) {
+    if (ctx->nranks <= 1) return;
+    NcclApi* a = nccl_api();
+    nccl_check(a->AllReduce(buf, buf, count, 3, 0, ctx->nccl_comm, ctx->stream), "ncclAllReduce(u32 sum)");
+    count_launch(ctx);
+}
+
 cudaEvent_t profile_event(Ctx* c) {
     if (c->prof_used == c->prof_events.size()) {
         if (c->prof_events.size() >= 16384) profile_drain(c);

@@ -78,6 +78,7 @@ void profile_drain(Ctx* c);      // fold recorded event pairs into prof_ms (sync
 cudaEvent_t profile_event(Ctx* c);
 void allreduce_sum(Ctx* ctx, void* buf, size_t count, bool is_double);
 void allreduce_max_u32(Ctx* ctx, unsigned int* buf, size_t count);
+void allreduce_sum_u32(Ctx* ctx, unsigned int* buf, size_t count);
 
 // ---- activation / sampling selectors of the fused epilogue ------------------------
 enum Act : int { ACT_LINEAR = 0, ACT_SIGMOID = 1, ACT_SOFTPLUS = 2 };

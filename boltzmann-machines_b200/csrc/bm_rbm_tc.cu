@@ -7,6 +7,7 @@
 // (binary samples are exact in bf16).  A bf16 shadow of W is refreshed by the weight-update
 // kernel.  Metrics (free energy / PLL) are evaluated in fp32 by the inherited CUDA-core kernels.
 #include "bm_rbm.h"
+#include "bm_peer.h"
 #include <stdlib.h>
 #include <map>
 #include <memory>
@@ -32,23 +33,33 @@ struct RbmTC : RbmSimt<float> {
     // cached programs, keyed by (rows, k, with_dw, input buffer is the resident dataset)
     std::map<std::tuple<int, int, int, int>, std::unique_ptr<TcProgram>> progs;
     int dw_splits = 1, v_splits = 1;
+    PeerExchange peer;             // data parallelism over NVLink peer memory (inactive on one rank / without peer access)
     // The batch buffers (X, v_k) carry two constant columns behind their V data columns -- (1, 0) for X, (1, 1) for v_k --
     // so that the dW GEMMs, run over V + 2 rows, also deliver sum(h0 - h_k) (row V) and -sum(h_k) (row V + 1): the
     // column statistics of base_rbm.py:453,457 cost no pass of their own.  sum(X - v_k) (:451) is two more ops of the
     // program ([V x 1] = X^T 1 - v_k^T 1).  Everything is summed and applied by ONE kernel (launch_cd_tail).
-    int VM() const { return V + 2; }
+    // The constant columns sit at VP = V rounded up to 64, i.e. behind the last 64-column box a TMA store of the visible
+    // activations can touch (observed on the B200: a store box that is clipped by the tensor edge inside a 16-byte unit
+    // overwrites the rest of that unit).  Rows V .. VP-1 of the statistics are don't-cares.
+    int VP() const { return (V + 63) / 64 * 64; }
+    int VM() const { return VP() + 2; }
     // distance between two split-K slices: rounded up to 8 floats, so that every slice starts on a 32-byte boundary
     // whatever the shape (the vector paths of the epilogue, reduce_partials and the update rely on it)
     size_t gstride() const { return ((size_t)VM() * H + 7) & ~(size_t)7; }
     size_t vstride() const { return ((size_t)V + 7) & ~(size_t)7; }
 
     RbmTC(Ctx* c, const bm_rbm_cfg& f) : RbmSimt<float>(c, f) {
-        ldw = round_up(H, 64); ldv = round_up(V + 2, 64); ldh = round_up(H, 64);
+        ldw = round_up(H, 64); ldv = round_up(V, 64) + 64; ldh = round_up(H, 64);
         Wb.ensure((size_t)V * ldw);
         Wb.zero(ctx->stream);
         q_alt.ensure(H); q_alt.zero(ctx->stream);
-        tc_kinds = (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
+        if (tc_kinds_of(f)) peer.setup(ctx, V, H, W.p, dW.p, Wb.p, ldw);      // collective when the context has peers
+        tc_kinds = tc_kinds_of(f);
         reserve_tc(f.max_batch > 0 ? f.max_batch : 1);
+    }
+
+    static bool tc_kinds_of(const bm_rbm_cfg& f) {
+        return (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
     }
 
     void reserve_tc(int rows) {
@@ -61,9 +72,10 @@ struct RbmTC : RbmSimt<float> {
         widen.ensure((size_t)rows * (V > H ? V : H));
         ones.ensure((size_t)rows * 64);
         launch_fill_bf16(ctx, ones.p, (size_t)rows * 64, 1.0f);
-        launch_set_column_pair(ctx, Xb.p, ldv, (size_t)rows, V, 1.0f, 0.0f);
-        launch_set_column_pair(ctx, vm_b.p, ldv, (size_t)rows, V, 1.0f, 1.0f);
-        launch_set_column_pair(ctx, vs_b.p, ldv, (size_t)rows, V, 1.0f, 1.0f);
+        for (DevBuf<bf16>* b : {&Xb, &vm_b, &vs_b}) b->zero(ctx->stream);       // (columns V .. VP-1 are read by the dW ops)
+        launch_set_column_pair(ctx, Xb.p, ldv, (size_t)rows, VP(), 1.0f, 0.0f);
+        launch_set_column_pair(ctx, vm_b.p, ldv, (size_t)rows, VP(), 1.0f, 1.0f);
+        launch_set_column_pair(ctx, vs_b.p, ldv, (size_t)rows, VP(), 1.0f, 1.0f);
         progs.clear();                         // buffers moved: cached descriptors are stale
     }
 
@@ -81,8 +93,9 @@ struct RbmTC : RbmSimt<float> {
     void set_data(const void* X, int64_t n_rows) override {
         RbmSimt<float>::set_data(X, n_rows);
         data_b.ensure((size_t)n_rows * ldv);
+        data_b.zero(ctx->stream);
         launch_f32_to_bf16(ctx, data.p, V, data_b.p, ldv, (int)n_rows, V);
-        launch_set_column_pair(ctx, data_b.p, ldv, (size_t)n_rows, V, 1.0f, 0.0f);
+        launch_set_column_pair(ctx, data_b.p, ldv, (size_t)n_rows, VP(), 1.0f, 0.0f);
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         progs.clear();
     }
@@ -306,9 +319,24 @@ struct RbmTC : RbmSimt<float> {
             run_metrics(mask, rows, seed, tick, row0, out);
         }
 
+        if (peer.active) {
+            // with NVLink peers: reduce-scatter, sharded update and all-gather of the weights as stores to peer memory (bm_peer.h)
+            DpStep s{};
+            peer.fill(s);
+            s.part = partials.p; s.stride = gstride(); s.splits = dw_splits; s.srow = VP();
+            s.vpart = vparts.p; s.vstride = vstride(); s.vsplits = v_splits;
+            s.n_div = (float)((double)rows * ctx->nranks);
+            s.lr = (float)lr; s.mom = (float)mom; s.l2 = (float)cfg.l2;
+            s.damp = (float)cfg.sparsity_damping; s.cost = (float)cfg.sparsity_cost; s.target = (float)cfg.sparsity_target;
+            s.vb = vb.p; s.hb = hb.p; s.dvb = dvb.p; s.dhb = dhb.p;
+            s.q_old = q.p; s.q_new = q_alt.p; s.pen = pen.p;
+            peer.run(s);
+            std::swap(q.p, q_alt.p);
+            return;
+        }
         CdTail t{};
         t.V = V; t.H = H;
-        t.part = partials.p; t.stride = gstride(); t.splits = dw_splits;
+        t.part = partials.p; t.stride = gstride(); t.splits = dw_splits; t.srow = VP();
         t.vpart = vparts.p; t.vstride = vstride(); t.vsplits = v_splits;
         if (ctx->nranks > 1) {
             // with peers: sum this rank's slices, one all-reduce over [G' | sum(X - v_k)], then the same update on every rank

@@ -67,15 +67,16 @@ struct TcLaunch {
 
 // ---- the whole parameter update of a CD step in ONE launch (base_rbm.py:445-474) --------------------------------------
 // The statistics arrive as split-K slices written by the step's program:
-//   part : `splits` slices of [(V + 2) x H] fp32: rows 0..V-1  = X^T h0_means - v_k^T h_k_means   (:447-448)
-//                                                 row  V       = sum_rows (h0_means - h_k_means)     (:453)
-//                                                 row  V + 1   = - sum_rows h_k_means                (:457, negated)
-//          (rows V and V+1 come out of the same GEMMs: the batch buffers carry two constant columns behind the V data columns)
+//   part : `splits` slices of [(srow + 2) x H] fp32: rows 0..V-1 = X^T h0_means - v_k^T h_k_means   (:447-448)
+//                                                   row  srow    = sum_rows (h0_means - h_k_means)     (:453)
+//                                                   row  srow+1  = - sum_rows h_k_means                (:457, negated)
+//          (these two rows come out of the same GEMMs: the batch buffers carry two constant columns at column srow >= V;
+//           rows V .. srow-1 are don't-cares)
 //   vpart: `vsplits` slices of [V] fp32 whose sum is sum_rows (X - v_k)                               (:451)
 // Blocks [0, weight blocks) update W / dW / the bf16 shadow (sparsity penalty recomputed from q_old and row V+1);
 // the remaining blocks update vb, hb, their accumulators, q_means (into q_new: q_old is still being read) and `pen`.
 struct CdTail {
-    int V, H;
+    int V, H, srow;
     const float* part;  size_t stride;  int splits;
     const float* vpart; size_t vstride; int vsplits;
     float n_div, lr, mom, l2, damp, cost, target;

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) cd_tail_kernel(const CdTail t, unsigned w
 #pragma unroll
         for (int j = 0; j < VEC; ++j) pen[j] = 0.f;
         if (t.cost != 0.f) {                                     // base_rbm.py:457-461
-            const size_t qrow = (size_t)(V + 1) * H + h;
+            const size_t qrow = (size_t)(t.srow + 1) * H + h;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float qs = 0.f;
@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(256) cd_tail_kernel(const CdTail t, unsigned w
     if (i < H) {
         float ds = 0.f, qs = 0.f;
         for (int s = 0; s < t.splits; ++s) {
-            ds += t.part[(size_t)s * t.stride + (size_t)V * H + i];
-            qs += t.part[(size_t)s * t.stride + (size_t)(V + 1) * H + i];
+            ds += t.part[(size_t)s * t.stride + (size_t)t.srow * H + i];
+            qs += t.part[(size_t)s * t.stride + (size_t)(t.srow + 1) * H + i];
         }
         const float q = t.damp * t.q_old[i] + (1.0f - t.damp) * (-qs);                     // :457-459
         t.q_new[i] = q;

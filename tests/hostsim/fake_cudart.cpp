@@ -243,6 +243,10 @@ cudaError_t cudaFree(void* p) {
     free(p);
     return cudaSuccess;
 }
+// no inter-process memory on the stand-in: the engine keeps its ncclAllReduce path (bm_peer.cu)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static void copy_checked(void* d, const void* s, size_t n, enum cudaMemcpyKind k) {

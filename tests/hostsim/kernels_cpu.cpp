@@ -223,6 +223,15 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L, Hazards* hz 
                     if (p.out_mean_bf) p.out_mean_bf[(size_t)m * p.ld_mean_bf + n] = f2bf(mean);
                     if (p.out_state_bf) p.out_state_bf[(size_t)m * p.ld_state_bf + n] = f2bf(state);
                     if (p.out_f32) (p.out_f32 + (size_t)split * p.split_stride)[(size_t)m * p.ld_f32 + n] = mean;
+                    if (n == p.N - 1 && (p.N & 7) != 0) {
+                        // Observed on the B200 (round 2): a TMA store box clipped by the tensor edge INSIDE a 16-byte unit leaves
+                        // the rest of that unit overwritten.  Modelled as poison, so that nothing may keep data there.
+                        const int end = (p.N + 7) & ~7;
+                        for (int c = p.N; c < end; ++c) {
+                            if (p.out_mean_bf && c < p.ld_mean_bf) p.out_mean_bf[(size_t)m * p.ld_mean_bf + c] = f2bf(NAN);
+                            if (p.out_state_bf && c < p.ld_state_bf) p.out_state_bf[(size_t)m * p.ld_state_bf + c] = f2bf(NAN);
+                        }
+                    }
                     if (hz) {
                         const int g = m / Hazards::ROWS;
                         if (p.out_mean_bf) hz->write(p.out_mean_bf + (size_t)m * p.ld_mean_bf + n, op, g);
@@ -323,7 +332,7 @@ static void k_cd_tail(void** a) {
     std::vector<float> pen(H, 0.f), qn(H);
     for (int h = 0; h < H; ++h) {
         float qs = 0.f;
-        for (int s = 0; s < t.splits; ++s) qs += t.part[(size_t)s * t.stride + (size_t)(V + 1) * H + h];
+        for (int s = 0; s < t.splits; ++s) qs += t.part[(size_t)s * t.stride + (size_t)(t.srow + 1) * H + h];
         qn[h] = t.damp * t.q_old[h] + (1.0f - t.damp) * (-qs);
         pen[h] = t.cost * (qn[h] - t.target);
     }
@@ -337,7 +346,7 @@ static void k_cd_tail(void** a) {
         }
     for (int h = 0; h < H; ++h) {
         float ds = 0.f;
-        for (int s = 0; s < t.splits; ++s) ds += t.part[(size_t)s * t.stride + (size_t)V * H + h];
+        for (int s = 0; s < t.splits; ++s) ds += t.part[(size_t)s * t.stride + (size_t)t.srow * H + h];
         t.q_new[h] = qn[h]; t.pen[h] = pen[h];
         const float d = t.lr * (t.mom * t.dhb[h] + (ds / t.n_div - pen[h]));
         t.dhb[h] = d; t.hb[h] += d;
