@@ -235,8 +235,10 @@ struct DbmTC : Dbm<float> {
             h_b[i].ensure((size_t)M * ldn[i + 1]); h2_b[i].ensure((size_t)M * ldn[i + 1]);
             for (DevBuf<bf16_t>* b : {&Wb[i], &mu_b[i], &mu2_b[i], &h_b[i], &h2_b[i]}) b->zero(ctx->stream);
         }
-        { const char* e = getenv("BM_DBM_MF_CHUNK"); mf_chunk = e ? atoi(e) : 0; }
-        { const char* e = getenv("BM_DBM_PCD_PROGRAM"); pcd_program = e && atoi(e) != 0; }
+        // default: persistent dataflow programs -- 5 speculated mean-field sweeps per launch, the committed particle sweeps
+        // as one launch (cfg4 on the B200: 1.56 ms/step with one launch per op, 1.06 ms with programs); = 0: one launch per op
+        { const char* e = getenv("BM_DBM_MF_CHUNK"); mf_chunk = e ? atoi(e) : 5; }
+        { const char* e = getenv("BM_DBM_PCD_PROGRAM"); pcd_program = e ? atoi(e) != 0 : true; }
         { const char* e = getenv("BM_DBM_TC_MIXED"); mixed_layouts = e && atoi(e) != 0; }
         WbT.resize(L);
         if (!mixed_layouts)
@@ -682,7 +684,108 @@ struct DbmTC : Dbm<float> {
     // kernels (v, h2) and ONE two-pair tensor-core op for x' = act(beta (v W_0 + h2 W_1^T) + beta c_1) with the
     // Bernoulli draw in its epilogue.
     // (sharding over ranks / calls: Dbm<float>::ais, ais_rows; run r draws from row row0 + r of the AIS sites)
+    // AIS with everything but the GEMMs' operands kept out of memory: per temperature step THREE tensor-core ops whose
+    // epilogues do the rest (TcPhaseLite::ais_kind) --
+    //   U_v : z = x W_0^T + b   -> logw += sum softplus(beta_i z) - softplus(beta_{i-1} z);  v  ~ sigmoid(beta_{i+1} z)
+    //   U_h2: z = x W_1 + c_2   -> logw += ...                                               h2 ~ sigmoid(beta_{i+1} z)
+    //   T   : x' ~ sigmoid(beta_{i+1} (v W_0 + h2 W_1^T + c_1))   -> logw += (beta_{i+1} - beta_i) x'.c_1
+    // -- "the same kernel with a scalar beta multiplied into the pre-activation" (north_star).  The fp32 pre-activations
+    // (145 MB per step at 20 000 runs) never exist; up to 30 steps run as one persistent dataflow launch, every op waiting
+    // per 256-run block on the op(s) it reads.  dbm.py:650-736; same draws (sites, ticks, rows) as the kernel-per-pass variant.
     void ais_local(int R, uint32_t row0, int n_betas, int k, uint64_t seed, double* logw_out) override {
+        bool epi = sample_h[0];                 // the transition's epilogue takes the linear term from sampled states
+        { const char* e = getenv("BM_DBM_AIS_EPILOGUE"); if (e && !atoi(e)) epi = false; }
+        if (!epi) { ais_local_passes(R, row0, n_betas, k, seed, logw_out); return; }
+        const int H0 = Hs[0], H1 = Hs[1];
+        const int ld0 = ldn[1], ldv = ldn[0], ld1 = ldn[2];
+        DevBuf<bf16_t> x, xn, va, hc;
+        x.ensure((size_t)R * ld0); xn.ensure((size_t)R * ld0); va.ensure((size_t)R * ldv); hc.ensure((size_t)R * ld1);
+        for (DevBuf<bf16_t>* b : {&x, &xn, &va, &hc}) b->zero(ctx->stream);
+        bf16_t* xc = x.p; bf16_t* xo = xn.p;
+        {   // x_0 ~ Ber(1/2)   (:700-702)
+            dim3 g(((H0 + 3) / 4 + 127) / 128, R);
+            ais_unit_bf16_kernel<<<g, 128, 0, ctx->stream>>>(nullptr, 0, 0.f, xc, ld0, R, H0, 1, make_rng(seed, SITE_AIS_INIT, 0, 0, row0));
+            count_launch(ctx);
+        }
+        // the temperatures of the transitions, accumulated in the storage dtype like the reference's loop (:710-711)
+        const float delta = (float)(1.0 / n_betas);
+        std::vector<float> t;
+        t.push_back(delta);
+        while (t.back() < 1.f - delta + 1e-5f) t.push_back(t.back() + delta);
+        const int nT = (int)t.size();                                    // transition j (at t[j]) produces x_{j+1}
+        auto inc_a = [&](int j) { return j == 0 ? 0.f : t[j - 1]; };       // x_{j+1} is weighted with log p_b - log p_a
+        auto inc_b = [&](int j) { return j == nT - 1 ? 1.0f : t[j]; };
+        std::vector<TcGemm> all;
+        std::vector<int> dep0, dep1;                                      // global producer indices (-1: none)
+        int last_T = -1;
+        auto unit_op = [&](bool vis, const bf16_t* xs, float a, float b, bool weigh, float next, bool emit, uint32_t tick) {
+            TcGemm g;
+            g.M = R; g.N = vis ? V : H1;
+            g.A[0] = mat(xs, R, H0, ld0); g.K[0] = H0;
+            if (vis) { g.B[0] = mat(Wb[0].p, V, H0, ld0); g.b_t[0] = false; g.bias = vb.p; }           // x W_0^T: W_0 stored [N, K]
+            else { g.B[0] = mat(Wb[1].p, H0, H1, ld1); g.b_t[0] = true; g.bias = hb[1].p; }             // x W_1:   W_1 stored [K, N]
+            g.act = ACT_LINEAR;
+            g.ais_kind = 1; g.ais_a = a; g.ais_b = b; g.ais_next = next; g.ais_logw = weigh ? logw_out : nullptr;
+            g.tick_off = tick;
+            if (emit) {
+                const bool smp = vis ? sample_vis : (sample_h[1] != 0);
+                g.sample = smp ? SMP_BERNOULLI : SMP_NONE;
+                g.out_state_bf = vis ? va.p : hc.p; g.ld_state_bf = vis ? ldv : ld1;
+                g.rng = make_rng(0, vis ? SITE_AIS_V : SITE_AIS_H2, 0, 0, 0);
+            }
+            all.push_back(g); dep0.push_back(last_T); dep1.push_back(-1);
+            return (int)all.size() - 1;
+        };
+        for (int j = 0; j < nT; ++j) {
+            for (int sw = 0; sw < k; ++sw) {
+                const uint32_t tick = (uint32_t)(j * k + sw);
+                const bool weigh = sw == 0 && j >= 1;                     // the increment of x_j (produced by transition j-1)
+                const float a = weigh ? inc_a(j - 1) : 0.f, b = weigh ? inc_b(j - 1) : 0.f;
+                const int ua = unit_op(true, xc, a, b, weigh, t[j], true, tick);
+                const int ub = unit_op(false, xc, a, b, weigh, t[j], true, tick);
+                TcGemm o;                                                 // x' = act(beta (v W_0 + h2 W_1^T), beta c_1)
+                o.M = R; o.N = H0;
+                o.A[0] = mat(va.p, R, V, ldv); o.K[0] = V; o.B[0] = mat(Wb[0].p, V, H0, ld0); o.b_t[0] = true;
+                above_pair(o, 0, hc.p, R);
+                o.acc_scale = t[j]; o.bias_scale = t[j]; o.bias = hb[0].p; o.act = ACT_SIGMOID;
+                o.sample = SMP_BERNOULLI; o.out_state_bf = xo; o.ld_state_bf = ld0;
+                o.rng = make_rng(0, SITE_AIS_H1, 0, 0, 0);
+                o.tick_off = tick;
+                o.ais_kind = 2;
+                if (sw == k - 1) {
+                    o.ais_logw = logw_out;
+                    o.ais_lin = (float)(((double)inc_b(j) - (double)inc_a(j)) / ((double)t[j] * -1.4426950408889634));
+                }
+                all.push_back(o); dep0.push_back(ua); dep1.push_back(ub);
+                last_T = (int)all.size() - 1;
+                std::swap(xc, xo);
+            }
+        }
+        unit_op(true, xc, inc_a(nT - 1), inc_b(nT - 1), true, 0.f, false, 0);      // + log p_M(x_M) - log p_{M-1}(x_M)   :728
+        unit_op(false, xc, inc_a(nT - 1), inc_b(nT - 1), true, 0.f, false, 0);
+        // launches of up to AIS_OPS ops; a dependency on an op of an earlier launch is the kernel boundary
+        int per = 90;
+        { const char* e = getenv("BM_DBM_AIS_OPS"); if (e && atoi(e) >= 1 && atoi(e) <= 96) per = atoi(e); }
+        TcProgram prog;
+        for (size_t lo = 0; lo < all.size(); lo += (size_t)per) {
+            const size_t hi = std::min(all.size(), lo + (size_t)per);
+            prog.ops.assign(all.begin() + lo, all.begin() + hi);
+            if (getenv("BM_DEBUG_AIS")) fprintf(stderr, "ais launch: ops [%zu, %zu) of %zu, per %d\n", lo, hi, all.size(), per);
+            for (size_t i = lo; i < hi; ++i) {
+                TcGemm& g = prog.ops[i - lo];
+                g.n_deps = 0;
+                for (int d : {dep0[i], dep1[i]})
+                    if (d >= (int)lo) { g.dep[g.n_deps] = d - (int)lo; g.dep_all[g.n_deps] = false; ++g.n_deps; }
+                g.lane = LANE_ALL;
+            }
+            launch_tc_program(ctx, prog, make_rng(seed, 0, 0, 0, row0), 0);
+        }
+        BM_CUDA(cudaStreamSynchronize(ctx->stream));            // the workspaces above are released on return
+    }
+
+    // the same ladder with one kernel per pass over fp32 pre-activations (BM_DBM_AIS_EPILOGUE=0; models whose first
+    // hidden layer is not sampled)
+    void ais_local_passes(int R, uint32_t row0, int n_betas, int k, uint64_t seed, double* logw_out) {
         const int H0 = Hs[0], H1 = Hs[1];
         const int ld0 = ldn[1], ldv = ldn[0], ld1 = ldn[2];
         DevBuf<bf16_t> x, xn, va, hc;

@@ -67,7 +67,9 @@ enum : int {
     MODE_SIG_BERN_MEAN_STATE = 1,    // h0: sigmoid, Bernoulli draw, bf16 means + bf16 states
     MODE_SIG_BERN_STATE = 2,         // mid-chain hidden: states only
     MODE_SIG_MEAN = 3,               // probabilities only (visible means, last hidden means)
-    MODE_RAW_F32 = 4                 // raw fp32 accumulators (dW partials, linear pre-activations)
+    MODE_RAW_F32 = 4,                // raw fp32 accumulators (dW partials, linear pre-activations)
+    MODE_AIS_UNITS = 5,              // AIS: importance-weight increment of the row + unit updates of the next transition
+    MODE_AIS_STATE = 6               // AIS: sampled transition (sigmoid, Bernoulli, states) + the linear term of log p*
 };
 
 constexpr int MAX_PHASES = 96;
@@ -308,10 +310,11 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
 // ------------------------------------------------------------------------------------------
 template <int MODE> struct EpiCfg {
     static constexpr bool fixed = MODE != MODE_GENERIC;
-    static constexpr int act = (MODE == MODE_RAW_F32) ? ACT_LINEAR : ACT_SIGMOID;
-    static constexpr int sample = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE) ? SMP_BERNOULLI : SMP_NONE;
+    static constexpr bool ais = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_STATE);
+    static constexpr int act = (MODE == MODE_RAW_F32 || MODE == MODE_AIS_UNITS) ? ACT_LINEAR : ACT_SIGMOID;
+    static constexpr int sample = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE || MODE == MODE_AIS_STATE) ? SMP_BERNOULLI : SMP_NONE;
     static constexpr bool mean_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_MEAN);
-    static constexpr bool state_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE);
+    static constexpr bool state_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE || MODE == MODE_AIS_STATE);
     static constexpr bool f32 = (MODE == MODE_RAW_F32);
 };
 
@@ -327,6 +330,8 @@ struct EpiPhase {
     __nv_bfloat16* __restrict__ out_state_bf; int ld_state_bf;
     float* __restrict__ out_f32;              int ld_f32;
     unsigned long long split_stride;
+    float ais_a, ais_b, ais_next, ais_lin;
+    double* ais_logw;
 };
 struct EpiCtx {
     EpiPhase p;
@@ -350,13 +355,28 @@ struct EpiCtx {
 // One CW-column chunk of one accumulator row: activation, sampling, then
 //   bf16 means / states -> this thread's row of the staging buffers (two 16-byte units each),
 //   fp32 -> global memory directly (dW partials and raw pre-activations only).
+// softplus(b z) - softplus(a z) = log1p(sigmoid(a z) * expm1((b - a) z)) without cancellation (b - a ~ 1e-3): short series
+// where both arguments are small (the common case), the library functions elsewhere
+__device__ __forceinline__ float ais_softplus_diff(float a, float b, float z) {
+    const float sa = sigmoid_from_neg_log2(a * z * -1.4426950408889634f);
+    const float t = (b - a) * z;
+    float em;
+    if (fabsf(t) < 0.03f) em = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.0f / 120.0f, 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+    else em = expm1f(t);
+    const float y = sa * em;
+    if (fabsf(y) < 0.03f) return y * fmaf(y, fmaf(y, fmaf(y, fmaf(y, 0.2f, -0.25f), 1.0f / 3.0f), -0.5f), 1.0f);
+    return log1pf(y);
+}
+
+// AIS_UNITS only: the chunk's contribution to the row's log-weight; AIS_STATE: sum of state * pre-scaled bias; else 0
 template <int MODE>
-__device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[CW], int ch, int n0, int n_valid,
-                                           uint32_t smem_mean, uint32_t smem_state, bool store_ok) {
+__device__ __forceinline__ float chunk_body(const EpiCtx& c, const uint32_t (&v)[CW], int ch, int n0, int n_valid,
+                                            uint32_t smem_mean, uint32_t smem_state, bool store_ok) {
     typedef EpiCfg<MODE> E;
     const EpiPhase& p = c.p;
+    float ais_part = 0.f;
     const int act = E::fixed ? E::act : p.act;
-    const int smp = E::fixed ? E::sample : p.sample;
+    const int smp = (E::fixed && MODE != MODE_AIS_UNITS) ? E::sample : p.sample;
     float* const out_f32 = ((E::fixed && !E::f32) || !p.out_f32) ? nullptr : p.out_f32 + (size_t)c.split * p.split_stride;
     // fold the sigmoid's -log2(e) into the affine map of the accumulator
     const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * -1.4426950408889634f : p.acc_scale;
@@ -364,7 +384,7 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
     const int m = c.m;
     // in the fixed modes which outputs exist is known at compile time (no per-group branches)
     const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
-    const bool do_state = E::fixed ? E::state_bf : (p.out_state_bf != nullptr);
+    const bool do_state = (E::fixed && MODE != MODE_AIS_UNITS) ? E::state_bf : (p.out_state_bf != nullptr);
     const bool do_f32 = E::fixed ? E::f32 : (out_f32 != nullptr);
     const bool f32_vec = n_valid == CW && (p.ld_f32 & 3) == 0;       // rows 16-byte aligned, whole chunk
     // rows 32-byte aligned (row pitch, split stride and base): one full sector per store instruction and thread
@@ -397,7 +417,22 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
             x += bq[j];
             float m_ = x;
             float s_;
-            if (MODE == MODE_SIG_BERN_STATE) {
+            if (MODE == MODE_AIS_UNITS) {
+                // x = z (acc_scale = bias_scale = 1): weight increment at (a, b), then the unit's update at beta_next
+                if (p.ais_logw && e < n_valid) ais_part += ais_softplus_diff(p.ais_a, p.ais_b, x);
+                float e_;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_) : "f"(x * p.ais_next * -1.4426950408889634f));
+                const float d_ = 1.0f + e_;
+                if (smp == SMP_BERNOULLI) {
+                    const float u12 = u32_to_one_two(words[j], c.mant_mask, c.one_bits);
+                    s_ = (fmaf(u12, d_, -d_) < 1.0f) ? 1.0f : 0.0f;
+                } else {
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s_) : "f"(d_));
+                }
+                mu[j] = 0.f; st[j] = s_;
+                continue;
+            }
+            if (MODE == MODE_SIG_BERN_STATE || MODE == MODE_AIS_STATE) {
                 // only the draw is needed: u < 1/(1+e)  <=>  u*(1+e) < 1, with u = u12 - 1 folded into one FMA
                 // (no reciprocal, no "- 1.0f"); e = inf (p = 0) gives NaN -> 0, e = 0 (p = 1) gives u < 1 -> 1
                 float e_;
@@ -406,6 +441,7 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
                 const float u12 = u32_to_one_two(words[j], c.mant_mask, c.one_bits);
                 s_ = (fmaf(u12, d_, -d_) < 1.0f) ? 1.0f : 0.0f;
                 mu[j] = 0.f; st[j] = s_;
+                if (MODE == MODE_AIS_STATE && e < n_valid) ais_part = fmaf(s_, bq[j], ais_part);
                 continue;
             }
             if (act == ACT_SIGMOID) m_ = sigmoid_from_neg_log2(x);
@@ -438,6 +474,7 @@ __device__ __forceinline__ void chunk_body(const EpiCtx& c, const uint32_t (&v)[
         if (do_mean) sts128(smem_mean + off, mean_pk[4 * i], mean_pk[4 * i + 1], mean_pk[4 * i + 2], mean_pk[4 * i + 3]);
         if (do_state) sts128(smem_state + off, state_pk[4 * i], state_pk[4 * i + 1], state_pk[4 * i + 2], state_pk[4 * i + 3]);
     }
+    return ais_part;
 }
 
 // One warp's share of a tile: TMEM lane quarter (warp % 4) x the CW-column chunks ch = sub (mod EPI_SUBS).
@@ -452,7 +489,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     const int n_chunks = BN / CW;                  // BN is a multiple of 16
     const bool row_ok = c.m < p.M;
     const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
-    const bool do_state = E::fixed ? E::state_bf : (p.out_state_bf != nullptr);
+    const bool do_state = (E::fixed && MODE != MODE_AIS_UNITS) ? E::state_bf : (p.out_state_bf != nullptr);
+    float ais_sum = 0.f;
     int last_ch = -1;
     for (int ch = c.sub; ch < n_chunks; ch += EPI_SUBS) last_ch = ch;
     if (last_ch < 0) {          // this warp has no chunk in the tile: release the accumulator at once
@@ -492,7 +530,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
                 }
             }
             const int n0 = c.n_blk * BN + ch * CW;
-            if (n0 < p.N) chunk_body<MODE>(c, v, ch, n0, min(CW, p.N - n0), smem_mean, smem_state, row_ok);
+            if (n0 < p.N) ais_sum += chunk_body<MODE>(c, v, ch, n0, min(CW, p.N - n0), smem_mean, smem_state, row_ok);
         }
         if (do_mean || do_state) {
             fence_proxy_async_smem();                // this thread's staging writes -> visible to the TMA unit
@@ -504,6 +542,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
         }
     }
     *c.seq = seq;
+    if constexpr (E::ais) {
+        // this thread's share of its row's log-weight: fp64 atomics (four threads per row and column tile)
+        if (p.ais_logw && row_ok) atomicAdd(p.ais_logw + c.m, (double)(MODE == MODE_AIS_STATE ? ais_sum * p.ais_lin : ais_sum));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -890,8 +932,9 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.p.out_mean_bf = ph->out_mean_bf; c.p.ld_mean_bf = ph->ld_mean_bf;
             c.p.out_state_bf = ph->out_state_bf; c.p.ld_state_bf = ph->ld_state_bf;
             c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
+            c.p.ais_a = ph->ais_a; c.p.ais_b = ph->ais_b; c.p.ais_next = ph->ais_next; c.p.ais_lin = ph->ais_lin; c.p.ais_logw = ph->ais_logw;
             const int ph_mode = ph->mode;
-            c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
+            c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick + ph->tick_off; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
             c.n_blk = u.n_blk; c.split = u.split;
             c.tempty = &tempty[acc];
@@ -904,6 +947,8 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 case MODE_SIG_BERN_STATE: epilogue_tile<MODE_SIG_BERN_STATE, pair>(c); break;
                 case MODE_SIG_MEAN: epilogue_tile<MODE_SIG_MEAN, pair>(c); break;
                 case MODE_RAW_F32: epilogue_tile<MODE_RAW_F32, pair>(c); break;
+                case MODE_AIS_UNITS: epilogue_tile<MODE_AIS_UNITS, pair>(c); break;
+                case MODE_AIS_STATE: epilogue_tile<MODE_AIS_STATE, pair>(c); break;
                 default: epilogue_tile<MODE_GENERIC, pair>(c); break;
             }
             if (threadIdx.x == 0) DBG_UNIT(5, ord);
@@ -1005,6 +1050,8 @@ static TilePick pick_tile(int N, bool b_mn, bool staged_out, int m_tiles, int sp
 }
 
 static int epilogue_mode(const TcGemm& g) {
+    if (g.ais_kind == 1) return MODE_AIS_UNITS;
+    if (g.ais_kind == 2) return MODE_AIS_STATE;
     if (g.sigma || g.noise_sigma) return MODE_GENERIC;
     const bool mb = g.out_mean_bf != nullptr, sb = g.out_state_bf != nullptr, f = g.out_f32 != nullptr;
     if (g.act == ACT_SIGMOID && g.sample == SMP_BERNOULLI && mb && sb && !f) return MODE_SIG_BERN_MEAN_STATE;
@@ -1055,6 +1102,15 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
     p.bias = g.bias; p.sigma = g.sigma; p.noise_sigma = g.noise_sigma;
     p.act = g.act; p.sample = g.sample; p.mode = epilogue_mode(g);
     p.rng_c2 = g.rng.c2;
+    p.ais_kind = g.ais_kind; p.ais_a = g.ais_a; p.ais_b = g.ais_b; p.ais_next = g.ais_next; p.ais_lin = g.ais_lin;
+    p.ais_logw = g.ais_logw; p.tick_off = g.tick_off;
+    if (g.ais_kind == 1)
+        BM_REQUIRE(!g.sigma && !g.noise_sigma && g.act == ACT_LINEAR && !g.out_mean_bf && !g.out_f32 && g.splits <= 1 &&
+                   g.acc_scale == 1.f && g.bias_scale == 1.f && (g.sample == SMP_NONE || g.sample == SMP_BERNOULLI),
+                   "AIS unit op: linear accumulator, optional state output only");
+    if (g.ais_kind == 2)
+        BM_REQUIRE(!g.sigma && !g.noise_sigma && g.act == ACT_SIGMOID && g.sample == SMP_BERNOULLI && g.out_state_bf && !g.out_mean_bf &&
+                   !g.out_f32 && g.splits <= 1 && g.bias, "AIS state op: sampled sigmoid states with a bias");
     p.out_mean_bf = g.out_mean_bf; p.ld_mean_bf = g.ld_mean_bf;
     p.out_state_bf = g.out_state_bf; p.ld_state_bf = g.ld_state_bf;
     p.out_f32 = g.out_f32; p.ld_f32 = g.ld_f32;

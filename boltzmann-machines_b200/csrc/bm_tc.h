@@ -57,6 +57,11 @@ struct TcGemm {
     //   LANE_SPARE: the pairs the chain ops never use (falls back to LANE_ALL when there are none)
     //   LANE_ALL  : every pair
     int lane = 0;
+    // AIS in the epilogue (TcPhaseLite::ais_kind and friends)
+    int ais_kind = 0;
+    float ais_a = 0.f, ais_b = 0.f, ais_next = 0.f, ais_lin = 0.f;
+    double* ais_logw = nullptr;
+    uint32_t tick_off = 0;
 };
 enum : int { LANE_CHAIN = 0, LANE_SPARE = 1, LANE_ALL = 2 };
 

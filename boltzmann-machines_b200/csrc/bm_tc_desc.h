@@ -41,6 +41,15 @@ struct TcPhaseLite {
     int dep_gran_row, dep_chunk_need;     // counters per producer row group; arrivals per granule
     unsigned char k_order[MAX_KCHUNKS];   // order in which this op consumes its K chunks
     unsigned char k_dep_a[MAX_KCHUNKS], k_dep_b[MAX_KCHUNKS];   // producer granules K chunk c overlaps
+    // AIS (dbm.py:650-736) inside the epilogue.  ais_kind 1 ("units"): the accumulator is the shared pre-activation z of a
+    // temperature step; the thread adds  sum_n [softplus(ais_b z) - softplus(ais_a z)]  of its row to ais_logw[row] (fp64 atomics;
+    // skipped when ais_logw is null) and, if a state output is given, emits sample(sigmoid(ais_next * z)) -- the unit updates of the
+    // next transition.  ais_kind 2 ("state"): an ordinary sigmoid / Bernoulli op whose epilogue also adds
+    // ais_lin * sum_n state[n] * (bias_scale * bias[n] * -log2 e)  to ais_logw[row]  (the linear term of log p*, dbm.py:658).
+    int ais_kind;
+    float ais_a, ais_b, ais_next, ais_lin;
+    double* ais_logw;
+    uint32_t tick_off;               // added to the launch's tick for this op's draws
 };
 struct alignas(64) TcPhase {
     CUtensorMap tmA[2], tmB[2];      // read by the TMA unit from global / parameter memory

@@ -196,8 +196,32 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L, Hazards* hz 
             }
         }
         // epilogue (bm_tc.cu::chunk_body, generic semantics)
-        bm::RngKey rng; rng.k0 = L.k0; rng.k1 = L.k1; rng.tick = L.tick; rng.row0 = L.row0; rng.c2 = p.rng_c2;
-        for (int m = 0; m < p.M; ++m)
+        bm::RngKey rng; rng.k0 = L.k0; rng.k1 = L.k1; rng.tick = L.tick + p.tick_off; rng.row0 = L.row0; rng.c2 = p.rng_c2;
+        if (p.ais_kind == 1) {
+            // AIS "units" op: z = C + bias; logw[m] += sum_n softplus(b z) - softplus(a z); state = sample(sigmoid(next z))
+            for (int m = 0; m < p.M; ++m) {
+                double acc_w = 0.0;
+                for (int nb = 0; nb < p.N; nb += 4) {
+                    bm::U4 w{0, 0, 0, 0};
+                    if (p.sample != SMP_NONE) w = bm::site_block(rng, (uint32_t)m, (uint32_t)(nb >> 2));
+                    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+                    for (int j = 0; j < 4 && nb + j < p.N; ++j) {
+                        const int n = nb + j;
+                        const float z = acc[(size_t)m * p.N + n] + (p.bias ? p.bias[n] : 0.f);
+                        const float sa = 1.0f / (1.0f + expf(-p.ais_a * z));
+                        acc_w += (double)log1pf(sa * expm1f((p.ais_b - p.ais_a) * z));
+                        const float pr = 1.0f / (1.0f + expf(-p.ais_next * z));
+                        const float st = p.sample == SMP_BERNOULLI ? ((bm::u32_to_unit_float(words[j]) < pr) ? 1.0f : 0.0f) : pr;
+                        if (p.out_state_bf) p.out_state_bf[(size_t)m * p.ld_state_bf + n] = f2bf(st);
+                        if (hz && p.out_state_bf) hz->write(p.out_state_bf + (size_t)m * p.ld_state_bf + n, op, m / Hazards::ROWS);
+                    }
+                }
+                if (p.ais_logw) p.ais_logw[m] += acc_w;
+            }
+            continue;
+        }
+        for (int m = 0; m < p.M; ++m) {
+          double lin = 0.0;
             for (int nb = 0; nb < p.N; nb += 4) {
                 bm::U4 w{0, 0, 0, 0};
                 if (p.sample != SMP_NONE) w = bm::site_block(rng, (uint32_t)m, (uint32_t)(nb >> 2));
@@ -220,6 +244,7 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L, Hazards* hz 
                     float state = mean;
                     if (p.sample == SMP_BERNOULLI) state = (bm::u32_to_unit_float(words[j]) < mean) ? 1.0f : 0.0f;
                     else if (p.sample == SMP_GAUSSIAN) state = mean + (p.noise_sigma ? p.noise_sigma[n] : 1.0f) * g[j];
+                    if (p.ais_kind == 2 && p.bias) lin += (double)(state * p.bias[n]);
                     if (p.out_mean_bf) p.out_mean_bf[(size_t)m * p.ld_mean_bf + n] = f2bf(mean);
                     if (p.out_state_bf) p.out_state_bf[(size_t)m * p.ld_state_bf + n] = f2bf(state);
                     if (p.out_f32) (p.out_f32 + (size_t)split * p.split_stride)[(size_t)m * p.ld_f32 + n] = mean;
@@ -240,6 +265,9 @@ static void run_tc_op(const bm::TcPhase& ph, const bm::TcLaunch& L, Hazards* hz 
                     }
                 }
             }
+          // ais_lin = (b - a) / (bias_scale * -log2 e) multiplies sum_n state * (bias_scale * bias * -log2 e) in the kernel
+          if (p.ais_kind == 2 && p.ais_logw) p.ais_logw[m] += (double)p.ais_lin * (double)(p.bias_scale * -1.4426950408889634f) * lin;
+        }
     }
 }
 static void k_tc_program(void** a) {

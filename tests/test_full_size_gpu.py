@@ -165,3 +165,41 @@ def test_full_size_dbm_step_matches_the_oracle():
     for n in ('v', 'h', 'h_1'):
         assert np.mean(g[n] != w[n]) < 2e-3, n                             # particles: same Philox stream
     eng.close()
+
+
+def test_north_star_gates_at_cfg2_after_three_epochs():
+    """BASELINE.json's parity gates evaluated at configs[1]'s own size: BernoulliRBM 784-1024, batch 4096, CD-5, three epochs
+    of the synthetic set (45 steps, the example's momentum schedule start and learning rate).  Validation PLL of the bf16
+    tensor-core engine within +-0.5 nats and MSRE within 2 % of (a) the fp32 CUDA-core engine (bit-comparable with the oracle,
+    tests/test_rbm_gpu.py) after all three epochs and (b) the CPU oracle itself after the first epoch."""
+    import bench
+    V, H, B, k = bench.V, bench.H, bench.B, bench.K_GIBBS
+    n_batches = 15
+    X = bench.synth_mnist(B * n_batches + B, seed=4321)
+    Xtr, Xval = X[:B * n_batches], X[B * n_batches:]
+    p = np.clip(Xtr.mean(axis=0), 1e-7, 1 - 1e-7)
+    init = {'W': (0.01 * np.random.RandomState(5).randn(V, H)).astype(np.float32), 'vb': np.log(p / (1 - p)).astype(np.float32)}
+    engines = {c: _native.CudaRBM(bench.model_cfg(c)) for c in ('bf16', 'fp32')}
+    ora = OracleRBM(bench.model_cfg('fp32'))
+    for e in list(engines.values()) + [ora]:
+        e.set_params(init)
+    seed, tick = 777, 0
+    after = {}
+    for epoch in range(3):
+        for name, e in engines.items():
+            e.train_epoch(Xtr, B, bench.LR, bench.MOMENTUM, k, seed, tick)
+        if epoch == 0:
+            for i in range(n_batches):
+                ora.train_step(Xtr[i * B:(i + 1) * B], bench.LR, bench.MOMENTUM, k, seed, tick + i)
+            after['oracle'] = ora.metrics(Xval, 1, seed, 10 ** 6, ('msre', 'pll'))
+            after['bf16@1'] = engines['bf16'].metrics(Xval, 1, seed, 10 ** 6, ('msre', 'pll'))
+        tick += n_batches
+    m = {name: e.metrics(Xval, 1, seed, 10 ** 6, ('msre', 'pll')) for name, e in engines.items()}
+    # training moved the model (the untrained model's PLL is about -V log 2 = -543)
+    assert m['fp32']['pll'] > -400.0, m
+    assert abs(m['bf16']['pll'] - m['fp32']['pll']) < 0.5, m
+    assert abs(m['bf16']['msre'] - m['fp32']['msre']) < 0.02 * m['fp32']['msre'], m
+    assert abs(after['bf16@1']['pll'] - after['oracle']['pll']) < 0.5, after
+    assert abs(after['bf16@1']['msre'] - after['oracle']['msre']) < 0.02 * after['oracle']['msre'], after
+    for e in engines.values():
+        e.close()

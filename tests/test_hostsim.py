@@ -103,8 +103,8 @@ DBM_SHAPES = [(784, (512, 1024), 1024, 1024, 25), (30, (18, 11), 10, 12, 6), (30
 def test_dbm_entry_points(sim, monkeypatch, V, Hs, B, M, max_mf, mode):
     from boltzmann_machines import _native
     compute = 'fp32' if mode == 'fp32' else 'bf16'
-    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
-    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', '0')
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '0')
     if mode == 'bf16-programs':
         monkeypatch.setenv('BM_DBM_MF_CHUNK', '4')
         monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
@@ -215,8 +215,8 @@ def no_skips(sim):
 @pytest.mark.parametrize('mixed', ['0', '1'])
 def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, programs, mixed):
     monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)        # 0: transposed second shadow (default); 1: one op, two B layouts
-    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
-    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', '0')
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '0')
     if programs:
         monkeypatch.setenv('BM_DBM_MF_CHUNK', '4')
         monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
@@ -247,8 +247,8 @@ def test_tc_dbm_queries_equal_the_bf16_emulation(executing, monkeypatch, Hs, pro
 @pytest.mark.parametrize('mixed', ['0', '1'])
 def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, Hs, gaussian, programs, mixed):
     monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
-    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
-    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', '0')
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '0')
     if programs:
         monkeypatch.setenv('BM_DBM_MF_CHUNK', '3')
         monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
@@ -268,11 +268,12 @@ def test_tc_dbm_training_steps_equal_the_bf16_emulation(executing, monkeypatch, 
     eng.close()
 
 
-@pytest.mark.parametrize('k,fused', [(1, '1'), (1, '0'), (3, '1')])
+@pytest.mark.parametrize('k,fused', [(1, 'epilogue'), (3, 'epilogue'), (1, '1'), (1, '0'), (3, '1')])
 @pytest.mark.parametrize('mixed', ['0', '1'])
 def test_tc_dbm_ais_equals_the_bf16_emulation(executing, monkeypatch, k, fused, mixed):
     monkeypatch.setenv('BM_DBM_TC_MIXED', mixed)
-    monkeypatch.setenv('BM_DBM_AIS_FUSED', fused)
+    monkeypatch.setenv('BM_DBM_AIS_EPILOGUE', '1' if fused == 'epilogue' else '0')
+    monkeypatch.setenv('BM_DBM_AIS_FUSED', '0' if fused == '0' else '1')
     cfg = small_cfg((5, 4), V=7, n_particles=4, batch_size=4)
     eng, emu = tc_pair(cfg)
     a = eng.ais(16, 60, k, 2222)

@@ -118,11 +118,13 @@ def test_first_gibbs_sweep_is_the_philox_draw():
     eng.close()
 
 
-@pytest.mark.parametrize('fused,k', [('1', 1), ('0', 1), ('1', 3), ('0', 3)])
-def test_ais_matches_exact_enumeration(monkeypatch, fused, k):
-    """fused: one pass over the pre-activations per temperature (weight increment + the next transition's first unit
-    updates); BM_DBM_AIS_FUSED=0: three passes.  Same expressions, same Philox sites."""
-    monkeypatch.setenv('BM_DBM_AIS_FUSED', fused)
+@pytest.mark.parametrize('variant,k', [('epilogue', 1), ('fused', 1), ('passes', 1), ('epilogue', 3), ('fused', 3), ('passes', 3)])
+def test_ais_matches_exact_enumeration(monkeypatch, variant, k):
+    """epilogue (default): weight increments and unit updates inside the epilogues of the three tensor-core ops of a temperature
+    step, up to 30 steps per persistent launch; fused (BM_DBM_AIS_EPILOGUE=0): fp32 pre-activations + one pass over them per
+    temperature; passes (also BM_DBM_AIS_FUSED=0): three passes.  Same expressions, same Philox sites."""
+    monkeypatch.setenv('BM_DBM_AIS_EPILOGUE', '1' if variant == 'epilogue' else '0')
+    monkeypatch.setenv('BM_DBM_AIS_FUSED', '0' if variant == 'passes' else '1')
     cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
     eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
     init(cfg, (eng, emu))
@@ -153,6 +155,24 @@ def test_ais_is_within_one_nat_of_the_pinned_oracle():
     eng.close()
 
 
+def test_ais_at_the_benchmark_shape_is_within_one_nat_of_the_float64_oracle():
+    """north_star's gate at BASELINE.json configs[3]'s own shape: DBM 784-512-1024, 256 runs x 1000 betas -- the tensor-core
+    ladder (bf16 operands, epilogue-fused) against the float64 oracle on identical weights, and against the fp32 CUDA-core
+    engine (same chains up to rounding)."""
+    cfg = make_cfg(V=784, Hs=(512, 1024), n_particles=4, batch_size=4)
+    eng, simt = _native.CudaDBM(cfg), _native.CudaDBM(dict(cfg, compute='fp32'))
+    ref = OracleDBM(dict(cfg, compute='fp32', dtype='float64'))
+    d = init(cfg, (eng, simt), scale=0.02)
+    ref.set_params({k: v.astype(np.float64) for k, v in d.items()})
+    ref.init_particles(4242)
+    lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
+    a, b, c = eng.ais(256, 1000, 1, 7), simt.ais(256, 1000, 1, 7), ref.ais(256, 1000, 1, 7)
+    assert abs(lm(a) - lm(c)) < 1.0, (lm(a), lm(c))
+    assert abs(lm(b) - lm(c)) < 1.0, (lm(b), lm(c))
+    assert abs(np.mean(a) - np.mean(c)) < 1.0
+    eng.close(); simt.close()
+
+
 def test_cfg4_shape_step_agrees_with_the_fp32_engine():
     """BASELINE.json configs[3] shape: DBM 784-512-1024, 1024 particles, batch 1024, 25 mean-field updates."""
     base = make_cfg(V=784, Hs=(512, 1024), n_particles=1024, batch_size=1024, max_mf_updates=25, mf_tol=1e-7,
@@ -179,7 +199,7 @@ def test_mean_field_programs_equal_the_sweep_by_sweep_loop(monkeypatch, chunk, H
     launch-per-op loop up to fp32 summation order."""
     V = 30 if Hs[0] < 100 else 784
     cfg = make_cfg(V=V, Hs=Hs, batch_size=max(rows, 10), max_mf_updates=7, mf_tol=2e-3)
-    monkeypatch.delenv('BM_DBM_MF_CHUNK', raising=False)
+    monkeypatch.setenv('BM_DBM_MF_CHUNK', '0')
     loop = _native.CudaDBM(cfg)
     monkeypatch.setenv('BM_DBM_MF_CHUNK', str(chunk))
     prog = _native.CudaDBM(cfg)
@@ -204,7 +224,7 @@ def test_particle_sweep_program_equals_the_launch_per_op_sweeps(monkeypatch, Hs,
     dataflow program; same ops, same Philox sites -> the same particles up to draws at rounding-level ties."""
     V = 30 if Hs[0] < 100 else 784
     cfg = make_cfg(V=V, Hs=Hs, n_particles=12 if V == 30 else 300, batch_size=10)
-    monkeypatch.delenv('BM_DBM_PCD_PROGRAM', raising=False)
+    monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '0')
     loop = _native.CudaDBM(cfg)
     monkeypatch.setenv('BM_DBM_PCD_PROGRAM', '1')
     prog = _native.CudaDBM(cfg)

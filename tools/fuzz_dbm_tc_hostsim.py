@@ -42,10 +42,8 @@ def draw(rng):
         # every element a program launch touches and reports hazards no declared dependency covers)
         cfg['batch_size'], cfg['n_particles'] = int(rng.randint(257, 700)), int(rng.randint(257, 700))
     env = dict(BM_DBM_TC_MIXED=str(rng.randint(0, 2)), BM_DBM_AIS_FUSED=str(rng.randint(0, 2)))
-    if rng.rand() < 0.6:
-        env['BM_DBM_MF_CHUNK'] = str(rng.randint(1, 6))
-    if rng.rand() < 0.6:
-        env['BM_DBM_PCD_PROGRAM'] = '1'
+    env['BM_DBM_MF_CHUNK'] = str(rng.randint(1, 6)) if rng.rand() < 0.6 else '0'        # 0: one launch per op (the default is 5)
+    env['BM_DBM_PCD_PROGRAM'] = '1' if rng.rand() < 0.6 else '0'
     run = dict(k=int(rng.randint(1, 4)), steps=int(rng.randint(1, 4)), lr=float(rng.choice([0.01, 0.05, 0.2])),
                momentum=float(rng.choice([0., 0.5, 0.9])), scale=float(rng.choice([0.05, 0.3, 1.0])),
                rows=[int(rng.randint(1, cfg['batch_size'] + 1)) if rng.rand() < 0.3 else cfg['batch_size'] for _ in range(3)])
@@ -68,7 +66,7 @@ def close(got, want, what, rtol=2.0 ** -7, atol=3e-5):
 def one(cfg, env, run, seed, sim):
     from boltzmann_machines import _native
     from oracle.dbm_bf16 import OracleDBMbf16
-    for k in ('BM_DBM_TC_MIXED', 'BM_DBM_AIS_FUSED', 'BM_DBM_MF_CHUNK', 'BM_DBM_PCD_PROGRAM'):
+    for k in ('BM_DBM_TC_MIXED', 'BM_DBM_AIS_FUSED', 'BM_DBM_MF_CHUNK', 'BM_DBM_PCD_PROGRAM', 'BM_DBM_AIS_EPILOGUE'):
         os.environ.pop(k, None)
     os.environ.update(env)
     sim.fakecuda_reset()
