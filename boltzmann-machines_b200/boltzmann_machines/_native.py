@@ -23,9 +23,10 @@ METRIC_SLOTS = {'l2_loss': 0, 'msre': 1, 'pll': 2, 'free_energy': 3}
 EXPORTS = (
     'bm_version', 'bm_last_error', 'bm_device_count', 'bm_ctx_create', 'bm_ctx_destroy', 'bm_ctx_sync',
     'bm_ctx_timer_start', 'bm_ctx_timer_stop', 'bm_ctx_flush_l2', 'bm_host_alloc', 'bm_host_free',
+    'bm_host_pack_u8', 'bm_host_pack_bf16',
     'bm_ctx_launch_count', 'bm_ctx_profile_tc', 'bm_ctx_profile_read', 'bm_comm_unique_id', 'bm_ctx_comm_init',
     'bm_rbm_create', 'bm_rbm_destroy', 'bm_rbm_set_param', 'bm_rbm_get_param', 'bm_rbm_init_weights',
-    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_train_epoch', 'bm_rbm_train_epoch_u8', 'bm_rbm_transform', 'bm_rbm_metrics',
+    'bm_rbm_train_step', 'bm_rbm_set_data', 'bm_rbm_train_step_at', 'bm_rbm_train_epoch', 'bm_rbm_train_epoch_u8', 'bm_rbm_train_epoch_bf16', 'bm_rbm_transform', 'bm_rbm_metrics',
     'bm_rbm_get_activation', 'bm_debug_tc_gemm',
     'bm_dbm_create', 'bm_dbm_destroy', 'bm_dbm_set_param', 'bm_dbm_get_param', 'bm_dbm_init_particles',
     'bm_dbm_train_step', 'bm_dbm_val_metrics', 'bm_dbm_transform', 'bm_dbm_reconstruct', 'bm_dbm_log_proba',
@@ -87,6 +88,7 @@ def load_library(path=None):
         'bm_ctx_create': [C.c_int, C.POINTER(vp)],
         'bm_ctx_sync': [vp], 'bm_ctx_timer_start': [vp], 'bm_ctx_timer_stop': [vp, C.POINTER(C.c_float)],
         'bm_ctx_flush_l2': [vp], 'bm_host_alloc': [C.POINTER(vp), sz], 'bm_host_free': [vp],
+        'bm_host_pack_u8': [vp, i32, sz, vp, C.POINTER(i32)], 'bm_host_pack_bf16': [vp, sz, vp],
         'bm_ctx_launch_count': [vp, C.POINTER(u64)],
         'bm_ctx_profile_tc': [vp, C.c_int],
         'bm_ctx_profile_read': [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(u64)],
@@ -99,6 +101,7 @@ def load_library(path=None):
         'bm_rbm_train_step_at': [vp, i64, i32, dbl, dbl, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_train_epoch': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
         'bm_rbm_train_epoch_u8': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
+        'bm_rbm_train_epoch_bf16': [vp, vp, i64, i32, dbl, dbl, i32, u64, u32, u32, i32, i64, vp],
         'bm_rbm_transform': [vp, vp, i32, i32, u64, u32, vp],
         'bm_rbm_metrics': [vp, vp, i32, i32, u64, u32, u32, C.POINTER(dbl)],
         'bm_rbm_get_activation': [vp, C.c_char_p, vp, sz],
@@ -222,15 +225,36 @@ def pinned_copy(X):
     return P
 
 
-def as_bytes(X):
-    """X as uint8 if that is lossless (all values integers in 0..255), else None."""
+def as_bytes(X, out=None):
+    """X (float32 / float64) as uint8 if that is lossless (all values integers in 0..255), else None.  One multi-threaded
+    native pass (bm_host_pack_u8); `out`: optional destination (e.g. page-locked memory) of X's shape."""
     if X.size == 0:
         return None
-    lo, hi = float(X.min()), float(X.max())
-    if not (lo >= 0.0 and hi <= 255.0):          # also false for NaN
-        return None
-    Xb = X.astype(np.uint8)
-    return Xb if np.array_equal(Xb, X) else None
+    if X.dtype not in (np.float32, np.float64) or not X.flags['C_CONTIGUOUS']:
+        lo, hi = float(X.min()), float(X.max())
+        if not (lo >= 0.0 and hi <= 255.0):          # also false for NaN
+            return None
+        Xb = X.astype(np.uint8)
+        return Xb if np.array_equal(Xb, X) else None
+    Xb = out if out is not None else np.empty(X.shape, dtype=np.uint8)
+    exact = C.c_int32(0)
+    check(load_library().bm_host_pack_u8(X.ctypes.data, DTYPES[X.dtype.name], X.size, Xb.ctypes.data, C.byref(exact)))
+    return Xb if exact.value else None
+
+
+class Bf16Array(np.ndarray):
+    """uint16 array whose elements are bfloat16 bit patterns (a real-valued training set packed for
+    bm_rbm_train_epoch_bf16).  `widen()` gives the float32 values back (exactly the rounded ones)."""
+    def widen(self):
+        return (np.asarray(self).astype(np.uint32) << 16).view(np.float32)
+
+
+def as_bf16(X, out=None):
+    """float32 X rounded to bfloat16 (round to nearest even, as the engine's own conversion), as a Bf16Array."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    P = out if out is not None else np.empty(X.shape, dtype=np.uint16)
+    check(load_library().bm_host_pack_bf16(X.ctypes.data, X.size, P.ctypes.data))
+    return P.view(Bf16Array)
 
 
 def debug_tc_gemm(A, B, a_t=False, b_t=False, A2=None, B2=None, neg2=False, splits=1, ctx=None,
@@ -330,6 +354,8 @@ class CudaRBM(object):
 
     # ---- compute -------------------------------------------------------------------
     def _batch(self, X):
+        if isinstance(X, Bf16Array):
+            X = X.widen()
         X = np.ascontiguousarray(X, dtype=self.dt)
         if X.ndim != 2 or X.shape[1] != self.V:
             raise ValueError('batch has shape {0}, expected (rows, {1})'.format(X.shape, self.V))
@@ -348,8 +374,9 @@ class CudaRBM(object):
         """One pass over the host dataset X in mini-batches (uploads overlap compute).  Returns
         {metric: [value of every reporting batch]}; batch i uses tick0 + i, exactly like
         train_step(X[i*batch:(i+1)*batch], ..., tick=tick0 + i)."""
-        byte_valued = getattr(X, 'dtype', None) == np.uint8     # see as_bytes(): exact, 4x less host->device traffic
-        if byte_valued:
+        byte_valued = getattr(X, 'dtype', None) == np.uint8 and not isinstance(X, Bf16Array)   # see as_bytes(): exact, 4x less traffic
+        packed_bf16 = isinstance(X, Bf16Array)                  # see pin(): real-valued data for the bf16 engine, 2x less traffic
+        if byte_valued or packed_bf16:
             X = np.ascontiguousarray(X)
             if X.ndim != 2 or X.shape[1] != self.V:
                 raise ValueError('batch has shape {0}, expected (rows, {1})'.format(X.shape, self.V))
@@ -357,7 +384,8 @@ class CudaRBM(object):
             X = self._batch(X)
         nb = (X.shape[0] + batch - 1) // batch
         out = np.zeros((nb, 4), dtype=np.float64)
-        fn = self._lib.bm_rbm_train_epoch_u8 if byte_valued else self._lib.bm_rbm_train_epoch
+        fn = (self._lib.bm_rbm_train_epoch_u8 if byte_valued else
+              self._lib.bm_rbm_train_epoch_bf16 if packed_bf16 else self._lib.bm_rbm_train_epoch)
         check(fn(self.handle, X.ctypes.data, X.shape[0], int(batch), lr, momentum, int(k),
                  int(seed), int(tick0), _mask(metrics), int(every), int(iter0), out.ctypes.data))
         rep = [i for i in range(nb) if every and (iter0 + i + 1) % every == 0]
@@ -368,11 +396,21 @@ class CudaRBM(object):
         0..255 (binarised MNIST: {0, 1}) is kept as one byte per unit: the engine widens it exactly on the
         device, so results do not change and each epoch moves a quarter of the bytes over PCIe."""
         X = self._batch(X)
-        Xb = as_bytes(X)
-        return pinned_copy(Xb if Xb is not None else X)
+        if X.size == 0:
+            return pinned_copy(X)
+        P = pinned_empty(X.shape, np.uint8)
+        if as_bytes(X, out=P) is not None:
+            return P
+        pinned_free(P)
+        # real-valued data: the bf16 engine rounds its input to bfloat16 before the first GEMM, so feeding the rounded
+        # values is bit-identical and halves the copy (not with dropout / sigma scaling, which act on the fp32 input first)
+        if (self.compute == 'bf16' and self.dt == np.float32 and self.cfg.get('v_kind', 'bernoulli') == 'bernoulli' and
+                self.cfg.get('h_kind', 'bernoulli') == 'bernoulli' and self.cfg.get('dropout') is None):
+            return as_bf16(X, out=pinned_empty(X.shape, np.uint16))
+        return pinned_copy(X)
 
     def unpin(self, P):
-        pinned_free(P)
+        pinned_free(np.asarray(P))
 
     def set_data(self, X):
         X = self._batch(X)

@@ -218,10 +218,20 @@ class BaseRBM(EnergyBasedModel):
         every = self.metrics_config['train_metrics_every_iter']
         sums = {m: [] for m in wanted}
         bounds = batch_bounds(len(X), self.batch_size)
-        if hasattr(self._engine, 'train_epoch') and not self.verbose:
-            # the whole batch loop in one native call: same ticks, same results, uploads overlapped
-            got = self._engine.train_epoch(X, self.batch_size, tick0=self._tick, metrics=wanted,
-                                           every=every or 0, iter0=self.iter_, **self._step_args())
+        if hasattr(self._engine, 'train_epoch'):
+            # the whole batch loop in native calls: same ticks, same results, uploads overlapped.  verbose: the epoch goes in
+            # up to 16 calls of whole batches so that the progress bar still moves (the results do not depend on the cut)
+            n_calls = min(16, len(bounds)) if self.verbose else 1
+            cuts = [len(bounds) * c // n_calls for c in range(n_calls + 1)]
+            got = {m: [] for m in wanted}
+            for c in _maybe_bar(range(n_calls), self.verbose, leave=False, ncols=64, desc='epoch'):
+                b0, b1 = cuts[c], cuts[c + 1]
+                if b0 == b1:
+                    continue
+                part = self._engine.train_epoch(X[bounds[b0][0]:bounds[b1 - 1][1]], self.batch_size, tick0=self._tick + b0,
+                                                metrics=wanted, every=every or 0, iter0=self.iter_ + b0, **self._step_args())
+                for m in wanted:
+                    got[m].extend(part[m])
             self._tick += len(bounds)
             if every:
                 steps = [self.iter_ + i + 1 for i in range(len(bounds)) if (self.iter_ + i + 1) % every == 0]

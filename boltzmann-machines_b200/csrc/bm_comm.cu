@@ -9,6 +9,9 @@
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <vector>
 #include <nvtx3/nvToolsExt.h>
 
 namespace bm {
@@ -113,6 +116,36 @@ void profile_drain(Ctx* c) {
 }
 
 }  // namespace bm
+
+// ---- host-side packing of a training set for the feed path (multi-threaded, one pass) -------------------------------------
+namespace {
+template <typename F> void parallel_ranges(size_t n, F&& body) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = hw ? hw : 8;
+    if (nt > 32) nt = 32;
+    if (n < (size_t)1 << 20) nt = 1;
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t lo = t * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        th.emplace_back([&body, lo, hi] { body(lo, hi); });
+    }
+    for (std::thread& x : th) x.join();
+}
+template <typename T> bool pack_u8(const T* X, size_t n, uint8_t* out) {
+    std::atomic<int> exact(1);
+    parallel_ranges(n, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const T v = X[i];
+            const uint8_t b = (v >= T(0) && v <= T(255)) ? (uint8_t)v : 0;
+            if ((T)b != v) { exact.store(0); return; }          // also false for NaN
+            out[i] = b;
+        }
+    });
+    return exact.load() != 0;
+}
+}  // namespace
 
 using namespace bm;
 
@@ -222,6 +255,27 @@ int bm_host_alloc(void** p, size_t bytes) {
 int bm_host_free(void* p) {
     BM_API_BEGIN
     if (p) BM_CUDA(cudaFreeHost(p));
+    BM_API_END
+}
+
+int bm_host_pack_u8(const void* X, int32_t dtype, size_t n, uint8_t* out, int32_t* exact) {
+    BM_API_BEGIN
+    BM_REQUIRE(X && out && exact && (dtype == BM_DTYPE_F32 || dtype == BM_DTYPE_F64), "bad argument");
+    *exact = (dtype == BM_DTYPE_F32 ? pack_u8((const float*)X, n, out) : pack_u8((const double*)X, n, out)) ? 1 : 0;
+    BM_API_END
+}
+
+int bm_host_pack_bf16(const float* X, size_t n, uint16_t* out) {
+    BM_API_BEGIN
+    BM_REQUIRE(X && out, "bad argument");
+    parallel_ranges(n, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            uint32_t u; memcpy(&u, X + i, 4);
+            if ((u & 0x7fffffffu) > 0x7f800000u) u |= 0x00400000u;          // NaN stays NaN (as __float2bfloat16_rn)
+            else u += 0x7fffu + ((u >> 16) & 1u);                            // round to nearest even
+            out[i] = (uint16_t)(u >> 16);
+        }
+    });
     BM_API_END
 }
 

@@ -78,13 +78,19 @@ int bm_rbm_train_step_at(bm_rbm* h, int64_t first_row, int32_t rows, double lr, 
 int bm_rbm_train_epoch(bm_rbm* h, const void* X, int64_t n_rows, int32_t batch, double lr, double momentum, int32_t k,
                        uint64_t seed, uint32_t tick0, uint32_t mask, int32_t metrics_every, int64_t iter0, double* out) {
     BM_API_BEGIN RBM_ENTER(h)
-    RBM(h)->train_epoch(X, n_rows, batch, lr, momentum, k, seed, tick0, mask, metrics_every, iter0, out, false);
+    RBM(h)->train_epoch(X, n_rows, batch, lr, momentum, k, seed, tick0, mask, metrics_every, iter0, out, SRC_NATIVE);
     BM_API_END
 }
 int bm_rbm_train_epoch_u8(bm_rbm* h, const uint8_t* X, int64_t n_rows, int32_t batch, double lr, double momentum, int32_t k,
                           uint64_t seed, uint32_t tick0, uint32_t mask, int32_t metrics_every, int64_t iter0, double* out) {
     BM_API_BEGIN RBM_ENTER(h)
-    RBM(h)->train_epoch(X, n_rows, batch, lr, momentum, k, seed, tick0, mask, metrics_every, iter0, out, true);
+    RBM(h)->train_epoch(X, n_rows, batch, lr, momentum, k, seed, tick0, mask, metrics_every, iter0, out, SRC_U8);
+    BM_API_END
+}
+int bm_rbm_train_epoch_bf16(bm_rbm* h, const uint16_t* X, int64_t n_rows, int32_t batch, double lr, double momentum, int32_t k,
+                            uint64_t seed, uint32_t tick0, uint32_t mask, int32_t metrics_every, int64_t iter0, double* out) {
+    BM_API_BEGIN RBM_ENTER(h)
+    RBM(h)->train_epoch(X, n_rows, batch, lr, momentum, k, seed, tick0, mask, metrics_every, iter0, out, SRC_BF16);
     BM_API_END
 }
 int bm_rbm_transform(bm_rbm* h, const void* X, int32_t rows, int32_t k, uint64_t seed, uint32_t tick, void* H_out) {

@@ -24,6 +24,8 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
+enum : int { SRC_NATIVE = 0, SRC_U8 = 1, SRC_BF16 = 2 };
+
 struct RbmBase {
     Ctx* ctx = nullptr;
     bm_rbm_cfg cfg{};
@@ -34,9 +36,10 @@ struct RbmBase {
     virtual void set_data(const void* X, int64_t n_rows) = 0;
     virtual void train_step(const void* X_host, int64_t first_row, int rows, double lr, double mom, int k,
                             uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
-    // src_u8: X_host holds one unsigned byte per visible unit (binary / byte-valued data) instead of cfg.dtype
+    // src: element type of X_host -- SRC_NATIVE: cfg.dtype; SRC_U8: one unsigned byte per visible unit (binary / byte-valued
+    // data, exact); SRC_BF16: bfloat16 bit patterns (real-valued data for the bf16 engine, which rounds its input to bf16 anyway)
     virtual void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
-                             uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, bool src_u8) = 0;
+                             uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, int src) = 0;
     virtual void transform(const void* X, int rows, int k, uint64_t seed, uint32_t tick, void* H_out) = 0;
     virtual void metrics(const void* X, int rows, int k, uint64_t seed, uint32_t tick, uint32_t mask, double* out) = 0;
     virtual void get_activation(const char* name, void* host, size_t bytes) = 0;
@@ -304,15 +307,20 @@ struct RbmSimt : RbmBase {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf<T> epoch_stage[2];
     DevBuf<uint8_t> epoch_stage_u8[2];
+    DevBuf<uint16_t> epoch_stage_bf16[2];
     const T* staged_dev = nullptr;
     const uint8_t* staged_u8 = nullptr;
+    const uint16_t* staged_bf16 = nullptr;
+    virtual bool accepts_bf16_feed() const { return false; }
     double* defer_dst = nullptr;
     double* epoch_host = nullptr;
     size_t epoch_host_cap = 0;
 
     void train_epoch(const void* X_host, int64_t n_rows, int batch, double lr, double mom, int k, uint64_t seed,
-                     uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, bool src_u8) override {
+                     uint32_t tick0, uint32_t mask, int every, int64_t iter0, double* out, int src) override {
         BM_REQUIRE(X_host != nullptr && n_rows >= 1 && batch >= 1, "empty dataset or batch");
+        const bool src_u8 = src == SRC_U8, src_bf16 = src == SRC_BF16;
+        BM_REQUIRE(!src_bf16 || accepts_bf16_feed(), "a bfloat16 feed needs the bf16 tensor-core engine without dropout / sigma scaling");
         BM_REQUIRE(!mask || out != nullptr, "metrics requested without an output buffer");
         const int64_t nb = (n_rows + batch - 1) / batch;
         if (!copy_stream) {
@@ -322,7 +330,11 @@ struct RbmSimt : RbmBase {
                 BM_CUDA(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
             }
         }
-        for (int b = 0; b < 2; ++b) { if (src_u8) epoch_stage_u8[b].ensure((size_t)batch * V); else epoch_stage[b].ensure((size_t)batch * V); }
+        for (int b = 0; b < 2; ++b) {
+            if (src_u8) epoch_stage_u8[b].ensure((size_t)batch * V);
+            else if (src_bf16) epoch_stage_bf16[b].ensure((size_t)batch * V);
+            else epoch_stage[b].ensure((size_t)batch * V);
+        }
         if ((size_t)nb * 8 > epoch_host_cap) {
             if (epoch_host) cudaFreeHost(epoch_host);
             epoch_host = nullptr; epoch_host_cap = 0;
@@ -333,6 +345,7 @@ struct RbmSimt : RbmBase {
         for (int b = 0; b < 2; ++b) BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
         const T* Xh = (const T*)X_host;
         const uint8_t* Xh8 = (const uint8_t*)X_host;
+        const uint16_t* Xh16 = (const uint16_t*)X_host;
         double unused[4];
         try {
             for (int64_t i = 0; i < nb; ++i) {
@@ -342,23 +355,28 @@ struct RbmSimt : RbmBase {
                 if (src_u8)
                     BM_CUDA(cudaMemcpyAsync(epoch_stage_u8[b].p, Xh8 + (size_t)i * batch * V, (size_t)rows * V,
                                             cudaMemcpyHostToDevice, copy_stream));
+                else if (src_bf16)
+                    BM_CUDA(cudaMemcpyAsync(epoch_stage_bf16[b].p, Xh16 + (size_t)i * batch * V, (size_t)rows * V * 2,
+                                            cudaMemcpyHostToDevice, copy_stream));
                 else
                     BM_CUDA(cudaMemcpyAsync(epoch_stage[b].p, Xh + (size_t)i * batch * V, (size_t)rows * V * sizeof(T),
                                             cudaMemcpyHostToDevice, copy_stream));
                 BM_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
                 BM_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
-                if (src_u8) staged_u8 = epoch_stage_u8[b].p; else staged_dev = epoch_stage[b].p;
+                if (src_u8) staged_u8 = epoch_stage_u8[b].p;
+                else if (src_bf16) staged_bf16 = epoch_stage_bf16[b].p;
+                else staged_dev = epoch_stage[b].p;
                 const bool report = mask && every > 0 && ((iter0 + i + 1) % every == 0);
                 defer_dst = epoch_host + 8 * i;
                 train_step(nullptr, 0, rows, lr, mom, k, seed, tick0 + (uint32_t)i, report ? mask : 0u, unused);
                 BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
             }
         } catch (...) {
-            staged_dev = nullptr; staged_u8 = nullptr; defer_dst = nullptr;
+            staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; defer_dst = nullptr;
             cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(ctx->stream);
             throw;
         }
-        staged_dev = nullptr; staged_u8 = nullptr; defer_dst = nullptr;
+        staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; defer_dst = nullptr;
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int64_t i = 0; i < nb && mask; ++i) {
             const bool report = every > 0 && ((iter0 + i + 1) % every == 0);

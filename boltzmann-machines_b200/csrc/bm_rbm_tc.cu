@@ -58,6 +58,7 @@ struct RbmTC : RbmSimt<float> {
         reserve_tc(f.max_batch > 0 ? f.max_batch : 1);
     }
 
+    bool accepts_bf16_feed() const override { return tc_kinds && cfg.v_kind != BM_UNIT_GAUSSIAN && cfg.dropout_keep < 0; }
     static bool tc_kinds_of(const bm_rbm_cfg& f) {
         return (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
     }
@@ -131,7 +132,16 @@ struct RbmTC : RbmSimt<float> {
     void stage_tc(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve_tc(rows);
         const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
-        if (staged_u8 && plain) {
+        if (staged_bf16) {
+            // real-valued epoch data fed as bfloat16 (accepted only when `plain`): the bits the fp32 -> bf16 conversion of the
+            // float feed would produce, so the chain is bit-identical at half the host->device bytes
+            BM_REQUIRE(plain, "a bfloat16 feed needs a model without dropout / sigma scaling");
+            reserve(rows);
+            BM_CUDA(cudaMemcpy2DAsync(Xb.p, (size_t)ldv * 2, staged_bf16, (size_t)V * 2, (size_t)V * 2, (size_t)rows,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+            X_b = Xb.p; X_ld = ldv; X_row0 = 0; X_rows_total = rows;
+            Xcur = nullptr;
+        } else if (staged_u8 && plain) {
             // byte-valued epoch data goes straight to the bf16 operand buffer; the fp32 copy the CUDA-core
             // metric kernels read is made only when such a metric is requested (ensure_fp32_input)
             reserve(rows);

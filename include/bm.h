@@ -76,6 +76,12 @@ int  bm_ctx_timer_stop(bm_ctx* ctx, float* ms);
 int  bm_ctx_flush_l2(bm_ctx* ctx);                              /* writes a >L2-sized scratch buffer */
 int  bm_host_alloc(void** p, size_t bytes);                     /* pinned host memory for the feed path */
 int  bm_host_free(void* p);
+/* packing of a host training set for the feed path (what BaseRBM.fit does once per call; multi-threaded, one pass):
+ * bm_host_pack_u8: *exact = 1 and out[i] = X[i] if every value is an integer in 0..255 (dtype BM_DTYPE_F32 / F64), else
+ * *exact = 0;  bm_host_pack_bf16: out[i] = round-to-nearest-even bfloat16 of X[i].  Replace the numpy casts feed_dict relied on
+ * (rbm/base_rbm.py:533-547). */
+int  bm_host_pack_u8(const void* X, int32_t dtype, size_t n, uint8_t* out, int32_t* exact);
+int  bm_host_pack_bf16(const float* X, size_t n, uint16_t* out);
 int  bm_ctx_launch_count(bm_ctx* ctx, uint64_t* n);             /* kernels launched by this library on ctx */
 /* per-launch CUDA-event timing of the tensor-core layer kernel (the roofline's dominant kernel):
  * enable, run, then read the accumulated algorithmic FLOPs, device milliseconds and launch count */
@@ -128,6 +134,13 @@ int  bm_rbm_train_epoch(bm_rbm* rbm, const void* X, int64_t n_rows, int32_t batc
 int  bm_rbm_train_epoch_u8(bm_rbm* rbm, const uint8_t* X, int64_t n_rows, int32_t batch, double lr, double momentum,
                            int32_t n_gibbs_steps, uint64_t seed, uint32_t tick0, uint32_t metric_mask,
                            int32_t metrics_every, int64_t iter0, double* out);
+/* Same epoch for REAL-VALUED data fed as bfloat16 bit patterns (grey levels: examples/rbm_mnist.py:209): the tensor-core
+ * engine rounds its input to bf16 before the first GEMM anyway, so the result is bit-identical to bm_rbm_train_epoch on the
+ * float32 rows while the host->device copy is half the size.  Only for float32 models on the bf16 engine without dropout or
+ * sigma scaling (BM_EINVAL otherwise); bm_host_pack_bf16 makes X. */
+int  bm_rbm_train_epoch_bf16(bm_rbm* rbm, const uint16_t* X, int64_t n_rows, int32_t batch, double lr, double momentum,
+                             int32_t n_gibbs_steps, uint64_t seed, uint32_t tick0, uint32_t metric_mask,
+                             int32_t metrics_every, int64_t iter0, double* out);
 int  bm_rbm_transform(bm_rbm* rbm, const void* X, int32_t rows, int32_t n_gibbs_steps,
                       uint64_t seed, uint32_t tick, void* H_out);
 /* msre / pll / l2_loss / free_energy_op on a batch without training (base_rbm.py:573-621) */
