@@ -197,6 +197,31 @@ def test_byte_valued_epoch_is_bit_identical_to_the_float_epoch(compute, dtype, d
     a.close(), b.close()
 
 
+def test_bfloat16_feed_epoch_is_bit_identical_to_the_float_epoch():
+    """bm_rbm_train_epoch_bf16 (real-valued data packed as bfloat16 by bm_host_pack_bf16) = bm_rbm_train_epoch on the float32
+    rows for the bf16 engine, which rounds its input to bfloat16 before the first GEMM: same parameters bit for bit; MSRE too
+    (it is computed from the bf16 activations); refused by the fp32 engine and with dropout."""
+    cfg = make_cfg('bernoulli', 100, 48, 16, compute='bf16', dtype='float32', sample_v=False)
+    a, _ = make_pair(cfg)
+    b, _ = make_pair(cfg)
+    X = (np.random.RandomState(3).rand(16 * 4 + 5, 100) ** 2).astype(np.float32)          # grey levels in [0, 1)
+    P = b.pin(X)
+    assert isinstance(P, _native.Bf16Array) and P.shape == X.shape
+    np.testing.assert_array_equal(P.widen(), np.asarray(_native.as_bf16(X)).view(_native.Bf16Array).widen())
+    assert np.max(np.abs(P.widen() - X)) <= 2.0 ** -8
+    want = a.train_epoch(X, 16, 0.05, 0.5, 2, 11, 3, metrics=('msre',), every=2, iter0=0)
+    got = b.train_epoch(P, 16, 0.05, 0.5, 2, 11, 3, metrics=('msre',), every=2, iter0=0)
+    np.testing.assert_allclose(got['msre'], want['msre'], rtol=1e-12)
+    for k, v in a.get_params().items():
+        np.testing.assert_array_equal(v, b.get_params()[k], err_msg=k)
+    c, _ = make_pair(make_cfg('bernoulli', 100, 48, 16, compute='fp32', dtype='float32', sample_v=False))
+    assert not isinstance(c.pin(X), _native.Bf16Array)               # (leaks one small pinned block; fine in a test)
+    with pytest.raises(RuntimeError, match='bfloat16 feed'):
+        c.train_epoch(P, 16, 0.05, 0.5, 2, 11, 3)
+    b.unpin(P)
+    a.close(), b.close(), c.close()
+
+
 def test_fit_takes_the_byte_path_for_binary_data_and_matches_float_feeding(workdir, monkeypatch):
     """BaseRBM.fit pins binary data as bytes (engine.pin -> as_bytes); the trained weights equal those of a fit
     whose data went through the float32 path (the reference's feed_dict values, base_rbm.py:549-571)."""

@@ -118,6 +118,19 @@ def test_first_gibbs_sweep_is_the_philox_draw():
     eng.close()
 
 
+_EMU_AIS = {}
+
+
+def _emulated_ladder(cfg, k, n_betas):
+    """the bf16 emulation's ladder (numpy loops: a minute per call) is the same for every engine variant: computed once"""
+    key = (k, n_betas)
+    if key not in _EMU_AIS:
+        emu = OracleDBMbf16(cfg)
+        init(cfg, (emu,))
+        _EMU_AIS[key] = (emu.ais(32, n_betas, k, 2222), emu.get_params())
+    return _EMU_AIS[key]
+
+
 @pytest.mark.parametrize('variant,k', [('epilogue', 1), ('fused', 1), ('passes', 1), ('epilogue', 3), ('fused', 3), ('passes', 3)])
 def test_ais_matches_exact_enumeration(monkeypatch, variant, k):
     """epilogue (default): weight increments and unit updates inside the epilogues of the three tensor-core ops of a temperature
@@ -126,13 +139,14 @@ def test_ais_matches_exact_enumeration(monkeypatch, variant, k):
     monkeypatch.setenv('BM_DBM_AIS_EPILOGUE', '1' if variant == 'epilogue' else '0')
     monkeypatch.setenv('BM_DBM_AIS_FUSED', '0' if variant == 'passes' else '1')
     cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
-    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
-    init(cfg, (eng, emu))
-    a = eng.ais(32, 500, k, 2222)
-    b = emu.ais(32, 500, k, 2222)
+    n_betas = 500 if k == 1 else 300
+    eng = _native.CudaDBM(cfg)
+    init(cfg, (eng,))
+    a = eng.ais(32, n_betas, k, 2222)
+    b, p = _emulated_ladder(cfg, k, n_betas)
     lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
     assert abs(lm(a) - lm(b)) < 0.1
-    p = emu.get_params()
+    assert np.mean(np.abs(a - b) < 2e-3) > 0.8           # the same chains, but for a draw at rounding distance of its probability
     W0, W1 = bf16_round(p['W']).astype(np.float64), bf16_round(p['W_1']).astype(np.float64)
     terms = []
     for s in range(2 ** 5):
