@@ -59,9 +59,15 @@ struct RbmTC : RbmSimt<float> {
     }
 
     bool accepts_bf16_feed() const override { return tc_kinds && cfg.v_kind != BM_UNIT_GAUSSIAN && cfg.dropout_keep < 0; }
+    // every built-in unit kind runs its GEMMs on the tensor cores.  Bernoulli / Gaussian conditionals are fused into the
+    // GEMM's epilogue and the whole chain is one program; a multinomial layer needs the whole row for its softmax
+    // (layers.py:65-70), so its conditional is GEMM (raw fp32 pre-activations) -> row softmax -> categorical draws as
+    // separate launches (`mixed`), the other layer's conditional staying fused.
     static bool tc_kinds_of(const bm_rbm_cfg& f) {
-        return (f.h_kind == BM_UNIT_BERNOULLI) && (f.v_kind == BM_UNIT_BERNOULLI || f.v_kind == BM_UNIT_GAUSSIAN);
+        auto ok = [](int k) { return k == BM_UNIT_BERNOULLI || k == BM_UNIT_MULTINOMIAL; };
+        return ok(f.h_kind) && (ok(f.v_kind) || f.v_kind == BM_UNIT_GAUSSIAN);
     }
+    bool mixed() const { return cfg.h_kind == BM_UNIT_MULTINOMIAL || cfg.v_kind == BM_UNIT_MULTINOMIAL; }
 
     void reserve_tc(int rows) {
         if (rows <= tc_cap) return;
@@ -188,25 +194,29 @@ struct RbmTC : RbmSimt<float> {
         const bool sh = cfg.sample_h != 0, sv = cfg.sample_v != 0;
         std::vector<TcGemm>& ops = prog.ops;
         ops.clear();
-        // rows of the resident dataset beyond this batch only produce output rows >= M, which are masked
-        ops.push_back(layer_op(true, mat(X_b, X_rows_total, V, X_ld), resident, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows));
-        if (!resident) ops.back().a_row0[0] = X_row0;
-        h0state_b = sh ? h0s_b.p : h0m_b.p;
-        const bf16* hstate = h0state_b;
-        int prev = 0;
-        for (int t = 1; t <= k; ++t) {
-            // outputs nobody reads are not written: sampled visibles need their means only at the
-            // last step (MSRE), sampled mid-chain hiddens never need theirs
-            const bool last = (t == k);
-            TcGemm gv = layer_op(false, mat(hstate, rows, H, ldh), false, (sv && !last) ? nullptr : vm_b.p, vs_b.p, sv, SITE_V, t, rows);
-            gv.n_deps = 1; gv.dep[0] = prev;
-            ops.push_back(gv); prev = (int)ops.size() - 1;
-            vstate_b = sv ? vs_b.p : vm_b.p;
-            const bool smp = sh && !last;
-            TcGemm gh = layer_op(true, mat(vstate_b, rows, V, ldv), false, smp ? nullptr : hm_b.p, hs_b.p, smp, SITE_H, t, rows);
-            gh.n_deps = 1; gh.dep[0] = prev;
-            ops.push_back(gh); prev = (int)ops.size() - 1;
-            hstate = smp ? hs_b.p : hm_b.p;
+        const bool in_program = !mixed();          // mixed: the chain has just run launch by launch (chain_mixed)
+        const bf16* hstate = nullptr;
+        if (in_program) {
+            // rows of the resident dataset beyond this batch only produce output rows >= M, which are masked
+            ops.push_back(layer_op(true, mat(X_b, X_rows_total, V, X_ld), resident, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows));
+            if (!resident) ops.back().a_row0[0] = X_row0;
+            h0state_b = sh ? h0s_b.p : h0m_b.p;
+            hstate = h0state_b;
+            int prev = 0;
+            for (int t = 1; t <= k; ++t) {
+                // outputs nobody reads are not written: sampled visibles need their means only at the
+                // last step (MSRE), sampled mid-chain hiddens never need theirs
+                const bool last = (t == k);
+                TcGemm gv = layer_op(false, mat(hstate, rows, H, ldh), false, (sv && !last) ? nullptr : vm_b.p, vs_b.p, sv, SITE_V, t, rows);
+                gv.n_deps = 1; gv.dep[0] = prev;
+                ops.push_back(gv); prev = (int)ops.size() - 1;
+                vstate_b = sv ? vs_b.p : vm_b.p;
+                const bool smp = sh && !last;
+                TcGemm gh = layer_op(true, mat(vstate_b, rows, V, ldv), false, smp ? nullptr : hm_b.p, hs_b.p, smp, SITE_H, t, rows);
+                gh.n_deps = 1; gh.dep[0] = prev;
+                ops.push_back(gh); prev = (int)ops.size() - 1;
+                hstate = smp ? hs_b.p : hm_b.p;
+            }
         }
         if (with_dw) {
             // dW_positive - dW_negative (base_rbm.py:447-448): G = X^T h0_means - v_k^T h_k_means, K = the batch rows,
@@ -248,7 +258,7 @@ struct RbmTC : RbmSimt<float> {
             if (prog.chain_units < 0)            // shapes are fixed per cached program: plan once
                 for (const TcGemm& o : ops) prog.chain_units = std::max(prog.chain_units, tc_plan_units(ctx, o));
             const int chain_units = prog.chain_units;
-            const int spare = total_pairs - chain_units;
+            const int spare = in_program ? total_pairs - chain_units : 0;
             int pos_splits = 0;
             if (spare >= 2 && pair_tiles > 0) {
                 pos_splits = std::max(1, std::min(spare / pair_tiles, row_chunks));
@@ -295,7 +305,7 @@ struct RbmTC : RbmSimt<float> {
                 gc.splits = vs;
                 vparts.ensure((size_t)vs * vstride());
                 gc.out_f32 = vparts.p;
-                gc.n_deps = 1; gc.dep[0] = last_v; gc.dep_all[0] = true;
+                if (in_program) { gc.n_deps = 1; gc.dep[0] = last_v; gc.dep_all[0] = true; }
                 gc.lane = LANE_ALL;
                 ops.push_back(gc);
                 TcGemm g = dw_op(true, true);
@@ -306,15 +316,71 @@ struct RbmTC : RbmSimt<float> {
                 g.splits = splits;
                 partials.ensure((size_t)splits * gstride());
                 g.out_f32 = partials.p;
-                g.n_deps = 3;
-                g.dep[0] = 0; g.dep[1] = last_v; g.dep[2] = last_h;
-                g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
+                if (in_program) {
+                    g.n_deps = 3;
+                    g.dep[0] = 0; g.dep[1] = last_v; g.dep[2] = last_h;
+                    g.dep_all[0] = g.dep_all[1] = g.dep_all[2] = true;
+                }
                 g.lane = LANE_ALL;
                 ops.push_back(g);
             }
         }
-        launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
+        if (!ops.empty()) launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
         last_was_tc = true;
+    }
+
+    // One conditional of a model with a multinomial layer, launch by launch: the GEMM on the tensor cores, then (multinomial
+    // side) M * softmax over the row and the categorical draws on the fp32 pre-activations (layers.py:65-70; sampling reads the
+    // UNROUNDED means, like the oracle), bf16 copies for the next GEMM.
+    void half_step_mixed(bool up, TcMat in, bool in_is_batch_cursor, bf16* means_b, bf16* states_b, bool sample,
+                         uint32_t site, uint32_t t, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
+        const int kind = up ? cfg.h_kind : cfg.v_kind;
+        const int N = up ? H : V, ldo = up ? ldh : ldv;
+        const RngKey rng = make_rng(seed, site, t, tick, row0);
+        if (kind != BM_UNIT_MULTINOMIAL) {
+            TcGemm g = layer_op(up, in, in_is_batch_cursor, means_b, states_b, sample, site, t, rows);
+            g.rng = rng;
+            if (in_is_batch_cursor) { g.a_batch[0] = false; g.a_row0[0] = X_row0; }       // single launches carry no batch cursor
+            launch_tc_gemm(ctx, g);
+            return;
+        }
+        float* pre = up ? hm.p : vm.p;             // fp32 workspaces of the storage-precision engine (reserve())
+        float* st = up ? hs.p : vs.p;
+        TcGemm g;
+        g.M = rows; g.N = N;
+        g.A[0] = in; g.K[0] = up ? V : H;
+        if (in_is_batch_cursor) g.a_row0[0] = X_row0;
+        g.B[0] = mat(Wb.p, V, H, ldw); g.b_t[0] = up;
+        const float mult = (float)(up ? cfg.propup_mult : cfg.propdown_mult);
+        g.acc_scale = mult; g.bias_scale = mult; g.bias = up ? hb.p : vb.p;
+        g.act = ACT_LINEAR;
+        g.out_f32 = pre; g.ld_f32 = N;
+        launch_tc_gemm(ctx, g);
+        const double M = up ? cfg.h_n_samples : cfg.v_n_samples;
+        launch_softmax_rows<float>(ctx, pre, N, rows, N, (float)M);
+        if (sample) {
+            launch_multinomial_rows<float>(ctx, pre, N, rows, N, (int)M, st, N, rng);
+            launch_f32_to_bf16(ctx, st, N, states_b, ldo, rows, N);
+        }
+        if (means_b) launch_f32_to_bf16(ctx, pre, N, means_b, ldo, rows, N);
+    }
+    void chain_mixed(int rows, int k, uint64_t seed, uint32_t tick, uint32_t row0) {
+        BM_REQUIRE(k >= 1, "n_gibbs_steps must be >= 1");
+        reserve(rows);
+        const bool resident = (X_b == data_b.p);
+        const bool sh = cfg.sample_h != 0, sv = cfg.sample_v != 0;
+        half_step_mixed(true, mat(X_b, X_rows_total, V, X_ld), true, h0m_b.p, h0s_b.p, sh, SITE_H0, 0, rows, seed, tick, row0);
+        (void)resident;
+        h0state_b = sh ? h0s_b.p : h0m_b.p;
+        const bf16* hstate = h0state_b;
+        for (int t = 1; t <= k; ++t) {
+            const bool last = (t == k);
+            half_step_mixed(false, mat(hstate, rows, H, ldh), false, vm_b.p, vs_b.p, sv, SITE_V, t, rows, seed, tick, row0);
+            vstate_b = sv ? vs_b.p : vm_b.p;
+            const bool smp = sh && !last;
+            half_step_mixed(true, mat(vstate_b, rows, V, ldv), false, hm_b.p, hs_b.p, smp, SITE_H, t, rows, seed, tick, row0);
+            hstate = smp ? hs_b.p : hm_b.p;
+        }
     }
 
     void train_step(const void* X_host, int64_t first_row, int rows, double lr, double mom, int k,
@@ -323,6 +389,7 @@ struct RbmTC : RbmSimt<float> {
         BM_REQUIRE(rows >= 1, "empty batch");
         const uint32_t row0 = (uint32_t)(ctx->rank * rows);
         stage_tc(X_host, first_row, rows, seed, tick, row0);
+        if (mixed()) chain_mixed(rows, k, seed, tick, row0);
         run_program(rows, k, true, seed, tick, row0);
         if (mask) {
             if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
@@ -370,6 +437,7 @@ struct RbmTC : RbmSimt<float> {
         if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::transform(X_host, rows, k, seed, tick, H_out); return; }
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
+        if (mixed()) chain_mixed(rows, k, seed, tick, 0);
         run_program(rows, k, false, seed, tick, 0);
         launch_bf16_to_f32(ctx, hm_b.p, ldh, widen.p, H, rows, H);
         BM_CUDA(cudaMemcpyAsync(H_out, widen.p, (size_t)rows * H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -380,6 +448,7 @@ struct RbmTC : RbmSimt<float> {
         if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::metrics(X_host, rows, k, seed, tick, mask, out); return; }
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
+        if ((mask & BM_METRIC_MSRE) && mixed()) chain_mixed(rows, k, seed, tick, 0);
         if (mask & BM_METRIC_MSRE) run_program(rows, k, false, seed, tick, 0);
         if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
         run_metrics(mask, rows, seed, tick, 0, out);

@@ -80,6 +80,10 @@ def make_cfg(kind, V, H, B, **kw):
                sample_v=False, sample_h=True, sparsity_cost=0.01, sparsity_target=0.2)
     if kind == 'gaussian':
         cfg.update(v_kind='gaussian', h_kind='bernoulli', sigma=np.linspace(0.5, 1.5, V))
+    elif kind == 'multinomial':
+        cfg.update(v_kind='bernoulli', h_kind='multinomial', h_n_samples=20)
+    elif kind == 'multinomial-v':
+        cfg.update(v_kind='multinomial', h_kind='bernoulli', v_n_samples=30, sample_v=True)
     else:
         cfg.update(v_kind='bernoulli', h_kind='bernoulli')
     cfg.update(kw)
@@ -178,3 +182,31 @@ def test_bf16_training_tracks_fp32_statistically():
     assert m['msre'] == pytest.approx(m0['msre'], rel=0.05)
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize('kind', ['multinomial', 'multinomial-v'])
+@pytest.mark.parametrize('V,H,B,k', [(130, 70, 65, 1), (784, 256, 128, 2), (37, 29, 19, 3)])
+def test_multinomial_layers_on_the_tensor_cores_match_the_rounding_oracle(kind, V, H, B, k):
+    """layers.py:54-70 with the GEMMs on tcgen05 (raw fp32 pre-activations -> row softmax -> categorical draws on the unrounded
+    means -> bf16 operands of the next GEMM), against the oracle that rounds at the same points: activations to a bf16 ulp,
+    counts from the shared Philox stream, the whole update."""
+    cfg = make_cfg(kind, V, H, B)
+    eng, ora = make_pair(cfg)
+    assert eng.compute == 'bf16'
+    X = data(cfg, B) if kind == 'multinomial' else np.random.RandomState(2).multinomial(30, np.ones(V) / V, size=B).astype(np.float32)
+    seed, tick = 0xBEEF, 4
+    Xp = ora.prepare_input(X, seed, tick)
+    h0_means, v_states, v_means, _, h_means = ora.chain(Xp, k, seed, tick)
+    eng.train_step(X, 0.05, 0.5, k, seed, tick)
+    np.testing.assert_allclose(eng.get_activation('h0_means', B), h0_means, rtol=2.0 ** -6, atol=2e-3, err_msg='h0_means')
+    if k == 1:
+        # (one categorical draw landing in a neighbouring bin moves two counts by one)
+        assert np.mean(eng.get_activation('v_states', B) != v_states) < 0.02
+        np.testing.assert_allclose(eng.get_activation('h_means', B), h_means, rtol=0.05, atol=0.05)
+    ora.train_step(X, 0.05, 0.5, k, seed, tick)
+    g, w = eng.get_params(), ora.get_params()
+    tol = 3e-3 + 0.06 * (30 if kind == 'multinomial-v' else 20) / 20 / B
+    for name in ('W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'):
+        np.testing.assert_allclose(g[name], w[name], atol=tol * max(1.0, float(np.abs(w[name]).max())), err_msg=name)
+    np.testing.assert_allclose(eng.transform(X, k, 5, 9), ora.transform(X, k, 5, 9), rtol=0.05, atol=0.05)
+    eng.close()

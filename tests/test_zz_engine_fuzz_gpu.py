@@ -45,12 +45,9 @@ def rbm_case(i):
 def test_rbm_two_steps_on_random_shapes(i, compute):
     cfg, k, init, X = rbm_case(i)
     cfg = dict(cfg, compute=compute)
-    # unit kinds the tensor-core epilogue does not implement (multinomial) run on the storage-precision kernels whatever
-    # `compute` says (bm_rbm_tc.cu: tc_kinds): the oracle that goes with them does not round to bf16
-    tc = cfg['h_kind'] == 'bernoulli' and cfg['v_kind'] in ('bernoulli', 'gaussian')
-    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg if tc else dict(cfg, compute='fp32'))
-    if not tc:
-        compute = 'fp32'                 # tolerances below
+    # every built-in unit kind runs its GEMMs on the tensor cores under compute='bf16' (multinomial layers: GEMM, then row
+    # softmax and draws as separate launches, bm_rbm_tc.cu: mixed()): the oracle rounds to bf16 at the same points
+    eng, ora = _native.CudaRBM(cfg), OracleRBM(cfg)
     eng.set_params(init), ora.set_params(init)
     for it in range(2):
         eng.train_step(X[it], 0.05, 0.5, k, 4242, it)
@@ -58,6 +55,8 @@ def test_rbm_two_steps_on_random_shapes(i, compute):
     g, w = eng.get_params(), ora.get_params()
     # fp32: summation order / libm; a draw differs only at rounding-level ties (one flipped unit moves dW by lr/B)
     tol = (5e-5 + 0.06 / X.shape[1]) if compute == 'fp32' else (3e-3 + 0.06 / X.shape[1])
+    if cfg['h_kind'] == 'multinomial' and compute == 'bf16':
+        tol *= 4.0                       # means up to n_samples (20) carry bf16 rounding of that size
     for name in ('W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'):
         assert np.all(np.isfinite(g[name])), name
         np.testing.assert_allclose(g[name], w[name], atol=tol, err_msg='{0} {1}'.format(name, cfg))
