@@ -158,9 +158,7 @@ class BaseRBM(EnergyBasedModel):
         )
         for side, layer in (('v', self._v_layer), ('h', self._h_layer)):
             if layer.kind is None:
-                raise NotImplementedError(
-                    'layer {0} does not name a built-in unit kind; the native engine '
-                    'implements bernoulli/multinomial/gaussian units only'.format(type(layer).__name__))
+                continue                       # user-defined layer: the host-driven plugin engine (_make_engine)
             ep = layer.engine_params()
             if 'n_samples' in ep:
                 cfg[side + '_n_samples'] = float(ep['n_samples'])
@@ -172,6 +170,11 @@ class BaseRBM(EnergyBasedModel):
         return cfg
 
     def _make_engine(self):
+        if self._v_layer.kind is None or self._h_layer.kind is None:
+            # a layer that is none of the built-in kinds (layers.py:8-36): GEMMs on the GPU, the layer's own
+            # activation / _sample on the host in between (boltzmann_machines/_plugin.py)
+            from .._plugin import HostLayerRBM
+            return HostLayerRBM(self._engine_cfg(), self._v_layer, self._h_layer)
         return get_engine_factory('rbm')(self._engine_cfg())
 
     _make_tf_model = _make_engine      # the reference's hook name

@@ -83,12 +83,12 @@ __global__ void colnorm_kernel(const T* __restrict__ W, int rows, int cols, T* _
 template <typename T>
 __global__ void max_norm_scale_kernel(T* __restrict__ W, int rows, int cols, const T* __restrict__ norm, T max_norm) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= cols || r >= rows) return;
+    if (c >= cols) return;
     const T n = norm[c];
     const T num = n < max_norm ? n : max_norm;                       // dbm.py:513: T * min(norm, c) / max(norm, 1e-8)
     const T den = n > T(1e-8) ? n : T(1e-8);
-    W[(size_t)r * cols + c] = W[(size_t)r * cols + c] * num / den;
+    // (rows stride over grid.y: the launch caps it at 32768 blocks, below the 65535 limit of that dimension)
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) W[(size_t)r * cols + c] = W[(size_t)r * cols + c] * num / den;
 }
 
 // per-row terms of the variational bound (dbm.py:743-757); t1 = X W_0, t2 = mu_0 W_1
@@ -524,7 +524,7 @@ struct Dbm : DbmBase {
             launch_weight_update<T>(ctx, G[i].p, H, T(1), W[i].p, dW[i].p, in, H, pen[i].p, (T)l2, (T)lr, (T)mom, nullptr, 0);
             colnorm_kernel<T><<<(H + 31) / 32, dim3(32, 8), 0, ctx->stream>>>(W[i].p, in, H, norm[i].p);       // :511-513
             count_launch(ctx);
-            max_norm_scale_kernel<T><<<dim3((H + 255) / 256, in), 256, 0, ctx->stream>>>(W[i].p, in, H, norm[i].p, (T)max_norm);
+            max_norm_scale_kernel<T><<<dim3((H + 255) / 256, in < 32768 ? in : 32768), 256, 0, ctx->stream>>>(W[i].p, in, H, norm[i].p, (T)max_norm);
             count_launch(ctx);
         }
     }

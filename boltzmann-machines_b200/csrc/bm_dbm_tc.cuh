@@ -629,7 +629,7 @@ struct DbmTC : Dbm<float> {
             launch_weight_update<float>(ctx, G[i].p, H, 1.f, W[i].p, dW[i].p, in, H, pen[i].p, (float)l2, (float)lr, (float)mom, nullptr, 0);
             colnorm_kernel<float><<<(H + 31) / 32, dim3(32, 8), 0, ctx->stream>>>(W[i].p, in, H, norm[i].p);       // :511-513
             count_launch(ctx);
-            max_norm_scale_kernel<float><<<dim3((H + 255) / 256, in), 256, 0, ctx->stream>>>(W[i].p, in, H, norm[i].p, (float)max_norm);
+            max_norm_scale_kernel<float><<<dim3((H + 255) / 256, in < 32768 ? in : 32768), 256, 0, ctx->stream>>>(W[i].p, in, H, norm[i].p, (float)max_norm);
             count_launch(ctx);
             refresh_shadow(i);
         }

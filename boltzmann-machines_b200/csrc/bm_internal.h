@@ -62,6 +62,10 @@ struct Ctx {
     size_t prof_used = 0;
     double prof_flops = 0.0, prof_ms = 0.0;
     uint64_t prof_launches = 0;
+    // scratch of the small reduction kernels: per CONTEXT (two contexts on one device run on different streams)
+    double* sqdiff_scratch = nullptr;
+    float* colsum_scratch = nullptr;
+    size_t colsum_scratch_floats = 0;
     // NCCL (resolved at run time with dlopen; see bm_comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;

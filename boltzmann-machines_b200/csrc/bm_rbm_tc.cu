@@ -33,6 +33,7 @@ struct RbmTC : RbmSimt<float> {
     // cached programs, keyed by (rows, k, with_dw, input buffer is the resident dataset)
     std::map<std::tuple<int, int, int, int>, std::unique_ptr<TcProgram>> progs;
     int dw_splits = 1, v_splits = 1;
+    static constexpr int PROGRAM_OPS = 90;      // ops per launch (the kernel's descriptor table holds 96)
     PeerExchange peer;             // data parallelism over NVLink peer memory (inactive on one rank / without peer access)
     // The batch buffers (X, v_k) carry two constant columns behind their V data columns -- (1, 0) for X, (1, 1) for v_k --
     // so that the dW GEMMs, run over V + 2 rows, also deliver sum(h0 - h_k) (row V) and -sum(h_k) (row V + 1): the
@@ -268,6 +269,7 @@ struct RbmTC : RbmSimt<float> {
                 if (pos_cycles > 0.8 * chain_cycles) pos_splits = 0;
             }
             { const char* e = getenv("BM_TC_DW_OVERLAP"); if (e && !atoi(e)) pos_splits = 0; }
+            if ((int)ops.size() + 4 > PROGRAM_OPS) pos_splits = 0;      // a chain cut into several launches keeps its statistics at the end
             const int last_v = (int)ops.size() - 2, last_h = (int)ops.size() - 1;
             if (pos_splits > 0) {
                 const int neg_splits = std::max(1, std::min(total_pairs / pair_tiles, row_chunks));
@@ -325,7 +327,29 @@ struct RbmTC : RbmSimt<float> {
                 ops.push_back(g);
             }
         }
-        if (!ops.empty()) launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
+        if ((int)ops.size() <= PROGRAM_OPS) {
+            if (!ops.empty()) launch_tc_program(ctx, prog, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
+        } else {
+            // a chain longer than one program holds (CD-k with 2k + 3 > 96 ops; the reference has no such limit,
+            // base_rbm.py:386-405): consecutive launches of up to PROGRAM_OPS ops -- a dependency on an op of an earlier launch is
+            // the kernel boundary
+            const std::vector<TcGemm> all = ops;
+            ops.clear();                         // (the cached whole-chain program object only keeps the plan)
+            for (size_t lo = 0, c = 1; lo < all.size(); lo += (size_t)PROGRAM_OPS, ++c) {
+                const size_t hi = std::min(all.size(), lo + (size_t)PROGRAM_OPS);
+                std::unique_ptr<TcProgram>& part = progs[std::make_tuple(rows, k, (with_dw ? 1 : 0) | (int)(c << 1), resident ? 1 : 0)];
+                if (!part) part.reset(new TcProgram());
+                part->ops.assign(all.begin() + lo, all.begin() + hi);
+                for (TcGemm& g : part->ops) {
+                    int n = 0;
+                    for (int d = 0; d < g.n_deps; ++d)
+                        if (g.dep[d] >= (int)lo) { g.dep[n] = g.dep[d] - (int)lo; g.dep_all[n] = g.dep_all[d]; ++n; }
+                    g.n_deps = n;
+                    if (g.lane == LANE_SPARE) g.lane = LANE_ALL;
+                }
+                launch_tc_program(ctx, *part, make_rng(seed, 0, 0, tick, row0), resident ? X_row0 : 0);
+            }
+        }
         last_was_tc = true;
     }
 

@@ -490,9 +490,14 @@ __global__ void weight_update_kernel(const T* __restrict__ G, int ldg, T g_div, 
 template <typename T>
 void launch_weight_update(Ctx* ctx, const T* G, int ldg, T g_div, T* W, T* dW, int V, int H,
                           const T* pen, T l2, T lr, T mom, __nv_bfloat16* Wb, int ldwb) {
-    dim3 grid((H + 255) / 256, V);
-    weight_update_kernel<T><<<grid, 256, 0, ctx->stream>>>(G, ldg, g_div, W, dW, V, H, pen, l2, lr, mom, Wb, ldwb);
-    count_launch(ctx);
+    // (the visible index travels in grid.y, limit 65535: models with more input units go in slabs of rows)
+    for (int r0 = 0; r0 < V; r0 += 32768) {
+        const int n = V - r0 < 32768 ? V - r0 : 32768;
+        dim3 grid((H + 255) / 256, n);
+        weight_update_kernel<T><<<grid, 256, 0, ctx->stream>>>(G + (size_t)r0 * ldg, ldg, g_div, W + (size_t)r0 * H, dW + (size_t)r0 * H, n, H,
+                                                               pen, l2, lr, mom, Wb ? Wb + (size_t)r0 * ldwb : nullptr, ldwb);
+        count_launch(ctx);
+    }
 }
 template void launch_weight_update<float>(Ctx*, const float*, int, float, float*, float*, int, int, const float*, float, float, float, __nv_bfloat16*, int);
 template void launch_weight_update<double>(Ctx*, const double*, int, double, double*, double*, int, int, const double*, double, double, double, __nv_bfloat16*, int);

@@ -1124,10 +1124,16 @@ static void fill_phase(Ctx* ctx, const TcGemm& g, int cluster, TcPhase& ph) {
 // The ops' descriptors (minus tensor maps) go to constant memory, stream-ordered before the launch;
 // skipped when the bank already holds exactly this image (the common case: the same program every step).
 static void upload_ops(Ctx* ctx, const TcPhase* ph, int n) {
-    static std::map<int, std::vector<unsigned char>> images;     // constant memory is per device
+    struct Bank { std::vector<unsigned char> image; cudaStream_t user = nullptr; };
+    static std::map<int, Bank> banks;                             // constant memory is per device
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    std::vector<unsigned char>& current = images[ctx->device];
+    Bank& bank = banks[ctx->device];
+    // another context of this device (another stream) may still be running a kernel that reads the bank: wait for it
+    // before the bank changes hands
+    if (bank.user && bank.user != ctx->stream) BM_CUDA(cudaStreamSynchronize(bank.user));
+    bank.user = ctx->stream;
+    std::vector<unsigned char>& current = bank.image;
     std::vector<unsigned char> img((size_t)n * sizeof(TcPhaseLite));
     for (int i = 0; i < n; ++i) memcpy(img.data() + (size_t)i * sizeof(TcPhaseLite), &ph[i].l, sizeof(TcPhaseLite));
     if (img.size() <= current.size() && memcmp(img.data(), current.data(), img.size()) == 0) return;

@@ -139,11 +139,10 @@ __global__ void sqdiff_bf16_finish_kernel(const double* __restrict__ partial, in
 }
 void launch_sqdiff_mean_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq, int rows, int cols,
                              double denom, double* out) {
-    static double* buf[64] = {nullptr};
-    if (!buf[ctx->device]) BM_CUDA(cudaMalloc(&buf[ctx->device], SQ_BLOCKS * sizeof(double)));
-    sqdiff_bf16_partial_kernel<<<SQ_BLOCKS, 256, 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, buf[ctx->device]);
+    if (!ctx->sqdiff_scratch) BM_CUDA(cudaMalloc(&ctx->sqdiff_scratch, SQ_BLOCKS * sizeof(double)));
+    sqdiff_bf16_partial_kernel<<<SQ_BLOCKS, 256, 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, ctx->sqdiff_scratch);
     count_launch(ctx);
-    sqdiff_bf16_finish_kernel<<<1, 256, 0, ctx->stream>>>(buf[ctx->device], SQ_BLOCKS, denom, out);
+    sqdiff_bf16_finish_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sqdiff_scratch, SQ_BLOCKS, denom, out);
     count_launch(ctx);
 }
 
@@ -214,14 +213,12 @@ __global__ void colsum_bf16_finish_kernel(ColsumJobs j, const float* __restrict_
     j.out[job][c] = s;
 }
 static float* colsum_scratch(Ctx* ctx, size_t floats) {
-    static float* buf[64] = {nullptr};
-    static size_t cap[64] = {0};
-    if (cap[ctx->device] < floats) {
-        if (buf[ctx->device]) { BM_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(buf[ctx->device]); }
-        BM_CUDA(cudaMalloc(&buf[ctx->device], floats * sizeof(float)));
-        cap[ctx->device] = floats;
+    if (ctx->colsum_scratch_floats < floats) {
+        if (ctx->colsum_scratch) { BM_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->colsum_scratch); ctx->colsum_scratch = nullptr; }
+        BM_CUDA(cudaMalloc(&ctx->colsum_scratch, floats * sizeof(float)));
+        ctx->colsum_scratch_floats = floats;
     }
-    return buf[ctx->device];
+    return ctx->colsum_scratch;
 }
 static void run_colsum_jobs(Ctx* ctx, const ColsumJobs& j) {
     int max_cols = 0;

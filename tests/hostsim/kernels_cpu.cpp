@@ -335,6 +335,7 @@ static void k_colsum_bf16_finish(void** a) {              // the two-stage reduc
 static void k_reduce_partials(void** a) {
     const float* partial = arg<const float*>(a, 0); const size_t stride = arg<size_t>(a, 1); const int splits = arg<int>(a, 2);
     float* G = arg<float*>(a, 3); const size_t n = arg<size_t>(a, 4);
+    // (the kernel takes its 16-byte path only when stride % 4 == 0 and both pointers are 16-byte aligned, else scalars)
     for (size_t i = 0; i < n; ++i) { float x = partial[i]; for (int s = 1; s < splits; ++s) x += partial[(size_t)s * stride + i]; G[i] = x; }
 }
 static void k_weight_update_splitk(void** a) {
@@ -342,6 +343,11 @@ static void k_weight_update_splitk(void** a) {
     float* W = arg<float*>(a, 4); float* dW = arg<float*>(a, 5); const int H = arg<int>(a, 6); const size_t n = arg<size_t>(a, 7);
     const float* pen = arg<const float*>(a, 8); const float l2 = arg<float>(a, 9), lr = arg<float>(a, 10), mom = arg<float>(a, 11);
     __nv_bfloat16* Wb = arg<__nv_bfloat16*>(a, 12); const int ldwb = arg<int>(a, 13);
+    // the kernel reads / writes 16 bytes per thread: every slice, W, dW on 16-byte boundaries, four elements in one row
+    if ((stride & 3) != 0 || (H & 3) != 0 || (ldwb & 3) != 0 || (n & 3) != 0 ||
+        ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dW)) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(Wb) & 7) != 0)
+        report_violation("weight_update_splitk_kernel: misaligned vector access (stride / n_hidden / pointers)");
     for (size_t i = 0; i < n; ++i) {
         float g = partial[i];
         for (int s = 1; s < splits; ++s) g += partial[(size_t)s * stride + i];

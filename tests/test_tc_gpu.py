@@ -210,3 +210,19 @@ def test_multinomial_layers_on_the_tensor_cores_match_the_rounding_oracle(kind, 
         np.testing.assert_allclose(g[name], w[name], atol=tol * max(1.0, float(np.abs(w[name]).max())), err_msg=name)
     np.testing.assert_allclose(eng.transform(X, k, 5, 9), ora.transform(X, k, 5, 9), rtol=0.05, atol=0.05)
     eng.close()
+
+
+def test_chains_longer_than_one_program_run_as_consecutive_launches():
+    """CD-50 (103 ops, a program holds 96; the reference's chain has no limit, base_rbm.py:386-405) against the rounding oracle:
+    same draws (one Philox stream whatever the cut), same update."""
+    cfg = make_cfg('bernoulli', 130, 70, 65)
+    eng, ora = make_pair(cfg)
+    X = data(cfg, 65)
+    l0 = _native.Context.default().launch_count()
+    eng.train_step(X, 0.05, 0.5, 50, 0xC0FFEE, 1)
+    assert _native.Context.default().launch_count() - l0 >= 4            # input conversion, two program launches, the update
+    ora.train_step(X, 0.05, 0.5, 50, 0xC0FFEE, 1)
+    g, w = eng.get_params(), ora.get_params()
+    for name in ('W', 'vb', 'hb', 'dW', 'dvb', 'dhb', 'q_means'):
+        np.testing.assert_allclose(g[name], w[name], atol=3e-3 + 0.06 / 65, err_msg=name)
+    eng.close()
