@@ -139,7 +139,7 @@ def test_ais_matches_exact_enumeration(monkeypatch, variant, k):
     monkeypatch.setenv('BM_DBM_AIS_EPILOGUE', '1' if variant == 'epilogue' else '0')
     monkeypatch.setenv('BM_DBM_AIS_FUSED', '0' if variant == 'passes' else '1')
     cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
-    n_betas = 500 if k == 1 else 300
+    n_betas = 240 if k == 1 else 120
     eng = _native.CudaDBM(cfg)
     init(cfg, (eng,))
     a = eng.ais(32, n_betas, k, 2222)
@@ -180,7 +180,16 @@ def test_ais_at_the_benchmark_shape_is_within_one_nat_of_the_float64_oracle():
     ref.set_params({k: v.astype(np.float64) for k, v in d.items()})
     ref.init_particles(4242)
     lm = lambda v: np.logaddexp.reduce(v) - np.log(len(v))
-    a, b, c = eng.ais(256, 1000, 1, 7), simt.ais(256, 1000, 1, 7), ref.ais(256, 1000, 1, 7)
+    a, b = eng.ais(256, 1000, 1, 7), simt.ais(256, 1000, 1, 7)
+    try:
+        from threadpoolctl import threadpool_limits            # a 128-thread BLAS pool crawls on these 256-row GEMMs
+    except ImportError:
+        threadpool_limits = None
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=16, user_api='blas'):
+            c = ref.ais(256, 1000, 1, 7)
+    else:
+        c = ref.ais(256, 1000, 1, 7)
     assert abs(lm(a) - lm(c)) < 1.0, (lm(a), lm(c))
     assert abs(lm(b) - lm(c)) < 1.0, (lm(b), lm(c))
     assert abs(np.mean(a) - np.mean(c)) < 1.0
