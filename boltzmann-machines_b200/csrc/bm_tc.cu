@@ -68,11 +68,18 @@ enum : int {
     MODE_SIG_BERN_STATE = 2,         // mid-chain hidden: states only
     MODE_SIG_MEAN = 3,               // probabilities only (visible means, last hidden means)
     MODE_RAW_F32 = 4,                // raw fp32 accumulators (dW partials, linear pre-activations)
-    MODE_AIS_UNITS = 5,              // AIS: importance-weight increment of the row + unit updates of the next transition
-    MODE_AIS_STATE = 6               // AIS: sampled transition (sigmoid, Bernoulli, states) + the linear term of log p*
+    MODE_AIS_UNITS = 5,              // AIS: importance-weight increment of the row + sampled unit updates of the next transition
+    MODE_AIS_STATE = 6,              // AIS: sampled transition (sigmoid, Bernoulli, states) + the linear term of log p*
+    MODE_AIS_UNITS_S = 7,            // AIS units op without a weight increment (first transition, sweeps > 0)
+    MODE_AIS_UNITS_G = 8             // AIS units op, run-time flags (unsampled units, the ladder's last increment, far-apart temperatures)
 };
 
 constexpr int MAX_PHASES = 96;
+// The series form of the AIS increment (chunk_body, MODE_AIS_UNITS) is used for ladders of >= 400 temperatures: with
+// t = (b - a) z and d = (next - (a + b) / 2) z its errors are t^2/24 sigma''/sigma (midpoint rule) and d^4/24 sigma''''/sigma
+// (third-order series) relative to the term -- < 3e-6 and < 1e-8 for |z| <= 10 at these spacings, and both vanish with
+// sigma' for large |z|.  Coarser ladders take the closed form (MODE_AIS_UNITS_G).
+constexpr float AIS_MAX_CT = 2.5e-3f, AIS_MAX_CD = 4.0e-3f;
 constexpr int SBIAS_BYTES = ACC_STAGES * 256 * (int)sizeof(float);
 
 constexpr int SMEM_BYTES = RING_BYTES + OUT_BYTES + SMEM_BARRIER_BYTES + SBIAS_BYTES;     // 231,744 of 232,448
@@ -310,8 +317,9 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
 // ------------------------------------------------------------------------------------------
 template <int MODE> struct EpiCfg {
     static constexpr bool fixed = MODE != MODE_GENERIC;
-    static constexpr bool ais = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_STATE);
-    static constexpr int act = (MODE == MODE_RAW_F32 || MODE == MODE_AIS_UNITS) ? ACT_LINEAR : ACT_SIGMOID;
+    static constexpr bool ais_units = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_UNITS_S || MODE == MODE_AIS_UNITS_G);
+    static constexpr bool ais = ais_units || MODE == MODE_AIS_STATE;
+    static constexpr int act = (MODE == MODE_RAW_F32 || ais_units) ? ACT_LINEAR : ACT_SIGMOID;
     static constexpr int sample = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE || MODE == MODE_AIS_STATE) ? SMP_BERNOULLI : SMP_NONE;
     static constexpr bool mean_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_MEAN);
     static constexpr bool state_bf = (MODE == MODE_SIG_BERN_MEAN_STATE || MODE == MODE_SIG_BERN_STATE || MODE == MODE_AIS_STATE);
@@ -331,6 +339,7 @@ struct EpiPhase {
     float* __restrict__ out_f32;              int ld_f32;
     unsigned long long split_stride;
     float ais_a, ais_b, ais_next, ais_lin;
+    float ais_ct, ais_cd;          // (b - a) and (next - (a + b) / 2): z-multipliers of the series form of the increment
     double* ais_logw;
 };
 struct EpiCtx {
@@ -376,7 +385,8 @@ __device__ __forceinline__ float chunk_body(const EpiCtx& c, const uint32_t (&v)
     const EpiPhase& p = c.p;
     float ais_part = 0.f;
     const int act = E::fixed ? E::act : p.act;
-    const int smp = (E::fixed && MODE != MODE_AIS_UNITS) ? E::sample : p.sample;
+    const int smp = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_UNITS_S) ? SMP_BERNOULLI :
+                    (E::fixed && MODE != MODE_AIS_UNITS_G) ? E::sample : p.sample;
     float* const out_f32 = ((E::fixed && !E::f32) || !p.out_f32) ? nullptr : p.out_f32 + (size_t)c.split * p.split_stride;
     // fold the sigmoid's -log2(e) into the affine map of the accumulator
     const float a_s = (act == ACT_SIGMOID) ? p.acc_scale * -1.4426950408889634f : p.acc_scale;
@@ -384,7 +394,8 @@ __device__ __forceinline__ float chunk_body(const EpiCtx& c, const uint32_t (&v)
     const int m = c.m;
     // in the fixed modes which outputs exist is known at compile time (no per-group branches)
     const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
-    const bool do_state = (E::fixed && MODE != MODE_AIS_UNITS) ? E::state_bf : (p.out_state_bf != nullptr);
+    const bool do_state = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_UNITS_S) ? true :
+                          (E::fixed && MODE != MODE_AIS_UNITS_G) ? E::state_bf : (p.out_state_bf != nullptr);
     const bool do_f32 = E::fixed ? E::f32 : (out_f32 != nullptr);
     const bool f32_vec = n_valid == CW && (p.ld_f32 & 3) == 0;       // rows 16-byte aligned, whole chunk
     // rows 32-byte aligned (row pitch, split stride and base): one full sector per store instruction and thread
@@ -417,8 +428,29 @@ __device__ __forceinline__ float chunk_body(const EpiCtx& c, const uint32_t (&v)
             x += bq[j];
             float m_ = x;
             float s_;
-            if (MODE == MODE_AIS_UNITS) {
-                // x = z (acc_scale = bias_scale = 1): weight increment at (a, b), then the unit's update at beta_next
+            if (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_UNITS_S) {
+                // x = z (acc_scale = bias_scale = 1).  p = sigmoid(beta_next z) serves the draw AND the weight increment:
+                //   softplus(b z) - softplus(a z) = int_a^b z sigmoid(beta z) dbeta = t sigmoid(m z)  (+ t^3 z^-2 ... / 24: < 1e-7 t)
+                //   with t = (b - a) z, m = (a + b) / 2, and sigmoid(m z) = sigmoid(beta_next z - d), d = (beta_next - m) z, as its
+                //   third-order series in d around p (error terms: AIS_MAX_CT / AIS_MAX_CD above).
+                float e_, p_;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_) : "f"(x * p.ais_next * -1.4426950408889634f));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p_) : "f"(1.0f + e_));
+                s_ = ((u32_to_one_two(words[j], c.mant_mask, c.one_bits) - 1.0f) < p_) ? 1.0f : 0.0f;
+                if (MODE == MODE_AIS_UNITS) {
+                    const float q_ = fmaf(-p_, p_, p_);                                 // sigma1 = p (1 - p)
+                    const float d_ = p.ais_cd * x;
+                    const float s2 = fmaf(-2.0f, p_, 1.0f);                             // sigma2 / sigma1
+                    const float s3 = fmaf(-6.0f, q_, 1.0f);                             // sigma3 / sigma1
+                    const float in = fmaf(-d_ * (1.0f / 3.0f), s3, s2);
+                    const float sm = fmaf(-d_ * q_, fmaf(-0.5f * d_, in, 1.0f), p_);    // sigmoid(m z)
+                    ais_part = fmaf((e < n_valid) ? p.ais_ct * x : 0.f, sm, ais_part);
+                }
+                mu[j] = 0.f; st[j] = s_;
+                continue;
+            }
+            if (MODE == MODE_AIS_UNITS_G) {
+                // any temperatures, optional sampling / output: the closed forms
                 if (p.ais_logw && e < n_valid) ais_part += ais_softplus_diff(p.ais_a, p.ais_b, x);
                 float e_;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_) : "f"(x * p.ais_next * -1.4426950408889634f));
@@ -489,7 +521,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     const int n_chunks = BN / CW;                  // BN is a multiple of 16
     const bool row_ok = c.m < p.M;
     const bool do_mean = E::fixed ? E::mean_bf : (p.out_mean_bf != nullptr);
-    const bool do_state = (E::fixed && MODE != MODE_AIS_UNITS) ? E::state_bf : (p.out_state_bf != nullptr);
+    const bool do_state = (MODE == MODE_AIS_UNITS || MODE == MODE_AIS_UNITS_S) ? true :
+                          (E::fixed && MODE != MODE_AIS_UNITS_G) ? E::state_bf : (p.out_state_bf != nullptr);
     float ais_sum = 0.f;
     int last_ch = -1;
     for (int ch = c.sub; ch < n_chunks; ch += EPI_SUBS) last_ch = ch;
@@ -544,7 +577,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& c) {
     *c.seq = seq;
     if constexpr (E::ais) {
         // this thread's share of its row's log-weight: fp64 atomics (four threads per row and column tile)
-        if (p.ais_logw && row_ok) atomicAdd(p.ais_logw + c.m, (double)(MODE == MODE_AIS_STATE ? ais_sum * p.ais_lin : ais_sum));
+        if (p.ais_logw && row_ok) {
+            const double inc = (double)(MODE == MODE_AIS_STATE ? ais_sum * p.ais_lin : ais_sum);
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p.ais_logw + c.m), "d"(inc) : "memory");     // (no return value wanted)
+        }
     }
 }
 
@@ -933,6 +969,7 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
             c.p.out_state_bf = ph->out_state_bf; c.p.ld_state_bf = ph->ld_state_bf;
             c.p.out_f32 = ph->out_f32; c.p.ld_f32 = ph->ld_f32; c.p.split_stride = ph->split_stride;
             c.p.ais_a = ph->ais_a; c.p.ais_b = ph->ais_b; c.p.ais_next = ph->ais_next; c.p.ais_lin = ph->ais_lin; c.p.ais_logw = ph->ais_logw;
+            c.p.ais_ct = ph->ais_b - ph->ais_a; c.p.ais_cd = ph->ais_next - 0.5f * (ph->ais_a + ph->ais_b);
             const int ph_mode = ph->mode;
             c.rng.k0 = L.k0; c.rng.k1 = L.k1; c.rng.tick = L.tick + ph->tick_off; c.rng.row0 = L.row0; c.rng.c2 = ph->rng_c2;
             c.m = (u.m_group * CL + crank) * BM + quarter * 32 + lane;
@@ -948,6 +985,8 @@ tc_program_kernel(const __grid_constant__ TcLaunch L) {
                 case MODE_SIG_MEAN: epilogue_tile<MODE_SIG_MEAN, pair>(c); break;
                 case MODE_RAW_F32: epilogue_tile<MODE_RAW_F32, pair>(c); break;
                 case MODE_AIS_UNITS: epilogue_tile<MODE_AIS_UNITS, pair>(c); break;
+                case MODE_AIS_UNITS_S: epilogue_tile<MODE_AIS_UNITS_S, pair>(c); break;
+                case MODE_AIS_UNITS_G: epilogue_tile<MODE_AIS_UNITS_G, pair>(c); break;
                 case MODE_AIS_STATE: epilogue_tile<MODE_AIS_STATE, pair>(c); break;
                 default: epilogue_tile<MODE_GENERIC, pair>(c); break;
             }
@@ -1050,7 +1089,14 @@ static TilePick pick_tile(int N, bool b_mn, bool staged_out, int m_tiles, int sp
 }
 
 static int epilogue_mode(const TcGemm& g) {
-    if (g.ais_kind == 1) return MODE_AIS_UNITS;
+    if (g.ais_kind == 1) {
+        const bool emit = g.out_state_bf != nullptr && g.sample == SMP_BERNOULLI;
+        const float ct = fabsf(g.ais_b - g.ais_a), cd = fabsf(g.ais_next - 0.5f * (g.ais_a + g.ais_b));
+        const bool close = ct <= AIS_MAX_CT && cd <= AIS_MAX_CD;
+        if (emit && !g.ais_logw) return MODE_AIS_UNITS_S;
+        if (emit && g.ais_logw && close) return MODE_AIS_UNITS;
+        return MODE_AIS_UNITS_G;
+    }
     if (g.ais_kind == 2) return MODE_AIS_STATE;
     if (g.sigma || g.noise_sigma) return MODE_GENERIC;
     const bool mb = g.out_mean_bf != nullptr, sb = g.out_state_bf != nullptr, f = g.out_f32 != nullptr;
@@ -1311,13 +1357,15 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row) {
     // descriptors live in device memory; re-uploaded only when they changed (buffers and shapes are
     // stable across steps; the per-step values -- tick, batch cursor -- travel in the kernel parameters)
     if (image.size() != prog.host_image.size() || memcmp(image.data(), prog.host_image.data(), image.size()) != 0) {
-        BM_CUDA(cudaStreamSynchronize(ctx->stream));       // a running launch may still read the old descriptors
         if (image.size() > prog.dev_phases_bytes) {
+            BM_CUDA(cudaStreamSynchronize(ctx->stream));   // a running launch may still read the old allocation
             if (prog.dev_phases) cudaFree(prog.dev_phases);
             BM_CUDA(cudaMalloc(&prog.dev_phases, image.size()));
             prog.dev_phases_bytes = image.size();
         }
-        BM_CUDA(cudaMemcpy(prog.dev_phases, image.data(), image.size(), cudaMemcpyHostToDevice));
+        // stream-ordered: the copy runs after every earlier launch of this stream has finished reading the descriptors (the
+        // pageable source is staged before the call returns) -- no host synchronisation between the launches of a ladder
+        BM_CUDA(cudaMemcpyAsync(prog.dev_phases, image.data(), image.size(), cudaMemcpyHostToDevice, ctx->stream));
         prog.host_image = image;
         prog.epoch = 0;                                   // another op list: other arrival counts per launch
     }

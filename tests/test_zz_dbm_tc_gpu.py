@@ -157,6 +157,19 @@ def test_ais_matches_exact_enumeration(monkeypatch, variant, k):
     eng.close()
 
 
+def test_ais_fine_ladder_takes_the_series_form_and_matches_the_emulation():
+    """ladders of >= 400 temperatures compute the weight increment of a unit as t * sigmoid(m z), the sigmoid taken as a
+    third-order series around the one the draw needs (bm_tc.cu: MODE_AIS_UNITS): same chains and log-weights as the emulation's
+    closed form softplus(b z) - softplus(a z)."""
+    cfg = make_cfg(V=7, Hs=(5, 4), n_particles=4, batch_size=4)
+    eng, emu = _native.CudaDBM(cfg), OracleDBMbf16(cfg)
+    init(cfg, (eng, emu), scale=1.0)                      # pre-activations of several units in magnitude
+    a, b = eng.ais(12, 500, 1, 31), emu.ais(12, 500, 1, 31)
+    assert np.mean(np.abs(a - b) < 2e-3) >= 0.75, np.abs(a - b)
+    assert abs(np.mean(a) - np.mean(b)) < 0.05
+    eng.close()
+
+
 def test_ais_is_within_one_nat_of_the_pinned_oracle():
     """BASELINE.json: AIS log Z within +-1.0 of the reference path (784-64-32, 64 runs x 200 betas)."""
     cfg = make_cfg(V=784, Hs=(64, 32), n_particles=4, batch_size=4)
