@@ -34,7 +34,7 @@ def test_bench_contract_on_the_host_simulation(tmp_path):
     code = RUNNER.format(root=ROOT, pkg=os.path.join(ROOT, 'boltzmann-machines_b200'),
                          sim=os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'), bench=os.path.join(ROOT, 'bench.py'))
     # 20 batches = 81920 rows: still taller than grid.y can index (the refused-launch case), half the host-side data shuffling
-    env = dict(os.environ, BM_BENCH_BATCHES='20')
+    env = dict(os.environ, BM_BENCH_BATCHES='20', BM_BENCH_FIT_STEPS='40')
     res = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path), env=env)
     assert res.returncode == 0, res.stdout[-3000:]
     assert 'VIOLATIONS=\n' in res.stdout + '\n', res.stdout[-1500:]
