@@ -3,6 +3,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <stdio.h>
 
 namespace bm {
 
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) dp_push_kernel(const __grid_constant__ Dp
     publish_when_all_blocks_done(s, s.counter, 0);
 }
 
-__global__ void __launch_bounds__(256) dp_update_kernel(const __grid_constant__ DpStep s, unsigned w_blocks) {
+__global__ void __launch_bounds__(256) dp_update_kernel(const __grid_constant__ DpStep s, unsigned w_blocks, int local_only) {
     if (threadIdx.x < s.nranks) wait_flag(s.peer[s.rank].flags + threadIdx.x, s.step);        // every rank's push has landed here
     __syncthreads();
     const int V = s.V, H = s.H, R = s.nranks;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) dp_update_kernel(const __grid_constant__ 
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
             const float4 dv = make_float4(d[0], d[1], d[2], d[3]), wv = make_float4(wn[0], wn[1], wn[2], wn[3]);
             for (int q = 0; q < R; ++q) {                        // the all-gather: one writer per row, every copy
+                if (local_only && q != s.rank) continue;         // (split variant: dp_scatter_kernel copies the rows out)
                 const PeerView& pq = s.peer[q];
                 *reinterpret_cast<float4*>(pq.dW + i) = dv;
                 *reinterpret_cast<float4*>(pq.W + i) = wv;
@@ -137,7 +139,38 @@ __global__ void __launch_bounds__(256) dp_update_kernel(const __grid_constant__ 
             s.vb[i] += dd;
         }
     }
-    publish_when_all_blocks_done(s, s.counter + 1, MAX_PEERS);
+    if (!local_only) publish_when_all_blocks_done(s, s.counter + 1, MAX_PEERS);
+}
+
+// split variant of the all-gather: every block of the grid copies a piece of this rank's freshly updated rows (fp32 W, momentum,
+// bf16 shadow) to ONE peer (blockIdx.y), so that the stores to the 7 peers come from all SMs instead of from the shard's own blocks
+__global__ void __launch_bounds__(256) dp_scatter_kernel(const __grid_constant__ DpStep s) {
+    const int V = s.V, H = s.H;
+    const int q = (int)blockIdx.y >= s.rank ? (int)blockIdx.y + 1 : (int)blockIdx.y;      // the peers other than this rank
+    const int r0 = s.rank * s.rows_per;
+    const int r1 = min(V, r0 + s.rows_per);
+    const size_t n4 = r1 > r0 ? (size_t)(r1 - r0) * H / 4 : 0;
+    const PeerView& me = s.peer[s.rank];
+    const PeerView& pq = s.peer[q];
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = (size_t)r0 * H + j * 4;
+        const int h = (int)(i % (size_t)H);
+        const size_t v = i / (size_t)H;
+        *reinterpret_cast<float4*>(pq.W + i) = *reinterpret_cast<const float4*>(me.W + i);
+        *reinterpret_cast<float4*>(pq.dW + i) = *reinterpret_cast<const float4*>(me.dW + i);
+        *reinterpret_cast<uint2*>(pq.Wb + v * (size_t)s.ldwb + h) = *reinterpret_cast<const uint2*>(me.Wb + v * (size_t)s.ldwb + h);
+    }
+    // (gridDim.x * gridDim.y blocks arrive on the counter)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(s.counter + 1, 1u);
+        if (old == gridDim.x * gridDim.y - 1) {
+            atomicExch(s.counter + 1, 0u);
+            __threadfence_system();
+            for (int p = 0; p < s.nranks; ++p) st_release_sys(s.peer[p].flags + MAX_PEERS + s.rank, s.step);
+        }
+    }
 }
 
 __global__ void dp_wait_kernel(const int* done, int nranks, int step) {
@@ -238,20 +271,44 @@ void PeerExchange::fill(DpStep& s) const {
 void PeerExchange::run(DpStep& s) {
     s.step = ++step;
     const int blocks = ctx->sm_count * 4;
+    // BM_PEER_PROFILE=1: CUDA events around the three kernels, averages printed when the exchange is released
+    static const bool prof = [] { const char* e = getenv("BM_PEER_PROFILE"); return e && atoi(e) != 0; }();
+    if (prof && !ev[0]) for (int i = 0; i < 4; ++i) BM_CUDA(cudaEventCreate(&ev[i]));
+    if (prof && prof_pending) {          // fold the previous step's events (they have completed: same stream)
+        BM_CUDA(cudaEventSynchronize(ev[3]));
+        for (int i = 0; i < 3; ++i) { float ms = 0.f; BM_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); prof_ms[i] += ms; }
+        ++prof_n; prof_pending = false;
+    }
+    if (prof) BM_CUDA(cudaEventRecord(ev[0], ctx->stream));
     dp_push_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
     count_launch(ctx);
+    if (prof) BM_CUDA(cudaEventRecord(ev[1], ctx->stream));
     const int r0 = ctx->rank * rows_per;
     const int r1 = V < r0 + rows_per ? V : r0 + rows_per;
     const size_t items = r1 > r0 ? (size_t)(r1 - r0) * H / 4 : 0;
     const unsigned w_blocks = (unsigned)((items + 255) / 256);
     const int nb = V > H ? V : H;
-    dp_update_kernel<<<w_blocks + (unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(s, w_blocks);
+    // BM_PEER_SPLIT (default: on from 4 ranks): the update writes this rank's copy only and a second, full-width kernel copies
+    // the rows out to the peers
+    static const int split_env = [] { const char* e = getenv("BM_PEER_SPLIT"); return e ? atoi(e) : -1; }();
+    const bool split = ctx->nranks > 1 && (split_env < 0 ? ctx->nranks >= 4 : split_env != 0);
+    dp_update_kernel<<<w_blocks + (unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(s, w_blocks, split ? 1 : 0);
     count_launch(ctx);
+    if (split) {
+        dp_scatter_kernel<<<dim3((unsigned)(ctx->sm_count * 2 / (ctx->nranks - 1) + 1), (unsigned)(ctx->nranks - 1)), 256, 0, ctx->stream>>>(s);
+        count_launch(ctx);
+    }
+    if (prof) BM_CUDA(cudaEventRecord(ev[2], ctx->stream));
     dp_wait_kernel<<<1, 32, 0, ctx->stream>>>(view[ctx->rank].flags + MAX_PEERS, ctx->nranks, s.step);
     count_launch(ctx);
+    if (prof) { BM_CUDA(cudaEventRecord(ev[3], ctx->stream)); prof_pending = true; }
 }
 
 void PeerExchange::release() {
+    if (prof_n > 0 && ctx)
+        fprintf(stderr, "[bm peer] rank %d of %d: %ld steps, mean us: push %.1f  update (incl. wait for the peers' pushes) %.1f  wait for the peers' updates %.1f\n",
+                ctx->rank, ctx->nranks, prof_n, 1e3 * prof_ms[0] / prof_n, 1e3 * prof_ms[1] / prof_n, 1e3 * prof_ms[2] / prof_n);
+    prof_n = 0;
     if (ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);

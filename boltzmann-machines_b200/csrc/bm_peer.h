@@ -52,6 +52,8 @@ struct PeerExchange {
     PeerView view[MAX_PEERS] = {};
     void* mapped[MAX_PEERS][4] = {};               // peers' bases opened with cudaIpcOpenMemHandle (arena, W, dW, Wb)
     int step = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};      // BM_PEER_PROFILE
+    double prof_ms[3] = {0, 0, 0}; long prof_n = 0; bool prof_pending = false;
 
     // collective over the context's communicator; W / dW / Wb are whole cudaMalloc allocations
     void setup(Ctx* c, int V_, int H_, float* W, float* dW, __nv_bfloat16* Wb, int ldwb_);
