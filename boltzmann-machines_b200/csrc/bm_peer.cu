@@ -173,6 +173,151 @@ __global__ void __launch_bounds__(256) dp_scatter_kernel(const __grid_constant__
     }
 }
 
+// ---- the same two kernels with the transfers as BULK asynchronous copies (shared memory -> peer global memory) -------------
+// Measured on 4 B200s (profiles/r02_notes.md): 16-byte stores to mapped peer memory move ~100 GB/s per GPU, the push of 2.4 MB
+// took 30 us and the update's 6 MB 40 us.  Here a block sums / updates whole rows into shared memory and one thread hands them to
+// the copy engine of its SM (cp.async.bulk.global.shared::cta: one transaction of n_hidden * 4 bytes per row and destination),
+// the local copy included.
+__device__ __forceinline__ uint32_t peer_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(peer_smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_smem_to_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256) dp_push_bulk_kernel(const __grid_constant__ DpStep s, int rows_per_block) {
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    float* buf = reinterpret_cast<float*>(dp_smem);                      // [rows_per_block][H]
+    const int V = s.V, H = s.H;
+    const int n_chunks = (V + rows_per_block - 1) / rows_per_block;
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int v0 = c * rows_per_block, v1 = min(V, v0 + rows_per_block);
+        const int n4 = (v1 - v0) * H / 4;
+        for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+            const size_t i = (size_t)v0 * H + (size_t)j * 4;
+            float4 a = *reinterpret_cast<const float4*>(s.part + i);
+            for (int k = 1; k < s.splits; ++k) {
+                const float4 b = *reinterpret_cast<const float4*>(s.part + (size_t)k * s.stride + i);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(buf + (size_t)j * 4) = a;
+        }
+        fence_smem_to_async_proxy();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int v = v0; v < v1; ++v) {
+                const int owner = v / s.rows_per;
+                bulk_store(s.peer[owner].inbox + (size_t)s.rank * s.shard_elems + (size_t)(v - owner * s.rows_per) * H,
+                           buf + (size_t)(v - v0) * H, (uint32_t)H * 4u);
+            }
+            bulk_commit_group();
+            bulk_wait_read_all();                                            // the buffer may be rewritten
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bulk_wait_all();                                   // ... and the rows have arrived
+    const int n_small = 2 * H + V;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_small; j += gridDim.x * blockDim.x) {
+        float x = 0.f;
+        if (j < 2 * H) { const size_t off = (size_t)s.srow * H + j; for (int k = 0; k < s.splits; ++k) x += s.part[(size_t)k * s.stride + off]; }
+        else { for (int k = 0; k < s.vsplits; ++k) x += s.vpart[(size_t)k * s.vstride + (j - 2 * H)]; }
+        for (int q = 0; q < s.nranks; ++q) s.peer[q].small[(size_t)s.rank * s.small_len + j] = x;
+    }
+    publish_when_all_blocks_done(s, s.counter, 0);
+}
+
+__global__ void __launch_bounds__(256) dp_update_bulk_kernel(const __grid_constant__ DpStep s, unsigned w_blocks, int rows_per_block) {
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    if (threadIdx.x < s.nranks) wait_flag(s.peer[s.rank].flags + threadIdx.x, s.step);        // every rank's push has landed here
+    __syncthreads();
+    const int V = s.V, H = s.H, R = s.nranks;
+    const PeerView& me = s.peer[s.rank];
+    if (blockIdx.x < w_blocks) {
+        float* Ws = reinterpret_cast<float*>(dp_smem);                                   // [rows_per_block][H] new weights
+        float* Ds = Ws + (size_t)rows_per_block * H;                                     // new momentum
+        __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(Ds + (size_t)rows_per_block * H);   // bf16 shadow
+        const int r0 = s.rank * s.rows_per;
+        const int r1 = min(V, r0 + s.rows_per);
+        const int n_chunks = r1 > r0 ? (r1 - r0 + rows_per_block - 1) / rows_per_block : 0;
+        for (int c = blockIdx.x; c < n_chunks; c += (int)w_blocks) {
+            const int v0 = r0 + c * rows_per_block, v1 = min(r1, v0 + rows_per_block);
+            const int n4 = (v1 - v0) * H / 4;
+            for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+                const size_t i = (size_t)v0 * H + (size_t)j * 4;
+                const size_t li = i - (size_t)r0 * H;
+                const int h = (int)(i % (size_t)H);
+                float4 g = *reinterpret_cast<const float4*>(me.inbox + li);
+                for (int r = 1; r < R; ++r) {
+                    const float4 b = *reinterpret_cast<const float4*>(me.inbox + (size_t)r * s.shard_elems + li);
+                    g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
+                }
+                float pen[4] = {0.f, 0.f, 0.f, 0.f};
+                if (s.cost != 0.f) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float qs = 0.f;
+                        for (int r = 0; r < R; ++r) qs += me.small[(size_t)r * s.small_len + H + h + k];
+                        const float q = s.damp * s.q_old[h + k] + (1.0f - s.damp) * (-qs);
+                        pen[k] = s.cost * (q - s.target);
+                    }
+                }
+                const float4 w4 = *reinterpret_cast<const float4*>(me.W + i), d4 = *reinterpret_cast<const float4*>(me.dW + i);
+                const float gg[4] = {g.x, g.y, g.z, g.w}, w[4] = {w4.x, w4.y, w4.z, w4.w}, d0[4] = {d4.x, d4.y, d4.z, d4.w};
+                float d[4], wn[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    d[k] = s.lr * (s.mom * d0[k] + (gg[k] / s.n_div - s.l2 * w[k] - pen[k]));       // base_rbm.py:449, 462, 467
+                    wn[k] = w[k] + d[k];                                                             // :468
+                }
+                *reinterpret_cast<float4*>(Ws + (size_t)j * 4) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+                *reinterpret_cast<float4*>(Ds + (size_t)j * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(wn[0], wn[1]), hi = __floats2bfloat162_rn(wn[2], wn[3]);
+                uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(Bs + (size_t)j * 4) = pk;
+            }
+            fence_smem_to_async_proxy();
+            __syncthreads();                        // (also: every thread's reads of the old rows precede the copies below)
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)(v1 - v0) * (uint32_t)H * 4u;
+                for (int q = 0; q < R; ++q) {        // the all-gather, this rank's own copy included: one writer per row
+                    const PeerView& pq = s.peer[q];
+                    bulk_store(pq.W + (size_t)v0 * H, Ws, bytes);
+                    bulk_store(pq.dW + (size_t)v0 * H, Ds, bytes);
+                    for (int v = v0; v < v1; ++v) bulk_store(pq.Wb + (size_t)v * s.ldwb, Bs + (size_t)(v - v0) * H, (uint32_t)H * 2u);
+                }
+                bulk_commit_group();
+                bulk_wait_read_all();
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) bulk_wait_all();
+    } else {
+        // biases and sparsity statistics: every rank computes the same sums in the same order
+        const int i = (int)(blockIdx.x - w_blocks) * blockDim.x + threadIdx.x;
+        if (i < H) {
+            float ds = 0.f, qs = 0.f;
+            for (int r = 0; r < R; ++r) { ds += me.small[(size_t)r * s.small_len + i]; qs += me.small[(size_t)r * s.small_len + H + i]; }
+            const float q = s.damp * s.q_old[i] + (1.0f - s.damp) * (-qs);                     // :457-459
+            s.q_new[i] = q;
+            const float pen = s.cost * (q - s.target);
+            s.pen[i] = pen;
+            const float dd = s.lr * (s.mom * s.dhb[i] + (ds / s.n_div - pen));                  // :453, :461, :473-474
+            s.dhb[i] = dd;
+            s.hb[i] += dd;
+        }
+        if (i < V) {
+            float vs = 0.f;
+            for (int r = 0; r < R; ++r) vs += me.small[(size_t)r * s.small_len + 2 * H + i];
+            const float dd = s.lr * (s.mom * s.dvb[i] + vs / s.n_div);                          // :451, :470-471
+            s.dvb[i] = dd;
+            s.vb[i] += dd;
+        }
+    }
+    publish_when_all_blocks_done(s, s.counter + 1, MAX_PEERS);
+}
+
 __global__ void dp_wait_kernel(const int* done, int nranks, int step) {
     if ((int)threadIdx.x < nranks) wait_flag(done + threadIdx.x, step);
 }
@@ -280,23 +425,50 @@ void PeerExchange::run(DpStep& s) {
         ++prof_n; prof_pending = false;
     }
     if (prof) BM_CUDA(cudaEventRecord(ev[0], ctx->stream));
+    // BM_PEER_BULK (default 1 when a bf16 row is a whole number of 16-byte units): transfers as bulk asynchronous copies
+    static const int bulk_env = [] { const char* e = getenv("BM_PEER_BULK"); return e ? atoi(e) : 1; }();
+    const bool bulk = bulk_env != 0 && H % 8 == 0 && (size_t)H * 4 * 2 + (size_t)H * 2 <= 96 * 1024;
+    const int r0 = ctx->rank * rows_per;
+    const int r1 = V < r0 + rows_per ? V : r0 + rows_per;
+    const int nb = V > H ? V : H;
+    if (bulk) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            BM_CUDA(cudaFuncSetAttribute(dp_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            BM_CUDA(cudaFuncSetAttribute(dp_update_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done = true;
+        }
+        // push: rows per block so that a block's buffer is <= 32 KB and the grid has about two blocks per SM
+        int prb = (int)(32768 / ((size_t)H * 4)); if (prb < 1) prb = 1;
+        while (prb > 1 && (V + prb - 1) / prb < 2 * ctx->sm_count) --prb;
+        const int pblocks = (V + prb - 1) / prb;
+        dp_push_bulk_kernel<<<pblocks < 4 * ctx->sm_count ? pblocks : 4 * ctx->sm_count, 256, (size_t)prb * H * 4, ctx->stream>>>(s, prb);
+        count_launch(ctx);
+        if (prof) BM_CUDA(cudaEventRecord(ev[1], ctx->stream));
+        // update: rows per block so that W + dW + bf16 rows fit in <= 40 KB, about one block per SM
+        const int shard_rows = r1 > r0 ? r1 - r0 : 0;
+        int urb = (int)(40960 / ((size_t)H * 10)); if (urb < 1) urb = 1;
+        while (urb > 1 && (shard_rows + urb - 1) / urb < ctx->sm_count) --urb;
+        unsigned w_blocks = (unsigned)((shard_rows + urb - 1) / urb);
+        if (w_blocks > (unsigned)(2 * ctx->sm_count)) w_blocks = (unsigned)(2 * ctx->sm_count);
+        dp_update_bulk_kernel<<<w_blocks + (unsigned)((nb + 255) / 256), 256, (size_t)urb * H * 10, ctx->stream>>>(s, w_blocks, urb);
+        count_launch(ctx);
+    } else {
     dp_push_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
     count_launch(ctx);
     if (prof) BM_CUDA(cudaEventRecord(ev[1], ctx->stream));
-    const int r0 = ctx->rank * rows_per;
-    const int r1 = V < r0 + rows_per ? V : r0 + rows_per;
     const size_t items = r1 > r0 ? (size_t)(r1 - r0) * H / 4 : 0;
     const unsigned w_blocks = (unsigned)((items + 255) / 256);
-    const int nb = V > H ? V : H;
-    // BM_PEER_SPLIT (default: on from 4 ranks): the update writes this rank's copy only and a second, full-width kernel copies
-    // the rows out to the peers
-    static const int split_env = [] { const char* e = getenv("BM_PEER_SPLIT"); return e ? atoi(e) : -1; }();
-    const bool split = ctx->nranks > 1 && (split_env < 0 ? ctx->nranks >= 4 : split_env != 0);
+    // BM_PEER_SPLIT=1: the update writes this rank's copy only and a second, full-width kernel copies the rows out to the peers
+    // (measured at 4 GPUs: no gain -- the limit is the rate of 16-byte peer stores, not the number of blocks issuing them)
+    static const int split_env = [] { const char* e = getenv("BM_PEER_SPLIT"); return e ? atoi(e) : 0; }();
+    const bool split = ctx->nranks > 1 && split_env != 0;
     dp_update_kernel<<<w_blocks + (unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(s, w_blocks, split ? 1 : 0);
     count_launch(ctx);
     if (split) {
         dp_scatter_kernel<<<dim3((unsigned)(ctx->sm_count * 2 / (ctx->nranks - 1) + 1), (unsigned)(ctx->nranks - 1)), 256, 0, ctx->stream>>>(s);
         count_launch(ctx);
+    }
     }
     if (prof) BM_CUDA(cudaEventRecord(ev[2], ctx->stream));
     dp_wait_kernel<<<1, 32, 0, ctx->stream>>>(view[ctx->rank].flags + MAX_PEERS, ctx->nranks, s.step);
