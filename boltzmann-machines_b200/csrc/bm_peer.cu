@@ -112,8 +112,12 @@ __global__ void __launch_bounds__(256) dp_update_kernel(const __grid_constant__ 
             for (int q = 0; q < R; ++q) {                        // the all-gather: one writer per row, every copy
                 if (local_only && q != s.rank) continue;         // (split variant: dp_scatter_kernel copies the rows out)
                 const PeerView& pq = s.peer[q];
-                *reinterpret_cast<float4*>(pq.dW + i) = dv;
-                *reinterpret_cast<float4*>(pq.W + i) = wv;
+                // what every rank's next program reads is the bf16 shadow; the fp32 master and the momentum rows stay with their
+                // owner unless s.replicate_fp32 (peers pull them when something reads them: dp_pull_kernel)
+                if (q == s.rank || s.replicate_fp32) {
+                    *reinterpret_cast<float4*>(pq.dW + i) = dv;
+                    *reinterpret_cast<float4*>(pq.W + i) = wv;
+                }
                 *reinterpret_cast<uint2*>(pq.Wb + v * (size_t)s.ldwb + h) = pk;
             }
         }
@@ -174,10 +178,11 @@ __global__ void __launch_bounds__(256) dp_scatter_kernel(const __grid_constant__
 }
 
 // ---- the same two kernels with the transfers as BULK asynchronous copies (shared memory -> peer global memory) -------------
-// Measured on 4 B200s (profiles/r02_notes.md): 16-byte stores to mapped peer memory move ~100 GB/s per GPU, the push of 2.4 MB
-// took 30 us and the update's 6 MB 40 us.  Here a block sums / updates whole rows into shared memory and one thread hands them to
-// the copy engine of its SM (cp.async.bulk.global.shared::cta: one transaction of n_hidden * 4 bytes per row and destination),
-// the local copy included.
+// An experiment (BM_PEER_BULK=1), kept for the record: event profile of the store version on 4 B200s (profiles/r02_notes.md): push
+// 30 us, update 40 us for 2.4 MB / 6 MB to the peers.  Here a block sums / updates whole rows into shared memory and one thread
+// hands them to the copy engine of its SM (cp.async.bulk.global.shared::cta: one transaction of n_hidden * 4 bytes per row and
+// destination), the local copy included.  Parity green on 2 GPUs, but slower than the stores (push 26 us, update 30 us at N = 2):
+// the exchange is bound by its two system-scope publish / wait hops and kernel boundaries, not by the stores' granularity.
 __device__ __forceinline__ uint32_t peer_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(peer_smem_u32(ssrc)), "r"(bytes) : "memory");
@@ -318,6 +323,21 @@ __global__ void __launch_bounds__(256) dp_update_bulk_kernel(const __grid_consta
     publish_when_all_blocks_done(s, s.counter + 1, MAX_PEERS);
 }
 
+// the fp32 master and momentum rows of the OTHER ranks' shards, read from their owners (who are not in an update: an update
+// needs this rank's push of the same step)
+__global__ void __launch_bounds__(256) dp_pull_kernel(const __grid_constant__ DpStep s) {
+    const int V = s.V, H = s.H;
+    const size_t n4 = (size_t)V * H / 4;
+    const PeerView& me = s.peer[s.rank];
+    for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = i4 * 4;
+        const int owner = (int)(i / (size_t)H) / s.rows_per;
+        if (owner == s.rank) continue;
+        *reinterpret_cast<float4*>(me.W + i) = *reinterpret_cast<const float4*>(s.peer[owner].W + i);
+        *reinterpret_cast<float4*>(me.dW + i) = *reinterpret_cast<const float4*>(s.peer[owner].dW + i);
+    }
+}
+
 __global__ void dp_wait_kernel(const int* done, int nranks, int step) {
     if ((int)threadIdx.x < nranks) wait_flag(done + threadIdx.x, step);
 }
@@ -413,8 +433,20 @@ void PeerExchange::fill(DpStep& s) const {
     s.counter = reinterpret_cast<unsigned int*>(view[ctx->rank].flags + 2 * MAX_PEERS);
 }
 
+void PeerExchange::pull_replicas() {
+    if (!active || !stale) return;
+    DpStep s{};
+    fill(s);
+    dp_pull_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(s);
+    count_launch(ctx);
+    stale = false;
+}
+
 void PeerExchange::run(DpStep& s) {
     s.step = ++step;
+    static const int repl_env = [] { const char* e = getenv("BM_PEER_REPLICATE_FP32"); return e ? atoi(e) : 0; }();
+    s.replicate_fp32 = repl_env != 0 ? 1 : 0;
+    stale = !s.replicate_fp32;
     const int blocks = ctx->sm_count * 4;
     // BM_PEER_PROFILE=1: CUDA events around the three kernels, averages printed when the exchange is released
     static const bool prof = [] { const char* e = getenv("BM_PEER_PROFILE"); return e && atoi(e) != 0; }();
@@ -425,8 +457,9 @@ void PeerExchange::run(DpStep& s) {
         ++prof_n; prof_pending = false;
     }
     if (prof) BM_CUDA(cudaEventRecord(ev[0], ctx->stream));
-    // BM_PEER_BULK (default 1 when a bf16 row is a whole number of 16-byte units): transfers as bulk asynchronous copies
-    static const int bulk_env = [] { const char* e = getenv("BM_PEER_BULK"); return e ? atoi(e) : 1; }();
+    // BM_PEER_BULK=1: transfers as bulk asynchronous copies from shared memory.  Measured (profiles/r02_notes.md): NOT faster --
+    // 2 GPUs: 0.2185 ms/step against 0.1902 with plain 16-byte stores (push 26 us, update 30 us) -- so the default stays off.
+    static const int bulk_env = [] { const char* e = getenv("BM_PEER_BULK"); return e ? atoi(e) : 0; }();
     const bool bulk = bulk_env != 0 && H % 8 == 0 && (size_t)H * 4 * 2 + (size_t)H * 2 <= 96 * 1024;
     const int r0 = ctx->rank * rows_per;
     const int r1 = V < r0 + rows_per ? V : r0 + rows_per;

@@ -30,7 +30,7 @@ struct PeerView {                 // one rank's exported buffers, as mapped in T
 };
 
 struct DpStep {
-    int rank, nranks, V, H, srow, rows_per, ldwb, small_len, step;
+    int rank, nranks, V, H, srow, rows_per, ldwb, small_len, step, replicate_fp32;
     unsigned long long shard_elems;
     PeerView peer[MAX_PEERS];
     unsigned int* counter;        // local scratch: blocks that have finished (two words: push, update)
@@ -59,6 +59,10 @@ struct PeerExchange {
     void setup(Ctx* c, int V_, int H_, float* W, float* dW, __nv_bfloat16* Wb, int ldwb_);
     void fill(DpStep& s) const;
     void run(DpStep& s);                      // push, update, wait on the context's stream
+    // after a step the fp32 master / momentum rows of the other ranks' shards are stale on this rank (only the bf16 shadow is
+    // all-gathered): whoever reads them (get_param, the free-energy metrics, the L2 loss) pulls them from their owners first
+    bool stale = false;
+    void pull_replicas();
     void release();
     ~PeerExchange() { release(); }
 };

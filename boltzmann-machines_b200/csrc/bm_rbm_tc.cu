@@ -88,6 +88,10 @@ struct RbmTC : RbmSimt<float> {
     }
 
     void refresh_shadow() { launch_f32_to_bf16(ctx, W.p, H, Wb.p, ldw, V, H); }
+    void get_param(const char* name, void* host, size_t bytes) override {
+        if (!strcmp(name, "W") || !strcmp(name, "dW")) peer.pull_replicas();      // (data parallel: rows of the other ranks' shards)
+        RbmSimt<float>::get_param(name, host, bytes);
+    }
 
     void set_param(const char* name, const void* host, size_t bytes) override {
         RbmSimt<float>::set_param(name, host, bytes);
@@ -416,6 +420,7 @@ struct RbmTC : RbmSimt<float> {
         if (mixed()) chain_mixed(rows, k, seed, tick, row0);
         run_program(rows, k, true, seed, tick, row0);
         if (mask) {
+            if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY | BM_METRIC_L2_LOSS)) peer.pull_replicas();   // these read the fp32 W
             if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
             run_metrics(mask, rows, seed, tick, row0, out);
         }
@@ -472,6 +477,7 @@ struct RbmTC : RbmSimt<float> {
         if (!tc_kinds) { last_was_tc = false; RbmSimt<float>::metrics(X_host, rows, k, seed, tick, mask, out); return; }
         BM_REQUIRE(rows >= 1, "empty batch");
         stage_tc(X_host, 0, rows, seed, tick, 0);
+        if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY | BM_METRIC_L2_LOSS)) peer.pull_replicas();
         if ((mask & BM_METRIC_MSRE) && mixed()) chain_mixed(rows, k, seed, tick, 0);
         if (mask & BM_METRIC_MSRE) run_program(rows, k, false, seed, tick, 0);
         if (mask & (BM_METRIC_PLL | BM_METRIC_FREE_ENERGY)) ensure_fp32_input(rows);
