@@ -72,7 +72,10 @@ def run_in_tf_session(check_initialized=True, update_seed=False):
                 else:
                     model._engine = model._make_engine()
                     model._init_engine_vars()
-            return f(model, *args, **kwargs)
+            try:
+                return f(model, *args, **kwargs)
+            finally:
+                model._flush_scalars()          # the scalar logs of the call are on disk when it returns
         return wrapped_f
     return wrap
 
@@ -171,13 +174,27 @@ class NativeModel(BaseModel, DtypeMixin):
         values = {k: float(v) for k, v in values.items() if v is not None}
         if not values and not allow_empty:
             return
-        d = self._train_summary_dirpath if kind == 'train' else self._val_summary_dirpath
-        if not os.path.isdir(d):
-            os.makedirs(d)
         rec = {'step': int(step)}
         rec.update(values)
-        with open(os.path.join(d, 'scalars.jsonl'), 'a') as fh:
-            fh.write(json.dumps(rec, sort_keys=True) + '\n')
+        # buffered: one append per public call (or per 4096 records), not one open / write / close per training iteration
+        buf = self.__dict__.setdefault('_scalar_buf', {'train': [], 'val': []})
+        buf[kind].append(json.dumps(rec, sort_keys=True))
+        if len(buf[kind]) >= 4096:
+            self._flush_scalars()
+
+    def _flush_scalars(self):
+        buf = self.__dict__.get('_scalar_buf')
+        if not buf:
+            return
+        for kind, lines in buf.items():
+            if not lines:
+                continue
+            d = self._train_summary_dirpath if kind == 'train' else self._val_summary_dirpath
+            if not os.path.isdir(d):
+                os.makedirs(d)
+            with open(os.path.join(d, 'scalars.jsonl'), 'a') as fh:
+                fh.write('\n'.join(lines) + '\n')
+            del lines[:]
 
     def _save_model(self, global_step=None):
         for d in (self._train_summary_dirpath, self._val_summary_dirpath):

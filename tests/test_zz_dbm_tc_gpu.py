@@ -200,9 +200,9 @@ def test_ais_at_the_benchmark_shape_is_within_one_nat_of_the_float64_oracle():
         threadpool_limits = None
     if threadpool_limits is not None:
         with threadpool_limits(limits=16, user_api='blas'):
-            c = ref.ais(256, 1000, 1, 7)
+            c = ref.ais(128, 1000, 1, 7)               # (the first 128 of the same 256 chains: half the minutes of numpy)
     else:
-        c = ref.ais(256, 1000, 1, 7)
+        c = ref.ais(128, 1000, 1, 7)
     assert abs(lm(a) - lm(c)) < 1.0, (lm(a), lm(c))
     assert abs(lm(b) - lm(c)) < 1.0, (lm(b), lm(c))
     assert abs(np.mean(a) - np.mean(c)) < 1.0
