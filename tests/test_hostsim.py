@@ -558,3 +558,22 @@ def test_program_dataflow_hazards_are_checked_and_a_missing_dependency_is_caught
     # granule by granule: launch_tc_program only lets an op do so when that producer is its single such dependency
     assert executing.fakecuda_unhonoured_dependencies() == 0
     executing.fakecuda_reset()
+
+
+@pytest.mark.parametrize('selection', [
+    ['tests/test_plugin_gpu.py'],
+    ['tests/test_tc_gpu.py', '-k', 'multinomial and not 784'],
+    ['tests/test_tc_gpu.py', '-k', 'longer_than_one_program'],
+    ['tests/test_rbm_gpu.py', '-k', 'bfloat16_feed or byte_valued or fit_takes'],
+])
+def test_gpu_tests_of_round_two_features_pass_on_the_interpreter(selection):
+    """The GPU tests written in round 2 -- user-defined layers on the plugin engine, multinomial layers on the tensor-core path,
+    chains cut into several program launches, the packed feeds -- dry-run here through the library's own host code with interpreted
+    kernels (BM_HOSTSIM=1, see conftest.py): their host side is covered by the CPU suite, their kernels by the B200 runs."""
+    import subprocess
+    import sys
+    env = dict(os.environ, BM_HOSTSIM='1')
+    res = subprocess.run([sys.executable, '-m', 'pytest', '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider'] + selection,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert 'runtime violations: none' in res.stdout and 'kernels without a CPU restatement: none' in res.stdout, res.stdout[-1500:]
