@@ -60,6 +60,36 @@ def test_particle_init_and_training_steps(Hs, dtype):
     eng.close()
 
 
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+@pytest.mark.parametrize('v_kind,h_kinds', [('bernoulli', ('bernoulli', 'multinomial')), ('gaussian', ('bernoulli', 'multinomial')),
+                                            ('bernoulli', ('multinomial', 'bernoulli')), ('gaussian', ('bernoulli', 'bernoulli'))])
+def test_non_bernoulli_layers_train_and_query_like_the_oracle(v_kind, h_kinds, dtype):
+    """Multinomial hidden layers and Gaussian visibles inside a DBM (examples/dbm_cifar_naive.py stacks a Gaussian-visible RBM
+    and a multinomial top RBM; reference: dbm.py:385-427 with the layers of layers.py:54-92): training steps, then the queries."""
+    cfg = make_cfg(V=24, Hs=(14, 9), dtype=dtype, v_kind=v_kind, h_kinds=list(h_kinds), h_n_samples=[100., 6.],
+                   sparsity_cost=[0., 0.])
+    if v_kind == 'gaussian':
+        cfg['sigma'] = list(np.linspace(0.6, 1.4, 24))
+    if 'multinomial' in h_kinds:
+        cfg['h_n_samples'] = [6. if k == 'multinomial' else 100. for k in h_kinds]
+    eng, ora = make_pair(cfg)
+    tol = 1e-4 if dtype == 'float32' else (5e-6 if v_kind == 'gaussian' else 1e-9)    # float32 Box-Muller noise in float64 models
+    same(eng, ora, ['v', 'h', 'h_1'], atol=1e-6 if v_kind == 'bernoulli' else tol)
+    rng = np.random.RandomState(3)
+    for it in range(3):
+        X = rng.randn(10, 24).astype(dtype) if v_kind == 'gaussian' else batch(cfg, 10, seed=it)
+        got = eng.train_step(X, 0.02, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        want = ora.train_step(X, 0.02, 0.5, 2, 99, it, metrics=('msre', 'n_mf_updates'))
+        assert abs(got['n_mf_updates'] - want['n_mf_updates']) <= (1 if dtype == 'float32' else 0)
+        assert got['msre'] == pytest.approx(want['msre'], rel=1e-3)
+    same(eng, ora, atol=tol)
+    Xq = rng.randn(7, 24).astype(dtype) if v_kind == 'gaussian' else batch(cfg, 7, seed=9)
+    np.testing.assert_allclose(eng.transform(Xq), ora.transform(Xq), atol=tol)
+    np.testing.assert_allclose(eng.reconstruct(Xq), ora.reconstruct(Xq), atol=tol)
+    np.testing.assert_allclose(eng.sample_v(2, 11, 4), ora.sample_v(2, 11, 4), atol=tol)
+    eng.close()
+
+
 def test_queries_match_oracle():
     cfg = make_cfg()
     eng, ora = make_pair(cfg)
