@@ -1,6 +1,11 @@
 import os
 import sys
 
+# The oracle is numpy on small matrices: on a many-core host (the GPU box has 128 hardware threads) a BLAS pool of that size
+# spends its time waking threads up -- the AIS ladders of the tiny test models took minutes there and a second here.
+for _v in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ.setdefault(_v, '8')
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -77,6 +82,18 @@ def pytest_unconfigure(config):
         print('\n[hostsim] runtime violations: {0}; kernels without a CPU restatement: {1}; program launches checked for dataflow '
               'hazards: {2}, declared dependencies the kernel would not wait for: {3}'.format(
                   v or 'none', sk or 'none', lib.fakecuda_hazard_launches(), lib.fakecuda_unhonoured_dependencies()))
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _bounded_blas_pool():
+    """the same bound for a numpy that was imported before this file set the environment"""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        yield
+        return
+    with threadpool_limits(limits=int(os.environ.get('OPENBLAS_NUM_THREADS', '8')), user_api='blas'):
+        yield
 
 
 @pytest.fixture
