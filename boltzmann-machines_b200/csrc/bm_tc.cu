@@ -1210,6 +1210,25 @@ static void do_launch(Ctx* ctx, TcLaunch& L, int cluster, double flops, int max_
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
+    if (L.n_phases) {
+        // a program's CTAs wait for each other through counters in global memory: all of them must be resident at once.  Ask the
+        // runtime once per device (a GPU shared through MPS / MIG, or a part with fewer SMs than it reports, would otherwise only
+        // show up as the kernel's 4-second trap); BM_TC_SKIP_RESIDENCY_CHECK=1 trusts the device properties instead.
+        static int resident[64] = {0};
+        int& r = resident[ctx->device & 63];
+        if (r == 0) {
+            const char* e = getenv("BM_TC_SKIP_RESIDENCY_CHECK");
+            int n = 0;
+            if (e && atoi(e) == 1) r = -1;
+            else if (cudaOccupancyMaxActiveClusters(&n, cluster == 2 ? (const void*)tc_program_kernel<2> : (const void*)tc_program_kernel<1>, &lc) == cudaSuccess) r = n > 0 ? n : -2;
+            else { cudaGetLastError(); r = -1; }
+            if (getenv("BM_TC_DEBUG_RESIDENCY"))
+                fprintf(stderr, "[bm] device %d: cudaOccupancyMaxActiveClusters(tc_program_kernel<%d>) = %d, the program grid has %d clusters\n",
+                        ctx->device, cluster, n, n_clusters);
+        }
+        BM_REQUIRE(r == -1 || r >= n_clusters,
+                   "the device cannot hold all CTA clusters of a dataflow program at once (cudaOccupancyMaxActiveClusters); it would deadlock");
+    }
     if (ctx->profile_tc) BM_CUDA(cudaEventRecord(profile_event(ctx), ctx->stream));
     // kernels that contain cta_group::2 instructions must be launched as clusters of 2: separate instantiations
     if (cluster == 2) BM_CUDA(cudaLaunchKernelEx(&lc, tc_program_kernel<2>, L));

@@ -215,6 +215,14 @@ static thread_local cudaError_t t_last_error = cudaSuccess;
 cudaError_t cudaGetLastError(void) { const cudaError_t e = t_last_error; t_last_error = cudaSuccess; return e; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "fake_cudart error"; }
 cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
+static int g_max_active_clusters = -1;        // -1: what 148 SMs with one CTA each hold
+void fakecuda_set_max_active_clusters(int n) { g_max_active_clusters = n; }
+cudaError_t cudaOccupancyMaxActiveClusters(int* n, const void*, const cudaLaunchConfig_t* c) {
+    int cluster = 1;
+    for (unsigned i = 0; i < c->numAttrs; ++i) if (c->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = (int)c->attrs[i].val.clusterDim.x;
+    *n = g_max_active_clusters >= 0 ? g_max_active_clusters : 148 / cluster;
+    return cudaSuccess;
+}
 cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* st) {
     if (symbol && !strcmp(symbol, "cuTensorMapEncodeTiled")) { *fn = (void*)&fake_encode_tiled; if (st) *st = cudaDriverEntryPointSuccess; return cudaSuccess; }
     *fn = nullptr; if (st) *st = cudaDriverEntryPointSymbolNotFound;

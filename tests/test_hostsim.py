@@ -577,3 +577,29 @@ def test_gpu_tests_of_round_two_features_pass_on_the_interpreter(selection):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stdout[-3000:]
     assert 'runtime violations: none' in res.stdout and 'kernels without a CPU restatement: none' in res.stdout, res.stdout[-1500:]
+
+
+def test_a_device_that_cannot_hold_every_cluster_of_a_program_is_refused(sim):
+    """The dataflow programs' CTAs wait for each other: launching one on a device that keeps fewer clusters resident than the grid
+    has (MPS / MIG share, other work on the SMs) must be an error at the boundary, not a kernel that traps after its 4-second
+    guard.  Fresh process: the runtime is asked once per device."""
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path[:0] = [%r, %r]
+        from boltzmann_machines import _native
+        lib = _native.load_library(%r)
+        _native._lib = lib
+        lib.fakecuda_set_max_active_clusters(10)
+        eng = _native.CudaRBM(dict(n_visible=64, n_hidden=64, compute='bf16', max_batch=256))
+        eng.set_params({'W': np.zeros((64, 64), np.float32)})
+        try:
+            eng.train_step((np.random.rand(256, 64) < 0.5).astype(np.float32), 0.1, 0.5, 1, 1, 0)
+        except RuntimeError as e:
+            print('REFUSED:', e)
+        else:
+            print('LAUNCHED')
+    ''') % (ROOT, os.path.join(ROOT, 'boltzmann-machines_b200'), os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'))
+    res = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert 'REFUSED:' in res.stdout and 'cannot hold all CTA clusters' in res.stdout, res.stdout[-2000:]
