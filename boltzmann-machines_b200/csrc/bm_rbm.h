@@ -311,6 +311,13 @@ struct RbmSimt : RbmBase {
     const T* staged_dev = nullptr;
     const uint8_t* staged_u8 = nullptr;
     const uint16_t* staged_bf16 = nullptr;
+    int staged_half = -1;             // >= 0: the engine converted the staged batch itself on the copy stream (convert_on_copy_stream)
+
+    // An engine that keeps its input in another format may convert the batch the copy stream has just uploaded ON that stream
+    // (off the compute stream's critical path), into half `b` of a double buffer of its own; it then reads `staged_half` in its
+    // train_step instead of the staged pointers.  Called after the upload has been queued and before ev_copied[b] is recorded.
+    virtual bool convert_on_copy_stream(int /*b*/, const void* /*staged*/, int /*rows*/, int /*batch*/, int /*src*/,
+                                        cudaStream_t /*copy*/) { return false; }
     virtual bool accepts_bf16_feed() const { return false; }
     double* defer_dst = nullptr;
     double* epoch_host = nullptr;
@@ -361,6 +368,9 @@ struct RbmSimt : RbmBase {
                 else
                     BM_CUDA(cudaMemcpyAsync(epoch_stage[b].p, Xh + (size_t)i * batch * V, (size_t)rows * V * sizeof(T),
                                             cudaMemcpyHostToDevice, copy_stream));
+                const void* staged = src_u8 ? (const void*)epoch_stage_u8[b].p
+                                            : (src_bf16 ? (const void*)epoch_stage_bf16[b].p : (const void*)epoch_stage[b].p);
+                staged_half = convert_on_copy_stream(b, staged, rows, batch, src, copy_stream) ? b : -1;
                 BM_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
                 BM_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
                 if (src_u8) staged_u8 = epoch_stage_u8[b].p;
@@ -372,11 +382,11 @@ struct RbmSimt : RbmBase {
                 BM_CUDA(cudaEventRecord(ev_consumed[b], ctx->stream));
             }
         } catch (...) {
-            staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; defer_dst = nullptr;
+            staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; staged_half = -1; defer_dst = nullptr;
             cudaStreamSynchronize(copy_stream); cudaStreamSynchronize(ctx->stream);
             throw;
         }
-        staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; defer_dst = nullptr;
+        staged_dev = nullptr; staged_u8 = nullptr; staged_bf16 = nullptr; staged_half = -1; defer_dst = nullptr;
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int64_t i = 0; i < nb && mask; ++i) {
             const bool report = every > 0 && ((iter0 + i + 1) % every == 0);

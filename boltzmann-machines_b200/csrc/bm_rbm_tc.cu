@@ -27,6 +27,7 @@ struct RbmTC : RbmSimt<float> {
     bool tc_kinds;
     // state of the last chain
     const bf16* X_b = nullptr; int X_ld = 0; int X_row0 = 0; int X_rows_total = 0;
+    int X_mode = 0;       // 0: a buffer of exactly this batch; 1: rows [X_row0, ..) of the resident dataset; 2: a half of the epoch double buffer (1, 2: the program takes the row as its batch cursor)
     const bf16* vstate_b = nullptr;
     const bf16* h0state_b = nullptr;
     bool last_was_tc = false;
@@ -74,17 +75,36 @@ struct RbmTC : RbmSimt<float> {
         if (rows <= tc_cap) return;
         BM_CUDA(cudaStreamSynchronize(ctx->stream));
         tc_cap = rows;
-        Xb.ensure((size_t)rows * ldv); vm_b.ensure((size_t)rows * ldv); vs_b.ensure((size_t)rows * ldv);
+        Xb.ensure((size_t)2 * rows * ldv);        // two halves: epochs convert batch i+1 on the copy stream while batch i is in use
+        vm_b.ensure((size_t)rows * ldv); vs_b.ensure((size_t)rows * ldv);
         h0m_b.ensure((size_t)rows * ldh); h0s_b.ensure((size_t)rows * ldh);
         hm_b.ensure((size_t)rows * ldh); hs_b.ensure((size_t)rows * ldh);
         widen.ensure((size_t)rows * (V > H ? V : H));
         ones.ensure((size_t)rows * 64);
         launch_fill_bf16(ctx, ones.p, (size_t)rows * 64, 1.0f);
         for (DevBuf<bf16>* b : {&Xb, &vm_b, &vs_b}) b->zero(ctx->stream);       // (columns V .. VP-1 are read by the dW ops)
-        launch_set_column_pair(ctx, Xb.p, ldv, (size_t)rows, VP(), 1.0f, 0.0f);
+        launch_set_column_pair(ctx, Xb.p, ldv, (size_t)2 * rows, VP(), 1.0f, 0.0f);
         launch_set_column_pair(ctx, vm_b.p, ldv, (size_t)rows, VP(), 1.0f, 1.0f);
         launch_set_column_pair(ctx, vs_b.p, ldv, (size_t)rows, VP(), 1.0f, 1.0f);
         progs.clear();                         // buffers moved: cached descriptors are stale
+    }
+
+    // epochs (bm_rbm.h train_epoch): the uploaded batch becomes the bf16 operand on the copy stream, in the half of Xb the step
+    // before last has finished with (ev_consumed[b], which the copy stream has already waited for)
+    bool convert_on_copy_stream(int b, const void* staged, int rows, int batch, int src, cudaStream_t copy) override {
+        static int enabled = -1;
+        if (enabled < 0) { const char* e = getenv("BM_EPOCH_CONVERT_ON_COPY_STREAM"); enabled = e ? atoi(e) : 1; }
+        const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
+        if (!enabled || !plain || !tc_kinds || (src != SRC_U8 && src != SRC_BF16)) return false;
+        if (batch > tc_cap) {
+            reserve_tc(batch);
+            BM_CUDA(cudaStreamSynchronize(ctx->stream));      // the buffers' constant columns are written on the compute stream
+        }
+        bf16* dst = Xb.p + (size_t)b * tc_cap * ldv;
+        if (src == SRC_U8) launch_u8_to_bf16(ctx, (const uint8_t*)staged, V, dst, ldv, rows, V, copy);
+        else BM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldv * 2, staged, (size_t)V * 2, (size_t)V * 2, (size_t)rows,
+                                       cudaMemcpyDeviceToDevice, copy));
+        return true;
     }
 
     void refresh_shadow() { launch_f32_to_bf16(ctx, W.p, H, Wb.p, ldw, V, H); }
@@ -143,7 +163,13 @@ struct RbmTC : RbmSimt<float> {
     void stage_tc(const void* X_host, int64_t first_row, int rows, uint64_t seed, uint32_t tick, uint32_t row0) {
         reserve_tc(rows);
         const bool plain = (cfg.v_kind != BM_UNIT_GAUSSIAN) && (cfg.dropout_keep < 0);
-        if (staged_bf16) {
+        X_mode = 0;
+        if (staged_half >= 0) {
+            // epoch data already converted into a half of Xb by the copy stream (convert_on_copy_stream)
+            reserve(rows);
+            X_b = Xb.p; X_ld = ldv; X_row0 = staged_half * tc_cap; X_rows_total = 2 * tc_cap; X_mode = 2;
+            Xcur = nullptr;
+        } else if (staged_bf16) {
             // real-valued epoch data fed as bfloat16 (accepted only when `plain`): the bits the fp32 -> bf16 conversion of the
             // float feed would produce, so the chain is bit-identical at half the host->device bytes
             BM_REQUIRE(plain, "a bfloat16 feed needs a model without dropout / sigma scaling");
@@ -162,7 +188,7 @@ struct RbmTC : RbmSimt<float> {
         } else if (!X_host && !staged_dev && !staged_u8 && plain) {
             BM_REQUIRE(first_row >= 0 && first_row + rows <= data_rows, "row range outside the resident dataset");
             reserve(rows);
-            X_b = data_b.p; X_ld = ldv; X_row0 = (int)first_row; X_rows_total = (int)data_rows;
+            X_b = data_b.p; X_ld = ldv; X_row0 = (int)first_row; X_rows_total = (int)data_rows; X_mode = 1;
             Xcur = data.p + (size_t)first_row * V;
         } else {
             const float* X = stage_input(X_host, first_row, rows, seed, tick, row0);
@@ -191,8 +217,8 @@ struct RbmTC : RbmSimt<float> {
     // (base_rbm.py:447-448) -- as ONE persistent launch.
     void run_program(int rows, int k, bool with_dw, uint64_t seed, uint32_t tick, uint32_t row0) {
         BM_REQUIRE(k >= 1, "n_gibbs_steps must be >= 1");
-        const bool resident = (X_b == data_b.p);
-        auto key = std::make_tuple(rows, k, with_dw ? 1 : 0, resident ? 1 : 0);
+        const bool resident = X_mode != 0;           // the input is addressed through the launch's batch cursor
+        auto key = std::make_tuple(rows, k, with_dw ? 1 : 0, X_mode);
         std::unique_ptr<TcProgram>& slot = progs[key];
         if (!slot) slot.reset(new TcProgram());
         TcProgram& prog = *slot;
@@ -341,7 +367,7 @@ struct RbmTC : RbmSimt<float> {
             ops.clear();                         // (the cached whole-chain program object only keeps the plan)
             for (size_t lo = 0, c = 1; lo < all.size(); lo += (size_t)PROGRAM_OPS, ++c) {
                 const size_t hi = std::min(all.size(), lo + (size_t)PROGRAM_OPS);
-                std::unique_ptr<TcProgram>& part = progs[std::make_tuple(rows, k, (with_dw ? 1 : 0) | (int)(c << 1), resident ? 1 : 0)];
+                std::unique_ptr<TcProgram>& part = progs[std::make_tuple(rows, k, (with_dw ? 1 : 0) | (int)(c << 1), X_mode)];
                 if (!part) part.reset(new TcProgram());
                 part->ops.assign(all.begin() + lo, all.begin() + hi);
                 for (TcGemm& g : part->ops) {

@@ -90,7 +90,8 @@ void launch_tc_program(Ctx* ctx, TcProgram& prog, RngKey rng, int batch_row);
 void launch_f32_to_bf16(Ctx* ctx, const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols);
 void launch_bf16_to_f32(Ctx* ctx, const __nv_bfloat16* src, int lds, float* dst, int ldd, int rows, int cols);
 // byte-valued datasets (exact for 0..255) and the MSRE of the bf16 activations
-void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols);
+void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols,
+                       cudaStream_t stream = nullptr);   // (nullptr: the context's stream)
 template <typename T> void launch_u8_to_real(Ctx* ctx, const uint8_t* src, T* dst, size_t n);
 void launch_sqdiff_mean_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq, int rows, int cols,
                              double denom, double* out);

@@ -67,11 +67,12 @@ __global__ void u8_to_bf16_kernel(const uint8_t* __restrict__ src, int lds, __nv
         for (int e = 0; e < 8 && c + e < cols; ++e) d[e] = __float2bfloat16_rn((float)s[e]);
     }
 }
-void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols) {
+void launch_u8_to_bf16(Ctx* ctx, const uint8_t* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols, cudaStream_t stream) {
+    if (!stream) stream = ctx->stream;
     for (int r0 = 0; r0 < rows; r0 += ROW_SLAB) {
         const int n = rows - r0 < ROW_SLAB ? rows - r0 : ROW_SLAB;
         dim3 grid(((cols + 7) / 8 + 127) / 128, n);
-        u8_to_bf16_kernel<<<grid, 128, 0, ctx->stream>>>(src + (size_t)r0 * lds, lds, dst + (size_t)r0 * ldd, ldd, n, cols);
+        u8_to_bf16_kernel<<<grid, 128, 0, stream>>>(src + (size_t)r0 * lds, lds, dst + (size_t)r0 * ldd, ldd, n, cols);
         count_launch(ctx);
     }
 }
@@ -91,9 +92,13 @@ template void launch_u8_to_real<double>(Ctx*, const uint8_t*, double*, size_t);
 
 // ---- MSRE on the bf16 activations (base_rbm.py:486-488): mean((X - v_means)^2), accumulated in fp64 ----
 constexpr int SQ_BLOCKS = 592;
-__global__ void sqdiff_bf16_partial_kernel(const __nv_bfloat16* __restrict__ P, int ldp, const __nv_bfloat16* __restrict__ Q, int ldq,
-                                           int rows, int cols, double* __restrict__ partial) {
+// one launch: every block leaves its partial sum, the block that arrives last adds them up in a fixed order (thread t takes
+// partials t, t+256, ...; then the same tree as above), so the value does not depend on which block that is
+__global__ void sqdiff_bf16_kernel(const __nv_bfloat16* __restrict__ P, int ldp, const __nv_bfloat16* __restrict__ Q, int ldq,
+                                   int rows, int cols, double* __restrict__ partial, unsigned int* __restrict__ arrived,
+                                   double denom, double* __restrict__ out) {
     __shared__ double sh[256];
+    __shared__ bool last;
     double s = 0.0;
     const int gpr = (cols + 7) / 8;                                   // 8-column groups per row
     const size_t total = (size_t)rows * gpr;
@@ -123,26 +128,32 @@ __global__ void sqdiff_bf16_partial_kernel(const __nv_bfloat16* __restrict__ P, 
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
-__global__ void sqdiff_bf16_finish_kernel(const double* __restrict__ partial, int n, double denom, double* __restrict__ out) {
-    __shared__ double sh[256];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0];
+        __threadfence();                                              // the partial is visible before the arrival is
+        last = atomicAdd(arrived, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s += __ldcg(partial + i);
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0] / denom;
+    if (threadIdx.x == 0) { *out = sh[0] / denom; *arrived = 0u; }   // (next launch on this stream starts from zero)
 }
 void launch_sqdiff_mean_bf16(Ctx* ctx, const __nv_bfloat16* P, int ldp, const __nv_bfloat16* Q, int ldq, int rows, int cols,
                              double denom, double* out) {
-    if (!ctx->sqdiff_scratch) BM_CUDA(cudaMalloc(&ctx->sqdiff_scratch, SQ_BLOCKS * sizeof(double)));
-    sqdiff_bf16_partial_kernel<<<SQ_BLOCKS, 256, 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, ctx->sqdiff_scratch);
-    count_launch(ctx);
-    sqdiff_bf16_finish_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sqdiff_scratch, SQ_BLOCKS, denom, out);
+    if (!ctx->sqdiff_scratch) {
+        BM_CUDA(cudaMalloc(&ctx->sqdiff_scratch, (SQ_BLOCKS + 1) * sizeof(double)));
+        BM_CUDA(cudaMemsetAsync(ctx->sqdiff_scratch, 0, (SQ_BLOCKS + 1) * sizeof(double), ctx->stream));
+    }
+    sqdiff_bf16_kernel<<<SQ_BLOCKS, 256, 0, ctx->stream>>>(P, ldp, Q, ldq, rows, cols, ctx->sqdiff_scratch,
+                                                          reinterpret_cast<unsigned int*>(ctx->sqdiff_scratch + SQ_BLOCKS), denom, out);
     count_launch(ctx);
 }
 

@@ -401,13 +401,19 @@ static void k_fill_bf16(void** a) {
     __nv_bfloat16* buf = arg<__nv_bfloat16*>(a, 0); const size_t n = arg<size_t>(a, 1); const float v = arg<float>(a, 2);
     for (size_t i = 0; i < n; ++i) buf[i] = f2bf(v);
 }
-static void k_sqdiff_bf16_partial(void** a, dim3 grid) {
+static void k_sqdiff_bf16(void** a, dim3 grid) {
     const __nv_bfloat16* P = arg<const __nv_bfloat16*>(a, 0); const int ldp = arg<int>(a, 1); const __nv_bfloat16* Q = arg<const __nv_bfloat16*>(a, 2);
     const int ldq = arg<int>(a, 3), rows = arg<int>(a, 4), cols = arg<int>(a, 5); double* partial = arg<double*>(a, 6);
+    unsigned int* arrived = arg<unsigned int*>(a, 7); const double denom = arg<double>(a, 8); double* out = arg<double*>(a, 9);
+    if (*arrived != 0u) report_violation("sqdiff_bf16_kernel: the arrival counter of the previous launch was not reset");
+    if (reinterpret_cast<uintptr_t>(P) % 16 || reinterpret_cast<uintptr_t>(Q) % 16 || ldp % 8 || ldq % 8)
+        report_violation("sqdiff_bf16_kernel: operands are read as 16-byte vectors (pointer / leading dimension alignment)");
     double s = 0.0;
     for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) { const float d = bf2f(P[(size_t)r * ldp + c]) - bf2f(Q[(size_t)r * ldq + c]); s += (double)(d * d); }
     for (unsigned i = 0; i < grid.x; ++i) partial[i] = 0.0;
     partial[0] = s;
+    *out = s / denom;
+    *arrived = 0u;
 }
 static void k_u8_to_bf16(void** a) {
     const uint8_t* src = arg<const uint8_t*>(a, 0); const int lds = arg<int>(a, 1); __nv_bfloat16* dst = arg<__nv_bfloat16*>(a, 2);
@@ -815,8 +821,7 @@ bool execute(const std::string& name, dim3 grid, dim3, void** args) {
     if (has("cd_tail_kernel")) { k_cd_tail(args); return true; }
     if (has("set_column_pair_kernel")) { k_set_column_pair(args); return true; }
     if (has("fill_bf16_kernel")) { k_fill_bf16(args); return true; }
-    if (has("sqdiff_bf16_partial_kernel")) { k_sqdiff_bf16_partial(args, grid); return true; }
-    if (has("sqdiff_bf16_finish_kernel")) { k_finish_sum(args); return true; }
+    if (has("sqdiff_bf16_kernel")) { k_sqdiff_bf16(args, grid); return true; }
     if (has("u8_to_bf16_kernel")) { k_u8_to_bf16(args); return true; }
     if (has("colsum_bf16_partial_kernel")) return true;                    // folded into the finish kernel's restatement
     if (has("colsum_bf16_finish_kernel")) { k_colsum_bf16_finish(args); return true; }
