@@ -12,6 +12,12 @@
 // With fakecuda_set_execute(1) the recorded launches are interpreted on the CPU (kernels_cpu.cpp), which also checks the dataflow of
 // every program launch for hazards no declared dependency covers (fakecuda_set_hazards: 0 off, 1 launches small enough to shadow
 // -- the default --, 2 always; fakecuda_drop_dependency pretends one declaration away, for tests of the checker).
+// With fakecuda_set_stream_order_check(1) (needs execute) the ORDER between streams is checked too: every copy, memset and
+// interpreted launch runs with all device allocations protected, so that the pages it reads and writes are known exactly (page
+// faults); each operation carries the vector clock its stream, the events it waited for and the host's synchronisations give it, and
+// two operations that touch the same page, at least one writing, without one happening before the other are a violation ("stream
+// race") -- the double-buffered epoch loops (copy stream against compute stream) are the customers.  fakecuda_ignore_event_waits(1)
+// makes cudaStreamWaitEvent a no-op, for the tests of the checker itself.
 // What the run proves: argument validation (every BM_REQUIRE), buffer sizing, pointer arithmetic, program construction and
 // the control flow around the kernels.  What it cannot prove: anything a kernel computes (results are whatever the zeroed
 // buffers hold).  It never ships: the product library links the real runtime and refuses to start without a B200.
@@ -24,6 +30,12 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <array>
+#include <signal.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <unistd.h>
 
 namespace fakecuda {
 bool execute(const std::string& name, dim3 grid, dim3 block, void** args);
@@ -152,6 +164,158 @@ std::string record_launch(const void* func) {
 
 }  // namespace
 
+namespace {
+
+// ---- stream-order check ---------------------------------------------------------------------------------------------------
+constexpr int MAX_STREAMS = 16;
+typedef std::array<unsigned, MAX_STREAMS> Clock;
+constexpr size_t PAGE = 4096;
+struct Access { uintptr_t lo, hi; bool write; int stream; Clock clock; std::string label; };   // pages [lo, hi)
+struct Order {
+    bool on = false, ignore_waits = false;
+    std::map<cudaStream_t, int> ids;                  // 0: the legacy default stream
+    std::map<int, bool> blocking;
+    Clock host{};                                     // what the host has synchronised with
+    Clock at[MAX_STREAMS]{};                          // per stream: everything that happens before its next operation
+    std::map<cudaEvent_t, Clock> events;
+    std::map<uintptr_t, std::vector<Access>> history; // per allocation
+    long ops = 0, races = 0;
+};
+Order& ord() { static Order* o = new Order(); return *o; }
+Clock merged(Clock a, const Clock& b) { for (int i = 0; i < MAX_STREAMS; ++i) a[i] = std::max(a[i], b[i]); return a; }
+int stream_id(cudaStream_t s) {
+    Order& o = ord();
+    if (!s) return 0;
+    auto it = o.ids.find(s);
+    if (it != o.ids.end()) return it->second;
+    const int id = (int)o.ids.size() + 1;
+    o.ids[s] = id < MAX_STREAMS ? id : MAX_STREAMS - 1;
+    return o.ids[s];
+}
+// page-fault recording: async-signal-safe, fixed storage
+struct Region { uintptr_t base, size; };
+Region g_regions[4096]; int g_n_regions = 0;
+struct Fault { uintptr_t page; bool write; };
+Fault* g_faults = nullptr; size_t g_n_faults = 0; constexpr size_t MAX_FAULTS = 1u << 22;
+volatile bool g_recording = false;
+struct sigaction g_prev_segv;
+void segv_handler(int sig, siginfo_t* info, void* uc) {
+    const uintptr_t a = (uintptr_t)info->si_addr;
+    if (g_recording) {
+        for (int i = 0; i < g_n_regions; ++i)
+            if (a >= g_regions[i].base && a < g_regions[i].base + g_regions[i].size) {
+                const bool wr = (((ucontext_t*)uc)->uc_mcontext.gregs[REG_ERR] & 2) != 0;
+                const uintptr_t page = a & ~(uintptr_t)(PAGE - 1);
+                if (g_n_faults < MAX_FAULTS) { g_faults[g_n_faults].page = page; g_faults[g_n_faults].write = wr; ++g_n_faults; }
+                mprotect((void*)page, PAGE, wr ? (PROT_READ | PROT_WRITE) : PROT_READ);
+                return;
+            }
+    }
+    // not ours: hand over to whoever was installed before (Python's faulthandler, or the default action)
+    if (g_prev_segv.sa_flags & SA_SIGINFO) { if (g_prev_segv.sa_sigaction) { g_prev_segv.sa_sigaction(sig, info, uc); return; } }
+    else if (g_prev_segv.sa_handler != SIG_DFL && g_prev_segv.sa_handler != SIG_IGN) { g_prev_segv.sa_handler(sig); return; }
+    signal(SIGSEGV, SIG_DFL);
+}
+void order_enable(bool on) {
+    Order& o = ord();
+    if (on && !g_faults) {
+        g_faults = (Fault*)mmap(nullptr, MAX_FAULTS * sizeof(Fault), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        struct sigaction sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sa_sigaction = segv_handler; sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+        sigemptyset(&sa.sa_mask);
+        sigaction(SIGSEGV, &sa, &g_prev_segv);
+    }
+    o.on = on;
+    o.history.clear();
+}
+struct OpScope {                                       // one copy / memset / interpreted launch
+    bool active = false; int sid = 0; Clock clock{}; std::string label;
+    OpScope(cudaStream_t s, const std::string& what, bool host_synchronous = false) {
+        Order& o = ord();
+        if (!o.on) return;
+        active = true; label = what; sid = stream_id(s);
+        Clock c = merged(o.at[sid], o.host);
+        if (host_synchronous || sid == 0)               // legacy default stream: after everything in the blocking streams
+            for (auto& kv : o.blocking) if (kv.second) c = merged(c, o.at[kv.first]);
+        c[sid] += 1;
+        clock = c; o.at[sid] = c; ++o.ops;
+        if (host_synchronous || sid == 0) {
+            for (auto& kv : o.blocking) if (kv.second) o.at[kv.first] = merged(o.at[kv.first], c);
+            if (host_synchronous) o.host = merged(o.host, c);
+        }
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_n_regions = 0;
+        for (auto& kv : g_alloc) if (g_n_regions < 4096) { g_regions[g_n_regions].base = kv.first; g_regions[g_n_regions].size = (kv.second + PAGE - 1) & ~(PAGE - 1); ++g_n_regions; }
+        for (int i = 0; i < g_n_regions; ++i) mprotect((void*)g_regions[i].base, g_regions[i].size, PROT_NONE);
+        g_n_faults = 0;
+        g_recording = true;
+    }
+    ~OpScope() {
+        if (!active) return;
+        g_recording = false;
+        for (int i = 0; i < g_n_regions; ++i) mprotect((void*)g_regions[i].base, g_regions[i].size, PROT_READ | PROT_WRITE);
+        Order& o = ord();
+        // pages -> per allocation, reads and writes separately, consecutive pages coalesced
+        std::vector<Fault> f(g_faults, g_faults + g_n_faults);
+        std::sort(f.begin(), f.end(), [](const Fault& a, const Fault& b) { return a.write != b.write ? a.write < b.write : a.page < b.page; });
+        std::vector<Access> mine;
+        for (size_t i = 0; i < f.size();) {
+            size_t j = i + 1;
+            while (j < f.size() && f[j].write == f[i].write && f[j].page <= f[j - 1].page + PAGE) ++j;
+            // (a coalesced run stays inside one allocation only if the allocations are not adjacent: split at region borders)
+            uintptr_t lo = f[i].page;
+            const uintptr_t end = f[j - 1].page + PAGE;
+            while (lo < end) {
+                uintptr_t base = 0, lim = 0;
+                for (int r = 0; r < g_n_regions; ++r) if (lo >= g_regions[r].base && lo < g_regions[r].base + g_regions[r].size) { base = g_regions[r].base; lim = base + g_regions[r].size; }
+                if (!base) break;
+                const uintptr_t hi = std::min(end, lim);
+                Access a; a.lo = lo; a.hi = hi; a.write = f[i].write; a.stream = sid; a.clock = clock; a.label = label;
+                mine.push_back(a);
+                (void)base;
+                lo = hi;
+            }
+            i = j;
+        }
+        std::string report;
+        for (const Access& a : mine) {
+            uintptr_t base = 0;
+            for (int r = 0; r < g_n_regions; ++r) if (a.lo >= g_regions[r].base && a.lo < g_regions[r].base + g_regions[r].size) base = g_regions[r].base;
+            std::vector<Access>& h = o.history[base];
+            for (const Access& p : h) {
+                if (!(a.write || p.write) || p.hi <= a.lo || a.hi <= p.lo) continue;
+                if (p.clock[p.stream] <= a.clock[p.stream]) continue;          // p happens before a
+                if (report.empty()) {
+                    char buf[512];
+                    snprintf(buf, sizeof(buf), "stream race: '%s' (stream %d, %s) and the earlier '%s' (stream %d, %s) touch bytes [%zu, %zu) of the allocation at %p with no ordering between them",
+                             a.label.c_str(), a.stream, a.write ? "writes" : "reads", p.label.c_str(), p.stream, p.write ? "writes" : "reads",
+                             (size_t)(std::max(a.lo, p.lo) - base), (size_t)(std::min(a.hi, p.hi) - base), (void*)base);
+                    report = buf;
+                }
+                ++o.races;
+            }
+        }
+        for (const Access& a : mine) {
+            uintptr_t base = 0;
+            for (int r = 0; r < g_n_regions; ++r) if (a.lo >= g_regions[r].base && a.lo < g_regions[r].base + g_regions[r].size) base = g_regions[r].base;
+            o.history[base].push_back(a);
+        }
+        if (!report.empty()) violation(report);
+    }
+};
+void order_host_sync(const Clock& with) {               // the host has waited for `with`: older accesses are ordered before everything new
+    Order& o = ord();
+    o.host = merged(o.host, with);
+    if (!o.on) return;
+    for (auto& kv : o.history) {
+        std::vector<Access>& h = kv.second;
+        h.erase(std::remove_if(h.begin(), h.end(), [&](const Access& p) { return p.clock[p.stream] <= o.host[p.stream]; }), h.end());
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 // ---- inspection hooks for the tests --------------------------------------------------------------------------------
@@ -172,6 +336,10 @@ void fakecuda_set_hazards(int mode) { st().hazards = mode; }
 long fakecuda_hazard_launches(void) { return st().hazard_launches; }
 long fakecuda_unhonoured_dependencies(void) { return st().unhonoured; }
 void fakecuda_drop_dependency(int op, int d) { st().drop_op = op; st().drop_dep = d; }
+void fakecuda_set_stream_order_check(int on) { order_enable(on != 0); }
+void fakecuda_ignore_event_waits(int on) { ord().ignore_waits = on != 0; }
+long fakecuda_stream_order_ops(void) { return ord().ops; }
+long fakecuda_stream_races(void) { return ord().races; }
 // kernels that were launched while executing but have no CPU restatement: "name xN; ..." ("" if none)
 const char* fakecuda_skipped(void) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -233,7 +401,8 @@ cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long
 cudaError_t cudaMalloc(void** p, size_t n) {
     void* q = nullptr;
     if (n == 0) n = 1;
-    if (posix_memalign(&q, 256, n) != 0) return cudaErrorMemoryAllocation;
+    // whole pages of its own (the stream-order check protects allocations page by page)
+    if (posix_memalign(&q, PAGE, (n + PAGE - 1) & ~(PAGE - 1)) != 0) return cudaErrorMemoryAllocation;
     memset(q, 0xCD, n);                                  // device memory is NOT zero-initialised
     std::lock_guard<std::mutex> lk(g_mu);
     g_alloc[(uintptr_t)q] = n;
@@ -248,6 +417,7 @@ cudaError_t cudaFree(void* p) {
         if (it == g_alloc.end()) { if (g_violation.empty()) g_violation = "cudaFree of a pointer that is not a live allocation"; return cudaErrorInvalidValue; }
         g_alloc.erase(it);
     }
+    ord().history.erase((uintptr_t)p);                   // (cudaFree waits for the device)
     free(p);
     return cudaSuccess;
 }
@@ -262,33 +432,62 @@ static void copy_checked(void* d, const void* s, size_t n, enum cudaMemcpyKind k
     if (k == cudaMemcpyHostToDevice) st().h2d_bytes += (long)n; else if (k == cudaMemcpyDeviceToHost) st().d2h_bytes += (long)n;
     memmove(d, s, n);
 }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind k) { st().syncs++; copy_checked(d, s, n, k); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind k, cudaStream_t) { copy_checked(d, s, n, k); return cudaSuccess; }
-cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t) {
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind k) {
+    st().syncs++;
+    OpScope op(nullptr, "cudaMemcpy", true);
+    copy_checked(d, s, n, k);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind k, cudaStream_t stream) {
+    OpScope op(stream, "cudaMemcpyAsync");
+    copy_checked(d, s, n, k);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t stream) {
     if (h) { check_range(d, (h - 1) * dp + w, "cudaMemcpy2D destination"); check_range(s, (h - 1) * sp + w, "cudaMemcpy2D source"); }
+    OpScope op(stream, "cudaMemcpy2DAsync");
     for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
     return cudaSuccess;
 }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { check_range(d, n, "cudaMemset"); memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t stream) {
+    check_range(d, n, "cudaMemset");
+    OpScope op(stream, "cudaMemsetAsync");
+    memset(d, v, n);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpyToSymbolAsync(const void* sym, const void* s, size_t n, size_t off, enum cudaMemcpyKind, cudaStream_t) {
     memcpy((char*)sym + off, s, n);                       // the host shadow of the __constant__ array
     return cudaSuccess;
 }
 
 // ---- streams / events -------------------------------------------------------------------------------------------------------
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { st().syncs++; return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) {
+    *s = (cudaStream_t)malloc(8);
+    ord().blocking[stream_id(*s)] = (flags & cudaStreamNonBlocking) == 0;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s) { ord().blocking.erase(stream_id(s)); ord().ids.erase(s); free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { st().syncs++; order_host_sync(ord().at[stream_id(s)]); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    Order& o = ord();
+    auto it = o.events.find(e);
+    if (!o.ignore_waits && it != o.events.end()) { const int id = stream_id(s); o.at[id] = merged(o.at[id], it->second); }
+    return cudaSuccess;
+}
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { st().syncs++; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { ord().events.erase(e); free(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { Order& o = ord(); o.events[e] = merged(o.at[stream_id(s)], o.host); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+    st().syncs++;
+    auto it = ord().events.find(e);
+    if (it != ord().events.end()) order_host_sync(it->second);
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1e-3f; return cudaSuccess; }
 
 // ---- launches: recorded, not executed --------------------------------------------------------------------------------------
-cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
+cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024 ||
         grid.y > 65535 || grid.z > 65535 || smem > 232448) {
         char buf[160];
@@ -298,7 +497,9 @@ cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** arg
         return cudaErrorInvalidConfiguration;
     }
     const std::string name = record_launch(func);
-    if (st().execute && !fakecuda::execute(name, grid, block, args)) { std::lock_guard<std::mutex> lk(g_mu); st().skipped[name]++; }
+    bool done = true;
+    if (st().execute) { OpScope op(stream, name); done = fakecuda::execute(name, grid, block, args); }
+    if (!done) { std::lock_guard<std::mutex> lk(g_mu); st().skipped[name]++; }
     return cudaSuccess;
 }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* func, void** args) {

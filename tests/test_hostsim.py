@@ -604,3 +604,62 @@ def test_a_device_that_cannot_hold_every_cluster_of_a_program_is_refused(sim):
     ''') % (ROOT, os.path.join(ROOT, 'boltzmann-machines_b200'), os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libbm_hostsim.so'))
     res = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert 'REFUSED:' in res.stdout and 'cannot hold all CTA clusters' in res.stdout, res.stdout[-2000:]
+
+
+def _stream_order_probe(code_body):
+    """runs `code_body` in a fresh process on the stand-in runtime with launches interpreted and the stream-order check on; returns
+    the process's stdout"""
+    import sys
+    import textwrap
+    head = textwrap.dedent('''
+        import ctypes as C, sys, numpy as np
+        sys.path[:0] = [%r, %r]
+        from boltzmann_machines import _native
+        lib = _native.load_library(%r)
+        lib.fakecuda_violation.restype = C.c_char_p
+        _native._lib = lib
+        lib.fakecuda_set_execute(1)
+        lib.fakecuda_set_stream_order_check(1)
+    ''') % (ROOT, os.path.join(ROOT, 'boltzmann-machines_b200'), SIM)
+    res = subprocess.run([sys.executable, '-c', head + textwrap.dedent(code_body)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=600)
+    return res.stdout
+
+
+EPOCH_PROBE = '''
+    V, H, B = 100, 64, 64            # (a half of the double-buffered operand = 64 rows x 192 columns x 2 bytes = 6 whole pages)
+    rng = np.random.RandomState(0)
+    eng = _native.CudaRBM(dict(n_visible=V, n_hidden=H, dtype='float32', compute=%r, l2=1e-4, max_batch=B, **%r))
+    eng.init_normal_W(0.01, 1)
+    X = %s
+    P = eng.pin(X)
+    for it in range(2):
+        eng.train_epoch(P, B, 0.05, 0.5, 2, 1, 10 * it, metrics=('msre',), every=1)
+    eng.unpin(P)
+    eng.close()
+    print('OPS', lib.fakecuda_stream_order_ops(), 'RACES', lib.fakecuda_stream_races())
+    print('VIOLATION:', lib.fakecuda_violation().decode())
+'''
+BYTES = "(rng.rand(7 * 64 + 10, 100) < 0.3).astype(np.float32)"
+REALS = "rng.rand(7 * 64 + 10, 100).astype(np.float32)"
+
+
+@pytest.mark.parametrize('compute,data,extra', [
+    ('bf16', BYTES, {}), ('bf16', REALS, {}), ('fp32', BYTES, {}), ('fp32', REALS, {}),
+    ('bf16', REALS, dict(v_kind='gaussian', sigma=1.0)),                 # not `plain`: fp32 staging + prepare_input on the compute stream
+    ('bf16', BYTES, dict(dropout=0.8)), ('bf16', BYTES, dict(h_kind='multinomial', h_n_samples=5))])
+def test_epoch_loops_are_ordered_between_the_copy_and_the_compute_stream(sim, compute, data, extra):
+    """bm_rbm_train_epoch[_u8|_bf16]: the copy stream uploads (and, for the bf16 engine, converts) batch i+1 into one half of a double
+    buffer while the compute stream works on batch i from the other.  The stand-in runtime knows exactly which pages every copy and
+    every interpreted kernel touches (page protection) and which operations are ordered by streams, events and host
+    synchronisation: no two conflicting accesses may be unordered."""
+    out = _stream_order_probe(EPOCH_PROBE % (compute, extra, data))
+    assert 'RACES 0' in out and 'VIOLATION: \n' in out + '\n', out[-3000:]
+    assert int(out.split('OPS')[1].split()[0]) > 50, out[-3000:]
+
+
+def test_the_stream_order_check_sees_a_missing_event_wait(sim):
+    """the same epoch with cudaStreamWaitEvent turned into a no-op: the copy stream now overwrites a staging buffer the compute
+    stream may still read (and the compute stream reads a batch that may not have arrived) -- the checker must say so"""
+    out = _stream_order_probe("\n    lib.fakecuda_ignore_event_waits(1)" + EPOCH_PROBE % ('bf16', {}, BYTES))
+    assert 'stream race' in out and 'RACES 0' not in out, out[-3000:]
