@@ -33,6 +33,7 @@ V, H, B, K_GIBBS = 784, 1024, 4096, 5
 N_BATCHES = int(os.environ.get('BM_BENCH_BATCHES', '40'))    # resident dataset: 40 x 4096 rows = 257 MB of bf16 > 126 MB L2
 #                                      (BM_BENCH_BATCHES: dry runs on the host simulation only -- `config.l2_policy` states the size)
 LR, MOMENTUM, L2 = 0.05, 0.5, 1e-5
+REFERENCE_BUDGET_S = float(os.environ.get('BM_BENCH_REFERENCE_SECONDS', '40'))   # --impl reference: timed + warm-up steps together
 FIT_MIN_STEPS = int(os.environ.get('BM_BENCH_FIT_STEPS', '2000'))   # e2e: fit() runs at least this many steps (50 epochs of 40 batches)
 FLOP_PER_STEP = 2.0 * B * V * H * (2 * K_GIBBS + 3)      # (2k+3) GEMMs of 2BVH
 
@@ -251,6 +252,15 @@ def time_cpu(step, n_steps, warmup, calibrate=True):
 # --------------------------------------------------------------------------------------------
 # workloads: each returns a dict of callables / constants the driver below times
 # --------------------------------------------------------------------------------------------
+def rbm_config(name, world):
+    """the `config` object of an RBM workload's JSON line -- the same in both arms (`--impl reference` prints this too)"""
+    kind, v, h, b, k, lr, w_std, n_batches, descr = RBM_WORKLOADS[name]
+    ldv = -(-(v + 2) // 64) * 64
+    return {'workload': descr, 'parallelism': 'dp{0}'.format(world),
+            'l2_policy': 'inputs larger than L2: resident dataset {0} MB bf16, batches cycle'.format(b * n_batches * ldv * 2 // 2 ** 20),
+            'flop_per_step': 2.0 * b * v * h * (2 * k + 3), 'global_batch': b * world, 'k': k}
+
+
 def rbm_workload(name, ctx, rank, world, compute):
     from boltzmann_machines import _native
     kind, v, h, b, k, lr, w_std, n_batches, descr = RBM_WORKLOADS[name]
@@ -430,8 +440,10 @@ def dbm_workload(name, ctx, rank, world, compute, ais_runs, ais_betas):
 # --------------------------------------------------------------------------------------------
 # CPU side: the oracle (numpy + C Philox) timed on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_arm(name, n_steps, warmup, ais_runs, ais_betas):
-    """(value in the metric's unit, seconds per step, threads, sample description, quality dict)"""
+def cpu_arm(name, n_steps, warmup, ais_runs, ais_betas, budget_s=None):
+    """(value in the metric's unit, seconds per step, threads, sample description, quality dict).  `budget_s` (RBM workloads): run
+    EXACTLY n_steps timed steps, each on as many rows of the batch as keeps the timed region near that many seconds -- a step is then
+    a bounded sample of the workload's step (same model, same k, fewer rows), and the rate is rows * k / time as always."""
     n_cpu = os.cpu_count()
     if name in RBM_WORKLOADS:
         from oracle.rbm import OracleRBM
@@ -440,12 +452,20 @@ def cpu_arm(name, n_steps, warmup, ais_runs, ais_betas):
         ora = OracleRBM(model_cfg('fp32', name))
         rng = np.random.RandomState(0)
         ora.set_params({'W': (w_std * rng.randn(v, h)).astype(np.float32)})
-        dt, threads = time_cpu(lambda i: ora.train_step(X[(i % 2) * b:(i % 2 + 1) * b], lr, MOMENTUM, k, 1, i), n_steps, warmup)
+        rows = b
+        if budget_s is not None:
+            # one full step per BLAS pool size first (it is also the pool calibration); then the rows that fit the budget
+            t_full, _ = time_cpu(lambda i: ora.train_step(X[:b], lr, MOMENTUM, k, 1, 10 ** 6 + i), 1, 1)
+            rows = int(min(b, max(64, b * budget_s / (max(1, n_steps + warmup) * t_full)))) // 64 * 64
+        dt, threads = time_cpu(lambda i: ora.train_step(X[(i % 2) * b:(i % 2) * b + rows], lr, MOMENTUM, k, 1, i), n_steps, warmup)
         Xv = synth_cifar(b, v, seed=99) if kind == 'gaussian' else synth_mnist(b, seed=99, n_vis=v)
         m = ora.metrics(Xv, 1, 1, 10 ** 6, ('msre', 'pll'))
         q = {'val_msre': float(m['msre']), 'val_pll': float(m['pll']), 'train_steps': n_steps + max(1, warmup) + 4}
         sample = '{0} CD-{1} steps of batch {2} ({3}-{4}) on the oracle (numpy/OpenBLAS + C Philox)'.format(n_steps, k, b, v, h)
-        return n_steps * b * k / dt, dt / n_steps, threads, sample, q
+        if rows != b:
+            sample = ('{0} CD-{1} steps on {5} rows each of the batch of {2} ({3}-{4}) on the oracle (numpy/OpenBLAS + C Philox): a '
+                      'full step takes {6:.2f} s here, the sample keeps the run within its time budget').format(n_steps, k, b, v, h, rows, t_full)
+        return n_steps * rows * k / dt, dt / n_steps, threads, sample, q
     from oracle.dbm import OracleDBM
     if name == 'cfg4-ais':
         cfg = dbm_cfg('fp32')
@@ -481,22 +501,29 @@ METRICS = {'cfg4': ('dbm_train_rows_per_sec', 'rows/s'), 'cfg4-ais': ('ais_chain
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU path (oracle/ -- TF 1.3 / Python 2 cannot run in this image) on
+    the host cores, with the BLAS pool at its fastest size.  Same `config`, `metric`, `unit` as the b200 arm; RBM workloads run
+    exactly --steps timed and --warmup untimed steps, each a bounded sample of the workload's step (cpu_arm)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 12))          # ~1.5 s of CPU work per step at cfg2: bounded sample
-    warm = max(1, min(args.warmup, 2))
-    if args.config in ('cfg3', 'cfg5'):
-        steps, warm = min(steps, 3), 1
-    val, sec, cores, sample, quality = cpu_arm(args.config, steps, warm, args.ais_runs, args.ais_betas)
+    note = 'TF1/py2 reference cannot run in this image; timed: oracle/ restatement of its CPU path'
+    if args.config in RBM_WORKLOADS:
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        val, sec, cores, sample, quality = cpu_arm(args.config, steps, warm, args.ais_runs, args.ais_betas, budget_s=REFERENCE_BUDGET_S)
+        config = rbm_config(args.config, args.gpus)
+    else:
+        steps = max(1, min(args.steps, 12))
+        warm = max(1, min(args.warmup, 2))
+        val, sec, cores, sample, quality = cpu_arm(args.config, steps, warm, args.ais_runs, args.ais_betas)
+        config = {'workload': args.config}
     metric, unit = METRICS.get(args.config, ('gibbs_updates_per_sec', 'updates/s'))
     sample += '; BLAS pool {0} of {1} hardware threads'.format(cores, os.cpu_count())
     print(json.dumps({
         'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit,
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * sec,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.config,
-                   'note': 'TF1/py2 reference cannot run in this image; timed: oracle/ restatement of its CPU path'},
+        'config': config, 'note': note,
         'quality': quality,
         'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -710,6 +737,8 @@ def main():
     config = {'workload': wl['descr'], 'parallelism': 'dp{0}'.format(world), 'l2_policy': wl['l2_policy'],
               'flop_per_step': flop_step}
     config.update(wl['cfg_extra'])
+    if args.config in RBM_WORKLOADS:
+        assert config == rbm_config(args.config, world), (config, rbm_config(args.config, world))
     out = {
         'metric': wl['metric'], 'value': value, 'unit': wl['unit'],
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,

@@ -50,3 +50,28 @@ def test_bench_contract_on_the_host_simulation(tmp_path):
     assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert out['e2e']['h2d_bytes_per_step'] == 4096 * 784          # one byte per visible unit and row
     assert out['gpu_launches'] == 2 * out['steps']                  # the step's program and the update kernel
+
+
+def test_reference_arm_prints_the_same_config_and_runs_exactly_the_steps_it_was_given(tmp_path):
+    """`bench.py --impl reference --steps K --warmup W`: the oracle port on the host cores; same `config` object as the b200 arm,
+    exactly K timed steps (each a bounded sample of the workload's step when K full steps would not fit the time budget), and the
+    cpu_baseline / e2e objects the contract asks of this arm."""
+    env = dict(os.environ, BM_BENCH_REFERENCE_SECONDS='3', BM_BENCH_BATCHES='20')
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '7', '--warmup', '2'],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert res.returncode == 0, res.stdout[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith('{"impl"')][0])
+    assert out['impl'] == 'reference' and out['steps'] == 7 and out['warmup'] == 2 and out['n_gpus'] == 1
+    assert out['metric'] == 'gibbs_updates_per_sec' and out['unit'] == 'updates/s' and out['higher_is_better'] is True
+    sys.path.insert(0, ROOT)
+    try:
+        os.environ['BM_BENCH_BATCHES'] = '20'
+        import importlib
+        bench = importlib.import_module('bench')
+        assert out['config'] == bench.rbm_config('cfg2', 1)
+    finally:
+        os.environ.pop('BM_BENCH_BATCHES', None)
+        sys.path.remove(ROOT)
+    assert out['cpu_baseline']['kind'] == 'port' and out['cpu_baseline']['value'] == out['value'] and out['cpu_baseline']['cores'] >= 1
+    assert 'rows each of the batch of 4096' in out['cpu_baseline']['sample']          # 9 full steps do not fit 3 seconds
+    assert out['e2e'] == {'value': out['value'], 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
