@@ -269,7 +269,9 @@ def rbm_workload(name, ctx, rank, world, compute):
     eng = _native.CudaRBM(model_cfg(compute, name), ctx=ctx)
     eng.init_normal_W(w_std, 1337)
     if kind != 'gaussian':
-        p = np.clip(X[:8192].mean(axis=0), 1e-7, 1 - 1e-7)
+        # (data parallel: every replica starts from the same parameters -- the visible bias comes from rank 0's rows on every rank)
+        X0 = X if rank == 0 else synth_mnist(8192, seed=1337, n_vis=v)
+        p = np.clip(X0[:8192].mean(axis=0), 1e-7, 1 - 1e-7)
         eng.set_params({'vb': np.log(p / (1 - p)).astype(np.float32)})
     eng.set_data(X)
     seed = 20260922
@@ -313,7 +315,7 @@ def rbm_workload(name, ctx, rank, world, compute):
         if kind == 'gaussian':
             model = GaussianRBM(sigma=1., **kw)
         else:
-            pm = np.clip(X[:8192].mean(axis=0), 1e-7, 1 - 1e-7)
+            pm = np.clip(X0[:8192].mean(axis=0), 1e-7, 1 - 1e-7)
             model = BernoulliRBM(vb_init=np.log(pm / (1 - pm)).astype(np.float32), **kw)
         old = _native.Context._default.get(None)
         _native.Context._default[None] = ctx            # the model's engine lives on this rank's context (and communicator)
