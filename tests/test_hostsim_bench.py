@@ -75,3 +75,28 @@ def test_reference_arm_prints_the_same_config_and_runs_exactly_the_steps_it_was_
     assert out['cpu_baseline']['kind'] == 'port' and out['cpu_baseline']['value'] == out['value'] and out['cpu_baseline']['cores'] >= 1
     assert 'rows each of the batch of 4096' in out['cpu_baseline']['sample']          # 9 full steps do not fit 3 seconds
     assert out['e2e'] == {'value': out['value'], 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_bench_with_two_ranks_on_the_host_simulation(tmp_path):
+    """the launch the driver uses for N > 1 (torchrun, one rank per GPU) with both ranks on the stand-in runtime and the shared-memory
+    stand-in for NCCL: rank 0 prints one line for the whole job, the engine-level regions and fit() run data parallel, nothing
+    breaks a runtime rule"""
+    pytest.importorskip('torch')
+    obj = os.path.join(ROOT, 'boltzmann-machines_b200', 'build')
+    if not (os.path.isdir(obj) and any(f.endswith('.o') for f in os.listdir(obj))):
+        pytest.skip('library objects not built (run build.sh / __graft_entry__.build())')
+    subprocess.check_call(['bash', os.path.join(ROOT, 'tests', 'hostsim', 'build.sh')], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, BM_BENCH_BATCHES='4', BM_BENCH_FIT_STEPS='8',
+               BM_NCCL_LIB=os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libfakenccl.so'))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(29900 + os.getpid() % 90), os.path.join(ROOT, 'tools', 'hostsim_run.py'), os.path.join(ROOT, 'bench.py'),
+           '--gpus', '2', '--steps', '6', '--warmup', '3', '--no-cpu-baseline']
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=str(tmp_path), env=env)
+    assert res.returncode == 0, res.stdout[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith('{"metric"')]
+    assert len(lines) == 1, res.stdout[-2000:]
+    out = json.loads(lines[0])
+    assert out['n_gpus'] == 2 and out['steps'] == 6 and out['scaling'] == 'weak'
+    assert out['config']['parallelism'] == 'dp2' and out['config']['global_batch'] == 2 * 4096
+    assert out['e2e']['h2d_bytes_per_step'] == 2 * 4096 * 784 and out['e2e']['steps'] >= 8
+    assert res.stdout.count('violations: none') == 2, res.stdout[-2000:]
