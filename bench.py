@@ -299,7 +299,7 @@ def rbm_workload(name, ctx, rank, world, compute):
     wl['h2d_native'] = lambda Xh: b * v * Xh.dtype.itemsize * world
     wl['d2h'] = 64 * world
 
-    def fit_e2e(n_steps):
+    def fit_e2e(n_steps, before_close=None):
         """The call a user of the library makes: Model(**kwargs).fit(X) on a HOST float32 array -- engine construction, weight
         initialisation, packing + page-locking of the training set, the epochs (every step uploads its own batch and reads its
         MSRE back) and the final save are all inside the timed region.  Returns (seconds, steps run, bytes up per step)."""
@@ -342,6 +342,10 @@ def rbm_workload(name, ctx, rank, world, compute):
                                     'everything_else (engine construction, init, epochs)': 1e3 * (dt - spent['pin'] - spent['save'])}
         finally:
             _native.CudaRBM.pin, NativeModel._save_model = real_pin, real_save
+            # data parallel: the final save reads the other ranks' weight rows through peer memory -- every rank must have
+            # finished reading before any rank frees its model (peer exchange)
+            if before_close is not None:
+                before_close()
             model.close() if hasattr(model, 'close') else None
             if old is None:
                 _native.Context._default.pop(None, None)
@@ -661,12 +665,12 @@ def main():
         # this 514 MB float32 set) that a K-step run does not amortise when K is a few dozen: the fit runs for at least
         # FIT_MIN_STEPS steps (whole epochs) whatever K is, and states how many it ran
         fit_target = max(args.steps, FIT_MIN_STEPS if args.config == 'cfg2' else args.steps)
-        fit_s, fit_steps, up = wl['fit_e2e'](min(fit_target, 2 * wl['n_batches']))          # (warm: library loaded, CUDA context up)
+        fit_s, fit_steps, up = wl['fit_e2e'](min(fit_target, 2 * wl['n_batches']), barrier)          # (warm: library loaded, CUDA context up)
         passes = []
         for _ in range(2):
             barrier()
             sampler.mark()
-            fit_s, fit_steps, up = wl['fit_e2e'](fit_target)
+            fit_s, fit_steps, up = wl['fit_e2e'](fit_target, barrier)
             barrier()
             sampler.unmark()
             passes.append(max_over_ranks(fit_s))
