@@ -220,7 +220,7 @@ def blas_threads():
         return None
 
 
-def time_cpu(step, n_steps, warmup, calibrate=True):
+def time_cpu(step, n_steps, warmup, calibrate=True, threads=None):
     """Times `step(i)` (the oracle, numpy/OpenBLAS + C Philox) on the host cores.  OpenBLAS with every hardware thread of
     a 128-core host is several times SLOWER on these GEMMs than with a few dozen threads, so the BLAS pool size is calibrated
     first (one step per candidate) and the fastest setting is the one reported -- the CPU arm at its best."""
@@ -240,6 +240,9 @@ def time_cpu(step, n_steps, warmup, calibrate=True):
             tick[0] += 1
         return time.perf_counter() - t0
 
+    if threads is not None:                       # pool size already calibrated by an earlier call
+        run(warmup, threads)
+        return run(n_steps, threads), threads
     run(max(1, warmup), n_cpu)
     if calibrate and limits is not None and n_cpu > 8:
         cands = sorted({c for c in (8, 16, 32, 64, n_cpu) if c <= n_cpu})
@@ -458,12 +461,13 @@ def cpu_arm(name, n_steps, warmup, ais_runs, ais_betas, budget_s=None):
         ora = OracleRBM(model_cfg('fp32', name))
         rng = np.random.RandomState(0)
         ora.set_params({'W': (w_std * rng.randn(v, h)).astype(np.float32)})
-        rows = b
+        rows, pool = b, None
         if budget_s is not None:
             # one full step per BLAS pool size first (it is also the pool calibration); then the rows that fit the budget
-            t_full, _ = time_cpu(lambda i: ora.train_step(X[:b], lr, MOMENTUM, k, 1, 10 ** 6 + i), 1, 1)
+            t_full, pool = time_cpu(lambda i: ora.train_step(X[:b], lr, MOMENTUM, k, 1, 10 ** 6 + i), 1, 1)
             rows = int(min(b, max(64, b * budget_s / (max(1, n_steps + warmup) * t_full)))) // 64 * 64
-        dt, threads = time_cpu(lambda i: ora.train_step(X[(i % 2) * b:(i % 2) * b + rows], lr, MOMENTUM, k, 1, i), n_steps, warmup)
+        dt, threads = time_cpu(lambda i: ora.train_step(X[(i % 2) * b:(i % 2) * b + rows], lr, MOMENTUM, k, 1, i), n_steps, warmup,
+                               threads=pool)
         Xv = synth_cifar(b, v, seed=99) if kind == 'gaussian' else synth_mnist(b, seed=99, n_vis=v)
         m = ora.metrics(Xv, 1, 1, 10 ** 6, ('msre', 'pll'))
         q = {'val_msre': float(m['msre']), 'val_pll': float(m['pll']), 'train_steps': n_steps + max(1, warmup) + 4}
