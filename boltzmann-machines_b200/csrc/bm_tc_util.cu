@@ -93,7 +93,7 @@ template void launch_u8_to_real<double>(Ctx*, const uint8_t*, double*, size_t);
 // ---- MSRE on the bf16 activations (base_rbm.py:486-488): mean((X - v_means)^2), accumulated in fp64 ----
 constexpr int SQ_BLOCKS = 592;
 // one launch: every block leaves its partial sum, the block that arrives last adds them up in a fixed order (thread t takes
-// partials t, t+256, ...; then the same tree as above), so the value does not depend on which block that is
+// partials t, t+256, ...; then the block's shared-memory tree), so the value does not depend on which block that is
 __global__ void sqdiff_bf16_kernel(const __nv_bfloat16* __restrict__ P, int ldp, const __nv_bfloat16* __restrict__ Q, int ldq,
                                    int rows, int cols, double* __restrict__ partial, unsigned int* __restrict__ arrived,
                                    double denom, double* __restrict__ out) {
