@@ -25,6 +25,6 @@ def test_two_ranks_through_the_host_simulation():
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-4000:]
     import re
-    for what in ('compute=fp32', 'compute=bf16', 'AIS:', 'DBM data parallel', 'tensor-core DBM data parallel'):
+    for what in ('compute=fp32', 'compute=bf16', 'epoch compute=fp32', 'epoch compute=bf16', 'AIS:', 'DBM data parallel', 'tensor-core DBM data parallel'):
         n = len(re.findall(r'rank \d ' + re.escape(what), res.stdout))
         assert n == 2, (what, n, res.stdout[-2000:])

@@ -53,6 +53,28 @@ def main():
             rank, compute, err, identical), flush=True)
         ok = ok and err < tol and identical
         eng.close()
+        # the whole-epoch entry point, data parallel: every rank feeds ITS rows of each global batch from a packed, page-locked
+        # training set (bytes here: bm_rbm_train_epoch_u8; upload and conversion of batch i+1 overlap batch i); the oracle steps
+        # through the concatenated batches
+        eng, ora = _native.CudaRBM(cfg, ctx=ctx), OracleRBM(cfg)
+        eng.set_params(init); ora.set_params(init)
+        nb = 3
+        Xe = (np.random.RandomState(5).rand(nb, world, rows, V) < 0.2).astype(np.float32)
+        mine_rows = np.ascontiguousarray(Xe[:, rank].reshape(nb * rows, V))
+        P = eng.pin(mine_rows)
+        got_m = eng.train_epoch(P, rows, 0.05, 0.5, 2, 77, 100, metrics=('msre',), every=1)
+        want_m = [ora.train_step(Xe[i].reshape(world * rows, V), 0.05, 0.5, 2, 77, 100 + i, metrics=('msre',))['msre'] for i in range(nb)]
+        eng.unpin(P)
+        got, want = eng.get_params(['W', 'vb', 'hb']), ora.get_params(['W', 'vb', 'hb'])
+        err = max(float(np.max(np.abs(got[k] - want[k]))) for k in got)
+        mine = np.concatenate([got[k].ravel() for k in sorted(got)])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        identical = all(np.array_equal(gathered[0], g) for g in gathered)
+        print('rank {0} epoch compute={1}: max |engine - oracle(full batches)| = {2:.3e}, ranks identical: {3}, feed {4}'.format(
+            rank, compute, err, identical, P.dtype), flush=True)
+        ok = ok and err < tol and identical and len(got_m['msre']) == nb and np.all(np.isfinite(got_m['msre']))
+        eng.close()
     # AIS: the runs shard over the ranks inside bm_dbm_ais (one sum-allreduce of n_runs doubles gathers them);
     # every rank must receive the ladder a single GPU computes (run r draws from row r whichever rank owns it)
     from oracle.dbm import OracleDBM
