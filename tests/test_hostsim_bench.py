@@ -49,6 +49,7 @@ def test_bench_contract_on_the_host_simulation(tmp_path):
     assert set(out['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert out['e2e']['h2d_bytes_per_step'] == 4096 * 784          # one byte per visible unit and row
+    assert 'fit_region_failed' not in out['e2e'] and out['e2e']['path'].startswith('Model(**kwargs).fit(X)')
     assert out['gpu_launches'] == 2 * out['steps']                  # the step's program and the update kernel
 
 
@@ -98,5 +99,5 @@ def test_bench_with_two_ranks_on_the_host_simulation(tmp_path):
     out = json.loads(lines[0])
     assert out['n_gpus'] == 2 and out['steps'] == 6 and out['scaling'] == 'weak'
     assert out['config']['parallelism'] == 'dp2' and out['config']['global_batch'] == 2 * 4096
-    assert out['e2e']['h2d_bytes_per_step'] == 2 * 4096 * 784 and out['e2e']['steps'] >= 8
+    assert out['e2e']['h2d_bytes_per_step'] == 2 * 4096 * 784 and out['e2e']['steps'] >= 8 and 'fit_region_failed' not in out['e2e']
     assert res.stdout.count('violations: none') == 2, res.stdout[-2000:]
