@@ -297,3 +297,37 @@ def test_resident_dataset_taller_than_the_grid_limit(compute):
         np.testing.assert_array_equal(ga[k], gb[k], err_msg=k)
     assert np.abs(ga['dW']).max() > 0
     a.close(); b.close()
+
+
+@pytest.mark.parametrize('feed', ['bytes', 'bf16'])
+def test_epochs_of_changing_batch_size_interleaved_with_single_steps(feed):
+    """The bf16 engine's operand buffer has two halves (the copy stream converts batch i+1 while batch i runs) and grows with the
+    largest batch seen: epochs with batch 16, then 40 (growth inside the epoch call), a single step, batch 16 again (halves now 40
+    rows apart), a ragged epoch shorter than one batch -- bit-identical to an engine that is only ever fed batch by batch."""
+    cfg = make_cfg('bernoulli', 100, 48, 64, compute='bf16', sample_v=False)
+    a, _ = make_pair(cfg)
+    b, _ = make_pair(cfg)
+    rng = np.random.RandomState(3)
+    if feed == 'bytes':
+        X = (rng.rand(200, 100) < 0.3).astype(np.float32)
+    else:
+        X = rng.rand(200, 100).astype(np.float32)
+    P = b.pin(X)
+    assert (P.dtype == np.uint8) if feed == 'bytes' else isinstance(P, _native.Bf16Array)
+    tick = 0
+    for batch, rows in ((16, 200), (40, 200), (0, 33), (16, 70), (64, 9), (40, 81)):
+        if batch == 0:                                        # a single step on rows of the float array
+            a.train_step(X[:rows], 0.05, 0.5, 2, 11, tick)
+            b.train_step(X[:rows], 0.05, 0.5, 2, 11, tick)
+            tick += 1
+            continue
+        want = []
+        for i, lo in enumerate(range(0, rows, batch)):
+            want.append(a.train_step(X[lo:min(lo + batch, rows)], 0.05, 0.5, 2, 11, tick + i, metrics=('msre',))['msre'])
+        got = b.train_epoch(P[:rows], batch, 0.05, 0.5, 2, 11, tick, metrics=('msre',), every=1)
+        tick += len(want)
+        np.testing.assert_allclose(got['msre'], want, rtol=1e-12)
+        for k, v in a.get_params().items():
+            np.testing.assert_array_equal(v, b.get_params()[k], err_msg='{0} after batch {1}'.format(k, batch))
+    b.unpin(P)
+    a.close(), b.close()
