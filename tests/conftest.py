@@ -55,7 +55,7 @@ def pytest_configure(config):
 
 # GPU tests written after the last visit to a B200 (they pass on the host simulation, tests/hostsim): run them after the tests that
 # have already passed on the hardware, so that `-x` reports a surprise in one of them without hiding the rest of the suite.
-NOT_YET_RUN_ON_A_B200 = ('test_epochs_of_changing_batch_size_interleaved',)   # (everything else passed on the hardware in visit q)
+NOT_YET_RUN_ON_A_B200 = ()       # (round 2, visits q / r: every GPU test has passed on the hardware)
 
 
 def pytest_collection_modifyitems(config, items):
